@@ -1,0 +1,171 @@
+"""Seeded synthetic compressed-EMASE alignment incidence data.
+
+This is the canonical generator of SURVEY.md section 8(d) / BASELINE.md section 3.  It produces the
+logical content of a compressed EMASE file (transcripts x haplotypes x alignment classes, with class
+counts), the gene -> transcript grouping, the per-(locus, haplotype) lengths and, optionally, a diploid
+genotype call per gene.  Everything is returned as plain numpy arrays in *class-major pair form*
+(class id, locus id, 8-bit haplotype mask); `to_csc_list()` turns that into the reference's storage
+(`list` of H scipy CSC matrices, each N_classes x T_loci, cf. reference
+`src/gbrs/emase/Sparse3DMatrix.py:26-66`).
+
+Nothing here is on the product path; tests, fixtures and bench.py use it to make inputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+BASE_SEED = 20261018
+HAPLOTYPES = ("A", "B", "C", "D", "E", "F", "G", "H")
+
+
+@dataclass
+class SynthData:
+    T: int
+    H: int
+    N: int
+    pair_class: np.ndarray  # int64 [pairs], non-decreasing
+    pair_locus: np.ndarray  # int64 [pairs]
+    pair_mask: np.ndarray  # uint8 [pairs], never 0
+    count: np.ndarray  # float64 [N], integer valued
+    gene_of: np.ndarray  # int64 [T], contiguous loci per gene, dense gene ids 0..G-1
+    lengths: np.ndarray  # float64 [T, H] raw transcript lengths (not yet effective lengths)
+    hname: tuple = HAPLOTYPES
+    lname: list = field(default_factory=list)
+    gname: list = field(default_factory=list)
+    genotype: list | None = None  # per gene two-letter diplotype (sorted letters) or None
+
+    @property
+    def G(self) -> int:
+        return len(self.gname)
+
+    @property
+    def pairs(self) -> int:
+        return int(self.pair_class.shape[0])
+
+    @property
+    def nnz(self) -> int:
+        return int(_popcount8(self.pair_mask).sum())
+
+    def groups(self) -> list[list[int]]:
+        """gene -> list of locus ids (reference `AlignmentPropertyMatrix.groups`)."""
+        bounds = np.flatnonzero(np.diff(self.gene_of)) + 1
+        return [list(map(int, x)) for x in np.split(np.arange(self.T), bounds)]
+
+
+def _popcount8(x: np.ndarray) -> np.ndarray:
+    table = np.array([bin(i).count("1") for i in range(256)], dtype=np.int64)
+    return table[x.astype(np.uint8)]
+
+
+def generate(T: int, N: int, H: int = 8, sample_index: int = 0, with_genotype: bool = False,
+             n_genes: int | None = None) -> SynthData:
+    """Generate one sample.  `sample_index` shifts the seed (cohort mode shares gene_of / lengths by
+    drawing them from the base seed first)."""
+    if not (1 <= H <= 8):
+        raise ValueError("synthetic generator supports 1..8 haplotypes")
+    shared = np.random.default_rng(BASE_SEED)
+    G0 = max(1, int(0.4 * T)) if n_genes is None else int(n_genes)
+    gene_raw = np.sort(shared.integers(0, G0, T))
+    # dense gene ids (drop genes that drew no locus)
+    _, gene_of = np.unique(gene_raw, return_inverse=True)
+    gene_of = gene_of.astype(np.int64)
+    lengths = shared.integers(300, 6000, size=(T, H)).astype(np.float64)
+    geno_idx = shared.integers(0, H, size=(int(gene_of.max()) + 1, 2))
+
+    rng = np.random.default_rng(BASE_SEED + 1 + sample_index)
+    k = np.minimum(1 + rng.poisson(1.5, N), 8).astype(np.int64)
+    scale = max(T / 50.0, 1.0)
+    base = np.minimum((rng.pareto(1.2, N) * scale).astype(np.int64), T - 1)
+    slots = int(k.sum())
+    cls = np.repeat(np.arange(N, dtype=np.int64), k)
+    first = np.zeros(slots, dtype=bool)
+    first[np.cumsum(k) - k] = True
+    off = rng.integers(0, 6, slots)
+    off[first] = 0
+    loc = (base[cls] + off) % T
+    key = np.unique(cls * T + loc)  # de-duplicate, sorted class-major then locus
+    pair_class = key // T
+    pair_locus = key % T
+    P = key.shape[0]
+    full = (1 << H) - 1
+    mask = np.where(rng.random(P) < 0.5, full, rng.integers(1, full + 1, P)).astype(np.uint8)
+    count = rng.geometric(0.2, N).astype(np.float64)
+
+    data = SynthData(T=T, H=H, N=N, pair_class=pair_class, pair_locus=pair_locus, pair_mask=mask,
+                     count=count, gene_of=gene_of, lengths=lengths, hname=HAPLOTYPES[:H])
+    data.lname = [f"T{t:07d}" for t in range(T)]
+    data.gname = [f"G{g:07d}" for g in range(int(gene_of.max()) + 1)]
+    if with_genotype:
+        gi = np.sort(geno_idx, axis=1)
+        data.genotype = [HAPLOTYPES[a] + HAPLOTYPES[b] for a, b in gi]
+    return data
+
+
+def to_csc_list(d: SynthData, dtype=np.float64):
+    """H scipy CSC matrices (N x T), values 1.0 on the incidence pattern."""
+    from scipy.sparse import csc_matrix
+
+    mats = []
+    for h in range(d.H):
+        sel = ((d.pair_mask >> h) & 1).astype(bool)
+        rows = d.pair_class[sel]
+        cols = d.pair_locus[sel]
+        order = np.lexsort((rows, cols))
+        rows = rows[order]
+        cols = cols[order]
+        indptr = np.zeros(d.T + 1, dtype=np.int64)
+        indptr[1:] = np.cumsum(np.bincount(cols, minlength=d.T))
+        idx_t = np.int32 if max(d.N, rows.size) < 2**31 - 1 else np.int64
+        m = csc_matrix((np.ones(rows.size, dtype=dtype), rows.astype(idx_t), indptr.astype(idx_t)),
+                       shape=(d.N, d.T))
+        m.has_sorted_indices = True
+        mats.append(m)
+    return mats
+
+
+def write_group_file(d: SynthData, path: str) -> None:
+    """gene<TAB>t1<TAB>t2... (reference `AlignmentPropertyMatrix.__load_groups`,
+    `src/gbrs/emase/AlignmentPropertyMatrix.py:113-130`)."""
+    with open(path, "w") as fh:
+        for g, tids in enumerate(d.groups()):
+            fh.write(d.gname[g] + "\t" + "\t".join(d.lname[t] for t in tids) + "\n")
+
+
+def write_length_file(d: SynthData, path: str) -> None:
+    """locus_hap<TAB>length (reference `EMfactory.prepare`, `src/gbrs/emase/EMfactory.py:61-84`)."""
+    with open(path, "w") as fh:
+        if d.H > 1:
+            for t in range(d.T):
+                for h in range(d.H):
+                    fh.write(f"{d.lname[t]}_{d.hname[h]}\t{int(d.lengths[t, h])}\n")
+        else:
+            for t in range(d.T):
+                fh.write(f"{d.lname[t]}\t{int(d.lengths[t, 0])}\n")
+
+
+def write_genotype_file(d: SynthData, path: str) -> None:
+    """#Gene_ID<TAB>Diplotype (reference `quantify`, `src/gbrs/gbrs/emase_utils.py:259-269`)."""
+    assert d.genotype is not None
+    with open(path, "w") as fh:
+        fh.write("#Gene_ID\tDiplotype\n")
+        for g, gt in enumerate(d.genotype):
+            fh.write(f"{d.gname[g]}\t{gt}\n")
+
+
+def effective_lengths(d: SynthData, read_length: int = 100) -> np.ndarray:
+    """H x T effective lengths, max(len - read_length + 1, 1) (reference `EMfactory.py:77,89`)."""
+    return np.maximum(d.lengths - read_length + 1.0, 1.0).T.copy()
+
+
+def genotype_mask(d: SynthData) -> np.ndarray:
+    """H x T 0/1 mask of the two diplotype haplotypes of each gene (reference
+    `src/gbrs/gbrs/emase_utils.py:247-269`)."""
+    assert d.genotype is not None
+    hid = {h: i for i, h in enumerate(d.hname)}
+    gm = np.zeros((d.H, d.T))
+    for g, tids in enumerate(d.groups()):
+        for c in d.genotype[g]:
+            gm[hid[c], tids] = 1.0
+    return gm
