@@ -1,0 +1,57 @@
+"""`gbrs quantify` command line -- same flags as the reference (/root/reference/src/gbrs/gbrs/commands.py:108-150):
+-i -g -L -G -o -M -p -m -t -a -w -v.  Errors are logged, not raised, and the process exits 0 (:146-150)."""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+from typing import Annotated
+
+import typer
+
+from . import utils
+from . import quantify as quantify_mod
+
+app = typer.Typer(help="GBRS (B200-native multiway EM quantifier)", add_completion=False)
+
+
+@app.callback()
+def _main() -> None:  # keeps `quantify` a sub-command, as in the reference's multi-command app
+    pass
+
+
+@app.command(help="quantify allele-specific expressions")
+def quantify(
+    alignment_file: Annotated[Path, typer.Option("-i", "--alignment-file", exists=True, dir_okay=False, resolve_path=True, help="EMASE alignment incidence file (hdf5 or npz twin)")],
+    group_file: Annotated[Path, typer.Option("-g", "--group-file", exists=True, dir_okay=False, resolve_path=True, help="tab delimited file of gene to transcript mapping")] = None,
+    length_file: Annotated[Path, typer.Option("-L", "--length-file", exists=True, dir_okay=False, resolve_path=True, help="tab delimited file of locus(transcript) and length")] = None,
+    genotype_file: Annotated[Path, typer.Option("-G", "--genotype", exists=True, dir_okay=False, resolve_path=True, help="tab delimited file of locus(transcipt) and diplotype")] = None,
+    outbase: Annotated[str, typer.Option("-o", "--outbase", help="basename of all the generated output files")] = "gbrs.quantified",
+    multiread_model: Annotated[int, typer.Option("-M", "--multiread-model", help="emase model (default: 4)")] = 4,
+    pseudocount: Annotated[float, typer.Option("-p", "--pseudocount", help="prior read count (default: 0.0)")] = 0.0,
+    max_iters: Annotated[int, typer.Option("-m", "--max-iters", help="maximum iterations for EM iteration")] = 999,
+    tolerance: Annotated[float, typer.Option("-t", "--tolerance", help="tolerance for EM termination (default: 0.0001 in TPM)")] = 0.0001,
+    report_alignment_counts: Annotated[bool, typer.Option("-a", "--report-alignment-counts", help="whether to report alignment counts")] = False,
+    report_posterior: Annotated[bool, typer.Option("-w", "--report-posterior", help="whether to report posterior probabilities")] = False,
+    verbose: Annotated[int, typer.Option("-v", "--verbose", count=True, help="specify multiple times for more verbose output")] = 0,
+) -> None:
+    logger = utils.configure_logging("gbrs", verbose)
+    logger.debug("quantify")
+    try:
+        if multiread_model not in (1, 2, 3, 4):
+            raise typer.Abort("-M, --multiread-model must be one of 1, 2, 3, or 4")
+        quantify_mod.quantify(
+            alignment_file=str(alignment_file),
+            group_file=str(group_file) if group_file else None,
+            length_file=str(length_file) if length_file else None,
+            genotype_file=str(genotype_file) if genotype_file else None,
+            outbase=outbase, multiread_model=multiread_model, pseudocount=pseudocount, max_iters=max_iters,
+            tolerance=tolerance, report_alignment_counts=report_alignment_counts, report_posterior=report_posterior)
+    except Exception as e:  # reference policy: log and return
+        if logger.level == logging.DEBUG:
+            logger.exception(e)
+        else:
+            logger.error(e)
+
+
+if __name__ == "__main__":
+    app()

@@ -1,0 +1,788 @@
+// sm_100a kernels + C-ABI launchers of the multiway EM quantifier.  See include/gbrs_em.h for the contract and
+// DESIGN.md for the layout / roofline discussion.  Reference lines are cited per kernel (paths under /root/reference).
+//
+// One EM update (EMfactory.update_allelic_expression, src/gbrs/emase/EMfactory.py:214-232) is
+//
+//   row pass     k_weights_m*     per class:  normaliser(s) of the model's hierarchy from theta  ->  weight(s)
+//   column pass  k_column_reduce  per locus work item:  sum of the weights of the classes hitting it, per haplotype
+//   k_locus_acc                   acc[t][h] = theta[t][h] * W[t][h]                (= sum_n count[n] * P[n,t,h])
+//   -- cross-rank sum of acc when the classes are row-sharded --
+//   k_locus_update                theta' = acc / efflen, isoform totals, block partial sums
+//   k_converge                    TPM-scaled L1 change, stop decision, ping-pong flip (EMfactory.py:267-279)
+//
+// Both passes are gathers over an incidence matrix stored twice (class-major / locus-major), so there are no atomics
+// and the result is bit-reproducible run to run.  The posterior P is never materialised.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gbrs_em.h"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void gbrs_set_error(const std::string& s) { g_last_error = s; }
+extern "C" const char* gbrs_last_error(void) { return g_last_error.c_str(); }
+extern "C" int gbrs_abi_version(void) { return GBRS_EM_ABI_VERSION; }
+
+#define GBRS_CUDA(call)                                                                              \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      gbrs_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                            \
+      return GBRS_E_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+
+#define GBRS_LAUNCH_CHECK(name)                                                                      \
+  do {                                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                                             \
+    if (e_ != cudaSuccess) {                                                                         \
+      gbrs_set_error(std::string("launch ") + name + ": " + cudaGetErrorString(e_));                 \
+      return GBRS_E_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kLocusMask = 0xFFFFFFu;
+
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+inline int grid_for(int64_t threads_needed, int blocks_per_sm = 8) {
+  int64_t b = (threads_needed + kThreads - 1) / kThreads;
+  int64_t cap = (int64_t) sm_count() * blocks_per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int) b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+// sum of the haplotype slots selected by `m` of one 64-byte locus line
+__device__ __forceinline__ double masked_sum8(const double* __restrict__ line, uint32_t m) {
+  const double2 a = ldg2(line), b = ldg2(line + 2), c = ldg2(line + 4), e = ldg2(line + 6);
+  double s = 0.0;
+  s += (m & 1u) ? a.x : 0.0;
+  s += (m & 2u) ? a.y : 0.0;
+  s += (m & 4u) ? b.x : 0.0;
+  s += (m & 8u) ? b.y : 0.0;
+  s += (m & 16u) ? c.x : 0.0;
+  s += (m & 32u) ? c.y : 0.0;
+  s += (m & 64u) ? e.x : 0.0;
+  s += (m & 128u) ? e.y : 0.0;
+  return s;
+}
+
+__device__ __forceinline__ void load8(const double* __restrict__ line, double (&v)[8]) {
+  const double2 a = ldg2(line), b = ldg2(line + 2), c = ldg2(line + 4), e = ldg2(line + 6);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = e.x; v[7] = e.y;
+}
+
+// Sum over the 8 lanes of an aligned lane group; every lane gets the total.  Fixed order => deterministic.
+__device__ __forceinline__ double group8_sum(double v) {
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+  v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+  return v;
+}
+
+// Transposing reduction: each of the 8 lanes of a group holds a[0..8); afterwards lane j holds sum over lanes of a[j].
+__device__ __forceinline__ double group8_transpose_sum(const double (&a)[8], int lane8) {
+  double b[4], c[2];
+  const bool hi4 = lane8 & 4, hi2 = lane8 & 2, hi1 = lane8 & 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = hi4 ? a[i] : a[i + 4];
+    const double keep = hi4 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = hi2 ? b[i] : b[i + 2];
+    const double keep = hi2 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, 2);
+  }
+  const double send = hi1 ? c[0] : c[1];
+  const double keep = hi1 ? c[1] : c[0];
+  return keep + __shfl_xor_sync(0xFFFFFFFFu, send, 1);
+}
+
+// Block-wide sum in a fixed order (warp shuffle tree, then warp 0 over the per-warp values).  All threads must call.
+__device__ __forceinline__ double block_sum(double v, double* smem /* [32] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double r = (lane < nw) ? smem[lane] : 0.0;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+    if (lane == 0) smem[0] = r;
+  }
+  __syncthreads();
+  r = smem[0];
+  return r;
+}
+
+__device__ __forceinline__ const double* theta_cur(const gbrs_em_dev& d) {
+  return d.theta + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T * GBRS_HPAD;
+}
+__device__ __forceinline__ const double* theta_next(const gbrs_em_dev& d) {
+  return d.theta + (size_t) (d.ctrl[GBRS_CTRL_PARITY] ^ 1) * d.T * GBRS_HPAD;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row pass, model 4:  w[n] = count[n] / sum_{(t,h) in n} theta[t][h]
+// reference: multiply(theta, READ) + normalize_reads(READ)   EMfactory.py:204-208, AlignmentPropertyMatrix.py:335-342
+// UNIT = true is the prepare() variant with theta == 1 on the pattern (EMfactory.py:95): w[n] = count[n] / nnz[n].
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool UNIT>
+__global__ void __launch_bounds__(kThreads) k_weights_m4(const gbrs_em_dev d) {
+  if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ th = theta_cur(d);
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+    const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
+    double s = 0.0;
+    for (uint32_t p = b; p < e; ++p) {
+      const uint32_t w = __ldg(d.pairs + p);
+      if (UNIT) s += (double) __popc(w >> 24);
+      else s += masked_sum8(th + (size_t) (w & kLocusMask) * GBRS_HPAD, w >> 24);
+    }
+    d.weights[n] = __ldg(d.count + n) / s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-gene totals for models 1-3:  gene_hap[g][h] = sum_{t in g} theta[t][h]  ( = theta * t2t_mat, EMfactory.py:167 ),
+// gamma[t] = sum_h gene_hap[g(t)][h]  ( = (theta * t2t_mat).sum(axis=0), EMfactory.py:173/188/200 ).  8 lanes per gene.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_gene_totals(const gbrs_em_dev d) {
+  if (d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ th = theta_cur(d);
+  const int lane8 = threadIdx.x & 7;
+  const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> 3;
+  const int64_t rounds = (d.n_gene_ids + ngroups - 1) / ngroups;
+  int64_t g = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  for (int64_t r = 0; r < rounds; ++r, g += ngroups) {
+    double s = 0.0;
+    uint32_t b = 0, e = 0;
+    if (g < d.n_gene_ids) { b = __ldg(d.gene_ptr + g); e = __ldg(d.gene_ptr + g + 1); }
+    for (uint32_t i = b; i < e; ++i) s += th[(size_t) __ldg(d.gene_loci + i) * GBRS_HPAD + lane8];
+    const double tot = group8_sum(s);
+    if (g < d.n_gene_ids) {
+      d.gene_hap[g * GBRS_HPAD + lane8] = s;
+      for (uint32_t i = b + lane8; i < e; i += 8) d.gamma[__ldg(d.gene_loci + i)] = tot;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row pass, model 3 (Gene -> Isoform*Allele, EMfactory.py:192-203): one weight per (class, gene) run
+//   u[r] = count[n] * Gamma_r / (sum_{r' of n} Gamma_r') / D_r,   D_r = sum_{(t,h) in n, t in gene r} theta[t][h]
+// Runs whose D_r is 0 drop out (eliminate_zeros before the GROUP division, AlignmentPropertyMatrix.py:350-352).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d) {
+  if (d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ th = theta_cur(d);
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+    const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
+    const double c = __ldg(d.count + n);
+    double total = 0.0;
+    // pass 1: sum of gene totals over the runs that are alive
+    for (uint32_t p = b; p < e;) {
+      const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
+      double D = 0.0, gam = 0.0;
+      for (; p < e; ++p) {
+        const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
+        if (__ldg(d.gene_of + t) != g) break;
+        D += masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24);
+        gam = d.gamma[t];
+      }
+      if (D != 0.0) total += gam;
+    }
+    // pass 2: weights
+    uint32_t run = __ldg(d.runptr + n);
+    for (uint32_t p = b; p < e; ++run) {
+      const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
+      double D = 0.0, gam = 0.0;
+      for (; p < e; ++p) {
+        const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
+        if (__ldg(d.gene_of + t) != g) break;
+        D += masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24);
+        gam = d.gamma[t];
+      }
+      d.weights[run] = (D != 0.0) ? c * gam / total / D : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row pass, model 2 (Gene -> Isoform -> Allele, EMfactory.py:176-191): one weight per (class, locus) pair
+//   u[p] = count[n] * (Gamma_r / sum_r' Gamma_r') * (I_t / S_r) / x_p
+//   x_p = sum_{h in mask_p} theta[t][h],  I_t = sum_h theta[t][h] (all h),  S_r = sum_{p in r, x_p != 0} I_t
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d) {
+  if (d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ th = theta_cur(d);
+  const double* __restrict__ iso = d.iso + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+    const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
+    const double c = __ldg(d.count + n);
+    double total = 0.0;
+    for (uint32_t p = b; p < e;) {
+      const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
+      double S = 0.0, gam = 0.0;
+      for (; p < e; ++p) {
+        const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
+        if (__ldg(d.gene_of + t) != g) break;
+        if (masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24) != 0.0) S += iso[t];
+        gam = d.gamma[t];
+      }
+      if (S != 0.0) total += gam;
+    }
+    for (uint32_t p = b; p < e;) {
+      const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
+      double S = 0.0, gam = 0.0;
+      uint32_t q = p;
+      for (; q < e; ++q) {
+        const uint32_t w = __ldg(d.pairs + q), t = w & kLocusMask;
+        if (__ldg(d.gene_of + t) != g) break;
+        if (masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24) != 0.0) S += iso[t];
+        gam = d.gamma[t];
+      }
+      const double wg = (S != 0.0) ? c * gam / total / S : 0.0;
+      for (; p < q; ++p) {
+        const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
+        const double x = masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24);
+        d.weights[p] = (x != 0.0) ? wg * iso[t] / x : 0.0;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// row pass, model 1 (Gene -> Allele -> Isoform, EMfactory.py:160-175): eight weights per (class, gene) run
+//   u[r][h] = count[n] * (Gamma_r / sum_r' Gamma_r') * (hg[g][h] / Hs_r) / Dh_r[h]
+//   Dh_r[h] = sum_{p in r, h in mask_p} theta[t_p][h],  Hs_r = sum_{h: Dh_r[h] != 0} hg[g][h],  hg = gene_hap
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d) {
+  if (d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ th = theta_cur(d);
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+    const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
+    const double c = __ldg(d.count + n);
+    double total = 0.0;
+    for (uint32_t p = b; p < e;) {
+      const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
+      double any = 0.0, gam = 0.0;
+      for (; p < e; ++p) {
+        const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
+        if (__ldg(d.gene_of + t) != g) break;
+        any += masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24);
+        gam = d.gamma[t];
+      }
+      if (any != 0.0) total += gam;
+    }
+    uint32_t run = __ldg(d.runptr + n);
+    for (uint32_t p = b; p < e; ++run) {
+      const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
+      double Dh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      double gam = 0.0;
+      for (; p < e; ++p) {
+        const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask, m = w >> 24;
+        if (__ldg(d.gene_of + t) != g) break;
+        double v[8];
+        load8(th + (size_t) t * GBRS_HPAD, v);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) Dh[h] += ((m >> h) & 1u) ? v[h] : 0.0;
+        gam = d.gamma[t];
+      }
+      double hg[8];
+      load8(d.gene_hap + (size_t) g * GBRS_HPAD, hg);
+      double Hs = 0.0;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) Hs += (Dh[h] != 0.0) ? hg[h] : 0.0;
+      const double wg = (Hs != 0.0) ? c * gam / total / Hs : 0.0;
+      double* out = d.weights + (size_t) run * GBRS_HPAD;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) out[h] = (Dh[h] != 0.0) ? wg * hg[h] / Dh[h] : 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// column pass: for every work item (<= item_len consecutive locus-major entries of ONE locus) the per-haplotype sum of
+// the weights of its entries.  8 lanes per item; lane j ends up holding haplotype j and writes wit[item][j].
+// reference: APM.sum(axis=READ)  AlignmentPropertyMatrix.py:288-298 (count-weighted column reduce), without the
+// per-haplotype matrix copy.  VEC = 1: scalar weight per index; VEC = 8: one weight per haplotype (model 1).
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename E, int VEC>
+__global__ void __launch_bounds__(kThreads) k_column_reduce(const gbrs_em_dev d, const E* __restrict__ ents, bool honour_done) {
+  if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
+  constexpr int SH = 8 * (int) sizeof(E) - 8;
+  constexpr E IDX = (E(1) << SH) - 1;
+  const double* __restrict__ wts = d.weights;
+  const int lane8 = threadIdx.x & 7;
+  const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> 3;
+  const int64_t rounds = (d.n_items + ngroups - 1) / ngroups;
+  int64_t item = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  for (int64_t r = 0; r < rounds; ++r, item += ngroups) {
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t b = 0, e = 0;
+    if (item < d.n_items) { b = __ldg(d.item_off + item); e = __ldg(d.item_off + item + 1); }
+    for (uint32_t p = b + lane8; p < e; p += 8) {
+      const E ent = __ldg(ents + p);
+      const uint32_t m = (uint32_t) (ent >> SH);
+      const size_t idx = (size_t) (ent & IDX);
+      if (VEC == 1) {
+        const double w = wts[idx];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) a[h] += ((m >> h) & 1u) ? w : 0.0;
+      } else {
+        double v[8];
+        load8(wts + idx * GBRS_HPAD, v);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) a[h] += ((m >> h) & 1u) ? v[h] : 0.0;
+      }
+    }
+    const double tot = group8_transpose_sum(a, lane8);
+    if (item < d.n_items) d.wit[item * GBRS_HPAD + lane8] = tot;
+  }
+}
+
+// acc[t][h] = theta[t][h] * sum_{items of t} wit[item][h]   ( = sum_n count[n] * P[n,t,h] ).  UNIT: theta == 1 (prepare).
+// Once the loop has stopped, k_converge has already flipped the ping-pong, so the theta that produced the weights in
+// `wit` is the *other* buffer: a single rank simply skips, a row-sharded rank recomputes the identical local numerator
+// from it (the in-place cross-rank sum that follows must always start from the local values).
+template <bool UNIT>
+__global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
+  const bool done = !UNIT && d.ctrl[GBRS_CTRL_DONE];
+  if (done && honour_done) return;
+  const double* __restrict__ th = done ? theta_next(d) : theta_cur(d);
+  const int64_t total = (int64_t) d.T * GBRS_HPAD;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t t = i >> 3;
+    const int h = (int) (i & 7);
+    const uint32_t b = __ldg(d.locus_item_ptr + t), e = __ldg(d.locus_item_ptr + t + 1);
+    double W = 0.0;
+    for (uint32_t it = b; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
+    d.acc[i] = UNIT ? ((h < d.H) ? W : 0.0) : th[i] * W;
+  }
+}
+
+// theta' = acc / efflen (EMfactory.py:228-232), iso'[t] = sum_h theta'[t][h], block partial sums of iso'.
+// FROM_ACC = false: only (re)compute iso / partials of the current theta (after prepare / set_theta / pseudocount).
+template <bool FROM_ACC>
+__global__ void __launch_bounds__(kThreads) k_locus_update(const gbrs_em_dev d) {
+  __shared__ double red[32];
+  if (FROM_ACC && d.ctrl[GBRS_CTRL_DONE]) return;
+  const int par = d.ctrl[GBRS_CTRL_PARITY];
+  const double* __restrict__ src = FROM_ACC ? d.acc : d.theta + (size_t) par * d.T * GBRS_HPAD;
+  double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
+  double* __restrict__ iso = d.iso + (size_t) (FROM_ACC ? (par ^ 1) : par) * d.T;
+  const int lane8 = threadIdx.x & 7;
+  const int64_t total = (int64_t) d.T * GBRS_HPAD;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  const int64_t rounds = (total + stride - 1) / stride;
+  int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  double mine = 0.0;
+  for (int64_t r = 0; r < rounds; ++r, i += stride) {
+    double v = 0.0;
+    if (i < total) {
+      v = src[i];
+      if (FROM_ACC) {
+        v = v / d.efflen[i];
+        dst[i] = v;
+      }
+    }
+    const double s = group8_sum(v);
+    if (i < total && lane8 == 0) {
+      iso[i >> 3] = s;
+      mine += s;
+    }
+  }
+  const double bs = block_sum(mine, red);
+  if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
+}
+
+// Stop test of EMfactory.run (EMfactory.py:267-279) on the device.
+//   INIT: record sum of the current isoform totals as "prev" (after prepare / set_theta).
+//   else: err = sum_t | iso'[t] * 1e6 / S' - iso[t] * 1e6 / S |, log it, flip the ping-pong, decide.
+template <bool INIT>
+__global__ void __launch_bounds__(1024) k_converge(const gbrs_em_dev d, int nparts) {
+  __shared__ double red[32];
+  if (!INIT && d.ctrl[GBRS_CTRL_DONE]) return;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) v += d.part[i];
+  const double S_new = block_sum(v, red);
+  if (INIT) {
+    if (threadIdx.x == 0) {
+      d.scal[GBRS_SCAL_SUM_PREV] = S_new;
+      d.scal[GBRS_SCAL_SUM_CUR] = S_new;
+      if (!isfinite(S_new)) d.ctrl[GBRS_CTRL_ERROR] = 1;
+    }
+    return;
+  }
+  const int par = d.ctrl[GBRS_CTRL_PARITY];
+  const double* __restrict__ iso_old = d.iso + (size_t) par * d.T;
+  const double* __restrict__ iso_new = d.iso + (size_t) (par ^ 1) * d.T;
+  const double f_new = 1000000.0 / S_new;
+  const double f_old = 1000000.0 / d.scal[GBRS_SCAL_SUM_PREV];
+  double e = 0.0;
+  for (int t = threadIdx.x; t < d.T; t += blockDim.x) e += fabs(iso_new[t] * f_new - iso_old[t] * f_old);
+  const double err = block_sum(e, red);
+  if (threadIdx.x == 0) {
+    const int it = d.ctrl[GBRS_CTRL_ITERS];
+    if (it < d.max_iters_cap) d.err_log[it] = err;
+    d.scal[GBRS_SCAL_ERR] = err;
+    d.scal[GBRS_SCAL_SUM_PREV] = S_new;
+    d.scal[GBRS_SCAL_SUM_CUR] = S_new;
+    d.ctrl[GBRS_CTRL_ITERS] = it + 1;
+    d.ctrl[GBRS_CTRL_PARITY] = par ^ 1;
+    const bool bad = !isfinite(err) || !isfinite(S_new);
+    if (bad) d.ctrl[GBRS_CTRL_ERROR] = 1;
+    const bool go_on = !bad && err > d.scal[GBRS_SCAL_TARGET] && (it + 1) < d.ctrl[GBRS_CTRL_MAX_ITERS];
+    d.ctrl[GBRS_CTRL_DONE] = go_on ? 0 : 1;
+  }
+}
+
+__global__ void k_flip_parity(const gbrs_em_dev d) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) d.ctrl[GBRS_CTRL_PARITY] ^= 1;
+}
+
+__global__ void k_run_begin(const gbrs_em_dev d, double tol, int max_iters) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    d.ctrl[GBRS_CTRL_ITERS] = 0;
+    d.ctrl[GBRS_CTRL_MAX_ITERS] = max_iters;
+    d.ctrl[GBRS_CTRL_ERROR] = 0;
+    d.scal[GBRS_SCAL_ERR] = 1000000.0;
+    d.scal[GBRS_SCAL_TARGET] = 1000000.0 * tol;
+    // while err_sum > target_err and num_iters < max_iters   (EMfactory.py:267) with err_sum = 1e6 initially
+    d.ctrl[GBRS_CTRL_DONE] = (1000000.0 > 1000000.0 * tol && 0 < max_iters) ? 0 : 1;
+  }
+}
+
+__global__ void k_reset_ctrl(const gbrs_em_dev d) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    d.ctrl[GBRS_CTRL_ITERS] = 0;
+    d.ctrl[GBRS_CTRL_DONE] = 0;
+    d.ctrl[GBRS_CTRL_ERROR] = 0;
+    d.ctrl[GBRS_CTRL_PARITY] = 0;
+    d.ctrl[GBRS_CTRL_MAX_ITERS] = 0;
+    d.ctrl[GBRS_CTRL_PREPARED] = 1;
+  }
+}
+
+// pseudocount rule of EMfactory.prepare (EMfactory.py:105-111): every haplotype of a locus with any non-zero theta gets
+// +pseudocount; afterwards theta is rescaled to its original sum.  Operates on the current theta in place.
+__global__ void __launch_bounds__(kThreads) k_pseudocount_add(const gbrs_em_dev d, double pc) {
+  double* th = d.theta + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T * GBRS_HPAD;
+  const int lane8 = threadIdx.x & 7;
+  const int64_t total = (int64_t) d.T * GBRS_HPAD;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  const int64_t rounds = (total + stride - 1) / stride;
+  int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t r = 0; r < rounds; ++r, i += stride) {
+    const double v = (i < total) ? th[i] : 0.0;
+    const unsigned nzmask = __ballot_sync(0xFFFFFFFFu, v != 0.0);
+    const unsigned grp = (nzmask >> ((threadIdx.x & 31) & ~7)) & 0xFFu;
+    if (i < total && grp != 0u && lane8 < d.H) th[i] = v + pc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_scale_theta(const gbrs_em_dev d, const double* num, const double* den) {
+  double* th = d.theta + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T * GBRS_HPAD;
+  const double f = *num / *den;
+  const int64_t total = (int64_t) d.T * GBRS_HPAD;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) th[i] *= f;
+}
+
+__global__ void k_copy_scalar(double* dst, const double* src) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
+}
+
+// report_alignment_counts (AlignmentPropertyMatrix.py:389-459); one-off, scatter with fp64 atomics.
+__global__ void __launch_bounds__(kThreads) k_alignment_counts(const gbrs_em_dev d, int gene_level, int n_real_genes,
+                                                               double* aln, double* uniq, double* locus_uniq) {
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+    const uint32_t b = d.rowptr[n], e = d.rowptr[n + 1];
+    const double c = d.count[n];
+    if (!gene_level) {
+      int nz = 0;
+      for (uint32_t p = b; p < e; ++p) nz += __popc(d.pairs[p] >> 24);
+      const bool u1 = nz == 1, l1 = (e - b) == 1;
+      for (uint32_t p = b; p < e; ++p) {
+        const uint32_t w = d.pairs[p], t = w & kLocusMask, m = w >> 24;
+        for (int h = 0; h < 8; ++h)
+          if ((m >> h) & 1u) {
+            atomicAdd(aln + (size_t) t * GBRS_HPAD + h, c);
+            if (u1) atomicAdd(uniq + (size_t) t * GBRS_HPAD + h, c);
+          }
+        if (l1) atomicAdd(locus_uniq + t, c);
+      }
+    } else {
+      int nb = 0, nr = 0;
+      for (uint32_t p = b; p < e;) {
+        const int32_t g = d.gene_of[d.pairs[p] & kLocusMask];
+        uint32_t um = 0;
+        for (; p < e && d.gene_of[d.pairs[p] & kLocusMask] == g; ++p) um |= d.pairs[p] >> 24;
+        if (g < n_real_genes) { nb += __popc(um); ++nr; }
+      }
+      for (uint32_t p = b; p < e;) {
+        const int32_t g = d.gene_of[d.pairs[p] & kLocusMask];
+        uint32_t um = 0;
+        for (; p < e && d.gene_of[d.pairs[p] & kLocusMask] == g; ++p) um |= d.pairs[p] >> 24;
+        if (g >= n_real_genes) continue;
+        for (int h = 0; h < 8; ++h)
+          if ((um >> h) & 1u) {
+            atomicAdd(aln + (size_t) g * GBRS_HPAD + h, c);
+            if (nb == 1) atomicAdd(uniq + (size_t) g * GBRS_HPAD + h, c);
+          }
+        if (nr == 1) atomicAdd(locus_uniq + g, c);
+      }
+    }
+  }
+}
+
+int check_dev(const gbrs_em_dev* d, const char* who) {
+  if (!d) { gbrs_set_error(std::string(who) + ": null descriptor"); return GBRS_E_ARG; }
+  if (d->T <= 0 || d->H < 1 || d->H > GBRS_HPAD || (d->entry_bytes != 4 && d->entry_bytes != 8)) {
+    gbrs_set_error(std::string(who) + ": bad descriptor shape"); return GBRS_E_ARG;
+  }
+  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
+      !d->iso || !d->weights || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
+    gbrs_set_error(std::string(who) + ": null device buffer in descriptor"); return GBRS_E_ARG;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    gbrs_set_error(std::string(who) + ": no CUDA device (there is no CPU fallback)"); return GBRS_E_CUDA;
+  }
+  return GBRS_OK;
+}
+
+inline int locus_grid(const gbrs_em_dev* d) {
+  int g = grid_for((int64_t) d->T * GBRS_HPAD, 4);
+  return g > GBRS_PART_SLOTS ? GBRS_PART_SLOTS : g;
+}
+
+template <int VEC>
+int launch_column(const gbrs_em_dev* d, const void* ents, bool honour_done, cudaStream_t s) {
+  if (!ents) { gbrs_set_error("column pass: entry array missing from descriptor"); return GBRS_E_ARG; }
+  if (d->n_items == 0) return GBRS_OK;
+  const int grid = grid_for(d->n_items * 8);
+  if (d->entry_bytes == 4)
+    k_column_reduce<uint32_t, VEC><<<grid, kThreads, 0, s>>>(*d, static_cast<const uint32_t*>(ents), honour_done);
+  else
+    k_column_reduce<unsigned long long, VEC><<<grid, kThreads, 0, s>>>(*d, static_cast<const unsigned long long*>(ents), honour_done);
+  GBRS_LAUNCH_CHECK("k_column_reduce");
+  return GBRS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream) {
+  if (int rc = check_dev(d, "gbrs_em_prepare_local")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  k_reset_ctrl<<<1, 32, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_reset_ctrl");
+  if (d->n_classes > 0) {
+    k_weights_m4<true><<<grid_for(d->n_classes), kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_weights_m4<unit>");
+  }
+  if (int rc = launch_column<1>(d, d->ent_cls, false, s)) return rc;
+  k_locus_acc<true><<<grid_for((int64_t) d->T * GBRS_HPAD), kThreads, 0, s>>>(*d, false);
+  GBRS_LAUNCH_CHECK("k_locus_acc<unit>");
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_prepare_finish(const gbrs_em_dev* d, double pseudocount, void* stream) {
+  if (int rc = check_dev(d, "gbrs_em_prepare_finish")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int lg = locus_grid(d);
+  // theta[1] = acc / efflen ; then make it the current estimate
+  k_locus_update<true><<<lg, kThreads, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_locus_update");
+  k_flip_parity<<<1, 32, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_flip_parity");
+  k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+  GBRS_LAUNCH_CHECK("k_converge<init>");
+  if (pseudocount > 0.0) {
+    // scal[4] keeps the original sum
+    k_copy_scalar<<<1, 32, 0, s>>>(d->scal + 4, d->scal + GBRS_SCAL_SUM_CUR);
+    k_pseudocount_add<<<lg, kThreads, 0, s>>>(*d, pseudocount);
+    GBRS_LAUNCH_CHECK("k_pseudocount_add");
+    k_locus_update<false><<<lg, kThreads, 0, s>>>(*d);
+    k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+    k_scale_theta<<<lg, kThreads, 0, s>>>(*d, d->scal + 4, d->scal + GBRS_SCAL_SUM_CUR);
+    GBRS_LAUNCH_CHECK("k_scale_theta");
+    k_locus_update<false><<<lg, kThreads, 0, s>>>(*d);
+    k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+    GBRS_LAUNCH_CHECK("pseudocount chain");
+  }
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_set_theta(const gbrs_em_dev* d, const double* theta_dev, void* stream) {
+  if (int rc = check_dev(d, "gbrs_em_set_theta")) return rc;
+  if (!theta_dev) { gbrs_set_error("gbrs_em_set_theta: null theta"); return GBRS_E_ARG; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  k_reset_ctrl<<<1, 32, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_reset_ctrl");
+  GBRS_CUDA(cudaMemcpyAsync(d->theta, theta_dev, sizeof(double) * (size_t) d->T * GBRS_HPAD, cudaMemcpyDeviceToDevice, s));
+  const int lg = locus_grid(d);
+  k_locus_update<false><<<lg, kThreads, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_locus_update<refresh>");
+  k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+  GBRS_LAUNCH_CHECK("k_converge<init>");
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_read_ctrl(const gbrs_em_dev* d, void* stream, int32_t* ctrl_host, double* scal_host) {
+  if (int rc = check_dev(d, "gbrs_em_read_ctrl")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ctrl_host) GBRS_CUDA(cudaMemcpyAsync(ctrl_host, d->ctrl, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, s));
+  if (scal_host) GBRS_CUDA(cudaMemcpyAsync(scal_host, d->scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
+  GBRS_CUDA(cudaStreamSynchronize(s));
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_current_theta(const gbrs_em_dev* d, void* stream, double** theta_dev) {
+  if (!theta_dev) { gbrs_set_error("gbrs_em_current_theta: null out pointer"); return GBRS_E_ARG; }
+  int32_t ctrl[16];
+  if (int rc = gbrs_em_read_ctrl(d, stream, ctrl, nullptr)) return rc;
+  *theta_dev = d->theta + (size_t) ctrl[GBRS_CTRL_PARITY] * d->T * GBRS_HPAD;
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_run_begin(const gbrs_em_dev* d, double tol, int max_iters, void* stream) {
+  if (int rc = check_dev(d, "gbrs_em_run_begin")) return rc;
+  if (max_iters < 0 || max_iters > d->max_iters_cap) {
+    gbrs_set_error("gbrs_em_run_begin: max_iters exceeds the err_log capacity of the descriptor"); return GBRS_E_ARG;
+  }
+  k_run_begin<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*d, tol, max_iters);
+  GBRS_LAUNCH_CHECK("k_run_begin");
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* stream) {
+  if (int rc = check_dev(d, "gbrs_em_launch_local")) return rc;
+  if (model < 1 || model > 4) {
+    gbrs_set_error("The read normalization model should be 1, 2, 3, or 4."); return GBRS_E_ARG;  // EMfactory.py:209-212
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool honour_done = d->n_ranks <= 1;
+  int rc = GBRS_OK;
+  if (model != 4) {
+    if (!d->gene_of || !d->gene_ptr || !d->gene_loci || !d->gene_hap || !d->gamma || !d->runptr) {
+      gbrs_set_error("Group information matrix is missing.");  // AlignmentPropertyMatrix.py:345-346
+      return GBRS_E_ARG;
+    }
+    k_gene_totals<<<grid_for((int64_t) d->n_gene_ids * 8), kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_gene_totals");
+  }
+  const int cg = grid_for(d->n_classes);
+  if (d->n_classes > 0) {
+    switch (model) {
+      case 4: k_weights_m4<false><<<cg, kThreads, 0, s>>>(*d); break;
+      case 3: k_weights_m3<<<cg, kThreads, 0, s>>>(*d); break;
+      case 2: k_weights_m2<<<cg, kThreads, 0, s>>>(*d); break;
+      default: k_weights_m1<<<cg, kThreads, 0, s>>>(*d); break;
+    }
+    GBRS_LAUNCH_CHECK("k_weights");
+  }
+  switch (model) {
+    case 4: rc = launch_column<1>(d, d->ent_cls, honour_done, s); break;
+    case 3: rc = launch_column<1>(d, d->ent_run, honour_done, s); break;
+    case 2: rc = launch_column<1>(d, d->ent_pair, honour_done, s); break;
+    default: rc = launch_column<8>(d, d->ent_run, honour_done, s); break;
+  }
+  if (rc) return rc;
+  k_locus_acc<false><<<grid_for((int64_t) d->T * GBRS_HPAD), kThreads, 0, s>>>(*d, honour_done);
+  GBRS_LAUNCH_CHECK("k_locus_acc");
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
+  if (int rc = check_dev(d, "gbrs_em_launch_update")) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int lg = locus_grid(d);
+  k_locus_update<true><<<lg, kThreads, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_locus_update");
+  k_converge<false><<<1, 1024, 0, s>>>(*d, lg);
+  GBRS_LAUNCH_CHECK("k_converge");
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_iters, int poll_every, void* stream,
+                           int32_t* iters_out, double* errs_host) {
+  if (int rc = check_dev(d, "gbrs_em_run")) return rc;
+  if (d->n_ranks > 1) {
+    gbrs_set_error("gbrs_em_run: row-sharded runs interleave the exchange step; drive launch_local / launch_update");
+    return GBRS_E_ARG;
+  }
+  if (poll_every < 1) poll_every = 4;
+  if (int rc = gbrs_em_run_begin(d, tol, max_iters, stream)) return rc;
+  int32_t ctrl[16];
+  std::memset(ctrl, 0, sizeof(ctrl));
+  if (int rc = gbrs_em_read_ctrl(d, stream, ctrl, nullptr)) return rc;
+  while (!ctrl[GBRS_CTRL_DONE]) {
+    for (int i = 0; i < poll_every; ++i) {
+      if (int rc = gbrs_em_launch_local(d, model, stream)) return rc;
+      if (int rc = gbrs_em_launch_update(d, stream)) return rc;
+    }
+    if (int rc = gbrs_em_read_ctrl(d, stream, ctrl, nullptr)) return rc;
+  }
+  if (iters_out) *iters_out = ctrl[GBRS_CTRL_ITERS];
+  if (errs_host && ctrl[GBRS_CTRL_ITERS] > 0) {
+    GBRS_CUDA(cudaMemcpyAsync(errs_host, d->err_log, sizeof(double) * (size_t) ctrl[GBRS_CTRL_ITERS], cudaMemcpyDeviceToHost,
+                              static_cast<cudaStream_t>(stream)));
+    GBRS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  }
+  if (ctrl[GBRS_CTRL_ERROR]) {
+    gbrs_set_error("non-finite value in the EM update (zero normaliser or overflow)");
+    return GBRS_E_NUMERIC;
+  }
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_em_alignment_counts(const gbrs_em_dev* d, int gene_level, int32_t n_real_genes, double* aln_dev,
+                                        double* uniq_dev, double* locus_uniq_dev, void* stream) {
+  if (int rc = check_dev(d, "gbrs_em_alignment_counts")) return rc;
+  if (!aln_dev || !uniq_dev || !locus_uniq_dev) { gbrs_set_error("gbrs_em_alignment_counts: null output"); return GBRS_E_ARG; }
+  if (gene_level && !d->gene_of) { gbrs_set_error("No group information is available for bundling."); return GBRS_E_ARG; }
+  if (d->n_classes == 0) return GBRS_OK;
+  k_alignment_counts<<<grid_for(d->n_classes), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      *d, gene_level, n_real_genes, aln_dev, uniq_dev, locus_uniq_dev);
+  GBRS_LAUNCH_CHECK("k_alignment_counts");
+  return GBRS_OK;
+}

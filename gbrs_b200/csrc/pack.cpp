@@ -1,0 +1,310 @@
+// Host-side packer: H x CSC(N x T) incidence  ->  class-major + locus-major packed rows (see include/gbrs_em.h).
+//
+// What it replaces in the reference: the reference keeps the incidence as a python list of H scipy CSC matrices
+// (src/gbrs/emase/Sparse3DMatrix.py:26-66) and walks all H of them several times per EM iteration
+// (reset :220-228, multiply :314-377, APM.sum / normalize_reads src/gbrs/emase/AlignmentPropertyMatrix.py:275-370).
+// Here the same information is re-laid once, on the host, into the two orders the GPU passes stream through:
+//
+//   class-major  rowptr / pairs[]   one 32-bit word per (class, locus): locus | hapmask << 24, classes re-ordered by
+//                                   their smallest locus so that neighbouring classes touch neighbouring theta lines
+//   locus-major  ent_*[] / item_off one word per (locus, class): index | hapmask << top byte, cut into work items
+//
+// The `-G` genotype restriction (src/gbrs/gbrs/emase_utils.py:247-273: multiply by gtmask + eliminate_zeros) is an AND of
+// every pair's mask with a per-locus byte; pairs and classes that become empty are dropped.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "gbrs_em.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+void gbrs_set_error(const std::string& s);  // capi.cu
+
+struct gbrs_pack {
+  gbrs_pack_info info{};
+  int32_t T = 0;
+  std::vector<uint32_t> rowptr, pairs, runptr, item_off, locus_item_ptr, gene_ptr, gene_loci;
+  std::vector<int32_t> gene_of;
+  std::vector<double> count;
+  std::vector<uint8_t> ent_cls, ent_pair, ent_run;  // entry words, 4 or 8 bytes each
+};
+
+namespace {
+
+inline int64_t index_at(const void* base, int bytes, int64_t i) {
+  return bytes == 4 ? (int64_t) static_cast<const int32_t*>(base)[i] : static_cast<const int64_t*>(base)[i];
+}
+
+inline void put_entry(std::vector<uint8_t>& v, int bytes, int64_t pos, uint64_t idx, uint32_t mask) {
+  if (bytes == 4) {
+    reinterpret_cast<uint32_t*>(v.data())[pos] = (uint32_t) idx | (mask << 24);
+  } else {
+    reinterpret_cast<uint64_t*>(v.data())[pos] = idx | ((uint64_t) mask << 56);
+  }
+}
+
+}  // namespace
+
+extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
+  if (!in || !out) { gbrs_set_error("gbrs_pack_create: null argument"); return GBRS_E_ARG; }
+  const int T = in->T, H = in->H;
+  const int64_t N = in->N;
+  if (T <= 0 || N < 0 || H <= 0 || !in->indptr || !in->indices || (in->index_bytes != 4 && in->index_bytes != 8) ||
+      in->shard_count < 1 || in->shard_rank < 0 || in->shard_rank >= in->shard_count) {
+    gbrs_set_error("gbrs_pack_create: bad shape / shard / index width");
+    return GBRS_E_ARG;
+  }
+  if (H > GBRS_HPAD) { gbrs_set_error("gbrs_pack_create: more than 8 haplotypes is not supported by the mask layout"); return GBRS_E_LIMIT; }
+  if (T >= (1 << 24)) { gbrs_set_error("gbrs_pack_create: T must be < 2^24"); return GBRS_E_LIMIT; }
+  if (N >= (int64_t(1) << 32)) { gbrs_set_error("gbrs_pack_create: N must be < 2^32"); return GBRS_E_LIMIT; }
+  for (int h = 0; h < H; ++h) {
+    if (!in->indptr[h] || (!in->indices[h] && in->indptr[h][T] > 0) || in->indptr[h][0] != 0) {
+      gbrs_set_error("gbrs_pack_create: bad CSC arrays"); return GBRS_E_ARG;
+    }
+    for (int t = 0; t < T; ++t)
+      if (in->indptr[h][t + 1] < in->indptr[h][t]) { gbrs_set_error("gbrs_pack_create: indptr not monotone"); return GBRS_E_ARG; }
+  }
+  const int item_len = in->item_len > 0 ? in->item_len : 64;
+
+  try {
+    // ---- 1. merge the H columns of every locus into (class, mask) pairs, locus-major, all classes -----------------
+    std::vector<int64_t> ub(T + 1, 0);  // upper bound offsets
+    for (int t = 0; t < T; ++t) {
+      int64_t s = 0;
+      for (int h = 0; h < H; ++h) s += in->indptr[h][t + 1] - in->indptr[h][t];
+      ub[t + 1] = ub[t] + s;
+    }
+    std::vector<uint64_t> tmp((size_t) ub[T]);  // class << 8 | mask
+    std::vector<int64_t> lcount(T, 0);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int t = 0; t < T; ++t) {
+      const uint32_t lm = in->locus_hapmask ? in->locus_hapmask[t] : 0xFFu;
+      uint64_t* dst = tmp.data() + ub[t];
+      int64_t n = 0;
+      for (int h = 0; h < H; ++h) {
+        if (!((lm >> h) & 1u)) continue;
+        const int64_t b = in->indptr[h][t], e = in->indptr[h][t + 1];
+        for (int64_t i = b; i < e; ++i) {
+          if (in->values && in->values[h] && in->values[h][i] == 0.0) continue;
+          const int64_t c = index_at(in->indices[h], in->index_bytes, i);
+          if (c < 0 || c >= N) { bad = 1; continue; }
+          dst[n++] = ((uint64_t) c << 8) | (uint64_t) h;
+        }
+      }
+      std::sort(dst, dst + n);
+      int64_t m = 0;
+      for (int64_t i = 0; i < n;) {
+        const uint64_t c = dst[i] >> 8;
+        uint64_t mask = 0;
+        while (i < n && (dst[i] >> 8) == c) { mask |= (uint64_t) 1 << (dst[i] & 0xFF); ++i; }
+        dst[m++] = (c << 8) | mask;
+      }
+      lcount[t] = m;
+    }
+    if (bad) { gbrs_set_error("gbrs_pack_create: class index out of range"); return GBRS_E_ARG; }
+
+    // ---- 2. per-class pair / nnz counts, shard boundaries balanced by nnz -----------------------------------------
+    std::vector<uint32_t> npair((size_t) N, 0), minloc((size_t) N, 0xFFFFFFFFu);
+    std::vector<uint32_t> nz((size_t) N, 0);
+    for (int t = 0; t < T; ++t) {
+      const uint64_t* src = tmp.data() + ub[t];
+      for (int64_t i = 0; i < lcount[t]; ++i) {
+        const uint64_t c = src[i] >> 8;
+        if (npair[c]++ == 0) minloc[c] = (uint32_t) t;
+        nz[c] += (uint32_t) __builtin_popcountll(src[i] & 0xFF);
+      }
+    }
+    int64_t nnz_total = 0, nclass_total = 0;
+    for (int64_t c = 0; c < N; ++c) { nnz_total += nz[c]; nclass_total += npair[c] > 0; }
+    // class c goes to shard floor(cum_before(c) * R / total)
+    const int R = in->shard_count, rank = in->shard_rank;
+    int64_t lo = 0, hi = N;
+    if (R > 1) {
+      int64_t cum = 0;
+      lo = N; hi = N;
+      bool lo_set = false;
+      for (int64_t c = 0; c < N; ++c) {
+        const int r = nnz_total > 0 ? (int) std::min<int64_t>(R - 1, (__int128) cum * R / nnz_total) : 0;
+        if (!lo_set && r >= rank) { lo = c; lo_set = true; }
+        if (r > rank) { hi = c; break; }
+        cum += nz[c];
+      }
+      if (!lo_set) lo = N;
+      if (hi < lo) hi = lo;
+    }
+
+    // ---- 3. order the shard's non-empty classes by smallest locus (stable counting sort) --------------------------
+    std::vector<int64_t> bucket(T + 1, 0);
+    int64_t n_classes = 0, n_pairs = 0, nnz = 0;
+    for (int64_t c = lo; c < hi; ++c)
+      if (npair[c]) { ++bucket[minloc[c] + 1]; ++n_classes; n_pairs += npair[c]; nnz += nz[c]; }
+    if (n_pairs >= (int64_t(1) << 32)) { gbrs_set_error("gbrs_pack_create: more than 2^32 pairs in one shard"); return GBRS_E_LIMIT; }
+    for (int t = 0; t < T; ++t) bucket[t + 1] += bucket[t];
+    std::vector<uint32_t> new_id((size_t) N, 0xFFFFFFFFu);
+    for (int64_t c = lo; c < hi; ++c)
+      if (npair[c]) new_id[c] = (uint32_t) bucket[minloc[c]]++;
+
+    auto* P = new gbrs_pack();
+    P->T = T;
+    P->rowptr.assign((size_t) n_classes + 1, 0);
+    P->count.assign((size_t) n_classes, 1.0);
+    for (int64_t c = lo; c < hi; ++c)
+      if (npair[c]) {
+        P->rowptr[new_id[c] + 1] = npair[c];
+        if (in->count) P->count[new_id[c]] = in->count[c];
+      }
+    for (int64_t n = 0; n < n_classes; ++n) P->rowptr[n + 1] += P->rowptr[n];
+
+    // ---- 4. class-major fill (loci ascending within a class), then order pairs by (gene, locus) and cut runs -----
+    P->pairs.assign((size_t) n_pairs, 0);
+    {
+      std::vector<uint32_t> cur(P->rowptr.begin(), P->rowptr.end() - 1);
+      for (int t = 0; t < T; ++t) {
+        const uint64_t* src = tmp.data() + ub[t];
+        for (int64_t i = 0; i < lcount[t]; ++i) {
+          const uint32_t nid = new_id[src[i] >> 8];
+          if (nid == 0xFFFFFFFFu) continue;
+          P->pairs[cur[nid]++] = (uint32_t) t | ((uint32_t)(src[i] & 0xFF) << 24);
+        }
+      }
+    }
+    std::vector<uint64_t>().swap(tmp);
+    P->gene_of.resize(T);
+    for (int t = 0; t < T; ++t) {
+      P->gene_of[t] = in->gene_of ? in->gene_of[t] : t;
+      if (P->gene_of[t] < 0) { delete P; gbrs_set_error("gbrs_pack_create: negative gene id"); return GBRS_E_ARG; }
+    }
+    const int32_t n_gene_ids = 1 + *std::max_element(P->gene_of.begin(), P->gene_of.end());
+    P->runptr.assign((size_t) n_classes + 1, 0);
+    int max_k = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_k)
+    for (int64_t n = 0; n < n_classes; ++n) {
+      uint32_t* b = P->pairs.data() + P->rowptr[n];
+      const int k = (int) (P->rowptr[n + 1] - P->rowptr[n]);
+      max_k = std::max(max_k, k);
+      const int32_t* go = P->gene_of.data();
+      // insertion sort by (gene, locus); k is small
+      for (int i = 1; i < k; ++i) {
+        const uint32_t w = b[i];
+        const int64_t key = ((int64_t) go[w & 0xFFFFFF] << 24) | (w & 0xFFFFFF);
+        int j = i - 1;
+        while (j >= 0 && (((int64_t) go[b[j] & 0xFFFFFF] << 24) | (b[j] & 0xFFFFFF)) > key) { b[j + 1] = b[j]; --j; }
+        b[j + 1] = w;
+      }
+      uint32_t runs = k > 0 ? 1 : 0;
+      for (int i = 1; i < k; ++i) runs += go[b[i] & 0xFFFFFF] != go[b[i - 1] & 0xFFFFFF];
+      P->runptr[n + 1] = runs;
+    }
+    for (int64_t n = 0; n < n_classes; ++n) P->runptr[n + 1] += P->runptr[n];
+    const int64_t n_runs = P->runptr[n_classes];
+
+    // ---- 5. locus-major entries of this shard, ascending new class id within a locus ------------------------------
+    const int entry_bytes = std::max({n_classes, n_pairs, n_runs}) < (int64_t(1) << 24) ? 4 : 8;
+    std::vector<int64_t> lptr(T + 1, 0);
+    for (int64_t p = 0; p < n_pairs; ++p) ++lptr[(P->pairs[p] & 0xFFFFFF) + 1];
+    for (int t = 0; t < T; ++t) lptr[t + 1] += lptr[t];
+    P->ent_cls.assign((size_t) n_pairs * entry_bytes, 0);
+    P->ent_pair.assign((size_t) n_pairs * entry_bytes, 0);
+    P->ent_run.assign((size_t) n_pairs * entry_bytes, 0);
+    {
+      std::vector<int64_t> cur(lptr.begin(), lptr.end() - 1);
+      const int32_t* go = P->gene_of.data();
+      for (int64_t n = 0; n < n_classes; ++n) {
+        uint64_t run = P->runptr[n];
+        for (uint32_t p = P->rowptr[n]; p < P->rowptr[n + 1]; ++p) {
+          const uint32_t w = P->pairs[p], t = w & 0xFFFFFF, m = w >> 24;
+          if (p > P->rowptr[n] && go[t] != go[P->pairs[p - 1] & 0xFFFFFF]) ++run;
+          const int64_t pos = cur[t]++;
+          put_entry(P->ent_cls, entry_bytes, pos, (uint64_t) n, m);
+          put_entry(P->ent_pair, entry_bytes, pos, (uint64_t) p, m);
+          put_entry(P->ent_run, entry_bytes, pos, run, m);
+        }
+      }
+    }
+
+    // ---- 6. column-pass work items ------------------------------------------------------------------------------
+    P->locus_item_ptr.assign((size_t) T + 1, 0);
+    for (int t = 0; t < T; ++t) {
+      const int64_t len = lptr[t + 1] - lptr[t];
+      P->locus_item_ptr[t + 1] = P->locus_item_ptr[t] + (uint32_t) ((len + item_len - 1) / item_len);
+    }
+    const int64_t n_items = P->locus_item_ptr[T];
+    P->item_off.assign((size_t) n_items + 1, 0);
+    for (int t = 0; t < T; ++t) {
+      const int64_t len = lptr[t + 1] - lptr[t];
+      uint32_t it = P->locus_item_ptr[t];
+      for (int64_t o = 0; o < len; o += item_len) P->item_off[it++] = (uint32_t) (lptr[t] + o);
+    }
+    P->item_off[n_items] = (uint32_t) n_pairs;
+
+    // ---- 7. gene -> loci CSR ------------------------------------------------------------------------------------
+    P->gene_ptr.assign((size_t) n_gene_ids + 1, 0);
+    for (int t = 0; t < T; ++t) ++P->gene_ptr[P->gene_of[t] + 1];
+    for (int g = 0; g < n_gene_ids; ++g) P->gene_ptr[g + 1] += P->gene_ptr[g];
+    P->gene_loci.assign((size_t) T, 0);
+    {
+      std::vector<uint32_t> cur(P->gene_ptr.begin(), P->gene_ptr.end() - 1);
+      for (int t = 0; t < T; ++t) P->gene_loci[cur[P->gene_of[t]]++] = (uint32_t) t;
+    }
+
+    P->info.n_classes = n_classes;
+    P->info.n_pairs = n_pairs;
+    P->info.n_runs = n_runs;
+    P->info.n_items = n_items;
+    P->info.nnz = nnz;
+    P->info.nnz_total = nnz_total;
+    P->info.n_classes_total = nclass_total;
+    P->info.entry_bytes = entry_bytes;
+    P->info.n_gene_ids = n_gene_ids;
+    P->info.max_pairs_per_class = max_k;
+    *out = P;
+    return GBRS_OK;
+  } catch (const std::bad_alloc&) {
+    gbrs_set_error("gbrs_pack_create: out of host memory");
+    return GBRS_E_NOMEM;
+  }
+}
+
+extern "C" int gbrs_pack_get_info(gbrs_pack_t p, gbrs_pack_info* info) {
+  if (!p || !info) { gbrs_set_error("gbrs_pack_get_info: null argument"); return GBRS_E_ARG; }
+  *info = p->info;
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64_t* bytes) {
+  if (!p || !name || !ptr || !bytes) { gbrs_set_error("gbrs_pack_get_array: null argument"); return GBRS_E_ARG; }
+  const std::string s(name);
+#define GBRS_ARR(nm, vec)                                                      \
+  if (s == nm) {                                                               \
+    *ptr = (vec).data();                                                       \
+    *bytes = (int64_t) ((vec).size() * sizeof((vec)[0]));                      \
+    return GBRS_OK;                                                            \
+  }
+  GBRS_ARR("rowptr", p->rowptr)
+  GBRS_ARR("pairs", p->pairs)
+  GBRS_ARR("count", p->count)
+  GBRS_ARR("runptr", p->runptr)
+  GBRS_ARR("ent_cls", p->ent_cls)
+  GBRS_ARR("ent_pair", p->ent_pair)
+  GBRS_ARR("ent_run", p->ent_run)
+  GBRS_ARR("item_off", p->item_off)
+  GBRS_ARR("locus_item_ptr", p->locus_item_ptr)
+  GBRS_ARR("gene_ptr", p->gene_ptr)
+  GBRS_ARR("gene_loci", p->gene_loci)
+  GBRS_ARR("gene_of", p->gene_of)
+#undef GBRS_ARR
+  gbrs_set_error("gbrs_pack_get_array: unknown array name '" + s + "'");
+  return GBRS_E_ARG;
+}
+
+extern "C" int gbrs_pack_free(gbrs_pack_t p) {
+  delete p;
+  return GBRS_OK;
+}

@@ -1,0 +1,501 @@
+"""`EMfactory` -- the reference's EM coordinator interface, backed by the sm_100a kernels.
+
+Same constructor / methods / attributes as /root/reference/src/gbrs/emase/EMfactory.py:15-392
+(`prepare`, `reset`, `get_allelic_expression`, `update_probability_at_read_level`,
+`update_allelic_expression`, `run`, `report_read_counts`, `report_depths`, `export_posterior_probability`;
+attributes `probability`, `allelic_expression`, `grp_conv_mat`, `t2t_mat`, `target_lengths`).
+
+Host code stays Python; all arithmetic of the loop runs in libgbrs_em.so through ctypes (gbrs_b200/_lib.py).
+PyTorch tensors are used purely as device buffers (`tensor.data_ptr()`), and `torch.distributed` supplies the one
+exchange step of a row-sharded run (sum of the T x H numerator).  There is no CPU fallback: without the built
+library or without a CUDA device every compute call raises.
+
+Differences from the reference that a caller can observe:
+  * the posterior P[n,t,h] is never materialised; after `run`, `self.probability` still holds the incidence pattern.
+    Expected read counts come from the device-side numerator (identical to `probability.sum(READ)` of the last
+    posterior).
+  * classes are re-ordered internally; nothing class-indexed is returned, so this is invisible.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib, utils
+from .apm import AlignmentPropertyMatrix as APM
+
+logger = utils.get_logger("gbrs")
+
+ERR_LOG_CAP = 1 << 16
+
+_PACK_ARRAYS = {  # name -> numpy dtype (None = entry word, depends on entry_bytes)
+    "rowptr": np.uint32, "pairs": np.uint32, "count": np.float64, "runptr": np.uint32,
+    "ent_cls": None, "ent_pair": None, "ent_run": None, "item_off": np.uint32, "locus_item_ptr": np.uint32,
+    "gene_ptr": np.uint32, "gene_loci": np.uint32, "gene_of": np.int32,
+}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _lib.GbrsCudaError("no CUDA device is available; the gbrs_b200 EM has no CPU fallback")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+class PackedPattern:
+    """Host result of gbrs_pack_create for one row shard (numpy views are copied out, the C object is freed)."""
+
+    def __init__(self, apm: APM, gene_of=None, hapmask=None, shard_rank=0, shard_count=1, item_len=0):
+        lib = _lib.load()
+        T, H, N = apm.shape
+        if not apm.finalized:
+            raise RuntimeError("The original matrix must be finalized.")
+        if H > _lib.GBRS_HPAD:
+            raise NotImplementedError("more than 8 haplotypes is not supported by the packed mask layout")
+        mats = [m if m.format == "csc" else m.tocsc() for m in apm.data]
+        indptr = [np.ascontiguousarray(m.indptr, dtype=np.int64) for m in mats]
+        wide = any(m.indices.dtype.itemsize == 8 for m in mats)
+        idx_t = np.int64 if wide else np.int32
+        indices = [np.ascontiguousarray(m.indices, dtype=idx_t) for m in mats]
+        keep = [indptr, indices]
+        inp = _lib.PackInput()
+        inp.T, inp.H, inp.N = T, H, N
+        inp.indptr = (C.c_void_p * H)(*[a.ctypes.data for a in indptr])
+        inp.indices = (C.c_void_p * H)(*[a.ctypes.data for a in indices])
+        inp.index_bytes = 8 if wide else 4
+        inp.values = None
+        count = None
+        if apm.count is not None:
+            count = np.ascontiguousarray(apm.count, dtype=np.float64)
+            if count.shape[0] != N:
+                raise RuntimeError("count vector length does not match the number of classes")
+            inp.count = count.ctypes.data
+        if hapmask is not None:
+            hapmask = np.ascontiguousarray(hapmask, dtype=np.uint8)
+            inp.locus_hapmask = hapmask.ctypes.data
+        if gene_of is not None:
+            gene_of = np.ascontiguousarray(gene_of, dtype=np.int32)
+            inp.gene_of = gene_of.ctypes.data
+        inp.shard_rank, inp.shard_count, inp.item_len = shard_rank, shard_count, item_len
+        keep += [count, hapmask, gene_of]
+        handle = C.c_void_p()
+        t0 = time.perf_counter()
+        _lib.check(lib.gbrs_pack_create(C.byref(inp), C.byref(handle)))
+        try:
+            info = _lib.PackInfo()
+            _lib.check(lib.gbrs_pack_get_info(handle, C.byref(info)))
+            self.info = {f: getattr(info, f) for f, _ in _lib.PackInfo._fields_}
+            self.arrays = {}
+            entry_t = np.uint32 if info.entry_bytes == 4 else np.uint64
+            for name, dt in _PACK_ARRAYS.items():
+                ptr, nbytes = C.c_void_p(), C.c_int64()
+                _lib.check(lib.gbrs_pack_get_array(handle, name.encode(), C.byref(ptr), C.byref(nbytes)))
+                dt = entry_t if dt is None else dt
+                if nbytes.value == 0:
+                    self.arrays[name] = np.zeros(0, dtype=dt)
+                else:
+                    buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
+                    self.arrays[name] = np.frombuffer(buf, dtype=dt).copy()
+        finally:
+            lib.gbrs_pack_free(handle)
+        self.pack_seconds = time.perf_counter() - t0
+        self.T, self.H, self.N = T, H, N
+        self.has_genes = gene_of is not None
+        del keep
+
+    def nbytes(self) -> int:
+        return int(sum(a.nbytes for a in self.arrays.values()))
+
+
+class DevicePattern:
+    """Packed incidence + state vectors resident on one GPU, and the `gbrs_em_dev` descriptor pointing at them."""
+
+    def __init__(self, apm: APM = None, gene_of=None, hapmask=None, device=None, shard_rank=0, shard_count=1,
+                 item_len=0, packed: PackedPattern = None, pin=False):
+        torch = _torch()
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        if packed is None:
+            packed = PackedPattern(apm, gene_of=gene_of, hapmask=hapmask, shard_rank=shard_rank,
+                                   shard_count=shard_count, item_len=item_len)
+        self.packed = packed
+        self.info = packed.info
+        self.T, self.H = packed.T, packed.H
+        self.n_ranks = shard_count
+        self.host = {}
+        for k, a in packed.arrays.items():
+            # torch has no uint32/uint64 arithmetic needs here: ship raw bytes
+            t = torch.from_numpy(a.view(np.uint8))
+            self.host[k] = t.pin_memory() if pin else t
+        self.dev = {}
+        self.h2d_bytes = 0
+        self.upload()
+        self._alloc_state()
+        self._build_descriptor()
+
+    # -- device residency -------------------------------------------------------------------------------------------
+    def upload(self):
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            for k, t in self.host.items():
+                if t.numel() == 0:  # keep a valid (non-null) pointer for empty shards
+                    self.dev[k] = torch.zeros(16, dtype=torch.uint8, device=self.device)
+                elif k in self.dev and self.dev[k].numel() == t.numel():
+                    self.dev[k].copy_(t, non_blocking=True)
+                else:
+                    self.dev[k] = t.to(self.device, non_blocking=True)
+                self.h2d_bytes += t.numel()
+
+    def _alloc_state(self):
+        torch = _torch()
+        T, dv, f64 = self.T, self.device, torch.float64
+        i = self.info
+        nw = max(i["n_classes"], i["n_pairs"], 8 * i["n_runs"] if self.packed.has_genes else 0, 1)
+        self.theta = torch.zeros((2, T, 8), dtype=f64, device=dv)
+        self.efflen = torch.ones((T, 8), dtype=f64, device=dv)
+        self.acc = torch.zeros((T, 8), dtype=f64, device=dv)
+        self.iso = torch.zeros((2, T), dtype=f64, device=dv)
+        self.weights = torch.empty(nw, dtype=f64, device=dv)
+        self.wit = torch.zeros((max(i["n_items"], 1), 8), dtype=f64, device=dv)
+        self.part = torch.zeros(_lib.GBRS_PART_SLOTS, dtype=f64, device=dv)
+        self.gene_hap = torch.zeros((max(i["n_gene_ids"], 1), 8), dtype=f64, device=dv)
+        self.gamma = torch.zeros(T, dtype=f64, device=dv)
+        self.err_log = torch.zeros(ERR_LOG_CAP, dtype=f64, device=dv)
+        self.scal = torch.zeros(8, dtype=f64, device=dv)
+        self.ctrl = torch.zeros(16, dtype=torch.int32, device=dv)
+
+    def _build_descriptor(self):
+        d = _lib.EmDev()
+        i = self.info
+        d.T, d.H, d.n_gene_ids, d.entry_bytes = self.T, self.H, i["n_gene_ids"], i["entry_bytes"]
+        d.n_classes, d.n_pairs, d.n_runs, d.n_items = i["n_classes"], i["n_pairs"], i["n_runs"], i["n_items"]
+        d.n_ranks, d.max_iters_cap = self.n_ranks, ERR_LOG_CAP
+        for k in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "locus_item_ptr"):
+            setattr(d, k, self.dev[k].data_ptr())
+        if self.packed.has_genes:
+            for k in ("gene_of", "gene_ptr", "gene_loci"):
+                setattr(d, k, self.dev[k].data_ptr())
+            d.gene_hap, d.gamma = self.gene_hap.data_ptr(), self.gamma.data_ptr()
+        else:
+            d.gene_of = d.gene_ptr = d.gene_loci = d.gene_hap = d.gamma = None
+        for k in ("theta", "efflen", "acc", "iso", "weights", "wit", "part", "err_log", "scal", "ctrl"):
+            setattr(d, k, getattr(self, k).data_ptr())
+        self.desc = d
+
+    def stream(self):
+        torch = _torch()
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- small conveniences -----------------------------------------------------------------------------------------
+    def set_lengths(self, target_lengths_HT):
+        """H x T effective lengths -> device [T][8] (1.0 in unused slots)."""
+        torch = _torch()
+        e = np.ones((self.T, 8), dtype=np.float64)
+        if target_lengths_HT is not None:
+            e[:, : self.H] = np.asarray(target_lengths_HT, dtype=np.float64).T
+        self.efflen.copy_(torch.from_numpy(e))
+
+    def read_ctrl(self):
+        ctrl = np.zeros(16, dtype=np.int32)
+        scal = np.zeros(8, dtype=np.float64)
+        _lib.check(self.lib.gbrs_em_read_ctrl(C.byref(self.desc), self.stream(), ctrl.ctypes.data, scal.ctypes.data))
+        return ctrl, scal
+
+    def current_theta_HT(self) -> np.ndarray:
+        ctrl, _ = self.read_ctrl()
+        th = self.theta[int(ctrl[_lib.CTRL_PARITY])].cpu().numpy()
+        return np.ascontiguousarray(th[:, : self.H].T)
+
+    def set_theta_HT(self, theta_HT):
+        torch = _torch()
+        t = np.zeros((self.T, 8), dtype=np.float64)
+        t[:, : self.H] = np.asarray(theta_HT, dtype=np.float64).T
+        staged = torch.from_numpy(t).to(self.device)
+        _lib.check(self.lib.gbrs_em_set_theta(C.byref(self.desc), C.c_void_p(staged.data_ptr()), self.stream()))
+        _torch().cuda.current_stream(self.device).synchronize()
+
+    def acc_HT(self) -> np.ndarray:
+        return np.ascontiguousarray(self.acc.cpu().numpy()[:, : self.H].T)
+
+    def alignment_counts(self, gene_level=False, n_real_genes=0):
+        torch = _torch()
+        rows = n_real_genes if gene_level else self.T
+        alloc = max(self.info["n_gene_ids"], rows) if gene_level else self.T
+        aln = torch.zeros((alloc, 8), dtype=torch.float64, device=self.device)
+        uniq = torch.zeros((alloc, 8), dtype=torch.float64, device=self.device)
+        lu = torch.zeros(alloc, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.gbrs_em_alignment_counts(C.byref(self.desc), int(gene_level), int(n_real_genes),
+                                                     aln.data_ptr(), uniq.data_ptr(), lu.data_ptr(), self.stream()))
+        H = self.H
+        return (np.ascontiguousarray(aln.cpu().numpy()[:rows, :H].T), np.ascontiguousarray(uniq.cpu().numpy()[:rows, :H].T),
+                lu.cpu().numpy()[:rows].copy())
+
+
+class EMfactory:
+    """A class that coordinates Expectation-Maximization (reference EMfactory.py:15-24)."""
+
+    def __init__(self, alignments: APM, device=None, group=None, shard: bool | None = None, item_len: int = 0,
+                 poll_every: int = 4):
+        self.probability = alignments
+        self._theta_host = None
+        self._theta_dirty = False
+        self.grp_conv_mat = None
+        self._t2t_mat = None
+        self.target_lengths = None
+        self._device = device
+        self._group = group
+        self._item_len = item_len
+        self._poll_every = poll_every
+        self._pattern: DevicePattern | None = None
+        self._gene_of = None
+        self._counts_host = None
+        self.num_iters = 0
+        self.err_history = np.zeros(0)
+        self.rank, self.world = 0, 1
+        if shard is None:
+            shard = group is not None
+        if shard:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # attributes mirrored from the reference
+    # ---------------------------------------------------------------------------------------------------------------
+    @property
+    def allelic_expression(self):
+        return self._theta_host
+
+    @allelic_expression.setter
+    def allelic_expression(self, value):
+        self._theta_host = None if value is None else np.array(value, dtype=np.float64, copy=True)
+        self._theta_dirty = value is not None
+
+    @property
+    def t2t_mat(self):
+        """T x T CSC: identity plus all same-gene pairs (EMfactory.py:48-59).  Built only on demand -- the kernels
+        use the equivalent `gene_of` table."""
+        if self._t2t_mat is None and self.grp_conv_mat is not None:
+            from scipy.sparse import eye
+
+            m = (self.grp_conv_mat @ self.grp_conv_mat.T + eye(self.probability.num_loci)).tocsc()
+            m.data[:] = 1.0
+            self._t2t_mat = m
+        return self._t2t_mat
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def _read_lengths(self, lenfile, read_length):
+        """EMfactory.prepare length handling (EMfactory.py:60-94)."""
+        p = self.probability
+        hid = dict(zip(p.hname, np.arange(len(p.hname))))
+        tl = np.zeros((p.num_loci, p.num_haplotypes))
+        if p.num_haplotypes > 1:
+            with open(lenfile) as fh:
+                for curline in fh:
+                    item = curline.rstrip().split("\t")
+                    locus, hap = item[0].split("_")
+                    tl[p.lid[locus], hid[hap]] = max(float(item[1]) - read_length + 1.0, 1.0)
+        elif p.num_haplotypes > 0:
+            with open(lenfile) as fh:
+                for curline in fh:
+                    item = curline.rstrip().split("\t")
+                    tl[p.lid[item[0]], 0] = max(float(item[1]) - read_length + 1.0, 1.0)
+        else:
+            raise RuntimeError("There is something wrong with your emase-format alignment file.")
+        tl = tl.transpose()
+        if not np.all(tl > 0.0):
+            raise RuntimeError("There exist transcripts missing length information.")
+        return tl
+
+    def _ensure_pattern(self):
+        if self._pattern is None:
+            p = self.probability
+            if not p.is_pure_incidence():
+                raise NotImplementedError(
+                    "stored values other than 1.0 (or explicit zeros) in the alignment matrix: call "
+                    "eliminate_zeros() after masking; weighted (non-incidence) matrices are not supported")
+            self._pattern = DevicePattern(p, gene_of=self._gene_of, device=self._device, shard_rank=self.rank,
+                                          shard_count=self.world, item_len=self._item_len)
+            self._pattern.set_lengths(self.target_lengths)
+        return self._pattern
+
+    def _exchange(self, pat):
+        """The one exchange step of a row-sharded run: sum the T x H numerator over ranks."""
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(pat.acc, op=dist.ReduceOp.SUM, group=self._group)
+
+    def _sync_theta_to_device(self):
+        if self._theta_dirty:
+            self._ensure_pattern().set_theta_HT(self._theta_host)
+            self._theta_dirty = False
+
+    def _fetch_theta(self):
+        self._theta_host = self._pattern.current_theta_HT()
+        self._theta_dirty = False
+
+    # ---------------------------------------------------------------------------------------------------------------
+    def prepare(self, pseudocount: float = 0.0, lenfile: str = None, read_length: int = 100) -> None:
+        """Initializes the probability of read origin according to the alignment profile (EMfactory.py:27-111)."""
+        p = self.probability
+        if p.num_groups > 0:
+            self.grp_conv_mat = utils.group_conversion_matrix(p.num_loci, p.groups)
+            self._gene_of = utils.gene_index(p.num_loci, p.groups)
+        if lenfile is not None:
+            self.target_lengths = self._read_lengths(lenfile, read_length)
+        self._pattern = None
+        self.reset(pseudocount)
+
+    def reset(self, pseudocount: float = 0.0) -> None:
+        """EMfactory.reset (EMfactory.py:113-138): theta0 from the incidence pattern."""
+        pat = self._ensure_pattern()
+        pat.set_lengths(self.target_lengths)
+        _lib.check(pat.lib.gbrs_em_prepare_local(C.byref(pat.desc), pat.stream()))
+        self._exchange(pat)
+        _lib.check(pat.lib.gbrs_em_prepare_finish(C.byref(pat.desc), float(pseudocount), pat.stream()))
+        ctrl, _ = pat.read_ctrl()
+        if ctrl[_lib.CTRL_ERROR]:
+            raise FloatingPointError("non-finite initial expression estimate")
+        self._fetch_theta()
+        self._counts_host = None
+        self.num_iters = 0
+
+    def get_allelic_expression(self, at_group_level: bool = False):
+        if at_group_level:
+            return self._theta_host * self.grp_conv_mat
+        return self._theta_host.copy()
+
+    def update_probability_at_read_level(self, model: int = 3) -> None:
+        """E-step (EMfactory.py:146-212).  On the device the posterior is implicit: this queues the row pass and
+        the column reduce for `model`, leaving the count-weighted numerator sum_n c[n] P[n,t,h] in `acc`."""
+        if model not in (1, 2, 3, 4):
+            raise RuntimeError("The read normalization model should be 1, 2, 3, or 4.")
+        pat = self._ensure_pattern()
+        self._sync_theta_to_device()
+        _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), 0.0, 1, pat.stream()))
+        _lib.check(pat.lib.gbrs_em_launch_local(C.byref(pat.desc), int(model), pat.stream()))
+        self._exchange(pat)
+        self._counts_host = None
+
+    def update_allelic_expression(self, model: int = 3) -> None:
+        """A single EM step (EMfactory.py:214-232)."""
+        self.update_probability_at_read_level(model)
+        pat = self._pattern
+        _lib.check(pat.lib.gbrs_em_launch_update(C.byref(pat.desc), pat.stream()))
+        ctrl, _ = pat.read_ctrl()
+        if ctrl[_lib.CTRL_ERROR]:
+            raise FloatingPointError("non-finite value in the EM update (zero normaliser or overflow)")
+        self._fetch_theta()
+
+    def run(self, model: int, tol: float = 0.001, max_iters: int = 999, verbose: bool = True) -> None:
+        """Runs EM iterations (EMfactory.py:234-287); the stop test runs on the device."""
+        if model not in (1, 2, 3, 4):
+            raise RuntimeError("The read normalization model should be 1, 2, 3, or 4.")
+        if max_iters > ERR_LOG_CAP:
+            raise ValueError(f"max_iters above {ERR_LOG_CAP} is not supported")
+        pat = self._ensure_pattern()
+        self._sync_theta_to_device()
+        if verbose:
+            print("")
+            print("Iter No  Time (hh:mm:ss)    Total change (TPM)  ")
+            print("-------  ---------------  ----------------------")
+        time0 = time.time()
+        if self.world == 1:
+            iters = C.c_int32(0)
+            errs = np.zeros(max(max_iters, 1), dtype=np.float64)
+            rc = pat.lib.gbrs_em_run(C.byref(pat.desc), int(model), float(tol), int(max_iters), int(self._poll_every),
+                                     pat.stream(), C.byref(iters), errs.ctypes.data)
+            _lib.check(rc)
+            n = int(iters.value)
+            self.err_history = errs[:n].copy()
+        else:
+            _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), float(tol), int(max_iters), pat.stream()))
+            ctrl, _ = pat.read_ctrl()
+            while not ctrl[_lib.CTRL_DONE]:
+                for _ in range(self._poll_every):
+                    _lib.check(pat.lib.gbrs_em_launch_local(C.byref(pat.desc), int(model), pat.stream()))
+                    self._exchange(pat)
+                    _lib.check(pat.lib.gbrs_em_launch_update(C.byref(pat.desc), pat.stream()))
+                ctrl, _ = pat.read_ctrl()
+            if ctrl[_lib.CTRL_ERROR]:
+                raise FloatingPointError("non-finite value in the EM update (zero normaliser or overflow)")
+            n = int(ctrl[_lib.CTRL_ITERS])
+            self.err_history = pat.err_log[:n].cpu().numpy()
+        self.num_iters = n
+        if verbose:
+            delmin, s = divmod(int(time.time() - time0), 60)
+            h, m = divmod(delmin, 60)
+            for i, e in enumerate(self.err_history):
+                print(" %5d      %4d:%02d:%02d     %9.1f / 1000000" % (i + 1, h, m, s, e))
+        self._fetch_theta()
+        self._counts_host = None
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # reports
+    # ---------------------------------------------------------------------------------------------------------------
+    def expected_read_counts(self) -> np.ndarray:
+        """H x T count-weighted posterior sums of the last E-step (`probability.sum(axis=READ)`, EMfactory.py:302)."""
+        if self._counts_host is None:
+            self._counts_host = self._ensure_pattern().acc_HT()
+        return self._counts_host
+
+    @staticmethod
+    def _order(total, reorder, n):
+        if reorder == "decreasing":
+            return np.argsort(total.flatten())[::-1]
+        if reorder == "increasing":
+            return np.argsort(total.flatten())
+        return np.arange(n)
+
+    def _write_report(self, filename, lname, data, reorder, notes):
+        total = data.sum(axis=0)
+        order = self._order(total, reorder, len(lname))
+        cntdata = np.vstack((data, total))
+        with open(filename, "w") as fh:
+            fh.write("locus\t" + "\t".join(self.probability.hname) + "\ttotal")
+            if notes is not None:
+                fh.write("\tnotes")
+            fh.write("\n")
+            utils.write_table_rows(fh, lname, cntdata, notes=notes, order=order)
+
+    def report_read_counts(self, filename, grp_wise=False, reorder="as-is", notes=None):
+        """Export read counts (EMfactory.py:289-331)."""
+        counts = self.expected_read_counts()
+        if grp_wise:
+            lname = self.probability.gname
+            counts = counts * self.grp_conv_mat
+        else:
+            lname = self.probability.lname
+        self._write_report(filename, lname, np.asarray(counts), reorder, notes)
+
+    def report_depths(self, filename, tpm=True, grp_wise=False, reorder="as-is", notes=None) -> None:
+        """Exports expected depths (EMfactory.py:333-380).  As in the reference, the isoform-level TPM report scales
+        `allelic_expression` in place (:352-354)."""
+        if grp_wise:
+            lname = self.probability.gname
+            depths = np.asarray(self._theta_host * self.grp_conv_mat)
+        else:
+            lname = self.probability.lname
+            depths = self._theta_host
+        if tpm:
+            depths *= 1000000.0 / depths.sum()
+            if not grp_wise:
+                self._theta_dirty = True
+        self._write_report(filename, lname, depths, reorder, notes)
+
+    def export_posterior_probability(self, filename: str, title: str = "Posterior Probability") -> None:
+        """Writes the pattern + counts, exactly what the reference's default `incidence_only=True` save emits
+        (EMfactory.py:382-392, AlignmentPropertyMatrix.py:484)."""
+        self.probability.save(h5file=filename, title=title)

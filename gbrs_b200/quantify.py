@@ -1,0 +1,109 @@
+"""`quantify` workflow -- same arguments, defaults, masking, output files and headers as the reference's
+`gbrs.gbrs.emase_utils.quantify` (/root/reference/src/gbrs/gbrs/emase_utils.py:180-332), with the EM itself on
+the GPU (gbrs_b200.EMfactory)."""
+from __future__ import annotations
+
+import os
+from itertools import dropwhile
+
+import numpy as np
+
+from . import utils
+from .apm import AlignmentPropertyMatrix
+from .emfactory import EMfactory
+
+DATA_DIR = os.getenv("GBRS_DATA", ".")
+logger = utils.get_logger("gbrs")
+
+
+def load_genotype_mask(aln_mat: AlignmentPropertyMatrix, genotype_file: str):
+    """Genotype TSV -> (gtmask H x T, gtcall_g, gtcall_t)   (emase_utils.py:240-269)."""
+    hid = dict(zip(aln_mat.hname, np.arange(aln_mat.num_haplotypes)))
+    gid = dict(zip(aln_mat.gname, np.arange(len(aln_mat.gname))))
+    gtmask = np.zeros((aln_mat.num_haplotypes, aln_mat.num_loci))
+    gtcall_g = dict.fromkeys(aln_mat.gname)
+    gtcall_t = dict.fromkeys(aln_mat.lname)
+    with open(genotype_file) as fh:
+        for curline in dropwhile(utils.is_comment, fh):
+            item = curline.rstrip().split("\t")
+            g, gt = item[:2]
+            gtcall_g[g] = gt
+            hid2set = np.array([hid[c] for c in gt])
+            tid2set = np.array(aln_mat.groups[gid[g]])
+            gtmask[tuple(np.meshgrid(hid2set, tid2set))] = 1.0
+            for t in tid2set:
+                gtcall_t[aln_mat.lname[t]] = gt
+    return gtmask, gtcall_g, gtcall_t
+
+
+def quantify(alignment_file: str, group_file: str = None, length_file: str = None, genotype_file: str = None,
+             outbase: str = "gbrs.quantified", multiread_model: int = 4, pseudocount: float = 0.0,
+             max_iters: int = 999, tolerance: float = 0.0001, report_alignment_counts: bool = False,
+             report_posterior: bool = False, device=None, group=None) -> None:
+    """Quantify expected read counts.  `device` / `group` are the only additions: the CUDA device to use and an
+    optional torch.distributed process group over which the alignment classes are row-sharded."""
+    if group_file is None:
+        group_file = os.path.join(DATA_DIR, "ref.gene2transcripts.tsv")
+        if not os.path.exists(group_file):
+            logger.warning("A group file is not given. Group-level results will not be reported.")
+    if length_file is None:
+        length_file = os.path.join(DATA_DIR, "gbrs.hybridized.targets.info")
+        if not os.path.exists(length_file):
+            logger.warning("A length file is not given. Transcript length adjustment will *not* be performed.")
+
+    report_group_counts = group_file is not None  # always true here, as in the reference (:219-222)
+
+    logger.info(f"Alignment File: {alignment_file}")
+    logger.info(f"Group File: {group_file}")
+    logger.info(f"Length File: {length_file}")
+    logger.info(f"Genotype File: {genotype_file}")
+    logger.info(f"Outbase: {outbase}")
+    logger.info(f"Multiread Model: {multiread_model}")
+    logger.info(f"Pseudocount: {pseudocount}")
+    logger.info(f"Tolerance: {tolerance}")
+    logger.info(f"Report Alignment Counts: {report_alignment_counts}")
+    logger.info(f"Report Posterior: {report_posterior}")
+
+    logger.info(f"Loading EMASE file: {alignment_file}")
+    aln_mat = AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
+
+    if genotype_file is not None:
+        outbase = f"{outbase}.diploid"
+        logger.info(f"Loading and processing genotype calls from: {genotype_file}")
+        gtmask, gtcall_g, gtcall_t = load_genotype_mask(aln_mat, genotype_file)
+        aln_mat.multiply(gtmask, axis=2)
+        aln_mat.eliminate_zeros()
+    else:
+        outbase = f"{outbase}.multiway"
+        gtcall_g = None
+        gtcall_t = None
+
+    logger.info("Running EMASE")
+    em_factory = EMfactory(aln_mat, device=device, group=group)
+    em_factory.prepare(pseudocount=pseudocount, lenfile=length_file)
+    em_factory.run(model=multiread_model, tol=tolerance, max_iters=max_iters, verbose=True)
+
+    rank0 = em_factory.rank == 0
+    if rank0:
+        logger.info(f"Generating isoform TPMs: {outbase}.isoforms.tpm")
+        em_factory.report_depths(filename=f"{outbase}.isoforms.tpm", tpm=True, notes=gtcall_t)
+        logger.info(f"Generating isoform Read Counts: {outbase}.isoforms.expected_read_counts")
+        em_factory.report_read_counts(filename=f"{outbase}.isoforms.expected_read_counts", notes=gtcall_t)
+        if report_posterior:
+            logger.info(f"Generating Posterior Probabilities: {outbase}.posterior.h5")
+            em_factory.export_posterior_probability(filename=f"{outbase}.posterior.h5")
+        if report_group_counts:
+            logger.info(f"Generating gene TPMs: {outbase}.genes.tpm")
+            em_factory.report_depths(filename=f"{outbase}.genes.tpm", tpm=True, grp_wise=True, notes=gtcall_g)
+            logger.info(f"Generating gene Read Counts: {outbase}.genes.expected_read_counts")
+            em_factory.report_read_counts(filename=f"{outbase}.genes.expected_read_counts", grp_wise=True,
+                                          notes=gtcall_g)
+        if report_alignment_counts:
+            # the reference reloads the file, i.e. counts are taken on the *unmasked* matrix (:319)
+            alnmat = AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
+            logger.info(f"Generating isoform Alignment Counts: {outbase}.isoforms.alignment_counts")
+            alnmat.report_alignment_counts(filename=f"{outbase}.isoforms.alignment_counts")
+            if report_group_counts:
+                logger.info(f"Generating gene Alignment Counts: {outbase}.genes.alignment_counts")
+                alnmat.report_alignment_counts(filename=f"{outbase}.genes.alignment_counts", gene_level=True)
+    logger.debug("Done")

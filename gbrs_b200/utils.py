@@ -1,0 +1,92 @@
+"""Small host helpers shared by the container, the EM driver and the workflow.
+
+Logging mirrors the reference's `gbrs.utils` (/root/reference/src/gbrs/utils.py:13-90): logger name 'gbrs',
+`-v` count -> WARNING / INFO / DEBUG.
+"""
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+
+
+def get_logger(logger_name: str = "gbrs") -> logging.Logger:
+    return logging.getLogger(logger_name)
+
+
+def configure_logging(logger_name: str = "gbrs", level: int = 0) -> logging.Logger:
+    """utils.configure_logging (utils.py:25-90): 0 -> WARNING, 1 -> INFO, 2+ -> DEBUG."""
+    log = logging.getLogger(logger_name)
+    try:
+        from rich.logging import RichHandler
+
+        handler = RichHandler(level=logging.NOTSET, show_level=False, show_time=True, show_path=False,
+                              omit_repeated_times=False)
+    except Exception:  # rich missing: plain stderr handler
+        handler = logging.StreamHandler()
+    debug_env = os.environ.get("GBRS_APP_DEBUG", "0") not in ("0", "", None)
+    fmt = "%(message)s" if not debug_env else "[%(name)s:%(lineno)d] %(message)s"
+    handler.setFormatter(logging.Formatter(fmt))
+    for h in list(log.handlers):
+        log.removeHandler(h)
+    log.addHandler(handler)
+    if level <= 0:
+        log.setLevel(logging.WARNING)
+    elif level == 1:
+        log.setLevel(logging.INFO)
+    else:
+        log.setLevel(logging.DEBUG)
+    log.propagate = False
+    return log
+
+
+def is_comment(s: str) -> bool:
+    """utils.is_comment (utils.py:147-157)."""
+    return s.startswith("#")
+
+
+def gene_index(num_loci: int, groups) -> np.ndarray:
+    """int32 gene id per locus.  Loci listed in `groups[g]` get id g; loci in no group get unique ids
+    >= len(groups) (they are their own singleton in the reference's `t2t_mat`, EMfactory.py:48-59)."""
+    g = np.full(num_loci, -1, dtype=np.int64)
+    n_groups = len(groups) if groups is not None else 0
+    if n_groups:
+        sizes = np.fromiter((len(x) for x in groups), dtype=np.int64, count=n_groups)
+        flat = np.fromiter((t for x in groups for t in x), dtype=np.int64, count=int(sizes.sum()))
+        gid = np.repeat(np.arange(n_groups, dtype=np.int64), sizes)
+        if flat.size and np.unique(flat).size != flat.size:
+            raise NotImplementedError("a transcript listed in more than one gene group is not supported")
+        g[flat] = gid
+    free = np.flatnonzero(g < 0)
+    g[free] = n_groups + np.arange(free.size)
+    return g.astype(np.int32)
+
+
+def group_conversion_matrix(num_loci: int, groups):
+    """T x G 0/1 CSC matrix (`grp_conv_mat`, EMfactory.py:42-47), built without the per-gene python loop."""
+    from scipy.sparse import csc_matrix
+
+    n_groups = len(groups)
+    sizes = np.fromiter((len(x) for x in groups), dtype=np.int64, count=n_groups)
+    rows = np.fromiter((t for x in groups for t in x), dtype=np.int64, count=int(sizes.sum()))
+    indptr = np.zeros(n_groups + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum(sizes)
+    m = csc_matrix((np.ones(rows.size), rows, indptr), shape=(num_loci, n_groups))
+    m.sum_duplicates()
+    m.data[:] = 1.0
+    return m
+
+
+def write_table_rows(fh, names, cntdata: np.ndarray, notes=None, order=None) -> None:
+    """Rows `name<TAB>v0<TAB>v1...[<TAB>note]` with values formatted like the reference's `str(numpy.float64)`
+    (EMfactory.py:325-331, :370-380)."""
+    idx = range(len(names)) if order is None else order
+    cols = cntdata.shape[0]
+    for i in idx:
+        name = names[i]
+        vals = cntdata[:, i]
+        line = str(name) + "\t" + "\t".join(repr(float(vals[k])) for k in range(cols))
+        if notes is not None:
+            line += f"\t{notes[name]}"
+        fh.write(line + "\n")

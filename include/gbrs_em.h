@@ -1,0 +1,184 @@
+/*
+ * gbrs_em.h -- C ABI of the B200-native multiway EM quantifier (the loop behind `gbrs quantify -M 1..4`).
+ *
+ * The reference (churchill-lab/gbrs) is pure Python and has no FFI boundary for this path; its boundary is the
+ * Python class `EMfactory` (src/gbrs/emase/EMfactory.py:15-392) working on an `AlignmentPropertyMatrix`
+ * (src/gbrs/emase/AlignmentPropertyMatrix.py:25-111).  This header is the boundary a maintainer would bind from that
+ * class with ctypes: each entry point names the reference method(s) whose inner loop it replaces.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (streams are passed as `void*` = cudaStream_t).
+ *   - every function returns 0 on success, a negative GBRS_E_* code on failure; `gbrs_last_error()` gives the text.
+ *   - the library owns NO device memory.  All device buffers are allocated by the caller (PyTorch tensors used as
+ *     raw buffers) and handed over in `gbrs_em_dev`; host-side packing results live in a `gbrs_pack_t` until freed.
+ *   - all launches are asynchronous on the given stream; only gbrs_em_run() / gbrs_em_read_ctrl() synchronise.
+ *   - there is no CPU fallback: every compute entry point fails with GBRS_E_CUDA if no sm_100 device is usable.
+ *
+ * Device layout: theta / effective lengths / numerators are stored locus-major with the haplotype
+ * index minor and padded to 8 ( [T][8] doubles = one 64-byte line per locus ).  An alignment class is a row of
+ * (locus, 8-bit haplotype mask) pair words; the incidence matrix is stored twice, class-major (row pass, E-step
+ * normaliser) and locus-major (column pass, M-step reduction), so that both passes are gathers and no atomics are needed.
+ */
+#ifndef GBRS_EM_H
+#define GBRS_EM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBRS_EM_ABI_VERSION 1
+#define GBRS_HPAD 8 /* haplotype slots per locus line */
+
+enum {
+  GBRS_OK = 0,
+  GBRS_E_ARG = -1,      /* bad argument (shape, model, null pointer) */
+  GBRS_E_LIMIT = -2,    /* input exceeds a packing limit (H > 8, T >= 2^24, pairs >= 2^32) */
+  GBRS_E_CUDA = -3,     /* CUDA runtime error / no usable device */
+  GBRS_E_NUMERIC = -4,  /* non-finite value in the EM (reference: FloatingPointError under np.seterr(all='raise'),
+                           src/gbrs/emase/EMfactory.py:256-257) */
+  GBRS_E_NOMEM = -5,
+  GBRS_E_STATE = -6     /* call order violated (e.g. run before prepare) */
+};
+
+const char* gbrs_last_error(void);
+int gbrs_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Host-side packing: H x CSC(N x T) incidence  ->  class-major + locus-major packed rows.
+ * Replaces the storage walked by Sparse3DMatrix (src/gbrs/emase/Sparse3DMatrix.py:26-66, reset :220-228,
+ * multiply :314-377) and the `-G` masking of quantify (src/gbrs/gbrs/emase_utils.py:240-273).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct gbrs_pack* gbrs_pack_t;
+
+typedef struct {
+  int32_t T;                   /* loci */
+  int32_t H;                   /* haplotypes, 1..8 */
+  int64_t N;                   /* alignment classes (rows of every CSC matrix) */
+  const int64_t* const* indptr;  /* H pointers, each [T+1]: column pointers of haplotype h */
+  const void* const* indices;    /* H pointers, each [indptr[h][T]]: class ids of the stored entries */
+  int32_t index_bytes;         /* 4 (int32) or 8 (int64) for `indices` */
+  const double* const* values; /* optional H pointers to the stored values; entries whose value is 0 are dropped
+                                  (explicit zeros behave like `eliminate_zeros`); NULL = pure incidence */
+  const double* count;         /* [N] class counts or NULL (= all ones, AlignmentPropertyMatrix.py:291-293) */
+  const uint8_t* locus_hapmask;/* [T] or NULL: bit h set = haplotype h of this locus survives the -G genotype
+                                  restriction (gtmask of emase_utils.py:247-269, one byte per locus) */
+  const int32_t* gene_of;      /* [T] gene id per locus (ungrouped loci carry unique ids) or NULL (each locus alone) */
+  int32_t shard_rank;          /* this rank's index ... */
+  int32_t shard_count;         /* ... of this many row shards (classes split in contiguous ranges balanced by nnz) */
+  int32_t item_len;            /* max entries per column-pass work item; 0 = default */
+} gbrs_pack_input;
+
+typedef struct {
+  int64_t n_classes;   /* non-empty classes in this shard (after masking) */
+  int64_t n_pairs;     /* (class, locus) pair words in this shard */
+  int64_t n_runs;      /* (class, gene) runs in this shard */
+  int64_t n_items;     /* column-pass work items */
+  int64_t nnz;         /* incidence entries in this shard (popcount over pair masks) */
+  int64_t nnz_total;   /* incidence entries over all shards */
+  int64_t n_classes_total;
+  int32_t entry_bytes; /* 4 or 8: width of the locus-major entry words */
+  int32_t n_gene_ids;  /* 1 + max gene id */
+  int32_t max_pairs_per_class;
+  int32_t reserved;
+} gbrs_pack_info;
+
+int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out);
+int gbrs_pack_get_info(gbrs_pack_t p, gbrs_pack_info* info);
+/* Borrowed host pointers to the packed arrays (valid until gbrs_pack_free).  `name` is one of:
+ *   "rowptr"  uint32 [n_classes+1]   "pairs"   uint32 [n_pairs]  (locus | mask<<24, sorted by (gene, locus) in a class)
+ *   "count"   double [n_classes]     "runptr"  uint32 [n_classes+1]
+ *   "ent_cls" / "ent_pair" / "ent_run"  entry words [n_pairs], locus-major (index | mask << (8*entry_bytes-8))
+ *   "item_off" uint32 [n_items+1]    "locus_item_ptr" uint32 [T+1]
+ *   "gene_ptr" uint32 [n_gene_ids+1] "gene_loci" uint32 [T]     "gene_of" int32 [T]
+ */
+int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64_t* bytes);
+int gbrs_pack_free(gbrs_pack_t p);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device descriptor: every pointer is a device pointer into a caller-owned buffer.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t T, H;
+  int32_t n_gene_ids;
+  int32_t entry_bytes;
+  int64_t n_classes, n_pairs, n_runs, n_items;
+  int32_t n_ranks;     /* row shards taking part (1 = no exchange step) */
+  int32_t max_iters_cap; /* capacity of err_log */
+  /* packed incidence (read-only) */
+  const uint32_t* rowptr;
+  const uint32_t* pairs;
+  const double* count;
+  const uint32_t* runptr;
+  const void* ent_cls;
+  const void* ent_pair;
+  const void* ent_run;
+  const uint32_t* item_off;
+  const uint32_t* locus_item_ptr;
+  const int32_t* gene_of;
+  const uint32_t* gene_ptr;
+  const uint32_t* gene_loci;
+  /* state */
+  double* theta;    /* [2][T][8] ping-pong allelic expression */
+  double* efflen;   /* [T][8] effective lengths (1.0 where unused / no length file) */
+  double* acc;      /* [T][8] M-step numerator: local after gbrs_em_launch_local, global after the exchange */
+  double* iso;      /* [2][T] isoform totals sum_h theta */
+  double* weights;  /* [max(n_classes, n_pairs, 8*n_runs)] per-class / per-pair / per-run weights */
+  double* wit;      /* [n_items][8] column-pass partials */
+  double* part;     /* [GBRS_PART_SLOTS] block partial sums */
+  double* gene_hap; /* [n_gene_ids][8] per-gene per-haplotype totals (models 1-3) */
+  double* gamma;    /* [T] gene total broadcast to loci (models 1-3) */
+  double* err_log;  /* [max_iters_cap] err_sum per iteration */
+  double* scal;     /* [8] device scalars */
+  int32_t* ctrl;    /* [16] control block, see GBRS_CTRL_* */
+} gbrs_em_dev;
+
+#define GBRS_PART_SLOTS 1024
+enum { GBRS_CTRL_ITERS = 0, GBRS_CTRL_DONE = 1, GBRS_CTRL_ERROR = 2, GBRS_CTRL_PARITY = 3, GBRS_CTRL_MAX_ITERS = 4,
+       GBRS_CTRL_PREPARED = 5 };
+enum { GBRS_SCAL_ERR = 0, GBRS_SCAL_SUM_PREV = 1, GBRS_SCAL_TARGET = 2, GBRS_SCAL_SUM_CUR = 3 };
+
+/* theta0 from the incidence alone.  EMfactory.prepare numeric part (EMfactory.py:95-111) / EMfactory.reset (:113-138).
+ * Split in two so that a row-sharded run can sum `acc` across ranks in between:
+ *   gbrs_em_prepare_local:   acc[t][h] = sum_n count[n] / nnz[n]           (normalize_reads(READ) + sum(READ))
+ *   gbrs_em_prepare_finish:  theta0 = acc / efflen, pseudocount rule (:105-111), isoform totals, control reset */
+int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream);
+int gbrs_em_prepare_finish(const gbrs_em_dev* d, double pseudocount, void* stream);
+
+/* Load a caller-supplied theta (device [T][8]) as the current estimate and reset the loop control. */
+int gbrs_em_set_theta(const gbrs_em_dev* d, const double* theta_dev, void* stream);
+/* Device pointer of the current theta ([T][8]) after all work queued on `stream` so far (synchronises the stream). */
+int gbrs_em_current_theta(const gbrs_em_dev* d, void* stream, double** theta_dev);
+
+/* Arm the loop: EMfactory.run prologue (EMfactory.py:262-266): err_sum = 1e6, target = 1e6 * tol, iteration cap. */
+int gbrs_em_run_begin(const gbrs_em_dev* d, double tol, int max_iters, void* stream);
+
+/* One EM update, first half, on this rank's shard: E-step normalisers for `model` (update_probability_at_read_level,
+ * EMfactory.py:146-212, with normalize_reads AlignmentPropertyMatrix.py:305-370 and multiply Sparse3DMatrix.py:314-377)
+ * and the count-weighted column reduce (APM.sum(READ), AlignmentPropertyMatrix.py:288-298) into `acc`. */
+int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* stream);
+/* Second half (after `acc` holds the sum over all shards): theta' = acc / efflen (EMfactory.py:228-232), TPM-scaled
+ * isoform-total L1 change and the stop test (EMfactory.py:267-279), entirely on the device. */
+int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream);
+
+/* Whole loop for a single rank (n_ranks == 1): EMfactory.run (EMfactory.py:234-287).  Iterations are queued
+ * `poll_every` at a time; the stop decision is taken on the device and read back at each poll.  Returns the number of
+ * iterations performed and copies their err_sum values into errs_host[0..iters) (may be NULL). */
+int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_iters, int poll_every, void* stream,
+                int32_t* iters_out, double* errs_host);
+
+/* Read the control block (synchronises the stream): ctrl_host[16], scal_host[8]. */
+int gbrs_em_read_ctrl(const gbrs_em_dev* d, void* stream, int32_t* ctrl_host, double* scal_host);
+
+/* report_alignment_counts columns (AlignmentPropertyMatrix.py:389-459) on the packed (unmasked) incidence:
+ *   aln[t][8], uniq[t][8] (classes with exactly one alignment), locus_uniq[t] (classes hitting exactly one locus).
+ * If gene_level != 0 the loci are first bundled into genes (_bundle_inline, :155-188) using gene_of / `n_real_genes`
+ * (gene ids >= n_real_genes are ungrouped loci and vanish); outputs are then indexed by gene id. */
+int gbrs_em_alignment_counts(const gbrs_em_dev* d, int gene_level, int32_t n_real_genes, double* aln_dev,
+                             double* uniq_dev, double* locus_uniq_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBRS_EM_H */

@@ -1,0 +1,177 @@
+"""Host packer (gbrs_pack_create) -- structure invariants, sharding, masking.  CPU only: no compute call."""
+import numpy as np
+import pytest
+
+from gbrs_b200 import _lib, synth
+from gbrs_b200.apm import AlignmentPropertyMatrix
+from gbrs_b200.emfactory import PackedPattern
+from gbrs_b200.utils import gene_index
+from oracle import em_oracle as eo
+from tests import helpers as hp
+from tests.packed_emulation import em_update_model4, unpack_entries
+
+
+def make_apm(d):
+    apm = AlignmentPropertyMatrix(shape=(d.T, d.H, d.N), haplotype_names=list(d.hname), locus_names=list(d.lname))
+    apm.data = synth.to_csc_list(d)
+    apm.finalized = True
+    apm.count = d.count.copy()
+    apm.gname = np.array(d.gname)
+    apm.groups = d.groups()
+    apm.num_groups = len(d.gname)
+    return apm
+
+
+def class_signatures(d, hapmask=None):
+    """multiset of (count, ((locus, mask), ...)) over non-empty classes of the input."""
+    sig = {}
+    for c, t, m in zip(d.pair_class, d.pair_locus, d.pair_mask):
+        m = int(m) & (int(hapmask[t]) if hapmask is not None else 0xFF)
+        if m:
+            sig.setdefault(int(c), []).append((int(t), m))
+    out = sorted((float(d.count[c]), tuple(sorted(v))) for c, v in sig.items())
+    return out
+
+
+def packed_signatures(p):
+    a = p.arrays
+    rp = a["rowptr"].astype(np.int64)
+    out = []
+    for n in range(p.info["n_classes"]):
+        w = a["pairs"][rp[n]:rp[n + 1]].astype(np.int64)
+        out.append((float(a["count"][n]), tuple(sorted((int(x & 0xFFFFFF), int(x >> 24)) for x in w))))
+    return sorted(out)
+
+
+@pytest.fixture(scope="module")
+def small():
+    return synth.generate(T=120, N=1500, H=8, with_genotype=True)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(_lib.HERE), "include", "gbrs_em.h")).read()
+    declared = set(re.findall(r"\b(gbrs_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"gbrs_pack", "gbrs_em"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.gbrs_abi_version() == 1
+
+
+def test_pack_preserves_pattern(small):
+    d = small
+    p = PackedPattern(make_apm(d), gene_of=gene_index(d.T, d.groups()))
+    assert p.info["n_pairs"] == d.pairs and p.info["nnz"] == d.nnz == p.info["nnz_total"]
+    assert packed_signatures(p) == class_signatures(d)
+    a = p.arrays
+    # classes ordered by smallest locus
+    rp = a["rowptr"].astype(np.int64)
+    minloc = np.array([(a["pairs"][rp[n]:rp[n + 1]] & 0xFFFFFF).min() for n in range(p.info["n_classes"])])
+    assert np.all(np.diff(minloc) >= 0)
+    # locus-major entries mirror the class-major pairs
+    idx_c, m_c = unpack_entries(a["ent_cls"], p.info["entry_bytes"])
+    idx_p, m_p = unpack_entries(a["ent_pair"], p.info["entry_bytes"])
+    idx_r, m_r = unpack_entries(a["ent_run"], p.info["entry_bytes"])
+    assert np.array_equal(m_c, m_p) and np.array_equal(m_c, m_r)
+    pw = a["pairs"].astype(np.int64)[idx_p]
+    assert np.array_equal(pw >> 24, m_p)
+    cls_of_pair = np.repeat(np.arange(p.info["n_classes"]), np.diff(rp))
+    assert np.array_equal(cls_of_pair[idx_p], idx_c)
+    # items tile the entries; every item belongs to one locus; entries of a locus are ascending in class id
+    io, lip = a["item_off"].astype(np.int64), a["locus_item_ptr"].astype(np.int64)
+    assert io[0] == 0 and io[-1] == p.info["n_pairs"] and np.all(np.diff(io) > 0) and np.all(np.diff(io) <= 64)
+    locus_of_entry = pw & 0xFFFFFF
+    for t in range(d.T):
+        lo, hi = (io[lip[t]], io[lip[t + 1]]) if lip[t + 1] > lip[t] else (0, 0)
+        assert np.all(locus_of_entry[lo:hi] == t)
+        assert np.all(np.diff(idx_c[lo:hi]) > 0)
+    assert lip[-1] == p.info["n_items"]
+    # runs: consecutive pairs of one class in the same gene
+    g = gene_index(d.T, d.groups())[pw_locus(a)]
+    runptr = a["runptr"].astype(np.int64)
+    run_of_pair = np.zeros(p.info["n_pairs"], dtype=np.int64)
+    for n in range(p.info["n_classes"]):
+        gg = g[rp[n]:rp[n + 1]]
+        assert np.all(np.diff(gg) >= 0)
+        run_of_pair[rp[n]:rp[n + 1]] = runptr[n] + np.concatenate(([0], np.cumsum(np.diff(gg) != 0)))
+        assert runptr[n + 1] - runptr[n] == 1 + np.count_nonzero(np.diff(gg))
+    assert np.array_equal(run_of_pair[idx_p], idx_r)
+
+
+def pw_locus(a):
+    return a["pairs"].astype(np.int64) & 0xFFFFFF
+
+
+def test_pack_genotype_mask(small):
+    d = small
+    gm = synth.genotype_mask(d)
+    hapmask = (gm.T.astype(np.uint8) << np.arange(8, dtype=np.uint8)[None, :]).sum(axis=1).astype(np.uint8)
+    p = PackedPattern(make_apm(d), hapmask=hapmask)
+    assert packed_signatures(p) == class_signatures(d, hapmask)
+    # same thing through the host container path used by quantify -G
+    apm = make_apm(d)
+    apm.multiply(gm, axis=2)
+    apm.eliminate_zeros()
+    assert apm.is_pure_incidence()
+    p2 = PackedPattern(apm)
+    assert packed_signatures(p2) == packed_signatures(p)
+
+
+@pytest.mark.parametrize("R", [2, 3, 8])
+def test_pack_shards_partition_the_classes(small, R):
+    d = small
+    apm = make_apm(d)
+    shards = [PackedPattern(apm, shard_rank=r, shard_count=R) for r in range(R)]
+    allsig = sorted(s for p in shards for s in packed_signatures(p))
+    assert allsig == class_signatures(d)
+    nnz = [p.info["nnz"] for p in shards]
+    assert sum(nnz) == d.nnz and all(p.info["nnz_total"] == d.nnz for p in shards)
+    assert max(nnz) - min(nnz) <= 0.1 * d.nnz / R + 64  # balanced by nnz
+
+
+def test_pack_handles_unsorted_indices_and_empty_classes():
+    d = synth.generate(T=40, N=300, H=4)
+    apm = make_apm(d)
+    rng = np.random.default_rng(1)
+    for m in apm.data:  # shuffle the entries inside every column
+        for t in range(d.T):
+            seg = m.indices[m.indptr[t]:m.indptr[t + 1]]
+            rng.shuffle(seg)
+        m.has_sorted_indices = False
+    apm.shape = (d.T, d.H, d.N + 7)  # trailing classes without any alignment
+    apm.num_reads = d.N + 7
+    apm.data = [type(m)((m.data, m.indices, m.indptr), shape=(d.N + 7, d.T)) for m in apm.data]
+    apm.count = np.concatenate([d.count, np.ones(7)])
+    p = PackedPattern(apm)
+    assert p.info["n_classes"] == len(class_signatures(d)) and packed_signatures(p) == class_signatures(d)
+
+
+def test_pack_limits():
+    d = synth.generate(T=10, N=20, H=2)
+    apm = make_apm(d)
+    apm.shape = (10, 9, 20)
+    apm.data = apm.data + [apm.data[0]] * 7
+    with pytest.raises(NotImplementedError):
+        PackedPattern(apm)
+
+
+@pytest.mark.parametrize("name", ["em_small_m4", "em_small_m4_diploid", "em_small_m4_h2"])
+def test_packed_layout_reproduces_reference_model4(name):
+    """One prepare + a few model-4 updates computed by walking the packed arrays equal the golden trajectory."""
+    g = hp.load_golden(name)
+    d = hp.synth_from_golden(g)
+    hapmask = None
+    if g["masked"]:
+        hapmask = (g["gtmask"].T.astype(np.uint8) << np.arange(8, dtype=np.uint8)[None, :]).sum(axis=1).astype(np.uint8)
+    p = PackedPattern(make_apm(d), hapmask=hapmask, item_len=16)
+    eff = np.ones((d.T, 8))
+    eff[:, :d.H] = eo.effective_length_table(d.lengths).T
+    _, theta = em_update_model4(p.arrays, p.info, d.T, None, eff, unit=True)
+    assert hp.relerr(theta[:, :d.H].T, g["theta0"]) < 1e-12
+    acc = None
+    for _ in range(g["iters"]):
+        acc, theta = em_update_model4(p.arrays, p.info, d.T, theta, eff)
+    assert hp.relerr(theta[:, :d.H].T, g["theta"]) < 1e-10
+    assert hp.relerr(acc[:, :d.H].T, g["counts"]) < 1e-10
