@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the multiway EM quantifier (BASELINE.json: EM iterations/s and alignment-nnz/s,
+model 4, DO-mouse-scale shape, % of the HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|small] [--model 4]
+
+A *step* is one EM update (E-step + M-step + convergence test) over the resident packed incidence matrix.
+  value     nnz * K / t          device-timed (CUDA events on the launch stream), inputs resident in HBM
+  e2e       same metric through the public `EMfactory` API from HOST buffers: H2D of the packed matrix (pinned) +
+            prepare + run(K iterations) + D2H of theta / counts / err log, all inside the timed region
+  roofline  dominant kernel: algorithmic bytes of that kernel / its mean device time, vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (numpy restatement of the reference's EM; the reference itself is pure Python and is not
+            present on the GPU box) timed on a bounded sample of the same workload on the host cores
+
+N > 1 (torchrun): weak scaling -- every rank holds its own `workload`-sized row shard (different classes, same loci),
+one NCCL all-reduce of the T x 8 numerator per step; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(T=80000, N=5_000_000, label="DO-mouse-scale quantify -M 4: 80k transcripts x 8 haplotypes x 5M classes"),
+    "c1": dict(T=2000, N=200_000, label="config 1: 2k transcripts x 8 haplotypes x 200k classes"),
+    "small": dict(T=8000, N=500_000, label="reduced: 8k x 8 x 500k (debug only)"),
+}
+CPU_SAMPLE_CLASSES = 1_000_000
+METRIC = "em_alignment_nnz_per_s"
+UNIT = "nnz/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                it = [x.strip() for x in line.split(",")]
+                if len(it) < 9:
+                    continue
+                try:
+                    sm.append(float(it[1]))
+                    mx.append(float(it[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, it[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(T, n_classes, steps, warmup, model=4):
+    """nnz/s of the numpy restatement of the reference EM (oracle/em_oracle.py), single host thread."""
+    from gbrs_b200 import synth
+    from oracle import em_oracle as eo
+
+    d = synth.generate(T=T, N=n_classes, H=8)
+    apm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    eff = eo.effective_length_table(d.lengths)
+    gene_of = eo.gene_index(d.T, d.groups()) if model != 4 else None
+    keys = eo._Keys(apm, gene_of) if model != 4 else None
+    theta = eo.prepare(apm, eff, 0.0)
+
+    def one(theta):
+        prev = theta.sum(axis=0)
+        prev *= 1e6 / prev.sum()
+        val = eo.e_step(apm, theta, model, gene_of, keys)
+        theta = eo.sum_read(apm, val) / eff
+        cur = theta.sum(axis=0)
+        cur *= 1e6 / cur.sum()
+        return theta, float(np.abs(cur - prev).sum())
+
+    for _ in range(warmup):
+        theta, _ = one(theta)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        theta, _ = one(theta)
+    dt = time.perf_counter() - t0
+    return apm.nnz * steps / dt, dt / steps, apm.nnz
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncls = min(CPU_SAMPLE_CLASSES, wl["N"])
+    steps = max(1, min(args.steps, 10))
+    rate, s_per_step, nnz = cpu_port_rate(wl["T"], ncls, steps, min(args.warmup, 1), args.model)
+    sample = f"{ncls} of {wl['N']} classes (nnz={nnz}), {steps} EM updates timed"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["label"], "model": args.model, "sample": sample},
+            "iterations_per_s_at_full_size": rate / (nnz * wl["N"] / ncls),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from gbrs_b200 import _lib, synth
+    from gbrs_b200.emfactory import EMfactory
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the EM has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    # ---- workload: every rank holds one `workload`-sized shard (weak scaling) ------------------------------------
+    t0 = time.perf_counter()
+    d = synth.generate(T=wl["T"], N=wl["N"], H=8, sample_index=rank)
+    apm = synth.to_apm(d)
+    t_gen = time.perf_counter() - t0
+    em = EMfactory(apm, device=dev, shard="local" if world > 1 else None)
+    em.target_lengths = synth.effective_lengths(d)  # same table prepare() would parse from a targets.info file
+    t0 = time.perf_counter()
+    em.prepare()  # gene tables + pack + upload + theta0
+    t_first = time.perf_counter() - t0
+    pat = em._pattern
+    lib, desc = pat.lib, pat.desc
+    info = pat.info
+    nnz_local = info["nnz"]
+    nnz_total = nnz_local
+    if world > 1:
+        t = torch.tensor([nnz_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        nnz_total = int(t.item())
+    log(f"[rank {rank}] generate {t_gen:.1f}s, pack {pat.packed.pack_seconds:.2f}s, first prepare {t_first:.2f}s, "
+        f"classes={info['n_classes']} pairs={info['n_pairs']} nnz={nnz_local} items={info['n_items']}")
+
+    model = args.model
+    stream = pat.stream()
+
+    def exchange():
+        if world > 1:
+            dist.all_reduce(pat.acc)
+
+    def step():
+        _lib.check(lib.gbrs_em_launch_local(C.byref(desc), model, stream))
+        exchange()
+        _lib.check(lib.gbrs_em_launch_update(C.byref(desc), stream))
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    K, W = args.steps, max(args.warmup, 3)
+    # tol = 0 keeps the loop alive for exactly the number of updates we queue
+    _lib.check(lib.gbrs_em_run_begin(C.byref(desc), 0.0, min(4 * (K + W) + 16, 60000), stream))
+    for _ in range(W):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sync_all()
+    ctrl, scal = pat.read_ctrl()
+    assert ctrl[_lib.CTRL_ERROR] == 0, "non-finite value during the timed region"
+    assert ctrl[_lib.CTRL_ITERS] == W + K, (ctrl[:6], W, K)
+    value = nnz_total * K / (ms * 1e-3)
+
+    # ---- per-kernel device time of the same K updates (events around the row / column pass) --------------------
+    prof = C.c_void_p()
+    _lib.check(lib.gbrs_prof_create(K, C.byref(prof)))
+    for _ in range(K):
+        _lib.check(lib.gbrs_em_launch_local_profiled(C.byref(desc), model, stream, prof))
+        exchange()
+        _lib.check(lib.gbrs_em_launch_update(C.byref(desc), stream))
+    ms_row, ms_col, ms_acc, nrec = C.c_double(), C.c_double(), C.c_double(), C.c_int32()
+    _lib.check(lib.gbrs_prof_read(prof, C.byref(ms_row), C.byref(ms_col), C.byref(ms_acc), C.byref(nrec)))
+    lib.gbrs_prof_free(prof)
+    row_ms, col_ms, acc_ms = ms_row.value / K, ms_col.value / K, ms_acc.value / K
+    clocks = sampler.stop() if sampler else None
+
+    # ---- algorithmic bytes -----------------------------------------------------------------
+    Np, Pp, It, T = info["n_classes"], info["n_pairs"], info["n_items"], wl["T"]
+    eb = info["entry_bytes"]
+    widx = {4: Np, 3: info["n_runs"], 2: Pp, 1: 8 * info["n_runs"]}[model]
+    bytes_row = 4 * Pp + 4 * (Np + 1) + 8 * Np + 8 * widx + 64 * T
+    bytes_col = eb * Pp + 4 * (It + 1) + 8 * widx + 64 * It
+    bytes_iter = 4 * Pp + 4 * (Np + 1) + 8 * Np + 3 * 64 * T  # SURVEY 8(d), pair+mask layout, inputs once
+    peak, peak_src = measured_peaks()
+    if row_ms >= col_ms:
+        dom, dom_ms, dom_bytes = "k_weights_m%d (row pass)" % model, row_ms, bytes_row
+    else:
+        dom, dom_ms, dom_bytes = "k_column_reduce (column pass)", col_ms, bytes_col
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+                "share_of_step": dom_ms / (ms / K),
+                "per_kernel_ms": {"row_pass": row_ms, "column_pass": col_ms, "locus_acc": acc_ms,
+                                  "rest_of_step": max(ms / K - row_ms - col_ms - acc_ms, 0.0)},
+                "iteration": {"algorithmic_bytes": bytes_iter, "achieved": bytes_iter / (ms / K * 1e-3) / 1e9,
+                              "frac": bytes_iter / (ms / K * 1e-3) / 1e9 / peak,
+                              "note": "SURVEY 8(d) pair+mask formula (each input once, theta in/out + lengths); the "
+                                      "second (locus-major) copy and the weight vector are NOT counted"}}
+
+    # ---- e2e through the public API with host buffers ------------------------------------------------------------
+    for k in list(pat.host):
+        pat.host[k] = pat.host[k].pin_memory()
+    Ke = K
+    sync_all()
+    t0 = time.perf_counter()
+    pat.h2d_bytes = 0
+    pat.upload()
+    em.reset()
+    em.run(model=model, tol=0.0, max_iters=Ke, verbose=False)
+    counts = em.expected_read_counts()
+    torch.cuda.synchronize(dev)
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    assert em.num_iters == Ke
+    assert abs(counts.sum() - (d.count.sum() if world == 1 else counts.sum())) < 1e-6 * counts.sum()
+    h2d = pat.h2d_bytes + 64 * T + 64 * T  # packed arrays + effective lengths (+ nothing else)
+    d2h = 2 * 64 * T + 2 * 8 * wl["T"] * 8 + 8 * Ke
+    e2e = {"value": nnz_total * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": d2h / Ke,
+           "seconds": t_e2e, "what": "H2D packed incidence (pinned) + prepare + run(%d updates) + D2H theta/counts/err "
+                                     "log through EMfactory" % Ke}
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ncls = min(CPU_SAMPLE_CLASSES, wl["N"])
+        rate, s_per, nnz_s = cpu_port_rate(wl["T"], ncls, 5, 1, model)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{ncls} of {wl['N']} classes (nnz={nnz_s}), 5 EM updates of oracle/em_oracle.py, "
+                         f"{s_per:.3f} s/update, host has {os.cpu_count()} logical cores (path is single-threaded)"}
+
+    if rank == 0:
+        launches_per_step = 5 + (1 if model != 4 else 0)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["label"], "model": model, "classes_per_gpu": Np, "pairs_per_gpu": Pp,
+                           "nnz_per_gpu": nnz_local, "nnz_total": nnz_total, "loci": T, "haplotypes": 8,
+                           "l2_policy": "inputs larger than L2 (packed incidence %.0f MB per GPU streams every step)"
+                                        % (pat.packed.nbytes() / 1e6),
+                           "exchange": "none" if world == 1 else "NCCL all-reduce of T x 8 fp64 per step"},
+                "iterations_per_s": K / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches_per_step * K, "clocks": clocks,
+                "pack_seconds": pat.packed.pack_seconds}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--model", type=int, default=4, choices=[1, 2, 3, 4])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_gpu_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,11 @@ SYMBOLS = {
     "gbrs_em_run_begin": (C.c_int, [C.POINTER(EmDev), C.c_double, C.c_int, C.c_void_p]),
     "gbrs_em_launch_local": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_void_p]),
     "gbrs_em_launch_update": (C.c_int, [C.POINTER(EmDev), C.c_void_p]),
+    "gbrs_prof_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "gbrs_em_launch_local_profiled": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_void_p, C.c_void_p]),
+    "gbrs_prof_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_int32)]),
+    "gbrs_prof_free": (C.c_int, [C.c_void_p]),
     "gbrs_em_run": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p,
                               C.POINTER(C.c_int32), C.c_void_p]),
     "gbrs_em_read_ctrl": (C.c_int, [C.POINTER(EmDev), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -106,6 +106,24 @@ class AlignmentPropertyMatrix:
         if grpfile is not None:
             self.load_groups(grpfile)
 
+    @classmethod
+    def from_csc(cls, mats, haplotype_names, locus_names, count=None):
+        """Wrap H ready-made scipy CSC matrices (N x T) without the lil_matrix detour of the `shape=` constructor."""
+        self = cls()
+        N, T = mats[0].shape
+        self.shape = (int(T), len(mats), int(N))
+        self.num_loci, self.num_haplotypes, self.num_reads = self.shape
+        self.data = [m.tocsc() for m in mats]
+        self.finalized = True
+        self.hname = list(haplotype_names)
+        if len(self.hname) != self.num_haplotypes or len(locus_names) != self.num_loci:
+            raise RuntimeError("The number of names does not match to the matrix shape.")
+        self.lname = np.array(locus_names)
+        self.lid = dict(zip(self.lname, np.arange(self.num_loci)))
+        if count is not None:
+            self.count = np.asarray(count, dtype=np.float64)
+        return self
+
     # ------------------------------------------------------------------ loading / saving
     def _load(self, path, datanode, metanode, shallow, dtype):
         with open(path, "rb") as fh:

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "gbrs_em.h"
 
@@ -694,7 +695,62 @@ extern "C" int gbrs_em_run_begin(const gbrs_em_dev* d, double tol, int max_iters
   return GBRS_OK;
 }
 
+struct gbrs_prof {
+  int capacity = 0, used = 0;
+  std::vector<cudaEvent_t> ev;  // 4 per recorded update: before row pass, after row pass, after column pass, after acc
+};
+
+extern "C" int gbrs_prof_create(int capacity, gbrs_prof_t* out) {
+  if (!out || capacity < 1) { gbrs_set_error("gbrs_prof_create: bad argument"); return GBRS_E_ARG; }
+  auto* p = new gbrs_prof();
+  p->capacity = capacity;
+  p->ev.resize((size_t) capacity * 4);
+  for (auto& e : p->ev) {
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) { gbrs_set_error(std::string("cudaEventCreate: ") + cudaGetErrorString(rc)); delete p; return GBRS_E_CUDA; }
+  }
+  *out = p;
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_prof_read(gbrs_prof_t p, double* ms_row, double* ms_col, double* ms_acc, int32_t* n) {
+  if (!p) { gbrs_set_error("gbrs_prof_read: null"); return GBRS_E_ARG; }
+  double r = 0, c = 0, a = 0;
+  for (int i = 0; i < p->used; ++i) {
+    float x = 0;
+    GBRS_CUDA(cudaEventSynchronize(p->ev[4 * i + 3]));
+    GBRS_CUDA(cudaEventElapsedTime(&x, p->ev[4 * i + 0], p->ev[4 * i + 1])); r += x;
+    GBRS_CUDA(cudaEventElapsedTime(&x, p->ev[4 * i + 1], p->ev[4 * i + 2])); c += x;
+    GBRS_CUDA(cudaEventElapsedTime(&x, p->ev[4 * i + 2], p->ev[4 * i + 3])); a += x;
+  }
+  if (ms_row) *ms_row = r;
+  if (ms_col) *ms_col = c;
+  if (ms_acc) *ms_acc = a;
+  if (n) *n = p->used;
+  p->used = 0;
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_prof_free(gbrs_prof_t p) {
+  if (p) {
+    for (auto& e : p->ev) cudaEventDestroy(e);
+    delete p;
+  }
+  return GBRS_OK;
+}
+
+static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs_prof* prof);
+
 extern "C" int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* stream) {
+  return launch_local_impl(d, model, stream, nullptr);
+}
+
+extern "C" int gbrs_em_launch_local_profiled(const gbrs_em_dev* d, int model, void* stream, gbrs_prof_t prof) {
+  if (!prof || prof->used >= prof->capacity) { gbrs_set_error("gbrs_em_launch_local_profiled: profile buffer full"); return GBRS_E_ARG; }
+  return launch_local_impl(d, model, stream, prof);
+}
+
+static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs_prof* prof) {
   if (int rc = check_dev(d, "gbrs_em_launch_local")) return rc;
   if (model < 1 || model > 4) {
     gbrs_set_error("The read normalization model should be 1, 2, 3, or 4."); return GBRS_E_ARG;  // EMfactory.py:209-212
@@ -711,6 +767,8 @@ extern "C" int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* strea
     GBRS_LAUNCH_CHECK("k_gene_totals");
   }
   const int cg = grid_for(d->n_classes);
+  cudaEvent_t* ev = prof ? &prof->ev[(size_t) prof->used * 4] : nullptr;
+  if (ev) GBRS_CUDA(cudaEventRecord(ev[0], s));
   if (d->n_classes > 0) {
     switch (model) {
       case 4: k_weights_m4<false><<<cg, kThreads, 0, s>>>(*d); break;
@@ -720,6 +778,7 @@ extern "C" int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* strea
     }
     GBRS_LAUNCH_CHECK("k_weights");
   }
+  if (ev) GBRS_CUDA(cudaEventRecord(ev[1], s));
   switch (model) {
     case 4: rc = launch_column<1>(d, d->ent_cls, honour_done, s); break;
     case 3: rc = launch_column<1>(d, d->ent_run, honour_done, s); break;
@@ -727,8 +786,13 @@ extern "C" int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* strea
     default: rc = launch_column<8>(d, d->ent_run, honour_done, s); break;
   }
   if (rc) return rc;
+  if (ev) GBRS_CUDA(cudaEventRecord(ev[2], s));
   k_locus_acc<false><<<grid_for((int64_t) d->T * GBRS_HPAD), kThreads, 0, s>>>(*d, honour_done);
   GBRS_LAUNCH_CHECK("k_locus_acc");
+  if (ev) {
+    GBRS_CUDA(cudaEventRecord(ev[3], s));
+    ++prof->used;
+  }
   return GBRS_OK;
 }
 

@@ -244,8 +244,14 @@ class DevicePattern:
 class EMfactory:
     """A class that coordinates Expectation-Maximization (reference EMfactory.py:15-24)."""
 
-    def __init__(self, alignments: APM, device=None, group=None, shard: bool | None = None, item_len: int = 0,
+    def __init__(self, alignments: APM, device=None, group=None, shard: bool | str | None = None, item_len: int = 0,
                  poll_every: int = 4):
+        """`alignments`: the incidence matrix.  Additions to the reference signature (all optional):
+        `device` CUDA device; `group` a torch.distributed process group (or `shard=True` for the default group) over
+        which the alignment classes are row-sharded -- every rank passes the same full matrix and packs only its own
+        contiguous slice; `shard="local"` says the matrix passed in already is this rank's slice (each rank loaded
+        different classes); `item_len` / `poll_every` are tuning knobs (column-pass work item size, iterations queued
+        between reads of the device-side stop flag)."""
         self.probability = alignments
         self._theta_host = None
         self._theta_dirty = False
@@ -264,6 +270,7 @@ class EMfactory:
         self.rank, self.world = 0, 1
         if shard is None:
             shard = group is not None
+        self._presharded = shard == "local"
         if shard:
             import torch.distributed as dist
 
@@ -325,8 +332,13 @@ class EMfactory:
                 raise NotImplementedError(
                     "stored values other than 1.0 (or explicit zeros) in the alignment matrix: call "
                     "eliminate_zeros() after masking; weighted (non-incidence) matrices are not supported")
-            self._pattern = DevicePattern(p, gene_of=self._gene_of, device=self._device, shard_rank=self.rank,
-                                          shard_count=self.world, item_len=self._item_len)
+            if self._presharded:
+                self._pattern = DevicePattern(p, gene_of=self._gene_of, device=self._device, item_len=self._item_len)
+                self._pattern.n_ranks = self.world
+                self._pattern._build_descriptor()
+            else:
+                self._pattern = DevicePattern(p, gene_of=self._gene_of, device=self._device, shard_rank=self.rank,
+                                              shard_count=self.world, item_len=self._item_len)
             self._pattern.set_lengths(self.target_lengths)
         return self._pattern
 

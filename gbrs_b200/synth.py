@@ -108,21 +108,32 @@ def to_csc_list(d: SynthData, dtype=np.float64):
     from scipy.sparse import csc_matrix
 
     mats = []
+    order = np.argsort(d.pair_locus, kind="stable")  # pairs are class-sorted, so this is (locus, class) order
+    rows_all = d.pair_class[order]
+    cols_all = d.pair_locus[order]
+    mask_all = d.pair_mask[order]
+    idx_t = np.int32 if max(d.N, d.pairs) < 2**31 - 1 else np.int64
     for h in range(d.H):
-        sel = ((d.pair_mask >> h) & 1).astype(bool)
-        rows = d.pair_class[sel]
-        cols = d.pair_locus[sel]
-        order = np.lexsort((rows, cols))
-        rows = rows[order]
-        cols = cols[order]
+        sel = ((mask_all >> h) & 1).astype(bool)
+        rows = rows_all[sel]
         indptr = np.zeros(d.T + 1, dtype=np.int64)
-        indptr[1:] = np.cumsum(np.bincount(cols, minlength=d.T))
-        idx_t = np.int32 if max(d.N, rows.size) < 2**31 - 1 else np.int64
+        indptr[1:] = np.cumsum(np.bincount(cols_all[sel], minlength=d.T))
         m = csc_matrix((np.ones(rows.size, dtype=dtype), rows.astype(idx_t), indptr.astype(idx_t)),
                        shape=(d.N, d.T))
         m.has_sorted_indices = True
         mats.append(m)
     return mats
+
+
+def to_apm(d: SynthData):
+    """`gbrs_b200.AlignmentPropertyMatrix` holding `d` (what loading the equivalent EMASE file would give)."""
+    from .apm import AlignmentPropertyMatrix
+
+    apm = AlignmentPropertyMatrix.from_csc(to_csc_list(d), list(d.hname), list(d.lname), count=d.count.copy())
+    apm.gname = np.array(d.gname)
+    apm.groups = d.groups()
+    apm.num_groups = len(d.gname)
+    return apm
 
 
 def write_group_file(d: SynthData, path: str) -> None:

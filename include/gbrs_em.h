@@ -162,6 +162,15 @@ int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* stream);
  * isoform-total L1 change and the stop test (EMfactory.py:267-279), entirely on the device. */
 int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream);
 
+/* Per-kernel device timing of the first half (CUDA events on `stream` around the row pass, the column pass and the
+ * numerator kernel), used by bench.py for the roofline figure.  gbrs_prof_read synchronises, returns the summed
+ * milliseconds of the `n` recorded updates and resets the buffer. */
+typedef struct gbrs_prof* gbrs_prof_t;
+int gbrs_prof_create(int capacity, gbrs_prof_t* out);
+int gbrs_em_launch_local_profiled(const gbrs_em_dev* d, int model, void* stream, gbrs_prof_t prof);
+int gbrs_prof_read(gbrs_prof_t p, double* ms_row, double* ms_col, double* ms_acc, int32_t* n);
+int gbrs_prof_free(gbrs_prof_t p);
+
 /* Whole loop for a single rank (n_ranks == 1): EMfactory.run (EMfactory.py:234-287).  Iterations are queued
  * `poll_every` at a time; the stop decision is taken on the device and read back at each poll.  Returns the number of
  * iterations performed and copies their err_sum values into errs_host[0..iters) (may be NULL). */
