@@ -319,7 +319,7 @@ def run_gpu_arm(args, wl):
                          f"{s_per:.3f} s/update, host has {os.cpu_count()} logical cores (path is single-threaded)"}
 
     if rank == 0:
-        launches_per_step = 5 + (1 if model != 4 else 0)
+        launches_per_step = (4 if world == 1 else 5) + (1 if model != 4 else 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "gbrs_em.h"
@@ -72,6 +73,24 @@ inline int grid_for(int64_t threads_needed, int blocks_per_sm = 8) {
   return (int) b;
 }
 
+// Persistent grid: exactly as many blocks as are resident at once (SMs x occupancy of this kernel), so that the
+// grid-stride loops run in a single full wave instead of 1.33 ragged ones.
+template <typename Kern>
+int resident_grid(Kern kern, int64_t threads_needed) {
+  static std::unordered_map<const void*, int> cache;
+  const void* key = reinterpret_cast<const void*>(kern);
+  auto it = cache.find(key);
+  int occ;
+  if (it == cache.end()) {
+    occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 0) != cudaSuccess || occ < 1) occ = 4;
+    cache[key] = occ;
+  } else {
+    occ = it->second;
+  }
+  return grid_for(threads_needed, occ);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------------
@@ -95,6 +114,29 @@ __device__ __forceinline__ double masked_sum8(const double* __restrict__ line, u
 __device__ __forceinline__ void load8(const double* __restrict__ line, double (&v)[8]) {
   const double2 a = ldg2(line), b = ldg2(line + 2), c = ldg2(line + 4), e = ldg2(line + 6);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = e.x; v[7] = e.y;
+}
+
+// a[h] += w for every haplotype slot h whose bit is set in m.  The column pass is bound by instruction issue; ptxas
+// turns both `if (bit) a += w` and `a += bit ? w : 0` (and even PTX-level predicated add.f64) into DADD + two 32-bit
+// selects per slot.  Multiplying by a 0.0 / 1.0 whose high word is selected from the bit is one select + one DFMA, and
+// fma(w, 1.0, a) == a + w exactly.
+__device__ __forceinline__ void masked_add8(double (&a)[8], double w, uint32_t m) {
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    const double one_or_zero = __hiloint2double(((m >> h) & 1u) ? 0x3FF00000 : 0, 0);
+    a[h] = fma(w, one_or_zero, a[h]);
+  }
+}
+
+// c / s without the library division's slow path: reciprocal seed + two Newton steps + one residual correction
+// (<= 1 ulp; s == 0 or non-finite input yields inf/NaN, which the convergence kernel turns into GBRS_E_NUMERIC).
+__device__ __forceinline__ double fast_div(double c, double s) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+  r = fma(fma(-s, r, 1.0), r, r);
+  r = fma(fma(-s, r, 1.0), r, r);
+  const double q = c * r;
+  return fma(fma(-s, q, c), r, q);
 }
 
 // Sum over the 8 lanes of an aligned lane group; every lane gets the total.  Fixed order => deterministic.
@@ -148,27 +190,140 @@ __device__ __forceinline__ double block_sum(double v, double* smem /* [32] */) {
 __device__ __forceinline__ const double* theta_cur(const gbrs_em_dev& d) {
   return d.theta + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T * GBRS_HPAD;
 }
-__device__ __forceinline__ const double* theta_next(const gbrs_em_dev& d) {
-  return d.theta + (size_t) (d.ctrl[GBRS_CTRL_PARITY] ^ 1) * d.T * GBRS_HPAD;
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // row pass, model 4:  w[n] = count[n] / sum_{(t,h) in n} theta[t][h]
 // reference: multiply(theta, READ) + normalize_reads(READ)   EMfactory.py:204-208, AlignmentPropertyMatrix.py:335-342
 // UNIT = true is the prepare() variant with theta == 1 on the pattern (EMfactory.py:95): w[n] = count[n] / nnz[n].
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool UNIT>
-__global__ void __launch_bounds__(kThreads) k_weights_m4(const gbrs_em_dev d) {
-  if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
+// Subset-sum tables: for every locus the 16 subset sums of haplotype slots 0-3 and the 16 subset sums of slots 4-7,
+//   sub[t][m]      = sum_{h<4,  bit h of m}  theta[t][h]        m = 0..15
+//   sub[t][16 + m] = sum_{h>=4, bit h-4 of m} theta[t][h]
+// so that the masked sum of a (class, locus) pair is two 8-byte loads and one add instead of a 64-byte line and eight
+// predicated adds: the row pass is instruction-issue bound, not bandwidth bound, and this removes ~80% of its
+// instructions.  One warp per locus, lane = table slot; 256-byte coalesced store.  Rebuilt once per EM update (20 MB
+// at 80k loci, L2 resident).
+__global__ void __launch_bounds__(kThreads) k_subset_tables(const gbrs_em_dev d) {
   const double* __restrict__ th = theta_cur(d);
+  const int lane = threadIdx.x & 31, half = lane >> 4, m = lane & 15;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < d.T; t += nwarps) {
+    const double2 a = *reinterpret_cast<const double2*>(th + (size_t) t * GBRS_HPAD + 4 * half);
+    const double2 b = *reinterpret_cast<const double2*>(th + (size_t) t * GBRS_HPAD + 4 * half + 2);
+    double s = 0.0;
+    s += (m & 1) ? a.x : 0.0;
+    s += (m & 2) ? a.y : 0.0;
+    s += (m & 4) ? b.x : 0.0;
+    s += (m & 8) ? b.y : 0.0;
+    d.subsets[(size_t) t * 32 + lane] = s;
+  }
+}
+
+__device__ __forceinline__ double pair_sum(const double* __restrict__ sub, uint32_t w) {
+  const double* row = sub + (size_t) (w & kLocusMask) * 32;
+  return __ldg(row + ((w >> 24) & 15u)) + __ldg(row + 16 + (w >> 28));
+}
+
+// Fixed-width part (classes with K <= GBRS_KMAX pairs, stored contiguously per width, so no row pointers): one thread
+// per class, UNR classes per thread; all pair words are loaded first, then all table loads are issued together
+// (memory-level parallelism), then the adds.  Classes are ordered by smallest locus within a width, so the lanes of a
+// warp mostly read the same few table rows.
+__host__ __device__ constexpr int unr_of(int K) { return K <= 2 ? 2 : 1; }
+
+struct RowPlan {                     // host-computed: work units ordered from the widest fixed bucket down to width 1
+  int64_t unit_end[GBRS_KMAX];       // unit_end[i] = one past the last unit (= 32 * unr classes) of width GBRS_KMAX - i
+};
+
+template <int K, bool UNIT>
+__device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t class0, int64_t class_end,
+                                               int64_t bucket_class0, int64_t bucket_pair0) {
+  constexpr int UNR = unr_of(K);
+  const int lane = threadIdx.x & 31;
+  uint32_t w[UNR][K];
+  int64_t n[UNR];
+  double cnt[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; ++u) {
+    n[u] = class0 + u * 32 + lane;
+    const bool valid = n[u] < class_end;
+    const uint32_t* __restrict__ pw = d.pairs + bucket_pair0 + (valid ? (n[u] - bucket_class0) : 0) * K;
+#pragma unroll
+    for (int p = 0; p < K; ++p) w[u][p] = valid ? __ldg(pw + p) : 0u;
+    cnt[u] = valid ? __ldg(d.count + n[u]) : 0.0;
+  }
+  double s[UNR];
+  if (UNIT) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      int c = 0;
+#pragma unroll
+      for (int p = 0; p < K; ++p) c += __popc(w[u][p] >> 24);
+      s[u] = (double) c;
+    }
+  } else {
+    double lo[UNR][K], hi[UNR][K];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+#pragma unroll
+      for (int p = 0; p < K; ++p) {
+        const double* row = d.subsets + (size_t) (w[u][p] & kLocusMask) * 32;
+        lo[u][p] = __ldg(row + ((w[u][p] >> 24) & 15u));
+        hi[u][p] = __ldg(row + 16 + (w[u][p] >> 28));
+      }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      double a = 0.0;
+#pragma unroll
+      for (int p = 0; p < K; ++p) a += lo[u][p] + hi[u][p];
+      s[u] = a;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UNR; ++u)
+    if (n[u] < class_end) d.weights[n[u]] = fast_div(cnt[u], s[u]);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__ gbrs_em_dev d,
+                                                          const __grid_constant__ RowPlan plan) {
+  if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  const int64_t total_units = plan.unit_end[GBRS_KMAX - 1];
+  int i = 0;  // bucket index only ever advances along the warp's grid-stride walk
+  int64_t unit0 = 0, unit1 = plan.unit_end[0];
+  for (int64_t u = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < total_units; u += nwarps) {
+    while (u >= unit1) {
+      unit0 = unit1;
+      unit1 = plan.unit_end[++i];
+    }
+    const int k = GBRS_KMAX - i;
+    const int64_t c0 = d.bucket_class0[k - 1], c1 = d.bucket_class0[k], p0 = d.bucket_pair0[k - 1];
+    const int64_t class0 = c0 + (u - unit0) * (32 * unr_of(k));
+    switch (k) {
+      case 1: row_classes_m4<1, UNIT>(d, class0, c1, c0, p0); break;
+      case 2: row_classes_m4<2, UNIT>(d, class0, c1, c0, p0); break;
+      case 3: row_classes_m4<3, UNIT>(d, class0, c1, c0, p0); break;
+      case 4: row_classes_m4<4, UNIT>(d, class0, c1, c0, p0); break;
+      case 5: row_classes_m4<5, UNIT>(d, class0, c1, c0, p0); break;
+      case 6: row_classes_m4<6, UNIT>(d, class0, c1, c0, p0); break;
+      case 7: row_classes_m4<7, UNIT>(d, class0, c1, c0, p0); break;
+      default: row_classes_m4<8, UNIT>(d, class0, c1, c0, p0); break;
+    }
+  }
+}
+
+// Classes with more than GBRS_KMAX pairs: one thread per class over the CSR row.
+template <bool UNIT>
+__global__ void __launch_bounds__(kThreads) k_weights_m4_long(const gbrs_em_dev d) {
+  if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+  for (int64_t n = d.bucket_class0[GBRS_KMAX] + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
     double s = 0.0;
     for (uint32_t p = b; p < e; ++p) {
       const uint32_t w = __ldg(d.pairs + p);
       if (UNIT) s += (double) __popc(w >> 24);
-      else s += masked_sum8(th + (size_t) (w & kLocusMask) * GBRS_HPAD, w >> 24);
+      else s += pair_sum(d.subsets, w);
     }
     d.weights[n] = __ldg(d.count + n) / s;
   }
@@ -341,58 +496,145 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d) {
 // reference: APM.sum(axis=READ)  AlignmentPropertyMatrix.py:288-298 (count-weighted column reduce), without the
 // per-haplotype matrix copy.  VEC = 1: scalar weight per index; VEC = 8: one weight per haplotype (model 1).
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename E, int VEC>
-__global__ void __launch_bounds__(kThreads) k_column_reduce(const gbrs_em_dev d, const E* __restrict__ ents, bool honour_done) {
-  if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
+// LANES = 8: four short items per warp (one per aligned 8-lane group); LANES = 32: one long item per warp.
+template <typename E, int VEC, int LANES>
+__device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __restrict__ ents, int64_t item, uint32_t b,
+                                            uint32_t e) {
   constexpr int SH = 8 * (int) sizeof(E) - 8;
   constexpr E IDX = (E(1) << SH) - 1;
   const double* __restrict__ wts = d.weights;
-  const int lane8 = threadIdx.x & 7;
-  const int64_t ngroups = ((int64_t) gridDim.x * blockDim.x) >> 3;
-  const int64_t rounds = (d.n_items + ngroups - 1) / ngroups;
-  int64_t item = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  for (int64_t r = 0; r < rounds; ++r, item += ngroups) {
-    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t b = 0, e = 0;
-    if (item < d.n_items) { b = __ldg(d.item_off + item); e = __ldg(d.item_off + item + 1); }
-    for (uint32_t p = b + lane8; p < e; p += 8) {
+  const int lane = threadIdx.x & 31, lane8 = lane & 7, lanex = lane & (LANES - 1);
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (VEC == 1) {
+    // chunks of 4 steps: entry words first, then the four weight gathers together, then the masked adds
+    uint32_t p0 = b + lanex;
+    for (; p0 + 3 * LANES < e; p0 += 4 * LANES) {
+      E ent[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ent[q] = __ldg(ents + p0 + LANES * q);
+      double w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = __ldg(wts + (size_t) (ent[q] & IDX));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) masked_add8(a, w[q], (uint32_t) (ent[q] >> SH));
+    }
+    for (; p0 < e; p0 += LANES) {
+      const E ent = __ldg(ents + p0);
+      masked_add8(a, __ldg(wts + (size_t) (ent & IDX)), (uint32_t) (ent >> SH));
+    }
+  } else {
+    for (uint32_t p = b + lanex; p < e; p += LANES) {
       const E ent = __ldg(ents + p);
       const uint32_t m = (uint32_t) (ent >> SH);
-      const size_t idx = (size_t) (ent & IDX);
-      if (VEC == 1) {
-        const double w = wts[idx];
+      double v[8];
+      load8(wts + (size_t) (ent & IDX) * GBRS_HPAD, v);
 #pragma unroll
-        for (int h = 0; h < 8; ++h) a[h] += ((m >> h) & 1u) ? w : 0.0;
-      } else {
-        double v[8];
-        load8(wts + idx * GBRS_HPAD, v);
-#pragma unroll
-        for (int h = 0; h < 8; ++h) a[h] += ((m >> h) & 1u) ? v[h] : 0.0;
-      }
+      for (int h = 0; h < 8; ++h) a[h] = fma(v[h], __hiloint2double(((m >> h) & 1u) ? 0x3FF00000 : 0, 0), a[h]);
     }
-    const double tot = group8_transpose_sum(a, lane8);
-    if (item < d.n_items) d.wit[item * GBRS_HPAD + lane8] = tot;
+  }
+  double tot = group8_transpose_sum(a, lane8);
+  if (LANES == 32) {
+    tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 8);
+    tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 16);
+  }
+  if (item >= 0 && lanex < 8) d.wit[item * GBRS_HPAD + lane8] = tot;
+}
+
+// Warp work slots: slot < n_long_items -> the slot-th item of item_order (a long item, whole warp); otherwise four
+// short items.  item_order lists the items longest first, so the deep loci start first and do not form the tail.
+template <typename E, int VEC>
+__global__ void __launch_bounds__(kThreads) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
+                                                             const E* __restrict__ ents, bool honour_done) {
+  if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  const int64_t n_long = d.n_long_items;
+  const int64_t total_slots = n_long + ((d.n_items - n_long + 3) >> 2);
+  for (int64_t ws = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; ws < total_slots; ws += nwarps) {
+    const int64_t pos = ws < n_long ? ws : n_long + ((ws - n_long) << 2) + (lane >> 3);
+    int64_t item = -1;
+    uint32_t b = 0, e = 0;
+    if (pos < d.n_items) {
+      item = __ldg(d.item_order + pos);
+      b = __ldg(d.item_off + item);
+      e = __ldg(d.item_off + item + 1);
+    }
+    if (ws < n_long) column_item<E, VEC, 32>(d, ents, item, b, e);
+    else column_item<E, VEC, 8>(d, ents, item, b, e);
   }
 }
 
 // acc[t][h] = theta[t][h] * sum_{items of t} wit[item][h]   ( = sum_n count[n] * P[n,t,h] ).  UNIT: theta == 1 (prepare).
+// One thread per (locus, haplotype slot); a locus has at most 128 items (packer), walked four loads at a time.
+// FUSE (single rank only): also theta' = acc / efflen, iso' and the block partial of sum(iso'), i.e. k_locus_update.
 // Once the loop has stopped, k_converge has already flipped the ping-pong, so the theta that produced the weights in
 // `wit` is the *other* buffer: a single rank simply skips, a row-sharded rank recomputes the identical local numerator
 // from it (the in-place cross-rank sum that follows must always start from the local values).
-template <bool UNIT>
+template <bool UNIT, bool FUSE>
 __global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
+  __shared__ double red[32];
   const bool done = !UNIT && d.ctrl[GBRS_CTRL_DONE];
-  if (done && honour_done) return;
-  const double* __restrict__ th = done ? theta_next(d) : theta_cur(d);
+  if (done && (honour_done || FUSE)) return;
+  const int par = d.ctrl[GBRS_CTRL_PARITY];
+  const double* __restrict__ th = d.theta + (size_t) (done ? (par ^ 1) : par) * d.T * GBRS_HPAD;
+  double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
+  double* __restrict__ iso = d.iso + (size_t) (par ^ 1) * d.T;
+  const int h = threadIdx.x & 7;
   const int64_t total = (int64_t) d.T * GBRS_HPAD;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+  const int64_t rounds = (total + stride - 1) / stride;
+  int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  double mine = 0.0;
+  for (int64_t r = 0; r < rounds; ++r, i += stride) {
+    const bool valid = i < total;
     const int64_t t = i >> 3;
-    const int h = (int) (i & 7);
-    const uint32_t b = __ldg(d.locus_item_ptr + t), e = __ldg(d.locus_item_ptr + t + 1);
+    uint32_t it = 0, e = 0;
+    if (valid) { it = __ldg(d.locus_item_ptr + t); e = __ldg(d.locus_item_ptr + t + 1); }
     double W = 0.0;
-    for (uint32_t it = b; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
-    d.acc[i] = UNIT ? ((h < d.H) ? W : 0.0) : th[i] * W;
+    for (; it + 3 < e; it += 4) {
+      const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 1) * GBRS_HPAD + h];
+      const double w2 = d.wit[(size_t) (it + 2) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 3) * GBRS_HPAD + h];
+      W += (w0 + w1) + (w2 + w3);
+    }
+    for (; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
+    double a = 0.0;
+    if (valid) {
+      a = UNIT ? ((h < d.H) ? W : 0.0) : th[i] * W;
+      d.acc[i] = a;
+    }
+    if (FUSE) {
+      double v = 0.0;
+      if (valid) {
+        v = a / d.efflen[i];
+        dst[i] = v;
+      }
+      const double s = group8_sum(v);
+      if (valid && h == 0) {
+        iso[t] = s;
+        mine += s;
+      }
+      // subset-sum table of theta' for the next row pass (same sums, same order as k_subset_tables): lane h of the
+      // locus' 8 lanes fills slots [4h, 4h + 4) = half (h >> 2), masks 4 * (h & 3) .. + 3
+      const int base = (threadIdx.x & 31) & ~7, half4 = base + (h & 4);
+      const double v0 = __shfl_sync(0xFFFFFFFFu, v, half4), v1 = __shfl_sync(0xFFFFFFFFu, v, half4 + 1);
+      const double v2 = __shfl_sync(0xFFFFFFFFu, v, half4 + 2), v3 = __shfl_sync(0xFFFFFFFFu, v, half4 + 3);
+      if (valid) {
+        // masks 4 * (h & 3) + q, q = 0..3: bits 0 and 1 enumerate, bits 2 and 3 are fixed by (h & 3)
+        const double t2 = (h & 1) ? v2 : 0.0, t3 = (h & 2) ? v3 : 0.0;
+        double4 o;
+        o.x = ((0.0 + 0.0) + t2) + t3;
+        o.y = ((v0 + 0.0) + t2) + t3;
+        o.z = ((0.0 + v1) + t2) + t3;
+        o.w = ((v0 + v1) + t2) + t3;
+        double* row = d.subsets + (size_t) t * 32 + 4 * h;
+        *reinterpret_cast<double2*>(row) = make_double2(o.x, o.y);
+        *reinterpret_cast<double2*>(row + 2) = make_double2(o.z, o.w);
+      }
+    }
+  }
+  if (FUSE) {
+    const double bs = block_sum(mine, red);
+    if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
   }
 }
 
@@ -432,17 +674,22 @@ __global__ void __launch_bounds__(kThreads) k_locus_update(const gbrs_em_dev d) 
 }
 
 // Stop test of EMfactory.run (EMfactory.py:267-279) on the device.
-//   INIT: record sum of the current isoform totals as "prev" (after prepare / set_theta).
-//   else: err = sum_t | iso'[t] * 1e6 / S' - iso[t] * 1e6 / S |, log it, flip the ping-pong, decide.
+//   INIT: record sum of the current isoform totals as "prev" (after prepare / set_theta).  Launched with one block.
+//   else: err = sum_t | iso'[t] * 1e6 / S' - iso[t] * 1e6 / S |, log it, flip the ping-pong, decide.  Many blocks:
+//         every block re-derives S' from the same partials in the same order (bit-identical), reduces its slice of
+//         the error, and the last block to arrive (ticket counter) sums the block errors in index order and takes the
+//         decision -- the result does not depend on which block that is.
+constexpr int kHalfSlots = GBRS_PART_SLOTS / 2;
 template <bool INIT>
-__global__ void __launch_bounds__(1024) k_converge(const gbrs_em_dev d, int nparts) {
+__global__ void __launch_bounds__(kThreads) k_converge(const gbrs_em_dev d, int nparts) {
   __shared__ double red[32];
+  __shared__ int s_last;
   if (!INIT && d.ctrl[GBRS_CTRL_DONE]) return;
   double v = 0.0;
   for (int i = threadIdx.x; i < nparts; i += blockDim.x) v += d.part[i];
   const double S_new = block_sum(v, red);
   if (INIT) {
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
       d.scal[GBRS_SCAL_SUM_PREV] = S_new;
       d.scal[GBRS_SCAL_SUM_CUR] = S_new;
       if (!isfinite(S_new)) d.ctrl[GBRS_CTRL_ERROR] = 1;
@@ -455,8 +702,21 @@ __global__ void __launch_bounds__(1024) k_converge(const gbrs_em_dev d, int npar
   const double f_new = 1000000.0 / S_new;
   const double f_old = 1000000.0 / d.scal[GBRS_SCAL_SUM_PREV];
   double e = 0.0;
-  for (int t = threadIdx.x; t < d.T; t += blockDim.x) e += fabs(iso_new[t] * f_new - iso_old[t] * f_old);
-  const double err = block_sum(e, red);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < d.T; t += gridDim.x * blockDim.x)
+    e += fabs(iso_new[t] * f_new - iso_old[t] * f_old);
+  const double eb = block_sum(e, red);
+  if (threadIdx.x == 0) {
+    d.part[kHalfSlots + blockIdx.x] = eb;
+    __threadfence();
+    const int ticket = atomicAdd(d.ctrl + GBRS_CTRL_TICKET, 1);
+    s_last = (ticket == (int) gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double x = 0.0;
+  for (int i = threadIdx.x; i < (int) gridDim.x; i += blockDim.x) x += __ldcg(d.part + kHalfSlots + i);
+  const double err = block_sum(x, red);
   if (threadIdx.x == 0) {
     const int it = d.ctrl[GBRS_CTRL_ITERS];
     if (it < d.max_iters_cap) d.err_log[it] = err;
@@ -465,6 +725,7 @@ __global__ void __launch_bounds__(1024) k_converge(const gbrs_em_dev d, int npar
     d.scal[GBRS_SCAL_SUM_CUR] = S_new;
     d.ctrl[GBRS_CTRL_ITERS] = it + 1;
     d.ctrl[GBRS_CTRL_PARITY] = par ^ 1;
+    d.ctrl[GBRS_CTRL_TICKET] = 0;
     const bool bad = !isfinite(err) || !isfinite(S_new);
     if (bad) d.ctrl[GBRS_CTRL_ERROR] = 1;
     const bool go_on = !bad && err > d.scal[GBRS_SCAL_TARGET] && (it + 1) < d.ctrl[GBRS_CTRL_MAX_ITERS];
@@ -481,6 +742,7 @@ __global__ void k_run_begin(const gbrs_em_dev d, double tol, int max_iters) {
     d.ctrl[GBRS_CTRL_ITERS] = 0;
     d.ctrl[GBRS_CTRL_MAX_ITERS] = max_iters;
     d.ctrl[GBRS_CTRL_ERROR] = 0;
+    d.ctrl[GBRS_CTRL_TICKET] = 0;
     d.scal[GBRS_SCAL_ERR] = 1000000.0;
     d.scal[GBRS_SCAL_TARGET] = 1000000.0 * tol;
     // while err_sum > target_err and num_iters < max_iters   (EMfactory.py:267) with err_sum = 1e6 initially
@@ -496,6 +758,7 @@ __global__ void k_reset_ctrl(const gbrs_em_dev d) {
     d.ctrl[GBRS_CTRL_PARITY] = 0;
     d.ctrl[GBRS_CTRL_MAX_ITERS] = 0;
     d.ctrl[GBRS_CTRL_PREPARED] = 1;
+    d.ctrl[GBRS_CTRL_TICKET] = 0;
   }
 }
 
@@ -577,8 +840,8 @@ int check_dev(const gbrs_em_dev* d, const char* who) {
   if (d->T <= 0 || d->H < 1 || d->H > GBRS_HPAD || (d->entry_bytes != 4 && d->entry_bytes != 8)) {
     gbrs_set_error(std::string(who) + ": bad descriptor shape"); return GBRS_E_ARG;
   }
-  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
-      !d->iso || !d->weights || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
+  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->item_order || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
+      !d->iso || !d->weights || !d->subsets || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
     gbrs_set_error(std::string(who) + ": null device buffer in descriptor"); return GBRS_E_ARG;
   }
   int dev = 0;
@@ -588,20 +851,56 @@ int check_dev(const gbrs_em_dev* d, const char* who) {
   return GBRS_OK;
 }
 
-inline int locus_grid(const gbrs_em_dev* d) {
-  int g = grid_for((int64_t) d->T * GBRS_HPAD, 4);
-  return g > GBRS_PART_SLOTS ? GBRS_PART_SLOTS : g;
+inline int locus_grid(const gbrs_em_dev* d) {  // k_locus_update: one thread per (locus, haplotype slot)
+  int g = grid_for((int64_t) d->T * GBRS_HPAD, 8);
+  return g > kHalfSlots ? kHalfSlots : g;
+}
+inline int acc_grid(const gbrs_em_dev* d) {  // k_locus_acc: one thread per (locus, haplotype slot)
+  int g = grid_for((int64_t) d->T * GBRS_HPAD, 6);
+  return g > kHalfSlots ? kHalfSlots : g;
+}
+inline int converge_grid(const gbrs_em_dev* d) {
+  int g = (d->T + 1023) / 1024;
+  return g < 1 ? 1 : (g > 128 ? 128 : g);
+}
+
+template <bool UNIT>
+int launch_row_m4(const gbrs_em_dev* d, cudaStream_t s) {
+  RowPlan plan;
+  int64_t units = 0;
+  if (!UNIT && d->n_ranks > 1) {  // single rank: the fused locus kernel of the previous update already wrote them
+    k_subset_tables<<<resident_grid(k_subset_tables, (int64_t) d->T * 32), kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_subset_tables");
+  }
+  for (int i = 0; i < GBRS_KMAX; ++i) {
+    const int k = GBRS_KMAX - i, cpu = 32 * unr_of(k);
+    units += (d->bucket_class0[k] - d->bucket_class0[k - 1] + cpu - 1) / cpu;
+    plan.unit_end[i] = units;
+  }
+  if (units > 0) {
+    k_weights_m4<UNIT><<<resident_grid(k_weights_m4<UNIT>, units * 32), kThreads, 0, s>>>(*d, plan);
+    GBRS_LAUNCH_CHECK("k_weights_m4");
+  }
+  const int64_t n_long = d->n_classes - d->bucket_class0[GBRS_KMAX];
+  if (n_long > 0) {
+    k_weights_m4_long<UNIT><<<grid_for(n_long), kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_weights_m4_long");
+  }
+  return GBRS_OK;
 }
 
 template <int VEC>
 int launch_column(const gbrs_em_dev* d, const void* ents, bool honour_done, cudaStream_t s) {
   if (!ents) { gbrs_set_error("column pass: entry array missing from descriptor"); return GBRS_E_ARG; }
   if (d->n_items == 0) return GBRS_OK;
-  const int grid = grid_for(d->n_items * 8);
+  const int64_t threads = (d->n_long_items + ((d->n_items - d->n_long_items + 3) >> 2)) * 32;
   if (d->entry_bytes == 4)
-    k_column_reduce<uint32_t, VEC><<<grid, kThreads, 0, s>>>(*d, static_cast<const uint32_t*>(ents), honour_done);
+    k_column_reduce<uint32_t, VEC><<<resident_grid(k_column_reduce<uint32_t, VEC>, threads), kThreads, 0, s>>>(
+        *d, static_cast<const uint32_t*>(ents), honour_done);
   else
-    k_column_reduce<unsigned long long, VEC><<<grid, kThreads, 0, s>>>(*d, static_cast<const unsigned long long*>(ents), honour_done);
+    k_column_reduce<unsigned long long, VEC>
+        <<<resident_grid(k_column_reduce<unsigned long long, VEC>, threads), kThreads, 0, s>>>(
+            *d, static_cast<const unsigned long long*>(ents), honour_done);
   GBRS_LAUNCH_CHECK("k_column_reduce");
   return GBRS_OK;
 }
@@ -616,12 +915,9 @@ extern "C" int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   k_reset_ctrl<<<1, 32, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_reset_ctrl");
-  if (d->n_classes > 0) {
-    k_weights_m4<true><<<grid_for(d->n_classes), kThreads, 0, s>>>(*d);
-    GBRS_LAUNCH_CHECK("k_weights_m4<unit>");
-  }
+  if (int rc = launch_row_m4<true>(d, s)) return rc;
   if (int rc = launch_column<1>(d, d->ent_cls, false, s)) return rc;
-  k_locus_acc<true><<<grid_for((int64_t) d->T * GBRS_HPAD), kThreads, 0, s>>>(*d, false);
+  k_locus_acc<true, false><<<acc_grid(d), kThreads, 0, s>>>(*d, false);
   GBRS_LAUNCH_CHECK("k_locus_acc<unit>");
   return GBRS_OK;
 }
@@ -635,7 +931,7 @@ extern "C" int gbrs_em_prepare_finish(const gbrs_em_dev* d, double pseudocount, 
   GBRS_LAUNCH_CHECK("k_locus_update");
   k_flip_parity<<<1, 32, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_flip_parity");
-  k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+  k_converge<true><<<1, kThreads, 0, s>>>(*d, lg);
   GBRS_LAUNCH_CHECK("k_converge<init>");
   if (pseudocount > 0.0) {
     // scal[4] keeps the original sum
@@ -643,13 +939,15 @@ extern "C" int gbrs_em_prepare_finish(const gbrs_em_dev* d, double pseudocount, 
     k_pseudocount_add<<<lg, kThreads, 0, s>>>(*d, pseudocount);
     GBRS_LAUNCH_CHECK("k_pseudocount_add");
     k_locus_update<false><<<lg, kThreads, 0, s>>>(*d);
-    k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+    k_converge<true><<<1, kThreads, 0, s>>>(*d, lg);
     k_scale_theta<<<lg, kThreads, 0, s>>>(*d, d->scal + 4, d->scal + GBRS_SCAL_SUM_CUR);
     GBRS_LAUNCH_CHECK("k_scale_theta");
     k_locus_update<false><<<lg, kThreads, 0, s>>>(*d);
-    k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+    k_converge<true><<<1, kThreads, 0, s>>>(*d, lg);
     GBRS_LAUNCH_CHECK("pseudocount chain");
   }
+  k_subset_tables<<<resident_grid(k_subset_tables, (int64_t) d->T * 32), kThreads, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_subset_tables");
   return GBRS_OK;
 }
 
@@ -663,8 +961,10 @@ extern "C" int gbrs_em_set_theta(const gbrs_em_dev* d, const double* theta_dev, 
   const int lg = locus_grid(d);
   k_locus_update<false><<<lg, kThreads, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_locus_update<refresh>");
-  k_converge<true><<<1, 1024, 0, s>>>(*d, lg);
+  k_converge<true><<<1, kThreads, 0, s>>>(*d, lg);
   GBRS_LAUNCH_CHECK("k_converge<init>");
+  k_subset_tables<<<resident_grid(k_subset_tables, (int64_t) d->T * 32), kThreads, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_subset_tables");
   return GBRS_OK;
 }
 
@@ -771,7 +1071,7 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   if (ev) GBRS_CUDA(cudaEventRecord(ev[0], s));
   if (d->n_classes > 0) {
     switch (model) {
-      case 4: k_weights_m4<false><<<cg, kThreads, 0, s>>>(*d); break;
+      case 4: if (int rc4 = launch_row_m4<false>(d, s)) return rc4; break;
       case 3: k_weights_m3<<<cg, kThreads, 0, s>>>(*d); break;
       case 2: k_weights_m2<<<cg, kThreads, 0, s>>>(*d); break;
       default: k_weights_m1<<<cg, kThreads, 0, s>>>(*d); break;
@@ -787,7 +1087,8 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   }
   if (rc) return rc;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[2], s));
-  k_locus_acc<false><<<grid_for((int64_t) d->T * GBRS_HPAD), kThreads, 0, s>>>(*d, honour_done);
+  if (d->n_ranks <= 1) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(*d, true);
+  else k_locus_acc<false, false><<<acc_grid(d), kThreads, 0, s>>>(*d, false);
   GBRS_LAUNCH_CHECK("k_locus_acc");
   if (ev) {
     GBRS_CUDA(cudaEventRecord(ev[3], s));
@@ -799,10 +1100,13 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
 extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
   if (int rc = check_dev(d, "gbrs_em_launch_update")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int lg = locus_grid(d);
-  k_locus_update<true><<<lg, kThreads, 0, s>>>(*d);
-  GBRS_LAUNCH_CHECK("k_locus_update");
-  k_converge<false><<<1, 1024, 0, s>>>(*d, lg);
+  int nparts = acc_grid(d);  // single rank: k_locus_acc already produced theta', iso' and the partial sums
+  if (d->n_ranks > 1) {
+    nparts = locus_grid(d);
+    k_locus_update<true><<<nparts, kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_locus_update");
+  }
+  k_converge<false><<<converge_grid(d), kThreads, 0, s>>>(*d, nparts);
   GBRS_LAUNCH_CHECK("k_converge");
   return GBRS_OK;
 }

@@ -29,7 +29,7 @@ void gbrs_set_error(const std::string& s);  // capi.cu
 struct gbrs_pack {
   gbrs_pack_info info{};
   int32_t T = 0;
-  std::vector<uint32_t> rowptr, pairs, runptr, item_off, locus_item_ptr, gene_ptr, gene_loci;
+  std::vector<uint32_t> rowptr, pairs, runptr, item_off, item_order, locus_item_ptr, gene_ptr, gene_loci;
   std::vector<int32_t> gene_of;
   std::vector<double> count;
   std::vector<uint8_t> ent_cls, ent_pair, ent_run;  // entry words, 4 or 8 bytes each
@@ -140,16 +140,28 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       if (hi < lo) hi = lo;
     }
 
-    // ---- 3. order the shard's non-empty classes by smallest locus (stable counting sort) --------------------------
-    std::vector<int64_t> bucket(T + 1, 0);
+    // ---- 3. order the shard's non-empty classes by (pairs capped at KMAX+1, smallest locus): stable counting sort ----
+    // Equal-width classes are contiguous so the row pass needs no row pointers for them; within a width the classes are
+    // ordered by smallest locus so that neighbouring classes touch neighbouring theta lines.
+    const int NB = GBRS_KMAX + 1;  // buckets: widths 1..KMAX, then "long"
+    auto bucket_of = [&](uint32_t np) { return (int) std::min<uint32_t>(np, GBRS_KMAX + 1) - 1; };
+    std::vector<int64_t> bucket((size_t) NB * T + 1, 0);
     int64_t n_classes = 0, n_pairs = 0, nnz = 0;
+    int64_t bclass[GBRS_KMAX + 2] = {0}, bpair[GBRS_KMAX + 2] = {0};
     for (int64_t c = lo; c < hi; ++c)
-      if (npair[c]) { ++bucket[minloc[c] + 1]; ++n_classes; n_pairs += npair[c]; nnz += nz[c]; }
+      if (npair[c]) {
+        const int b = bucket_of(npair[c]);
+        ++bucket[(size_t) b * T + minloc[c] + 1];
+        ++bclass[b + 1];
+        bpair[b + 1] += npair[c];
+        ++n_classes; n_pairs += npair[c]; nnz += nz[c];
+      }
     if (n_pairs >= (int64_t(1) << 32)) { gbrs_set_error("gbrs_pack_create: more than 2^32 pairs in one shard"); return GBRS_E_LIMIT; }
-    for (int t = 0; t < T; ++t) bucket[t + 1] += bucket[t];
+    for (size_t i = 0; i < (size_t) NB * T; ++i) bucket[i + 1] += bucket[i];
+    for (int b = 0; b < NB; ++b) { bclass[b + 1] += bclass[b]; bpair[b + 1] += bpair[b]; }
     std::vector<uint32_t> new_id((size_t) N, 0xFFFFFFFFu);
     for (int64_t c = lo; c < hi; ++c)
-      if (npair[c]) new_id[c] = (uint32_t) bucket[minloc[c]]++;
+      if (npair[c]) new_id[c] = (uint32_t) bucket[(size_t) bucket_of(npair[c]) * T + minloc[c]]++;
 
     auto* P = new gbrs_pack();
     P->T = T;
@@ -230,19 +242,40 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     }
 
     // ---- 6. column-pass work items ------------------------------------------------------------------------------
+    // A locus with up to 8 * item_len entries is cut into short items (<= item_len entries, one aligned 8-lane group
+    // each); a deeper locus into long items (<= 16 * item_len entries, a whole warp each), so that the per-locus combine
+    // in k_locus_acc, which walks a locus' items serially, stays short even for the deepest loci.
+    const int64_t long_len = 16 * (int64_t) item_len;
+    auto item_len_of = [&](int64_t len) -> int64_t {
+      if (len <= 8 * (int64_t) item_len) return item_len;
+      const int64_t n = (len + long_len - 1) / long_len;
+      return ((len + n - 1) / n + 31) / 32 * 32;
+    };
     P->locus_item_ptr.assign((size_t) T + 1, 0);
     for (int t = 0; t < T; ++t) {
-      const int64_t len = lptr[t + 1] - lptr[t];
-      P->locus_item_ptr[t + 1] = P->locus_item_ptr[t] + (uint32_t) ((len + item_len - 1) / item_len);
+      const int64_t len = lptr[t + 1] - lptr[t], il = item_len_of(len);
+      P->locus_item_ptr[t + 1] = P->locus_item_ptr[t] + (uint32_t) ((len + il - 1) / il);
     }
     const int64_t n_items = P->locus_item_ptr[T];
     P->item_off.assign((size_t) n_items + 1, 0);
     for (int t = 0; t < T; ++t) {
-      const int64_t len = lptr[t + 1] - lptr[t];
+      const int64_t len = lptr[t + 1] - lptr[t], il = item_len_of(len);
       uint32_t it = P->locus_item_ptr[t];
-      for (int64_t o = 0; o < len; o += item_len) P->item_off[it++] = (uint32_t) (lptr[t] + o);
+      for (int64_t o = 0; o < len; o += il) P->item_off[it++] = (uint32_t) (lptr[t] + o);
     }
     P->item_off[n_items] = (uint32_t) n_pairs;
+    // longest-processing-time-first visiting order (stable counting sort by length, descending)
+    {
+      int64_t max_len = 0;
+      for (int64_t i = 0; i < n_items; ++i) max_len = std::max<int64_t>(max_len, P->item_off[i + 1] - P->item_off[i]);
+      std::vector<int64_t> start((size_t) max_len + 2, 0);
+      for (int64_t i = 0; i < n_items; ++i) ++start[(size_t) (max_len - (P->item_off[i + 1] - P->item_off[i])) + 1];
+      for (int64_t l = 0; l <= max_len; ++l) start[l + 1] += start[l];
+      for (int64_t i = 0; i < n_items; ++i) P->info.n_long_items += (P->item_off[i + 1] - P->item_off[i]) > item_len;
+      P->item_order.assign((size_t) n_items, 0);
+      for (int64_t i = 0; i < n_items; ++i)
+        P->item_order[start[(size_t) (max_len - (P->item_off[i + 1] - P->item_off[i]))]++] = (uint32_t) i;
+    }
 
     // ---- 7. gene -> loci CSR ------------------------------------------------------------------------------------
     P->gene_ptr.assign((size_t) n_gene_ids + 1, 0);
@@ -264,6 +297,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     P->info.entry_bytes = entry_bytes;
     P->info.n_gene_ids = n_gene_ids;
     P->info.max_pairs_per_class = max_k;
+    for (int b = 0; b < GBRS_KMAX + 2; ++b) { P->info.bucket_class0[b] = bclass[b]; P->info.bucket_pair0[b] = bpair[b]; }
     *out = P;
     return GBRS_OK;
   } catch (const std::bad_alloc&) {
@@ -295,6 +329,7 @@ extern "C" int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void**
   GBRS_ARR("ent_pair", p->ent_pair)
   GBRS_ARR("ent_run", p->ent_run)
   GBRS_ARR("item_off", p->item_off)
+  GBRS_ARR("item_order", p->item_order)
   GBRS_ARR("locus_item_ptr", p->locus_item_ptr)
   GBRS_ARR("gene_ptr", p->gene_ptr)
   GBRS_ARR("gene_loci", p->gene_loci)

@@ -32,7 +32,7 @@ ERR_LOG_CAP = 1 << 16
 
 _PACK_ARRAYS = {  # name -> numpy dtype (None = entry word, depends on entry_bytes)
     "rowptr": np.uint32, "pairs": np.uint32, "count": np.float64, "runptr": np.uint32,
-    "ent_cls": None, "ent_pair": None, "ent_run": None, "item_off": np.uint32, "locus_item_ptr": np.uint32,
+    "ent_cls": None, "ent_pair": None, "ent_run": None, "item_off": np.uint32, "item_order": np.uint32, "locus_item_ptr": np.uint32,
     "gene_ptr": np.uint32, "gene_loci": np.uint32, "gene_of": np.int32,
 }
 
@@ -95,6 +95,8 @@ class PackedPattern:
             info = _lib.PackInfo()
             _lib.check(lib.gbrs_pack_get_info(handle, C.byref(info)))
             self.info = {f: getattr(info, f) for f, _ in _lib.PackInfo._fields_}
+            self.info["bucket_class0"] = list(info.bucket_class0)
+            self.info["bucket_pair0"] = list(info.bucket_pair0)
             self.arrays = {}
             entry_t = np.uint32 if info.entry_bytes == 4 else np.uint64
             for name, dt in _PACK_ARRAYS.items():
@@ -166,6 +168,7 @@ class DevicePattern:
         self.acc = torch.zeros((T, 8), dtype=f64, device=dv)
         self.iso = torch.zeros((2, T), dtype=f64, device=dv)
         self.weights = torch.empty(nw, dtype=f64, device=dv)
+        self.subsets = torch.zeros((T, 32), dtype=f64, device=dv)
         self.wit = torch.zeros((max(i["n_items"], 1), 8), dtype=f64, device=dv)
         self.part = torch.zeros(_lib.GBRS_PART_SLOTS, dtype=f64, device=dv)
         self.gene_hap = torch.zeros((max(i["n_gene_ids"], 1), 8), dtype=f64, device=dv)
@@ -179,8 +182,13 @@ class DevicePattern:
         i = self.info
         d.T, d.H, d.n_gene_ids, d.entry_bytes = self.T, self.H, i["n_gene_ids"], i["entry_bytes"]
         d.n_classes, d.n_pairs, d.n_runs, d.n_items = i["n_classes"], i["n_pairs"], i["n_runs"], i["n_items"]
+        d.n_long_items = i["n_long_items"]
         d.n_ranks, d.max_iters_cap = self.n_ranks, ERR_LOG_CAP
-        for k in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "locus_item_ptr"):
+        for k in range(_lib.GBRS_KMAX + 2):
+            d.bucket_class0[k] = i["bucket_class0"][k]
+            d.bucket_pair0[k] = i["bucket_pair0"][k]
+        for k in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "item_order",
+                  "locus_item_ptr"):
             setattr(d, k, self.dev[k].data_ptr())
         if self.packed.has_genes:
             for k in ("gene_of", "gene_ptr", "gene_loci"):
@@ -188,7 +196,7 @@ class DevicePattern:
             d.gene_hap, d.gamma = self.gene_hap.data_ptr(), self.gamma.data_ptr()
         else:
             d.gene_of = d.gene_ptr = d.gene_loci = d.gene_hap = d.gamma = None
-        for k in ("theta", "efflen", "acc", "iso", "weights", "wit", "part", "err_log", "scal", "ctrl"):
+        for k in ("theta", "efflen", "acc", "iso", "weights", "subsets", "wit", "part", "err_log", "scal", "ctrl"):
             setattr(d, k, getattr(self, k).data_ptr())
         self.desc = d
 

@@ -30,6 +30,7 @@ extern "C" {
 
 #define GBRS_EM_ABI_VERSION 1
 #define GBRS_HPAD 8 /* haplotype slots per locus line */
+#define GBRS_KMAX 8 /* classes with up to this many (class, locus) pairs take the fixed-width row pass */
 
 enum {
   GBRS_OK = 0,
@@ -75,6 +76,7 @@ typedef struct {
   int64_t n_pairs;     /* (class, locus) pair words in this shard */
   int64_t n_runs;      /* (class, gene) runs in this shard */
   int64_t n_items;     /* column-pass work items */
+  int64_t n_long_items;/* of which long (deep loci, up to 16 * item_len entries, processed by a whole warp) */
   int64_t nnz;         /* incidence entries in this shard (popcount over pair masks) */
   int64_t nnz_total;   /* incidence entries over all shards */
   int64_t n_classes_total;
@@ -82,15 +84,21 @@ typedef struct {
   int32_t n_gene_ids;  /* 1 + max gene id */
   int32_t max_pairs_per_class;
   int32_t reserved;
+  /* Classes are ordered by (min(pairs, GBRS_KMAX + 1), smallest locus).  bucket_class0[k-1] / bucket_pair0[k-1] is the
+   * first class / first pair word of the classes with exactly k pairs (k = 1..GBRS_KMAX); index GBRS_KMAX starts the
+   * "long" classes (more than GBRS_KMAX pairs), index GBRS_KMAX+1 is the end (= n_classes / n_pairs). */
+  int64_t bucket_class0[GBRS_KMAX + 2];
+  int64_t bucket_pair0[GBRS_KMAX + 2];
 } gbrs_pack_info;
 
 int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out);
 int gbrs_pack_get_info(gbrs_pack_t p, gbrs_pack_info* info);
 /* Borrowed host pointers to the packed arrays (valid until gbrs_pack_free).  `name` is one of:
- *   "rowptr"  uint32 [n_classes+1]   "pairs"   uint32 [n_pairs]  (locus | mask<<24, sorted by (gene, locus) in a class)
+ *   "rowptr"  uint32 [n_classes+1]   "pairs"   uint32 [n_pairs]  (locus | mask<<24, sorted by (gene, locus) in a class;
+ *                                     class n < bucket_class0[GBRS_KMAX] with k pairs starts at bucket_pair0[k-1] + (n - bucket_class0[k-1]) * k)
  *   "count"   double [n_classes]     "runptr"  uint32 [n_classes+1]
  *   "ent_cls" / "ent_pair" / "ent_run"  entry words [n_pairs], locus-major (index | mask << (8*entry_bytes-8))
- *   "item_off" uint32 [n_items+1]    "locus_item_ptr" uint32 [T+1]
+ *   "item_off" uint32 [n_items+1]    "locus_item_ptr" uint32 [T+1]   "item_order" uint32 [n_items] (longest first)
  *   "gene_ptr" uint32 [n_gene_ids+1] "gene_loci" uint32 [T]     "gene_of" int32 [T]
  */
 int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64_t* bytes);
@@ -104,8 +112,11 @@ typedef struct {
   int32_t n_gene_ids;
   int32_t entry_bytes;
   int64_t n_classes, n_pairs, n_runs, n_items;
+  int64_t n_long_items; /* the first n_long_items entries of item_order are long items (one warp each) */
   int32_t n_ranks;     /* row shards taking part (1 = no exchange step) */
   int32_t max_iters_cap; /* capacity of err_log */
+  int64_t bucket_class0[GBRS_KMAX + 2]; /* see gbrs_pack_info */
+  int64_t bucket_pair0[GBRS_KMAX + 2];
   /* packed incidence (read-only) */
   const uint32_t* rowptr;
   const uint32_t* pairs;
@@ -115,6 +126,7 @@ typedef struct {
   const void* ent_pair;
   const void* ent_run;
   const uint32_t* item_off;
+  const uint32_t* item_order;   /* [n_items] item ids, longest item first */
   const uint32_t* locus_item_ptr;
   const int32_t* gene_of;
   const uint32_t* gene_ptr;
@@ -125,6 +137,7 @@ typedef struct {
   double* acc;      /* [T][8] M-step numerator: local after gbrs_em_launch_local, global after the exchange */
   double* iso;      /* [2][T] isoform totals sum_h theta */
   double* weights;  /* [max(n_classes, n_pairs, 8*n_runs)] per-class / per-pair / per-run weights */
+  double* subsets;  /* [T][32] subset sums of theta per locus: [0,16) over haplotype slots 0-3, [16,32) over slots 4-7 */
   double* wit;      /* [n_items][8] column-pass partials */
   double* part;     /* [GBRS_PART_SLOTS] block partial sums */
   double* gene_hap; /* [n_gene_ids][8] per-gene per-haplotype totals (models 1-3) */
@@ -134,9 +147,9 @@ typedef struct {
   int32_t* ctrl;    /* [16] control block, see GBRS_CTRL_* */
 } gbrs_em_dev;
 
-#define GBRS_PART_SLOTS 1024
+#define GBRS_PART_SLOTS 4096 /* [0, 2048): block partial sums of the isoform totals; [2048, 4096): of the error */
 enum { GBRS_CTRL_ITERS = 0, GBRS_CTRL_DONE = 1, GBRS_CTRL_ERROR = 2, GBRS_CTRL_PARITY = 3, GBRS_CTRL_MAX_ITERS = 4,
-       GBRS_CTRL_PREPARED = 5 };
+       GBRS_CTRL_PREPARED = 5, GBRS_CTRL_TICKET = 8 };
 enum { GBRS_SCAL_ERR = 0, GBRS_SCAL_SUM_PREV = 1, GBRS_SCAL_TARGET = 2, GBRS_SCAL_SUM_CUR = 3 };
 
 /* theta0 from the incidence alone.  EMfactory.prepare numeric part (EMfactory.py:95-111) / EMfactory.reset (:113-138).

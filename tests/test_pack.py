@@ -59,10 +59,17 @@ def test_pack_preserves_pattern(small):
     assert p.info["n_pairs"] == d.pairs and p.info["nnz"] == d.nnz == p.info["nnz_total"]
     assert packed_signatures(p) == class_signatures(d)
     a = p.arrays
-    # classes ordered by smallest locus
+    # classes ordered by (number of pairs capped at KMAX+1, smallest locus); bucket tables consistent with rowptr
     rp = a["rowptr"].astype(np.int64)
     minloc = np.array([(a["pairs"][rp[n]:rp[n + 1]] & 0xFFFFFF).min() for n in range(p.info["n_classes"])])
-    assert np.all(np.diff(minloc) >= 0)
+    width = np.minimum(np.diff(rp), _lib.GBRS_KMAX + 1)
+    key = width * (1 << 24) + minloc
+    assert np.all(np.diff(key) >= 0)
+    bc, bp = p.info["bucket_class0"], p.info["bucket_pair0"]
+    assert bc[0] == 0 and bc[-1] == p.info["n_classes"] and bp[-1] == p.info["n_pairs"]
+    for k in range(1, _lib.GBRS_KMAX + 1):
+        assert np.all(width[bc[k - 1]:bc[k]] == k)
+        assert bp[k - 1] == rp[bc[k - 1]] and bp[k] - bp[k - 1] == k * (bc[k] - bc[k - 1])
     # locus-major entries mirror the class-major pairs
     idx_c, m_c = unpack_entries(a["ent_cls"], p.info["entry_bytes"])
     idx_p, m_p = unpack_entries(a["ent_pair"], p.info["entry_bytes"])
@@ -74,13 +81,17 @@ def test_pack_preserves_pattern(small):
     assert np.array_equal(cls_of_pair[idx_p], idx_c)
     # items tile the entries; every item belongs to one locus; entries of a locus are ascending in class id
     io, lip = a["item_off"].astype(np.int64), a["locus_item_ptr"].astype(np.int64)
-    assert io[0] == 0 and io[-1] == p.info["n_pairs"] and np.all(np.diff(io) > 0) and np.all(np.diff(io) <= 64)
+    assert io[0] == 0 and io[-1] == p.info["n_pairs"] and np.all(np.diff(io) > 0)
+    lens = np.diff(io)
+    assert p.info["n_long_items"] == np.count_nonzero(lens > 64) and lens.max() <= 16 * 64
     locus_of_entry = pw & 0xFFFFFF
     for t in range(d.T):
         lo, hi = (io[lip[t]], io[lip[t + 1]]) if lip[t + 1] > lip[t] else (0, 0)
         assert np.all(locus_of_entry[lo:hi] == t)
         assert np.all(np.diff(idx_c[lo:hi]) > 0)
     assert lip[-1] == p.info["n_items"]
+    order = a["item_order"].astype(np.int64)
+    assert sorted(order) == list(range(p.info["n_items"])) and np.all(np.diff(np.diff(io)[order]) <= 0)
     # runs: consecutive pairs of one class in the same gene
     g = gene_index(d.T, d.groups())[pw_locus(a)]
     runptr = a["runptr"].astype(np.int64)
