@@ -39,7 +39,7 @@ class PackInput(C.Structure):
 
 class PackInfo(C.Structure):
     _fields_ = [("n_classes", C.c_int64), ("n_pairs", C.c_int64), ("n_runs", C.c_int64), ("n_items", C.c_int64),
-                ("n_long_items", C.c_int64), ("nnz", C.c_int64), ("nnz_total", C.c_int64), ("n_classes_total", C.c_int64),
+                ("n_entries", C.c_int64), ("n_long_items", C.c_int64), ("nnz", C.c_int64), ("nnz_total", C.c_int64), ("n_classes_total", C.c_int64),
                 ("entry_bytes", C.c_int32), ("n_gene_ids", C.c_int32), ("max_pairs_per_class", C.c_int32),
                 ("reserved", C.c_int32), ("bucket_class0", C.c_int64 * (GBRS_KMAX + 2)),
                 ("bucket_pair0", C.c_int64 * (GBRS_KMAX + 2))]
@@ -48,11 +48,12 @@ class PackInfo(C.Structure):
 class EmDev(C.Structure):
     _fields_ = [("T", C.c_int32), ("H", C.c_int32), ("n_gene_ids", C.c_int32), ("entry_bytes", C.c_int32),
                 ("n_classes", C.c_int64), ("n_pairs", C.c_int64), ("n_runs", C.c_int64), ("n_items", C.c_int64),
-                ("n_long_items", C.c_int64), ("n_ranks", C.c_int32), ("max_iters_cap", C.c_int32),
+                ("n_entries", C.c_int64), ("n_long_items", C.c_int64), ("n_ranks", C.c_int32), ("max_iters_cap", C.c_int32),
                 ("bucket_class0", C.c_int64 * (GBRS_KMAX + 2)), ("bucket_pair0", C.c_int64 * (GBRS_KMAX + 2)),
                 ("rowptr", C.c_void_p), ("pairs", C.c_void_p), ("count", C.c_void_p), ("runptr", C.c_void_p),
                 ("ent_cls", C.c_void_p), ("ent_pair", C.c_void_p), ("ent_run", C.c_void_p),
-                ("item_off", C.c_void_p), ("item_order", C.c_void_p), ("locus_item_ptr", C.c_void_p),
+                ("item_off", C.c_void_p), ("item_order", C.c_void_p), ("item_desc", C.c_void_p),
+                ("locus_order", C.c_void_p), ("locus_item_ptr", C.c_void_p),
                 ("gene_of", C.c_void_p), ("gene_ptr", C.c_void_p), ("gene_loci", C.c_void_p),
                 ("theta", C.c_void_p), ("efflen", C.c_void_p), ("acc", C.c_void_p), ("iso", C.c_void_p),
                 ("weights", C.c_void_p), ("subsets", C.c_void_p), ("wit", C.c_void_p), ("part", C.c_void_p), ("gene_hap", C.c_void_p),

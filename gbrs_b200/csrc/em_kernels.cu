@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -228,7 +229,7 @@ __device__ __forceinline__ double pair_sum(const double* __restrict__ sub, uint3
 // per class, UNR classes per thread; all pair words are loaded first, then all table loads are issued together
 // (memory-level parallelism), then the adds.  Classes are ordered by smallest locus within a width, so the lanes of a
 // warp mostly read the same few table rows.
-__host__ __device__ constexpr int unr_of(int K) { return K <= 2 ? 2 : 1; }
+__host__ __device__ constexpr int unr_of(int K) { return K <= 2 ? 4 : (K <= 4 ? 2 : 1); }
 
 struct RowPlan {                     // host-computed: work units ordered from the widest fixed bucket down to width 1
   int64_t unit_end[GBRS_KMAX];       // unit_end[i] = one past the last unit (= 32 * unr classes) of width GBRS_KMAX - i
@@ -248,8 +249,8 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
     const bool valid = n[u] < class_end;
     const uint32_t* __restrict__ pw = d.pairs + bucket_pair0 + (valid ? (n[u] - bucket_class0) : 0) * K;
 #pragma unroll
-    for (int p = 0; p < K; ++p) w[u][p] = valid ? __ldg(pw + p) : 0u;
-    cnt[u] = valid ? __ldg(d.count + n[u]) : 0.0;
+    for (int p = 0; p < K; ++p) w[u][p] = valid ? __ldcs(pw + p) : 0u;
+    cnt[u] = valid ? __ldcs(d.count + n[u]) : 0.0;
   }
   double s[UNR];
   if (UNIT) {
@@ -283,10 +284,13 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
     if (n[u] < class_end) d.weights[n[u]] = fast_div(cnt[u], s[u]);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <bool UNIT>
 __global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__ gbrs_em_dev d,
-                                                          const __grid_constant__ RowPlan plan) {
+                                                          const __grid_constant__ RowPlan plan, const bool prefetch) {
   if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
+  const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
   const int64_t total_units = plan.unit_end[GBRS_KMAX - 1];
   int i = 0;  // bucket index only ever advances along the warp's grid-stride walk
@@ -298,7 +302,15 @@ __global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__
     }
     const int k = GBRS_KMAX - i;
     const int64_t c0 = d.bucket_class0[k - 1], c1 = d.bucket_class0[k], p0 = d.bucket_pair0[k - 1];
-    const int64_t class0 = c0 + (u - unit0) * (32 * unr_of(k));
+    const int cpu = 32 * unr_of(k);
+    const int64_t class0 = c0 + (u - unit0) * cpu;
+    if (prefetch && u + nwarps < unit1) {
+      // pull the pair words and counts of this warp's next unit (same width) towards L2: cpu * k * 4 contiguous bytes
+      // of pair words and cpu * 8 bytes of counts, one 128-byte line per lane
+      const int64_t first = class0 + nwarps * cpu;
+      if (lane * 128 < cpu * k * 4) prefetch_l2(reinterpret_cast<const char*>(d.pairs + p0 + (first - c0) * k) + lane * 128);
+      if (lane * 128 < cpu * 8) prefetch_l2(reinterpret_cast<const char*>(d.count + first) + lane * 128);
+    }
     switch (k) {
       case 1: row_classes_m4<1, UNIT>(d, class0, c1, c0, p0); break;
       case 2: row_classes_m4<2, UNIT>(d, class0, c1, c0, p0); break;
@@ -497,7 +509,8 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d) {
 // per-haplotype matrix copy.  VEC = 1: scalar weight per index; VEC = 8: one weight per haplotype (model 1).
 // ---------------------------------------------------------------------------------------------------------------------
 // LANES = 8: four short items per warp (one per aligned 8-lane group); LANES = 32: one long item per warp.
-template <typename E, int VEC, int LANES>
+// FULL: every entry of the item hits all H haplotypes -- a plain sum, broadcast to the H slots, no masking.
+template <typename E, int VEC, int LANES, bool FULL>
 __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __restrict__ ents, int64_t item, uint32_t b,
                                             uint32_t e) {
   constexpr int SH = 8 * (int) sizeof(E) - 8;
@@ -505,22 +518,48 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
   const double* __restrict__ wts = d.weights;
   const int lane = threadIdx.x & 31, lane8 = lane & 7, lanex = lane & (LANES - 1);
   double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (VEC == 1) {
-    // chunks of 4 steps: entry words first, then the four weight gathers together, then the masked adds
-    uint32_t p0 = b + lanex;
-    for (; p0 + 3 * LANES < e; p0 += 4 * LANES) {
-      E ent[4];
+  if (VEC == 1 && sizeof(E) == 4) {
+    // Items start at a multiple of 4 entries and are padded with empty words, so every lane fetches four consecutive
+    // entries per 128-bit load; two such loads and their eight weight gathers are in flight per lane before the adds.
+    // An out-of-range quad reads the item's first quad again with the masks stripped, which adds nothing.
+    constexpr int CH = 2;
+    const uint32_t* __restrict__ e32 = reinterpret_cast<const uint32_t*>(ents);
+    for (uint32_t p0 = b + 4 * lanex; p0 < e; p0 += 4 * LANES * CH) {
+      uint4 en[CH];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) ent[q] = __ldg(ents + p0 + LANES * q);
-      double w[4];
+      for (int q = 0; q < CH; ++q) {
+        const uint32_t p = p0 + 4 * LANES * q;
+        en[q] = __ldcs(reinterpret_cast<const uint4*>(e32 + (p < e ? p : b)));
+        if (p >= e) { en[q].x &= 0xFFFFFFu; en[q].y &= 0xFFFFFFu; en[q].z &= 0xFFFFFFu; en[q].w &= 0xFFFFFFu; }
+      }
+      double w[CH][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = __ldg(wts + (size_t) (ent[q] & IDX));
+      for (int q = 0; q < CH; ++q) {
+        w[q][0] = __ldg(wts + (en[q].x & 0xFFFFFFu));
+        w[q][1] = __ldg(wts + (en[q].y & 0xFFFFFFu));
+        w[q][2] = __ldg(wts + (en[q].z & 0xFFFFFFu));
+        w[q][3] = __ldg(wts + (en[q].w & 0xFFFFFFu));
+      }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) masked_add8(a, w[q], (uint32_t) (ent[q] >> SH));
+      for (int q = 0; q < CH; ++q) {
+        if (FULL) {
+          // padding words (and re-read quads) must not count: their mask is empty
+          a[0] += ((en[q].x >> 24) ? w[q][0] : 0.0) + ((en[q].y >> 24) ? w[q][1] : 0.0);
+          a[0] += ((en[q].z >> 24) ? w[q][2] : 0.0) + ((en[q].w >> 24) ? w[q][3] : 0.0);
+        } else {
+          masked_add8(a, w[q][0], en[q].x >> 24);
+          masked_add8(a, w[q][1], en[q].y >> 24);
+          masked_add8(a, w[q][2], en[q].z >> 24);
+          masked_add8(a, w[q][3], en[q].w >> 24);
+        }
+      }
     }
-    for (; p0 < e; p0 += LANES) {
-      const E ent = __ldg(ents + p0);
-      masked_add8(a, __ldg(wts + (size_t) (ent & IDX)), (uint32_t) (ent >> SH));
+  } else if (VEC == 1) {
+    for (uint32_t p = b + lanex; p < e; p += LANES) {
+      const E ent = __ldcs(ents + p);
+      const double w = __ldg(wts + (size_t) (ent & IDX));
+      if (FULL) a[0] += (ent >> SH) ? w : 0.0;
+      else masked_add8(a, w, (uint32_t) (ent >> SH));
     }
   } else {
     for (uint32_t p = b + lanex; p < e; p += LANES) {
@@ -532,35 +571,54 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
       for (int h = 0; h < 8; ++h) a[h] = fma(v[h], __hiloint2double(((m >> h) & 1u) ? 0x3FF00000 : 0, 0), a[h]);
     }
   }
-  double tot = group8_transpose_sum(a, lane8);
+  double tot;
+  if (FULL && VEC == 1) {
+    tot = group8_sum(a[0]);
+  } else {
+    tot = group8_transpose_sum(a, lane8);
+  }
   if (LANES == 32) {
     tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 8);
     tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 16);
   }
+  if (FULL && VEC == 1 && lane8 >= d.H) tot = 0.0;
   if (item >= 0 && lanex < 8) d.wit[item * GBRS_HPAD + lane8] = tot;
 }
 
 // Warp work slots: slot < n_long_items -> the slot-th item of item_order (a long item, whole warp); otherwise four
-// short items.  item_order lists the items longest first, so the deep loci start first and do not form the tail.
+// short items.  item_order lists long items first, partial-mask items before full-mask ones, longest first.
 template <typename E, int VEC>
-__global__ void __launch_bounds__(kThreads) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
+__global__ void __launch_bounds__(kThreads, 4) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
                                                              const E* __restrict__ ents, bool honour_done) {
   if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
   const int64_t n_long = d.n_long_items;
   const int64_t total_slots = n_long + ((d.n_items - n_long + 3) >> 2);
-  for (int64_t ws = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; ws < total_slots; ws += nwarps) {
-    const int64_t pos = ws < n_long ? ws : n_long + ((ws - n_long) << 2) + (lane >> 3);
-    int64_t item = -1;
-    uint32_t b = 0, e = 0;
-    if (pos < d.n_items) {
-      item = __ldg(d.item_order + pos);
-      b = __ldg(d.item_off + item);
-      e = __ldg(d.item_off + item + 1);
+  const uint4* __restrict__ desc = reinterpret_cast<const uint4*>(d.item_desc);
+  auto slot_pos = [&](int64_t ws) { return ws < n_long ? ws : n_long + ((ws - n_long) << 2) + (lane >> 3); };
+  int64_t ws = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint4 nx = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);  // descriptor of the slot this lane handles in the coming iteration
+  if (ws < total_slots && slot_pos(ws) < d.n_items) nx = __ldg(desc + slot_pos(ws));
+  for (; ws < total_slots; ws += nwarps) {
+    const uint4 cur = nx;
+    {  // fetch the descriptor of the following slot now and pull its entries towards L2
+      const int64_t wn = ws + nwarps;
+      nx = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+      if (wn < total_slots && slot_pos(wn) < d.n_items) nx = __ldg(desc + slot_pos(wn));
     }
-    if (ws < n_long) column_item<E, VEC, 32>(d, ents, item, b, e);
-    else column_item<E, VEC, 8>(d, ents, item, b, e);
+    const int64_t item = cur.z == 0xFFFFFFFFu ? -1 : (int64_t) cur.z;
+    const uint32_t b = cur.x, e = cur.y;
+    const bool full = cur.w & 1u;
+    // all 32 lanes must run both kinds when a warp straddles the partial/full boundary (shuffles are warp-wide)
+    const unsigned any_full = __ballot_sync(0xFFFFFFFFu, full), any_part = __ballot_sync(0xFFFFFFFFu, !full);
+    if (ws < n_long) {
+      if (full) column_item<E, VEC, 32, true>(d, ents, item, b, e);
+      else column_item<E, VEC, 32, false>(d, ents, item, b, e);
+    } else {
+      if (any_part) column_item<E, VEC, 8, false>(d, ents, full ? -1 : item, full ? 0u : b, full ? 0u : e);
+      if (any_full) column_item<E, VEC, 8, true>(d, ents, full ? item : -1, full ? b : 0u, full ? e : 0u);
+    }
   }
 }
 
@@ -583,11 +641,15 @@ __global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, boo
   const int64_t total = (int64_t) d.T * GBRS_HPAD;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   const int64_t rounds = (total + stride - 1) / stride;
-  int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   double mine = 0.0;
-  for (int64_t r = 0; r < rounds; ++r, i += stride) {
-    const bool valid = i < total;
-    const int64_t t = i >> 3;
+  for (int64_t r = 0; r < rounds; ++r) {
+    // deepest loci first, and consecutive entries of locus_order go to different blocks (the deep loci are few: spread
+    // them over all SMs instead of piling them into the first blocks)
+    const int64_t g_in_round = (int64_t) (threadIdx.x >> 3) * gridDim.x + blockIdx.x;
+    const int64_t slot = r * (stride >> 3) + g_in_round;
+    const bool valid = slot < d.T;
+    const int64_t t = valid ? (int64_t) __ldg(d.locus_order + slot) : 0;
+    const int64_t o = t * GBRS_HPAD + h;
     uint32_t it = 0, e = 0;
     if (valid) { it = __ldg(d.locus_item_ptr + t); e = __ldg(d.locus_item_ptr + t + 1); }
     double W = 0.0;
@@ -599,14 +661,14 @@ __global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, boo
     for (; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
     double a = 0.0;
     if (valid) {
-      a = UNIT ? ((h < d.H) ? W : 0.0) : th[i] * W;
-      d.acc[i] = a;
+      a = UNIT ? ((h < d.H) ? W : 0.0) : th[o] * W;
+      d.acc[o] = a;
     }
     if (FUSE) {
       double v = 0.0;
       if (valid) {
-        v = a / d.efflen[i];
-        dst[i] = v;
+        v = fast_div(a, d.efflen[o]);
+        dst[o] = v;
       }
       const double s = group8_sum(v);
       if (valid && h == 0) {
@@ -659,7 +721,7 @@ __global__ void __launch_bounds__(kThreads) k_locus_update(const gbrs_em_dev d) 
     if (i < total) {
       v = src[i];
       if (FROM_ACC) {
-        v = v / d.efflen[i];
+        v = fast_div(v, d.efflen[i]);
         dst[i] = v;
       }
     }
@@ -840,7 +902,7 @@ int check_dev(const gbrs_em_dev* d, const char* who) {
   if (d->T <= 0 || d->H < 1 || d->H > GBRS_HPAD || (d->entry_bytes != 4 && d->entry_bytes != 8)) {
     gbrs_set_error(std::string(who) + ": bad descriptor shape"); return GBRS_E_ARG;
   }
-  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->item_order || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
+  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->item_order || !d->item_desc || !d->locus_order || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
       !d->iso || !d->weights || !d->subsets || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
     gbrs_set_error(std::string(who) + ": null device buffer in descriptor"); return GBRS_E_ARG;
   }
@@ -878,7 +940,8 @@ int launch_row_m4(const gbrs_em_dev* d, cudaStream_t s) {
     plan.unit_end[i] = units;
   }
   if (units > 0) {
-    k_weights_m4<UNIT><<<resident_grid(k_weights_m4<UNIT>, units * 32), kThreads, 0, s>>>(*d, plan);
+    static const bool prefetch = std::getenv("GBRS_PREFETCH") != nullptr;  // measured: no gain on B200, off by default
+    k_weights_m4<UNIT><<<resident_grid(k_weights_m4<UNIT>, units * 32), kThreads, 0, s>>>(*d, plan, prefetch);
     GBRS_LAUNCH_CHECK("k_weights_m4");
   }
   const int64_t n_long = d->n_classes - d->bucket_class0[GBRS_KMAX];
@@ -985,8 +1048,33 @@ extern "C" int gbrs_em_current_theta(const gbrs_em_dev* d, void* stream, double*
   return GBRS_OK;
 }
 
+// Keep the per-class weight vector (written by the row pass, gathered by the column pass) resident in L2: everything
+// else the two passes read is streamed once.  Best effort -- failures are ignored.
+static void pin_weights_in_l2(const gbrs_em_dev* d, cudaStream_t s) {
+  static const bool enabled = std::getenv("GBRS_NO_L2_PIN") == nullptr;
+  if (!enabled) return;
+  int dev = 0, max_persist = 0, max_window = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  size_t bytes = (size_t) d->n_classes * sizeof(double);
+  if (max_persist <= 0 || max_window <= 0 || bytes == 0) return;
+  const size_t want = bytes < (size_t) max_persist ? bytes : (size_t) max_persist;
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  cudaStreamAttrValue attr;
+  std::memset(&attr, 0, sizeof(attr));
+  attr.accessPolicyWindow.base_ptr = d->weights;
+  attr.accessPolicyWindow.num_bytes = bytes < (size_t) max_window ? bytes : (size_t) max_window;
+  attr.accessPolicyWindow.hitRatio = (float) ((double) want / (double) attr.accessPolicyWindow.num_bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();
+}
+
 extern "C" int gbrs_em_run_begin(const gbrs_em_dev* d, double tol, int max_iters, void* stream) {
   if (int rc = check_dev(d, "gbrs_em_run_begin")) return rc;
+  pin_weights_in_l2(d, static_cast<cudaStream_t>(stream));
   if (max_iters < 0 || max_iters > d->max_iters_cap) {
     gbrs_set_error("gbrs_em_run_begin: max_iters exceeds the err_log capacity of the descriptor"); return GBRS_E_ARG;
   }

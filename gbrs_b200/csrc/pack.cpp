@@ -29,7 +29,7 @@ void gbrs_set_error(const std::string& s);  // capi.cu
 struct gbrs_pack {
   gbrs_pack_info info{};
   int32_t T = 0;
-  std::vector<uint32_t> rowptr, pairs, runptr, item_off, item_order, locus_item_ptr, gene_ptr, gene_loci;
+  std::vector<uint32_t> rowptr, pairs, runptr, item_off, item_order, item_desc, locus_item_ptr, locus_order, gene_ptr, gene_loci;
   std::vector<int32_t> gene_of;
   std::vector<double> count;
   std::vector<uint8_t> ent_cls, ent_pair, ent_run;  // entry words, 4 or 8 bytes each
@@ -70,7 +70,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     for (int t = 0; t < T; ++t)
       if (in->indptr[h][t + 1] < in->indptr[h][t]) { gbrs_set_error("gbrs_pack_create: indptr not monotone"); return GBRS_E_ARG; }
   }
-  const int item_len = in->item_len > 0 ? in->item_len : 64;
+  const int item_len = in->item_len > 0 ? (in->item_len + 7) / 8 * 8 : 64;
 
   try {
     // ---- 1. merge the H columns of every locus into (class, mask) pairs, locus-major, all classes -----------------
@@ -217,23 +217,51 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     for (int64_t n = 0; n < n_classes; ++n) P->runptr[n + 1] += P->runptr[n];
     const int64_t n_runs = P->runptr[n_classes];
 
-    // ---- 5. locus-major entries of this shard, ascending new class id within a locus ------------------------------
-    const int entry_bytes = std::max({n_classes, n_pairs, n_runs}) < (int64_t(1) << 24) ? 4 : 8;
-    std::vector<int64_t> lptr(T + 1, 0);
-    for (int64_t p = 0; p < n_pairs; ++p) ++lptr[(P->pairs[p] & 0xFFFFFF) + 1];
-    for (int t = 0; t < T; ++t) lptr[t + 1] += lptr[t];
-    P->ent_cls.assign((size_t) n_pairs * entry_bytes, 0);
-    P->ent_pair.assign((size_t) n_pairs * entry_bytes, 0);
-    P->ent_run.assign((size_t) n_pairs * entry_bytes, 0);
+    // ---- 5. locus-major entries of this shard.  Within a locus: first the entries whose mask is partial, then the
+    // entries hitting all H haplotypes ("full"), each part in ascending new class id.  Full entries need no per-haplotype
+    // masking in the column pass (one add instead of eight masked ones) and are the commonest kind.
+    // Every part is padded to a multiple of 4 entries with dummy words (empty mask, index = one past the last real
+    // index, whose weight slot is kept at zero), so that items start 16-byte aligned and the column pass can fetch four
+    // entries per load.
+    const int entry_bytes = std::max({n_classes, n_pairs, n_runs}) + 1 < (int64_t(1) << 24) ? 4 : 8;
+    const uint32_t full_mask = (1u << H) - 1u;
+    auto pad4 = [](int64_t x) { return (x + 3) / 4 * 4; };
+    std::vector<int64_t> lcnt(T, 0), lpart(T, 0);
+    for (int64_t p = 0; p < n_pairs; ++p) {
+      ++lcnt[P->pairs[p] & 0xFFFFFF];
+      lpart[P->pairs[p] & 0xFFFFFF] += (P->pairs[p] >> 24) != full_mask;
+    }
+    // only deep loci are split into a partial and a full part; a shallow locus stays one (mixed) part, otherwise the
+    // many tiny loci would double their item count for nothing
+    std::vector<uint8_t> split(T, 0);
+    std::vector<int64_t> lptr(T + 1, 0), ppart(T, 0), pfull(T, 0);  // padded start of the locus, padded part lengths
+    for (int t = 0; t < T; ++t) {
+      split[t] = lcnt[t] > 8 * (int64_t) item_len;
+      if (!split[t]) lpart[t] = lcnt[t];
+      ppart[t] = pad4(lpart[t]);
+      pfull[t] = pad4(lcnt[t] - lpart[t]);
+      lptr[t + 1] = lptr[t] + ppart[t] + pfull[t];
+    }
+    const int64_t n_entries = lptr[T];
+    if (n_entries >= (int64_t(1) << 32)) { delete P; gbrs_set_error("gbrs_pack_create: more than 2^32 entries in one shard"); return GBRS_E_LIMIT; }
+    P->ent_cls.assign((size_t) n_entries * entry_bytes, 0);
+    P->ent_pair.assign((size_t) n_entries * entry_bytes, 0);
+    P->ent_run.assign((size_t) n_entries * entry_bytes, 0);
+    for (int64_t i = 0; i < n_entries; ++i) {
+      put_entry(P->ent_cls, entry_bytes, i, (uint64_t) n_classes, 0);
+      put_entry(P->ent_pair, entry_bytes, i, (uint64_t) n_pairs, 0);
+      put_entry(P->ent_run, entry_bytes, i, (uint64_t) n_runs, 0);
+    }
     {
-      std::vector<int64_t> cur(lptr.begin(), lptr.end() - 1);
+      std::vector<int64_t> cur_part(lptr.begin(), lptr.end() - 1), cur_full(T);
+      for (int t = 0; t < T; ++t) cur_full[t] = lptr[t] + ppart[t];
       const int32_t* go = P->gene_of.data();
       for (int64_t n = 0; n < n_classes; ++n) {
         uint64_t run = P->runptr[n];
         for (uint32_t p = P->rowptr[n]; p < P->rowptr[n + 1]; ++p) {
           const uint32_t w = P->pairs[p], t = w & 0xFFFFFF, m = w >> 24;
           if (p > P->rowptr[n] && go[t] != go[P->pairs[p - 1] & 0xFFFFFF]) ++run;
-          const int64_t pos = cur[t]++;
+          const int64_t pos = (split[t] && m == full_mask) ? cur_full[t]++ : cur_part[t]++;
           put_entry(P->ent_cls, entry_bytes, pos, (uint64_t) n, m);
           put_entry(P->ent_pair, entry_bytes, pos, (uint64_t) p, m);
           put_entry(P->ent_run, entry_bytes, pos, run, m);
@@ -242,39 +270,65 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     }
 
     // ---- 6. column-pass work items ------------------------------------------------------------------------------
-    // A locus with up to 8 * item_len entries is cut into short items (<= item_len entries, one aligned 8-lane group
-    // each); a deeper locus into long items (<= 16 * item_len entries, a whole warp each), so that the per-locus combine
-    // in k_locus_acc, which walks a locus' items serially, stays short even for the deepest loci.
+    // Each part (partial / full) of a locus is cut separately.  A part with up to 8 * item_len entries becomes short
+    // items (<= item_len entries, one aligned 8-lane group each); a deeper part becomes long items (<= 16 * item_len
+    // entries, a whole warp each), so that the per-locus combine in k_locus_acc, which walks a locus' items serially,
+    // stays short even for the deepest loci.
     const int64_t long_len = 16 * (int64_t) item_len;
     auto item_len_of = [&](int64_t len) -> int64_t {
       if (len <= 8 * (int64_t) item_len) return item_len;
       const int64_t n = (len + long_len - 1) / long_len;
       return ((len + n - 1) / n + 31) / 32 * 32;
     };
+    auto items_of = [&](int64_t len) -> int64_t { return len ? (len + item_len_of(len) - 1) / item_len_of(len) : 0; };
     P->locus_item_ptr.assign((size_t) T + 1, 0);
     for (int t = 0; t < T; ++t) {
-      const int64_t len = lptr[t + 1] - lptr[t], il = item_len_of(len);
-      P->locus_item_ptr[t + 1] = P->locus_item_ptr[t] + (uint32_t) ((len + il - 1) / il);
+      P->locus_item_ptr[t + 1] = P->locus_item_ptr[t] + (uint32_t) (items_of(ppart[t]) + items_of(pfull[t]));
     }
     const int64_t n_items = P->locus_item_ptr[T];
+    if (n_items >= (int64_t(1) << 31)) { delete P; gbrs_set_error("gbrs_pack_create: too many work items"); return GBRS_E_LIMIT; }
     P->item_off.assign((size_t) n_items + 1, 0);
+    std::vector<uint8_t> item_full((size_t) n_items, 0);
     for (int t = 0; t < T; ++t) {
-      const int64_t len = lptr[t + 1] - lptr[t], il = item_len_of(len);
       uint32_t it = P->locus_item_ptr[t];
-      for (int64_t o = 0; o < len; o += il) P->item_off[it++] = (uint32_t) (lptr[t] + o);
+      const int64_t np = ppart[t], nf = pfull[t];
+      const int64_t ilp = item_len_of(np), ilf = item_len_of(nf);
+      for (int64_t o = 0; o < np; o += ilp) P->item_off[it++] = (uint32_t) (lptr[t] + o);
+      for (int64_t o = 0; o < nf; o += ilf) { item_full[it] = 1; P->item_off[it++] = (uint32_t) (lptr[t] + np + o); }
     }
-    P->item_off[n_items] = (uint32_t) n_pairs;
-    // longest-processing-time-first visiting order (stable counting sort by length, descending)
+    P->item_off[n_items] = (uint32_t) n_entries;
+    P->info.n_entries = n_entries;
+    // Visiting order: long items first, then short ones; inside each, partial before full (a warp works on items of
+    // one kind), longest first (the deep loci must not form the tail).  Bit 31 of an item_order word marks a full item.
     {
-      int64_t max_len = 0;
-      for (int64_t i = 0; i < n_items; ++i) max_len = std::max<int64_t>(max_len, P->item_off[i + 1] - P->item_off[i]);
-      std::vector<int64_t> start((size_t) max_len + 2, 0);
-      for (int64_t i = 0; i < n_items; ++i) ++start[(size_t) (max_len - (P->item_off[i + 1] - P->item_off[i])) + 1];
-      for (int64_t l = 0; l <= max_len; ++l) start[l + 1] += start[l];
-      for (int64_t i = 0; i < n_items; ++i) P->info.n_long_items += (P->item_off[i + 1] - P->item_off[i]) > item_len;
+      std::vector<uint32_t> idx((size_t) n_items);
+      std::iota(idx.begin(), idx.end(), 0u);
+      auto len_of = [&](uint32_t i) { return (int64_t) P->item_off[i + 1] - (int64_t) P->item_off[i]; };
+      std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
+        const int64_t lx = len_of(x), ly = len_of(y);
+        const int kx = (lx > item_len ? 0 : 2) + item_full[x], ky = (ly > item_len ? 0 : 2) + item_full[y];
+        if (kx != ky) return kx < ky;
+        return lx > ly;
+      });
       P->item_order.assign((size_t) n_items, 0);
-      for (int64_t i = 0; i < n_items; ++i)
-        P->item_order[start[(size_t) (max_len - (P->item_off[i + 1] - P->item_off[i]))]++] = (uint32_t) i;
+      P->item_desc.assign((size_t) n_items * 4, 0);
+      for (int64_t i = 0; i < n_items; ++i) {
+        P->item_order[i] = idx[i] | (item_full[idx[i]] ? 0x80000000u : 0u);
+        P->info.n_long_items += len_of(idx[i]) > item_len;
+        // one 16-byte descriptor per visiting slot: begin, end, item id, flags (bit 0 = full)
+        P->item_desc[4 * i + 0] = P->item_off[idx[i]];
+        P->item_desc[4 * i + 1] = P->item_off[idx[i] + 1];
+        P->item_desc[4 * i + 2] = idx[i];
+        P->item_desc[4 * i + 3] = item_full[idx[i]];
+      }
+    }
+    // (3) loci in descending item count: the per-locus combine starts with the deepest loci
+    {
+      P->locus_order.resize((size_t) T);
+      std::iota(P->locus_order.begin(), P->locus_order.end(), 0u);
+      std::stable_sort(P->locus_order.begin(), P->locus_order.end(), [&](uint32_t x, uint32_t y) {
+        return P->locus_item_ptr[x + 1] - P->locus_item_ptr[x] > P->locus_item_ptr[y + 1] - P->locus_item_ptr[y];
+      });
     }
 
     // ---- 7. gene -> loci CSR ------------------------------------------------------------------------------------
@@ -330,6 +384,8 @@ extern "C" int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void**
   GBRS_ARR("ent_run", p->ent_run)
   GBRS_ARR("item_off", p->item_off)
   GBRS_ARR("item_order", p->item_order)
+  GBRS_ARR("item_desc", p->item_desc)
+  GBRS_ARR("locus_order", p->locus_order)
   GBRS_ARR("locus_item_ptr", p->locus_item_ptr)
   GBRS_ARR("gene_ptr", p->gene_ptr)
   GBRS_ARR("gene_loci", p->gene_loci)

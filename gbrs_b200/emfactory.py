@@ -19,6 +19,7 @@ Differences from the reference that a caller can observe:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -32,7 +33,8 @@ ERR_LOG_CAP = 1 << 16
 
 _PACK_ARRAYS = {  # name -> numpy dtype (None = entry word, depends on entry_bytes)
     "rowptr": np.uint32, "pairs": np.uint32, "count": np.float64, "runptr": np.uint32,
-    "ent_cls": None, "ent_pair": None, "ent_run": None, "item_off": np.uint32, "item_order": np.uint32, "locus_item_ptr": np.uint32,
+    "ent_cls": None, "ent_pair": None, "ent_run": None, "item_off": np.uint32, "item_order": np.uint32, "item_desc": np.uint32, "locus_order": np.uint32,
+    "locus_item_ptr": np.uint32,
     "gene_ptr": np.uint32, "gene_loci": np.uint32, "gene_of": np.int32,
 }
 
@@ -162,12 +164,12 @@ class DevicePattern:
         torch = _torch()
         T, dv, f64 = self.T, self.device, torch.float64
         i = self.info
-        nw = max(i["n_classes"], i["n_pairs"], 8 * i["n_runs"] if self.packed.has_genes else 0, 1)
+        nw = max(i["n_classes"], i["n_pairs"], 8 * i["n_runs"] if self.packed.has_genes else 0, 1) + 8
         self.theta = torch.zeros((2, T, 8), dtype=f64, device=dv)
         self.efflen = torch.ones((T, 8), dtype=f64, device=dv)
         self.acc = torch.zeros((T, 8), dtype=f64, device=dv)
         self.iso = torch.zeros((2, T), dtype=f64, device=dv)
-        self.weights = torch.empty(nw, dtype=f64, device=dv)
+        self.weights = torch.zeros(nw, dtype=f64, device=dv)  # trailing slots stay zero (read by padding entries)
         self.subsets = torch.zeros((T, 32), dtype=f64, device=dv)
         self.wit = torch.zeros((max(i["n_items"], 1), 8), dtype=f64, device=dv)
         self.part = torch.zeros(_lib.GBRS_PART_SLOTS, dtype=f64, device=dv)
@@ -182,13 +184,13 @@ class DevicePattern:
         i = self.info
         d.T, d.H, d.n_gene_ids, d.entry_bytes = self.T, self.H, i["n_gene_ids"], i["entry_bytes"]
         d.n_classes, d.n_pairs, d.n_runs, d.n_items = i["n_classes"], i["n_pairs"], i["n_runs"], i["n_items"]
-        d.n_long_items = i["n_long_items"]
+        d.n_long_items, d.n_entries = i["n_long_items"], i["n_entries"]
         d.n_ranks, d.max_iters_cap = self.n_ranks, ERR_LOG_CAP
         for k in range(_lib.GBRS_KMAX + 2):
             d.bucket_class0[k] = i["bucket_class0"][k]
             d.bucket_pair0[k] = i["bucket_pair0"][k]
         for k in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "item_order",
-                  "locus_item_ptr"):
+                  "item_desc", "locus_order", "locus_item_ptr"):
             setattr(d, k, self.dev[k].data_ptr())
         if self.packed.has_genes:
             for k in ("gene_of", "gene_ptr", "gene_loci"):
@@ -268,7 +270,7 @@ class EMfactory:
         self.target_lengths = None
         self._device = device
         self._group = group
-        self._item_len = item_len
+        self._item_len = item_len or int(os.environ.get("GBRS_ITEM_LEN", "0"))
         self._poll_every = poll_every
         self._pattern: DevicePattern | None = None
         self._gene_of = None

@@ -76,6 +76,7 @@ typedef struct {
   int64_t n_pairs;     /* (class, locus) pair words in this shard */
   int64_t n_runs;      /* (class, gene) runs in this shard */
   int64_t n_items;     /* column-pass work items */
+  int64_t n_entries;   /* locus-major entry words incl. padding (every item starts at a multiple of 4 entries) */
   int64_t n_long_items;/* of which long (deep loci, up to 16 * item_len entries, processed by a whole warp) */
   int64_t nnz;         /* incidence entries in this shard (popcount over pair masks) */
   int64_t nnz_total;   /* incidence entries over all shards */
@@ -97,8 +98,10 @@ int gbrs_pack_get_info(gbrs_pack_t p, gbrs_pack_info* info);
  *   "rowptr"  uint32 [n_classes+1]   "pairs"   uint32 [n_pairs]  (locus | mask<<24, sorted by (gene, locus) in a class;
  *                                     class n < bucket_class0[GBRS_KMAX] with k pairs starts at bucket_pair0[k-1] + (n - bucket_class0[k-1]) * k)
  *   "count"   double [n_classes]     "runptr"  uint32 [n_classes+1]
- *   "ent_cls" / "ent_pair" / "ent_run"  entry words [n_pairs], locus-major (index | mask << (8*entry_bytes-8))
- *   "item_off" uint32 [n_items+1]    "locus_item_ptr" uint32 [T+1]   "item_order" uint32 [n_items] (longest first)
+ *   "ent_cls" / "ent_pair" / "ent_run"  entry words [n_entries], locus-major (index | mask << (8*entry_bytes-8));
+ *                                     padding words carry an empty mask and index n_classes / n_pairs / n_runs
+ *   "item_off" uint32 [n_items+1]    "locus_item_ptr" uint32 [T+1]   "item_order" uint32 [n_items]
+ *   "item_desc" uint32 [n_items][4]  "locus_order" uint32 [T]
  *   "gene_ptr" uint32 [n_gene_ids+1] "gene_loci" uint32 [T]     "gene_of" int32 [T]
  */
 int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64_t* bytes);
@@ -112,6 +115,7 @@ typedef struct {
   int32_t n_gene_ids;
   int32_t entry_bytes;
   int64_t n_classes, n_pairs, n_runs, n_items;
+  int64_t n_entries;    /* locus-major entry words incl. padding */
   int64_t n_long_items; /* the first n_long_items entries of item_order are long items (one warp each) */
   int32_t n_ranks;     /* row shards taking part (1 = no exchange step) */
   int32_t max_iters_cap; /* capacity of err_log */
@@ -126,7 +130,9 @@ typedef struct {
   const void* ent_pair;
   const void* ent_run;
   const uint32_t* item_off;
-  const uint32_t* item_order;   /* [n_items] item ids, longest item first */
+  const uint32_t* item_order;   /* [n_items] item ids in visiting order, bit 31 = full-mask item */
+  const uint32_t* item_desc;    /* [n_items][4] per visiting slot: first entry, one-past-last entry, item id, flags */
+  const uint32_t* locus_order;  /* [T] loci in descending item count */
   const uint32_t* locus_item_ptr;
   const int32_t* gene_of;
   const uint32_t* gene_ptr;
@@ -136,7 +142,8 @@ typedef struct {
   double* efflen;   /* [T][8] effective lengths (1.0 where unused / no length file) */
   double* acc;      /* [T][8] M-step numerator: local after gbrs_em_launch_local, global after the exchange */
   double* iso;      /* [2][T] isoform totals sum_h theta */
-  double* weights;  /* [max(n_classes, n_pairs, 8*n_runs)] per-class / per-pair / per-run weights */
+  double* weights;  /* [max(n_classes, n_pairs, 8*n_runs) + 8] per-class / per-pair / per-run weights; the slot(s) after
+                       the last real index are read by padding entries and must stay zero */
   double* subsets;  /* [T][32] subset sums of theta per locus: [0,16) over haplotype slots 0-3, [16,32) over slots 4-7 */
   double* wit;      /* [n_items][8] column-pass partials */
   double* part;     /* [GBRS_PART_SLOTS] block partial sums */

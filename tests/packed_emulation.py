@@ -21,7 +21,7 @@ def em_update_model4(arr, info, T, theta_T8, efflen_T8, unit=False):
     cls_of_pair = np.repeat(np.arange(info["n_classes"]), np.diff(rowptr))
     x = (bits(mask) * (1.0 if unit else theta_T8[locus])).sum(axis=1)
     s = np.bincount(cls_of_pair, weights=x, minlength=info["n_classes"])
-    w = arr["count"] / s
+    w = np.append(arr["count"] / s, 0.0)  # trailing zero slot: padding entries point at it
     idx, emask = unpack_entries(arr["ent_cls"], info["entry_bytes"])
     item_off = arr["item_off"].astype(np.int64)
     item_of_entry = np.repeat(np.arange(info["n_items"]), np.diff(item_off))

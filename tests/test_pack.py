@@ -75,25 +75,48 @@ def test_pack_preserves_pattern(small):
     idx_p, m_p = unpack_entries(a["ent_pair"], p.info["entry_bytes"])
     idx_r, m_r = unpack_entries(a["ent_run"], p.info["entry_bytes"])
     assert np.array_equal(m_c, m_p) and np.array_equal(m_c, m_r)
-    pw = a["pairs"].astype(np.int64)[idx_p]
+    assert len(m_c) == p.info["n_entries"] and np.count_nonzero(m_c) == p.info["n_pairs"]
+    real = m_c != 0  # padding words: empty mask, index one past the last real one
+    assert np.all(idx_c[~real] == p.info["n_classes"]) and np.all(idx_p[~real] == p.info["n_pairs"])
+    assert np.all(idx_r[~real] == p.info["n_runs"])
+    pairs_ext = np.append(a["pairs"].astype(np.int64), 0)
+    pw = pairs_ext[idx_p]
     assert np.array_equal(pw >> 24, m_p)
-    cls_of_pair = np.repeat(np.arange(p.info["n_classes"]), np.diff(rp))
+    cls_of_pair = np.append(np.repeat(np.arange(p.info["n_classes"]), np.diff(rp)), p.info["n_classes"])
     assert np.array_equal(cls_of_pair[idx_p], idx_c)
     # items tile the entries; every item belongs to one locus; entries of a locus are ascending in class id
     io, lip = a["item_off"].astype(np.int64), a["locus_item_ptr"].astype(np.int64)
-    assert io[0] == 0 and io[-1] == p.info["n_pairs"] and np.all(np.diff(io) > 0)
+    assert io[0] == 0 and io[-1] == p.info["n_entries"] and np.all(np.diff(io) > 0) and np.all(io % 4 == 0)
     lens = np.diff(io)
     assert p.info["n_long_items"] == np.count_nonzero(lens > 64) and lens.max() <= 16 * 64
     locus_of_entry = pw & 0xFFFFFF
     for t in range(d.T):
         lo, hi = (io[lip[t]], io[lip[t + 1]]) if lip[t + 1] > lip[t] else (0, 0)
-        assert np.all(locus_of_entry[lo:hi] == t)
-        assert np.all(np.diff(idx_c[lo:hi]) > 0)
+        rl = real[lo:hi]
+        assert np.all(locus_of_entry[lo:hi][rl] == t)
+        if np.count_nonzero(rl) > 8 * 64:  # deep locus: partial-mask entries first, then the full ones
+            full = m_c[lo:hi][rl] == 0xFF
+            assert np.all(np.diff(full.astype(int)) >= 0)
+            assert np.all(np.diff(idx_c[lo:hi][rl][~full]) > 0) and np.all(np.diff(idx_c[lo:hi][rl][full]) > 0)
+        else:
+            assert np.all(np.diff(idx_c[lo:hi][rl]) > 0)
     assert lip[-1] == p.info["n_items"]
-    order = a["item_order"].astype(np.int64)
-    assert sorted(order) == list(range(p.info["n_items"])) and np.all(np.diff(np.diff(io)[order]) <= 0)
+    order = a["item_order"].astype(np.int64) & 0x7FFFFFFF
+    isfull = a["item_order"].astype(np.int64) >> 31
+    assert sorted(order) == list(range(p.info["n_items"]))
+    for i, f in zip(order, isfull):  # full items hold only full-mask entries
+        assert not f or np.all(np.isin(m_c[io[i]:io[i + 1]], (0, 0xFF)))
+    desc = a["item_desc"].astype(np.int64).reshape(-1, 4)
+    assert np.array_equal(desc[:, 2], order) and np.array_equal(desc[:, 3], isfull)
+    assert np.array_equal(desc[:, 0], io[order]) and np.array_equal(desc[:, 1], io[order + 1])
+    lo_ = a["locus_order"].astype(np.int64)
+    assert sorted(lo_) == list(range(d.T)) and np.all(np.diff(np.diff(lip)[lo_]) <= 0)
+    lens_o = np.diff(io)[order]
+    key = np.where(lens_o > 64, 0, 2) + isfull
+    assert np.all(np.diff(key) >= 0) and np.all(np.diff(lens_o)[np.diff(key) == 0] <= 0)
     # runs: consecutive pairs of one class in the same gene
     g = gene_index(d.T, d.groups())[pw_locus(a)]
+    idx_p, idx_r = idx_p[real], idx_r[real]
     runptr = a["runptr"].astype(np.int64)
     run_of_pair = np.zeros(p.info["n_pairs"], dtype=np.int64)
     for n in range(p.info["n_classes"]):
