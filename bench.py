@@ -273,8 +273,15 @@ def run_gpu_arm(args, wl):
     else:
         dom, dom_ms, dom_bytes = "k_column_reduce (column pass)", col_ms, bytes_col
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes of that kernel from the committed ncu --set full capture (same workload and model only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("workload") == args.workload and tj.get("model") == model and world == 1:
+            traffic = tj.get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
                 "share_of_step": dom_ms / (ms / K),
                 "per_kernel_ms": {"row_pass": row_ms, "column_pass": col_ms, "locus_acc": acc_ms,
