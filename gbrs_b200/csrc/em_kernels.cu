@@ -1207,23 +1207,69 @@ extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_
     return GBRS_E_ARG;
   }
   if (poll_every < 1) poll_every = 4;
-  if (int rc = gbrs_em_run_begin(d, tol, max_iters, stream)) return rc;
+  // The loop body (poll_every updates = 4 * poll_every kernels) is captured once into a CUDA graph and replayed until
+  // the device-side stop flag is seen; the kernels read the ping-pong parity / stop flag from device memory, so one
+  // graph serves every update.  Capture needs a non-legacy stream: work submitted to the legacy default stream is
+  // moved onto a private stream (after draining the caller's).
+  static const bool use_graph = std::getenv("GBRS_NO_GRAPH") == nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaStream_t own = nullptr;
+  if (use_graph && (s == nullptr || s == cudaStreamLegacy)) {
+    GBRS_CUDA(cudaStreamSynchronize(s));
+    GBRS_CUDA(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    s = own;
+  }
+  int rc = gbrs_em_run_begin(d, tol, max_iters, s);
   int32_t ctrl[16];
   std::memset(ctrl, 0, sizeof(ctrl));
-  if (int rc = gbrs_em_read_ctrl(d, stream, ctrl, nullptr)) return rc;
-  while (!ctrl[GBRS_CTRL_DONE]) {
-    for (int i = 0; i < poll_every; ++i) {
-      if (int rc = gbrs_em_launch_local(d, model, stream)) return rc;
-      if (int rc = gbrs_em_launch_update(d, stream)) return rc;
+  if (!rc) rc = gbrs_em_read_ctrl(d, s, ctrl, nullptr);
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (!rc && !ctrl[GBRS_CTRL_DONE] && use_graph) {
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      for (int i = 0; i < poll_every && !rc; ++i) {
+        rc = gbrs_em_launch_local(d, model, s);
+        if (!rc) rc = gbrs_em_launch_update(d, s);
+      }
+      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc || ce != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        graph = nullptr;
+        exec = nullptr;
+        cudaGetLastError();
+        if (!rc) rc = GBRS_OK;  // fall back to plain launches below
+      }
+    } else {
+      cudaGetLastError();
     }
-    if (int rc = gbrs_em_read_ctrl(d, stream, ctrl, nullptr)) return rc;
   }
+  while (!rc && !ctrl[GBRS_CTRL_DONE]) {
+    if (exec) {
+      if (cudaGraphLaunch(exec, s) != cudaSuccess) { gbrs_set_error("cudaGraphLaunch failed"); rc = GBRS_E_CUDA; break; }
+    } else {
+      for (int i = 0; i < poll_every && !rc; ++i) {
+        rc = gbrs_em_launch_local(d, model, s);
+        if (!rc) rc = gbrs_em_launch_update(d, s);
+      }
+    }
+    if (!rc) rc = gbrs_em_read_ctrl(d, s, ctrl, nullptr);
+  }
+  if (!rc && errs_host && ctrl[GBRS_CTRL_ITERS] > 0) {
+    if (cudaMemcpyAsync(errs_host, d->err_log, sizeof(double) * (size_t) ctrl[GBRS_CTRL_ITERS], cudaMemcpyDeviceToHost, s) !=
+            cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      gbrs_set_error("copying the error log failed");
+      rc = GBRS_E_CUDA;
+    }
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
+  if (own) {
+    cudaStreamSynchronize(own);
+    cudaStreamDestroy(own);
+  }
+  if (rc) return rc;
   if (iters_out) *iters_out = ctrl[GBRS_CTRL_ITERS];
-  if (errs_host && ctrl[GBRS_CTRL_ITERS] > 0) {
-    GBRS_CUDA(cudaMemcpyAsync(errs_host, d->err_log, sizeof(double) * (size_t) ctrl[GBRS_CTRL_ITERS], cudaMemcpyDeviceToHost,
-                              static_cast<cudaStream_t>(stream)));
-    GBRS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-  }
   if (ctrl[GBRS_CTRL_ERROR]) {
     gbrs_set_error("non-finite value in the EM update (zero normaliser or overflow)");
     return GBRS_E_NUMERIC;

@@ -359,6 +359,44 @@ class EMfactory:
 
             dist.all_reduce(pat.acc, op=dist.ReduceOp.SUM, group=self._group)
 
+    def _run_sharded(self, pat, model, tol, max_iters):
+        """Row-sharded loop: `poll_every` updates (local passes -> all-reduce of the numerator -> update + stop test)
+        are captured once into a CUDA graph and replayed until the device-side stop flag is read back as set.  Every rank
+        sees the same all-reduced numerator, hence the same error and the same decision, so no second collective is
+        needed for the stop test."""
+        torch = _torch()
+        import torch.distributed as dist
+
+        def body():
+            for _ in range(self._poll_every):
+                _lib.check(pat.lib.gbrs_em_launch_local(C.byref(pat.desc), model, pat.stream()))
+                self._exchange(pat)
+                _lib.check(pat.lib.gbrs_em_launch_update(C.byref(pat.desc), pat.stream()))
+
+        use_graph = os.environ.get("GBRS_NO_GRAPH") is None and dist.get_backend(self._group) == "nccl"
+        side = torch.cuda.Stream(device=pat.device)
+        side.wait_stream(torch.cuda.current_stream(pat.device))
+        with torch.cuda.stream(side):
+            _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), tol, max_iters, pat.stream()))
+            ctrl, _ = pat.read_ctrl()
+            graph = None
+            if use_graph and not ctrl[_lib.CTRL_DONE]:
+                scratch = torch.zeros(8, dtype=torch.float64, device=pat.device)
+                dist.all_reduce(scratch, group=self._group)  # communicator set-up must not happen during capture
+                side.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    body()
+            while not ctrl[_lib.CTRL_DONE]:
+                if graph is not None:
+                    graph.replay()
+                else:
+                    body()
+                ctrl, _ = pat.read_ctrl()
+        torch.cuda.current_stream(pat.device).wait_stream(side)
+        side.synchronize()
+        return ctrl
+
     def _sync_theta_to_device(self):
         if self._theta_dirty:
             self._ensure_pattern().set_theta_HT(self._theta_host)
@@ -443,14 +481,7 @@ class EMfactory:
             n = int(iters.value)
             self.err_history = errs[:n].copy()
         else:
-            _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), float(tol), int(max_iters), pat.stream()))
-            ctrl, _ = pat.read_ctrl()
-            while not ctrl[_lib.CTRL_DONE]:
-                for _ in range(self._poll_every):
-                    _lib.check(pat.lib.gbrs_em_launch_local(C.byref(pat.desc), int(model), pat.stream()))
-                    self._exchange(pat)
-                    _lib.check(pat.lib.gbrs_em_launch_update(C.byref(pat.desc), pat.stream()))
-                ctrl, _ = pat.read_ctrl()
+            ctrl = self._run_sharded(pat, int(model), float(tol), int(max_iters))
             if ctrl[_lib.CTRL_ERROR]:
                 raise FloatingPointError("non-finite value in the EM update (zero normaliser or overflow)")
             n = int(ctrl[_lib.CTRL_ITERS])
