@@ -364,9 +364,14 @@ def run_gpu_arm(args, wl):
                 "gpu_launches": launches_per_step * K, "clocks": clocks,
                 "pack_seconds": pat.packed.pack_seconds}
         print(json.dumps(line), flush=True)
+    # teardown: drop the captured graph (it holds NCCL work) before the communicator, and never hang on exit
+    graph = None
+    torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
