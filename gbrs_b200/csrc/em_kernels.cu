@@ -193,6 +193,91 @@ __device__ __forceinline__ const double* theta_cur(const gbrs_em_dev& d) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Fused cross-rank exchange over NVLink peer memory (row-sharded runs, up to 8 ranks of one NVSwitch domain).
+// Every rank owns one symmetric buffer, peer-mapped into all ranks (`xchg_peer[r]`):
+//     [0, 64T)   acc_local   this rank's local numerator (written by k_locus_acc)
+//     [64T,128T) acc_total   the numerator summed over ranks (written by the owners of each slice, k_xchg_reduce)
+//     then       ready[8], done[8]   u32 epoch flags, written remotely by the rank they are indexed by
+// Two-shot all-reduce inside our own kernels: k_locus_acc publishes acc_local and raises ready[me] = e on every peer;
+// k_xchg_reduce waits for all ready flags, sums ITS slice of the loci over the ranks in rank order with peer loads,
+// stores the total into every rank's acc_total with peer stores and raises done[me] = e everywhere; k_locus_update
+// waits for all done flags and carries on locally.  Each element is summed by exactly one rank, so all ranks see
+// bit-identical totals and take identical stop decisions.  Waits are bounded: a missing peer raises the error flag
+// instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double2 ld_relaxed_sys_f64x2(const double* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64x2(double* p, double2 v) {
+  asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double* xchg_acc_local(const gbrs_em_dev& d, int r) { return static_cast<double*>(d.xchg_peer[r]); }
+__device__ __forceinline__ double* xchg_acc_total(const gbrs_em_dev& d, int r) {
+  return static_cast<double*>(d.xchg_peer[r]) + (size_t) d.T * GBRS_HPAD;
+}
+__device__ __forceinline__ uint32_t* xchg_flags(const gbrs_em_dev& d, int r, int which /* 0 ready, 1 done */) {
+  return reinterpret_cast<uint32_t*>(static_cast<double*>(d.xchg_peer[r]) + 2 * (size_t) d.T * GBRS_HPAD) + which * 8;
+}
+// thread 0 of the block waits until every rank's flag has reached epoch e; the block then proceeds together
+__device__ __forceinline__ void xchg_wait_all(const gbrs_em_dev& d, int which, uint32_t e) {
+  if (threadIdx.x == 0) {
+    const uint32_t* f = xchg_flags(d, d.xchg_rank, which);
+    for (int r = 0; r < d.n_ranks; ++r) {
+      long spins = 0;
+      while ((int32_t) (ld_acquire_sys(f + r) - e) < 0) {
+        if (++spins > (1L << 24)) { d.ctrl[GBRS_CTRL_ERROR] = 3; break; }
+        __nanosleep(100);
+      }
+    }
+  }
+  __syncthreads();
+}
+// called by every block at the end of a kernel: when the whole grid is through, raise flag[me] = e on every rank
+__device__ __forceinline__ void xchg_signal_all(const gbrs_em_dev& d, int which, uint32_t e, int ticket_slot) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const int ticket = atomicAdd(d.ctrl + ticket_slot, 1);
+    if (ticket == (int) gridDim.x - 1) {
+      d.ctrl[ticket_slot] = 0;
+      if (which == 1) d.ctrl[GBRS_CTRL_XEPOCH] = (int32_t) e;  // the exchange e is complete on this rank's side
+      __threadfence_system();
+      for (int r = 0; r < d.n_ranks; ++r) st_release_sys(xchg_flags(d, r, which) + d.xchg_rank, e);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_xchg_reduce(const __grid_constant__ gbrs_em_dev d) {
+  const uint32_t e = (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH] + 1u;
+  xchg_wait_all(d, 0, e);
+  // this rank's slice of the T*8 numerator, in units of double2
+  const int64_t n2 = (int64_t) d.T * GBRS_HPAD / 2;
+  const int64_t per = (n2 + d.n_ranks - 1) / d.n_ranks;
+  const int64_t lo = per * d.xchg_rank, hi = lo + per < n2 ? lo + per : n2;
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+    double2 s = make_double2(0.0, 0.0);
+    for (int r = 0; r < d.n_ranks; ++r) {  // rank order: every element is summed once, in one fixed order
+      const double2 v = ld_relaxed_sys_f64x2(xchg_acc_local(d, r) + 2 * i);
+      s.x += v.x;
+      s.y += v.y;
+    }
+    for (int r = 0; r < d.n_ranks; ++r) st_relaxed_sys_f64x2(xchg_acc_total(d, r) + 2 * i, s);
+  }
+  xchg_signal_all(d, 1, e, GBRS_CTRL_TICKET + 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // row pass, model 4:  w[n] = count[n] / sum_{(t,h) in n} theta[t][h]
 // reference: multiply(theta, READ) + normalize_reads(READ)   EMfactory.py:204-208, AlignmentPropertyMatrix.py:335-342
 // UNIT = true is the prepare() variant with theta == 1 on the pattern (EMfactory.py:95): w[n] = count[n] / nnz[n].
@@ -622,6 +707,21 @@ __global__ void __launch_bounds__(kThreads, 4) k_column_reduce(const __grid_cons
   }
 }
 
+// Subset-sum table rows of one locus from the 8 lanes holding its theta' (same sums, same order as k_subset_tables):
+// lane h fills slots [4h, 4h + 4) = half (h >> 2), masks 4 * (h & 3) + q, q = 0..3 (bits 0, 1 enumerate; bits 2, 3
+// are fixed by h & 3).  All 32 lanes must call (warp shuffles).
+__device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t t, int h, double v, bool valid) {
+  const int base = (threadIdx.x & 31) & ~7, half4 = base + (h & 4);
+  const double v0 = __shfl_sync(0xFFFFFFFFu, v, half4), v1 = __shfl_sync(0xFFFFFFFFu, v, half4 + 1);
+  const double v2 = __shfl_sync(0xFFFFFFFFu, v, half4 + 2), v3 = __shfl_sync(0xFFFFFFFFu, v, half4 + 3);
+  if (valid) {
+    const double t2 = (h & 1) ? v2 : 0.0, t3 = (h & 2) ? v3 : 0.0;
+    double* row = d.subsets + (size_t) t * 32 + 4 * h;
+    *reinterpret_cast<double2*>(row) = make_double2(((0.0 + 0.0) + t2) + t3, ((v0 + 0.0) + t2) + t3);
+    *reinterpret_cast<double2*>(row + 2) = make_double2(((0.0 + v1) + t2) + t3, ((v0 + v1) + t2) + t3);
+  }
+}
+
 // acc[t][h] = theta[t][h] * sum_{items of t} wit[item][h]   ( = sum_n count[n] * P[n,t,h] ).  UNIT: theta == 1 (prepare).
 // One thread per (locus, haplotype slot); a locus has at most 128 items (packer), walked four loads at a time.
 // FUSE (single rank only): also theta' = acc / efflen, iso' and the block partial of sum(iso'), i.e. k_locus_update.
@@ -662,7 +762,8 @@ __global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, boo
     double a = 0.0;
     if (valid) {
       a = UNIT ? ((h < d.H) ? W : 0.0) : th[o] * W;
-      d.acc[o] = a;
+      if (!FUSE && d.xchg_enabled) xchg_acc_local(d, d.xchg_rank)[o] = a;
+      else d.acc[o] = a;
     }
     if (FUSE) {
       double v = 0.0;
@@ -675,39 +776,30 @@ __global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, boo
         iso[t] = s;
         mine += s;
       }
-      // subset-sum table of theta' for the next row pass (same sums, same order as k_subset_tables): lane h of the
-      // locus' 8 lanes fills slots [4h, 4h + 4) = half (h >> 2), masks 4 * (h & 3) .. + 3
-      const int base = (threadIdx.x & 31) & ~7, half4 = base + (h & 4);
-      const double v0 = __shfl_sync(0xFFFFFFFFu, v, half4), v1 = __shfl_sync(0xFFFFFFFFu, v, half4 + 1);
-      const double v2 = __shfl_sync(0xFFFFFFFFu, v, half4 + 2), v3 = __shfl_sync(0xFFFFFFFFu, v, half4 + 3);
-      if (valid) {
-        // masks 4 * (h & 3) + q, q = 0..3: bits 0 and 1 enumerate, bits 2 and 3 are fixed by (h & 3)
-        const double t2 = (h & 1) ? v2 : 0.0, t3 = (h & 2) ? v3 : 0.0;
-        double4 o;
-        o.x = ((0.0 + 0.0) + t2) + t3;
-        o.y = ((v0 + 0.0) + t2) + t3;
-        o.z = ((0.0 + v1) + t2) + t3;
-        o.w = ((v0 + v1) + t2) + t3;
-        double* row = d.subsets + (size_t) t * 32 + 4 * h;
-        *reinterpret_cast<double2*>(row) = make_double2(o.x, o.y);
-        *reinterpret_cast<double2*>(row + 2) = make_double2(o.z, o.w);
-      }
+      write_subset_rows(d, t, h, v, valid);
     }
   }
   if (FUSE) {
     const double bs = block_sum(mine, red);
     if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
+  } else if (d.xchg_enabled) {
+    xchg_signal_all(d, 0, (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH] + 1u, GBRS_CTRL_TICKET + 1);
   }
 }
 
 // theta' = acc / efflen (EMfactory.py:228-232), iso'[t] = sum_h theta'[t][h], block partial sums of iso'.
 // FROM_ACC = false: only (re)compute iso / partials of the current theta (after prepare / set_theta / pseudocount).
 template <bool FROM_ACC>
-__global__ void __launch_bounds__(kThreads) k_locus_update(const gbrs_em_dev d) {
+__global__ void __launch_bounds__(kThreads) k_locus_update(const __grid_constant__ gbrs_em_dev d) {
   __shared__ double red[32];
+  const bool xchg = FROM_ACC && d.xchg_enabled;
+  // fused exchange: k_xchg_reduce (same stream, just before) has set XEPOCH to the epoch of this exchange; the totals are
+  // complete once every rank has raised its done flag for it
+  if (xchg) xchg_wait_all(d, 1, (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH]);
   if (FROM_ACC && d.ctrl[GBRS_CTRL_DONE]) return;
   const int par = d.ctrl[GBRS_CTRL_PARITY];
-  const double* __restrict__ src = FROM_ACC ? d.acc : d.theta + (size_t) par * d.T * GBRS_HPAD;
+  const double* __restrict__ src =
+      FROM_ACC ? (xchg ? xchg_acc_total(d, d.xchg_rank) : d.acc) : d.theta + (size_t) par * d.T * GBRS_HPAD;
   double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
   double* __restrict__ iso = d.iso + (size_t) (FROM_ACC ? (par ^ 1) : par) * d.T;
   const int lane8 = threadIdx.x & 7;
@@ -718,18 +810,21 @@ __global__ void __launch_bounds__(kThreads) k_locus_update(const gbrs_em_dev d) 
   double mine = 0.0;
   for (int64_t r = 0; r < rounds; ++r, i += stride) {
     double v = 0.0;
-    if (i < total) {
+    const bool valid = i < total;
+    if (valid) {
       v = src[i];
       if (FROM_ACC) {
+        if (xchg) d.acc[i] = v;  // keep the summed numerator where the reports read it
         v = fast_div(v, d.efflen[i]);
         dst[i] = v;
       }
     }
     const double s = group8_sum(v);
-    if (i < total && lane8 == 0) {
+    if (valid && lane8 == 0) {
       iso[i >> 3] = s;
       mine += s;
     }
+    if (FROM_ACC) write_subset_rows(d, i >> 3, lane8, v, valid);  // theta' tables for the next row pass
   }
   const double bs = block_sum(mine, red);
   if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
@@ -926,14 +1021,27 @@ inline int converge_grid(const gbrs_em_dev* d) {
   return g < 1 ? 1 : (g > 128 ? 128 : g);
 }
 
+// Fused NVLink exchange (descriptor flag); otherwise the caller all-reduces `acc` between the two halves of an update.
+int launch_exchange(const gbrs_em_dev* d, cudaStream_t s) {
+  if (!d->xchg_enabled) return GBRS_OK;
+  if (d->n_ranks < 2 || d->n_ranks > 8 || d->xchg_rank < 0 || d->xchg_rank >= d->n_ranks) {
+    gbrs_set_error("fused exchange: 2..8 ranks and a valid rank index are required");
+    return GBRS_E_ARG;
+  }
+  for (int r = 0; r < d->n_ranks; ++r)
+    if (!d->xchg_peer[r]) { gbrs_set_error("fused exchange: null peer buffer"); return GBRS_E_ARG; }
+  const int64_t slice = ((int64_t) d->T * GBRS_HPAD / 2 + d->n_ranks - 1) / d->n_ranks;
+  k_xchg_reduce<<<resident_grid(k_xchg_reduce, slice), kThreads, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_xchg_reduce");
+  return GBRS_OK;
+}
+
 template <bool UNIT>
 int launch_row_m4(const gbrs_em_dev* d, cudaStream_t s) {
   RowPlan plan;
   int64_t units = 0;
-  if (!UNIT && d->n_ranks > 1) {  // single rank: the fused locus kernel of the previous update already wrote them
-    k_subset_tables<<<resident_grid(k_subset_tables, (int64_t) d->T * 32), kThreads, 0, s>>>(*d);
-    GBRS_LAUNCH_CHECK("k_subset_tables");
-  }
+  // the subset-sum tables of the current theta were written by the locus kernel of the previous update (or by
+  // prepare / set_theta)
   for (int i = 0; i < GBRS_KMAX; ++i) {
     const int k = GBRS_KMAX - i, cpu = 32 * unr_of(k);
     units += (d->bucket_class0[k] - d->bucket_class0[k - 1] + cpu - 1) / cpu;
@@ -989,6 +1097,7 @@ extern "C" int gbrs_em_prepare_finish(const gbrs_em_dev* d, double pseudocount, 
   if (int rc = check_dev(d, "gbrs_em_prepare_finish")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int lg = locus_grid(d);
+  if (int rc = launch_exchange(d, s)) return rc;
   // theta[1] = acc / efflen ; then make it the current estimate
   k_locus_update<true><<<lg, kThreads, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_locus_update");
@@ -1191,6 +1300,7 @@ extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
   int nparts = acc_grid(d);  // single rank: k_locus_acc already produced theta', iso' and the partial sums
   if (d->n_ranks > 1) {
     nparts = locus_grid(d);
+    if (int rc = launch_exchange(d, s)) return rc;
     k_locus_update<true><<<nparts, kThreads, 0, s>>>(*d);
     GBRS_LAUNCH_CHECK("k_locus_update");
   }

@@ -278,6 +278,7 @@ class EMfactory:
         self.num_iters = 0
         self.err_history = np.zeros(0)
         self.rank, self.world = 0, 1
+        self.fused_exchange = False
         if shard is None:
             shard = group is not None
         self._presharded = shard == "local"
@@ -350,14 +351,54 @@ class EMfactory:
                 self._pattern = DevicePattern(p, gene_of=self._gene_of, device=self._device, shard_rank=self.rank,
                                               shard_count=self.world, item_len=self._item_len)
             self._pattern.set_lengths(self.target_lengths)
+            if self.world > 1:
+                self.fused_exchange = self._setup_fused_exchange(self._pattern)
         return self._pattern
 
     def _exchange(self, pat):
-        """The one exchange step of a row-sharded run: sum the T x H numerator over ranks."""
-        if self.world > 1:
+        """The one exchange step of a row-sharded run: sum the T x H numerator over ranks.  With the
+        fused NVLink exchange enabled the kernels do it themselves (k_locus_acc -> k_xchg_reduce -> k_locus_update over
+        peer memory) and this is a no-op; otherwise NCCL all-reduces `acc` in place."""
+        if self.world > 1 and not pat.desc.xchg_enabled:
             import torch.distributed as dist
 
             dist.all_reduce(pat.acc, op=dist.ReduceOp.SUM, group=self._group)
+
+    def _setup_fused_exchange(self, pat):
+        """Give the kernels every rank's exchange buffer as peer memory (torch symmetric memory does the mapping:
+        PyTorch as plumbing).  Falls back to the NCCL all-reduce if any rank cannot set it up."""
+        torch = _torch()
+        import torch.distributed as dist
+
+        if self.world < 2 or self.world > 8 or os.environ.get("GBRS_XCHG", "fused") != "fused":
+            return False
+        if dist.get_backend(self._group) != "nccl":
+            return False
+        ok, buf, hdl = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            n_doubles = 2 * 8 * pat.T + 16
+            buf = symm_mem.empty(n_doubles, dtype=torch.float64, device=pat.device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, group=self._group if self._group is not None else dist.group.WORLD)
+            ptrs = list(hdl.buffer_ptrs)
+            if len(ptrs) != self.world or any(int(p) == 0 for p in ptrs):
+                ok = 0
+        except Exception as e:  # noqa: BLE001 - any failure means "use NCCL"
+            logger.info(f"fused NVLink exchange unavailable ({e}); using the NCCL all-reduce")
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=pat.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._group)  # also orders the zero-fill before first use
+        torch.cuda.synchronize(pat.device)
+        if int(flag.item()) != 1:
+            return False
+        pat._xchg = (buf, hdl)
+        pat.desc.xchg_enabled = 1
+        pat.desc.xchg_rank = self.rank
+        for r in range(self.world):
+            pat.desc.xchg_peer[r] = int(ptrs[r])
+        return True
 
     def _run_sharded(self, pat, model, tol, max_iters):
         """Row-sharded loop: `poll_every` updates (local passes -> all-reduce of the numerator -> update + stop test)
@@ -482,6 +523,8 @@ class EMfactory:
             self.err_history = errs[:n].copy()
         else:
             ctrl = self._run_sharded(pat, int(model), float(tol), int(max_iters))
+            if ctrl[_lib.CTRL_ERROR] == 3:
+                raise _lib.GbrsError("fused NVLink exchange timed out waiting for a peer rank")
             if ctrl[_lib.CTRL_ERROR]:
                 raise FloatingPointError("non-finite value in the EM update (zero normaliser or overflow)")
             n = int(ctrl[_lib.CTRL_ITERS])

@@ -121,6 +121,12 @@ typedef struct {
   int32_t max_iters_cap; /* capacity of err_log */
   int64_t bucket_class0[GBRS_KMAX + 2]; /* see gbrs_pack_info */
   int64_t bucket_pair0[GBRS_KMAX + 2];
+  /* Fused cross-rank exchange over NVLink peer memory (optional, 2..8 ranks).  xchg_peer[r] is rank r's symmetric
+   * exchange buffer as mapped into THIS process ( (2 * 64 * T + 128) bytes, zeroed once before first use ); with
+   * xchg_enabled == 0 the caller sums `acc` over ranks between gbrs_em_launch_local and gbrs_em_launch_update. */
+  int32_t xchg_enabled;
+  int32_t xchg_rank;
+  void* xchg_peer[8];
   /* packed incidence (read-only) */
   const uint32_t* rowptr;
   const uint32_t* pairs;
@@ -156,7 +162,7 @@ typedef struct {
 
 #define GBRS_PART_SLOTS 4096 /* [0, 2048): block partial sums of the isoform totals; [2048, 4096): of the error */
 enum { GBRS_CTRL_ITERS = 0, GBRS_CTRL_DONE = 1, GBRS_CTRL_ERROR = 2, GBRS_CTRL_PARITY = 3, GBRS_CTRL_MAX_ITERS = 4,
-       GBRS_CTRL_PREPARED = 5, GBRS_CTRL_TICKET = 8 };
+       GBRS_CTRL_PREPARED = 5, GBRS_CTRL_TICKET = 8 /* 8, 9, 10: block tickets */, GBRS_CTRL_XEPOCH = 12 };
 enum { GBRS_SCAL_ERR = 0, GBRS_SCAL_SUM_PREV = 1, GBRS_SCAL_TARGET = 2, GBRS_SCAL_SUM_CUR = 3 };
 
 /* theta0 from the incidence alone.  EMfactory.prepare numeric part (EMfactory.py:95-111) / EMfactory.reset (:113-138).

@@ -29,11 +29,14 @@ for name in ("em_small_m4", "em_small_m2", "em_small_m1_biggenes", "em_small_m3_
     if g["masked"]:
         apm.multiply(g["gtmask"], axis=2); apm.eliminate_zeros()
     em = EMfactory(apm, shard=True, poll_every=3)
+    want_fused = os.environ.get("GBRS_XCHG", "fused") == "fused"
     em.target_lengths = synth.effective_lengths(d)
     em.prepare(pseudocount=g["pseudocount"])
     assert hp.relerr(em.get_allelic_expression(), g["theta0"]) < 1e-9
     em.run(model=g["model"], tol=g["tol"], max_iters=g["max_iters"], verbose=False)
     assert em.num_iters == g["iters"], (name, em.num_iters, g["iters"])
+    if want_fused and rank == 0 and name == "em_small_m4":
+        print("fused exchange in use:", em.fused_exchange)
     assert hp.relerr(em.allelic_expression, g["theta"]) < 1e-9
     assert hp.relerr(em.expected_read_counts(), g["counts"]) < 1e-9
     np.testing.assert_allclose(em.err_history, g["errs"], rtol=1e-7, atol=1e-7)
@@ -47,16 +50,19 @@ print("rank", rank, "ok")
 '''
 
 
-def test_two_gpu_sharded_run_matches_reference(tmp_path):
+@pytest.mark.parametrize("xchg", ["fused", "nccl"])
+def test_two_gpu_sharded_run_matches_reference(tmp_path, xchg):
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, GBRS_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, GBRS_ROOT=ROOT, MASTER_ADDR="127.0.0.1", GBRS_XCHG=xchg)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", str(script)]
-    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
+    if xchg == "fused":
+        print(res.stdout[-400:])
