@@ -246,7 +246,10 @@ __device__ __forceinline__ void xchg_wait_all(const gbrs_em_dev& d, int which, u
 __device__ __forceinline__ void xchg_signal_all(const gbrs_em_dev& d, int which, uint32_t e, int ticket_slot) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    // every block orders its own writes before its ticket at gpu scope; the last block, having observed all tickets,
+    // issues the one system-scope fence before the flags (release cumulativity) -- a system fence per block costs
+    // ~15 us over the ~900 blocks of the locus kernel
+    __threadfence();
     const int ticket = atomicAdd(d.ctrl + ticket_slot, 1);
     if (ticket == (int) gridDim.x - 1) {
       d.ctrl[ticket_slot] = 0;
