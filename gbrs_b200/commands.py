@@ -8,8 +8,12 @@ from typing import Annotated
 
 import typer
 
+import importlib
+
 from . import utils
-from . import quantify as quantify_mod
+
+# the package re-exports the *function* `quantify`, which shadows the sub-module of the same name on `from . import`
+quantify_mod = importlib.import_module(".quantify", __package__)
 
 app = typer.Typer(help="GBRS (B200-native multiway EM quantifier)", add_completion=False)
 
@@ -47,6 +51,39 @@ def quantify(
             outbase=outbase, multiread_model=multiread_model, pseudocount=pseudocount, max_iters=max_iters,
             tolerance=tolerance, report_alignment_counts=report_alignment_counts, report_posterior=report_posterior)
     except Exception as e:  # reference policy: log and return
+        if logger.level == logging.DEBUG:
+            logger.exception(e)
+        else:
+            logger.error(e)
+
+
+@app.command(help="run EMASE (the same quantifier without genotype restriction; reference `emase run`)")
+def run(
+    alignment_file: Annotated[Path, typer.Option("-i", "--alignment-file", exists=True, dir_okay=False, resolve_path=True, help="EMASE alignment incidence file (hdf5 or npz twin)")],
+    group_file: Annotated[Path, typer.Option("-g", "--group-file", exists=True, dir_okay=False, resolve_path=True, help="tab delimited file of gene to transcript mapping")] = None,
+    length_file: Annotated[Path, typer.Option("-L", "--length-file", exists=True, dir_okay=False, resolve_path=True, help="tab delimited file of locus(transcript) and length")] = None,
+    outbase: Annotated[str, typer.Option("-o", "--outbase", help="basename of all the generated output files")] = "emase",
+    multiread_model: Annotated[int, typer.Option("-M", "--multiread-model", help="emase model (default: 4)")] = 4,
+    pseudocount: Annotated[float, typer.Option("-p", "--pseudocount", help="prior read count (default: 0.0)")] = 0.0,
+    read_length: Annotated[int, typer.Option("-l", "--read-length", help="specify read length")] = 100,
+    max_iters: Annotated[int, typer.Option("-m", "--max-iters", help="maximum iterations for EM iteration")] = 999,
+    tolerance: Annotated[float, typer.Option("-t", "--tolerance", help="tolerance for EM termination (default: 0.0001 in TPM)")] = 0.0001,
+    report_alignment_counts: Annotated[bool, typer.Option("-c", "--report-alignment-counts", help="whether to report alignment counts")] = False,
+    report_posterior: Annotated[bool, typer.Option("-w", "--report-posterior", help="whether to report posterior probabilities")] = False,
+    verbose: Annotated[int, typer.Option("-v", "--verbose", count=True, help="specify multiple times for more verbose output")] = 0,
+) -> None:
+    """Flag surface of the reference's `emase run` (/root/reference/src/gbrs/emase/commands.py:315-356)."""
+    logger = utils.configure_logging("gbrs", verbose)
+    logger.debug("run")
+    try:
+        if multiread_model not in (1, 2, 3, 4):
+            raise typer.Abort("-M, --multiread-model must be one of 1, 2, 3, or 4")
+        quantify_mod.run(
+            alignment_file=str(alignment_file), group_file=str(group_file) if group_file else None,
+            length_file=str(length_file) if length_file else None, outbase=outbase, multiread_model=multiread_model,
+            read_length=read_length, pseudocount=pseudocount, max_iters=max_iters, tolerance=tolerance,
+            report_alignment_counts=report_alignment_counts, report_posterior=report_posterior)
+    except Exception as e:
         if logger.level == logging.DEBUG:
             logger.exception(e)
         else:

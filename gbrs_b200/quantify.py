@@ -36,6 +36,56 @@ def load_genotype_mask(aln_mat: AlignmentPropertyMatrix, genotype_file: str):
     return gtmask, gtcall_g, gtcall_t
 
 
+def _write_reports(em_factory, outbase, alignment_file, group_file, report_group_counts, report_alignment_counts,
+                   report_posterior, notes_t=None, notes_g=None):
+    """The output section shared by `quantify` (gbrs/emase_utils.py:288-331) and `run` (emase/emase_utils.py:650-695)."""
+    logger.info(f"Generating isoform TPMs: {outbase}.isoforms.tpm")
+    em_factory.report_depths(filename=f"{outbase}.isoforms.tpm", tpm=True, notes=notes_t)
+    logger.info(f"Generating isoform Read Counts: {outbase}.isoforms.expected_read_counts")
+    em_factory.report_read_counts(filename=f"{outbase}.isoforms.expected_read_counts", notes=notes_t)
+    if report_posterior:
+        logger.info(f"Generating Posterior Probabilities: {outbase}.posterior.h5")
+        em_factory.export_posterior_probability(filename=f"{outbase}.posterior.h5")
+    if report_group_counts:
+        logger.info(f"Generating gene TPMs: {outbase}.genes.tpm")
+        em_factory.report_depths(filename=f"{outbase}.genes.tpm", tpm=True, grp_wise=True, notes=notes_g)
+        logger.info(f"Generating gene Read Counts: {outbase}.genes.expected_read_counts")
+        em_factory.report_read_counts(filename=f"{outbase}.genes.expected_read_counts", grp_wise=True, notes=notes_g)
+    if report_alignment_counts:
+        # the reference reloads the file, i.e. counts are taken on the *unmasked* matrix (gbrs/emase_utils.py:319)
+        alnmat = AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
+        logger.info(f"Generating isoform Alignment Counts: {outbase}.isoforms.alignment_counts")
+        alnmat.report_alignment_counts(filename=f"{outbase}.isoforms.alignment_counts")
+        if report_group_counts:
+            logger.info(f"Generating gene Alignment Counts: {outbase}.genes.alignment_counts")
+            alnmat.report_alignment_counts(filename=f"{outbase}.genes.alignment_counts", gene_level=True)
+
+
+def run(alignment_file: str, group_file: str = None, length_file: str = None, outbase: str = "emase",
+        multiread_model: int = 4, read_length: int = 100, pseudocount: float = 0.0, max_iters: int = 999,
+        tolerance: float = 0.0001, report_alignment_counts: bool = False, report_posterior: bool = False,
+        device=None, group=None) -> None:
+    """`emase run` workflow (reference `gbrs.emase.emase_utils.run`, emase/emase_utils.py:594-696): the same EM without
+    the genotype restriction, with an explicit read length and no default group / length files."""
+    report_group_counts = group_file is not None
+    logger.info(f"Alignment File: {alignment_file}")
+    logger.info(f"Group File: {group_file}")
+    logger.info(f"Read Length File: {length_file}")
+    logger.info(f"Read Length: {read_length}")
+    logger.info(f"Outbase: {outbase}")
+    logger.info(f"Multiread Model: {multiread_model}")
+    logger.info(f"Loading EMASE file: {alignment_file}")
+    aln_mat = AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
+    logger.info("Running EMASE")
+    em_factory = EMfactory(aln_mat, device=device, group=group)
+    em_factory.prepare(pseudocount=pseudocount, lenfile=length_file, read_length=read_length)
+    em_factory.run(model=multiread_model, tol=tolerance, max_iters=max_iters, verbose=True)
+    if em_factory.rank == 0:
+        _write_reports(em_factory, outbase, alignment_file, group_file, report_group_counts, report_alignment_counts,
+                       report_posterior)
+    logger.debug("Done")
+
+
 def quantify(alignment_file: str, group_file: str = None, length_file: str = None, genotype_file: str = None,
              outbase: str = "gbrs.quantified", multiread_model: int = 4, pseudocount: float = 0.0,
              max_iters: int = 999, tolerance: float = 0.0001, report_alignment_counts: bool = False,
@@ -83,27 +133,7 @@ def quantify(alignment_file: str, group_file: str = None, length_file: str = Non
     em_factory.prepare(pseudocount=pseudocount, lenfile=length_file)
     em_factory.run(model=multiread_model, tol=tolerance, max_iters=max_iters, verbose=True)
 
-    rank0 = em_factory.rank == 0
-    if rank0:
-        logger.info(f"Generating isoform TPMs: {outbase}.isoforms.tpm")
-        em_factory.report_depths(filename=f"{outbase}.isoforms.tpm", tpm=True, notes=gtcall_t)
-        logger.info(f"Generating isoform Read Counts: {outbase}.isoforms.expected_read_counts")
-        em_factory.report_read_counts(filename=f"{outbase}.isoforms.expected_read_counts", notes=gtcall_t)
-        if report_posterior:
-            logger.info(f"Generating Posterior Probabilities: {outbase}.posterior.h5")
-            em_factory.export_posterior_probability(filename=f"{outbase}.posterior.h5")
-        if report_group_counts:
-            logger.info(f"Generating gene TPMs: {outbase}.genes.tpm")
-            em_factory.report_depths(filename=f"{outbase}.genes.tpm", tpm=True, grp_wise=True, notes=gtcall_g)
-            logger.info(f"Generating gene Read Counts: {outbase}.genes.expected_read_counts")
-            em_factory.report_read_counts(filename=f"{outbase}.genes.expected_read_counts", grp_wise=True,
-                                          notes=gtcall_g)
-        if report_alignment_counts:
-            # the reference reloads the file, i.e. counts are taken on the *unmasked* matrix (:319)
-            alnmat = AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
-            logger.info(f"Generating isoform Alignment Counts: {outbase}.isoforms.alignment_counts")
-            alnmat.report_alignment_counts(filename=f"{outbase}.isoforms.alignment_counts")
-            if report_group_counts:
-                logger.info(f"Generating gene Alignment Counts: {outbase}.genes.alignment_counts")
-                alnmat.report_alignment_counts(filename=f"{outbase}.genes.alignment_counts", gene_level=True)
+    if em_factory.rank == 0:
+        _write_reports(em_factory, outbase, alignment_file, group_file, report_group_counts, report_alignment_counts,
+                       report_posterior, notes_t=gtcall_t, notes_g=gtcall_g)
     logger.debug("Done")

@@ -59,3 +59,59 @@ def test_quantify_tables_match_reference(case, kind, genotype, tmp_path, capsys)
         else:
             scale = np.abs(ref[2]).max()
             assert np.abs(got[2] - ref[2]).max() <= 1e-9 * scale, sfx
+
+
+def test_cli_quantify_and_run_end_to_end(tmp_path):
+    """The typer commands drive the GPU path and write the reference's file set."""
+    from typer.testing import CliRunner
+
+    from gbrs_b200 import commands
+
+    gdir = os.path.join(hp.GOLDEN, "quantify_multiway")
+    z = np.load(os.path.join(gdir, "input.npz"))
+    d = synth.generate(T=int(z["T"]), N=int(z["N"]), H=int(z["H"]), with_genotype=True)
+    aln = os.path.join(str(tmp_path), "aln.emase")
+    make_apm(d).save(aln)
+    outbase = os.path.join(str(tmp_path), "cli")
+    res = CliRunner().invoke(commands.app, ["quantify", "-i", aln, "-g", os.path.join(gdir, "grp.tsv"), "-L",
+                                            os.path.join(gdir, "len.tsv"), "-o", outbase, "-M", "4", "-a"])
+    assert res.exit_code == 0, res.output
+    for sfx in ["isoforms.tpm", "isoforms.expected_read_counts", "genes.tpm", "genes.expected_read_counts",
+                "isoforms.alignment_counts", "genes.alignment_counts"]:
+        ref = read_table(os.path.join(gdir, f"out.multiway.{sfx}"))
+        got = read_table(f"{outbase}.multiway.{sfx}")
+        assert got[0] == ref[0] and got[1] == ref[1]
+        assert np.abs(got[2] - ref[2]).max() <= 1e-9 * np.abs(ref[2]).max()
+    # `emase run`: same EM, explicit read length, -c for alignment counts, no .multiway suffix
+    out2 = os.path.join(str(tmp_path), "em")
+    res = CliRunner().invoke(commands.app, ["run", "-i", aln, "-g", os.path.join(gdir, "grp.tsv"), "-L",
+                                            os.path.join(gdir, "len.tsv"), "-o", out2, "-l", "100", "-c"])
+    assert res.exit_code == 0, res.output
+    a = read_table(f"{out2}.isoforms.expected_read_counts")
+    b = read_table(f"{outbase}.multiway.isoforms.expected_read_counts")
+    assert np.array_equal(a[2], b[2])
+    assert os.path.exists(f"{out2}.genes.alignment_counts")
+
+
+def test_cohort_mode_equals_individual_runs(tmp_path):
+    from gbrs_b200 import cohort
+    from gbrs_b200.emfactory import EMfactory
+
+    samples = [0, 1, 2]
+    lenfile = os.path.join(str(tmp_path), "len.tsv")
+    base = synth.generate(T=300, N=4000, H=8, sample_index=0)
+    synth.write_length_file(base, lenfile)
+
+    def load(i):
+        return make_apm(synth.generate(T=300, N=4000, H=8, sample_index=i))
+
+    res = cohort.quantify_cohort(samples, load, model=4, lenfile=lenfile)
+    assert sorted(res) == samples
+    for i in samples:
+        em = EMfactory(load(i))
+        em.prepare(lenfile=lenfile)
+        em.run(model=4, tol=1e-4, verbose=False)
+        assert res[i]["iters"] == em.num_iters and np.array_equal(res[i]["theta"], em.allelic_expression)
+    # different samples give different answers (they share loci and lengths only)
+    assert not np.array_equal(res[0]["theta"], res[1]["theta"])
+    assert [r["iters"] for r in cohort.gather_results(res, 3)] == [res[i]["iters"] for i in samples]
