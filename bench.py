@@ -178,7 +178,7 @@ def run_gpu_arm(args, wl):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("GBRS_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL prints its version banner to stdout otherwise
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}")

@@ -458,11 +458,10 @@ __global__ void __launch_bounds__(kThreads) k_gene_totals(const gbrs_em_dev d) {
 //   u[r] = count[n] * Gamma_r / (sum_{r' of n} Gamma_r') / D_r,   D_r = sum_{(t,h) in n, t in gene r} theta[t][h]
 // Runs whose D_r is 0 drop out (eliminate_zeros before the GROUP division, AlignmentPropertyMatrix.py:350-352).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d) {
+__global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d, int64_t first_class) {
   if (d.ctrl[GBRS_CTRL_DONE]) return;
-  const double* __restrict__ th = theta_cur(d);
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+  for (int64_t n = first_class + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
     const double c = __ldg(d.count + n);
     double total = 0.0;
@@ -473,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d) {
       for (; p < e; ++p) {
         const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
         if (__ldg(d.gene_of + t) != g) break;
-        D += masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24);
+        D += pair_sum(d.subsets, w);
         gam = d.gamma[t];
       }
       if (D != 0.0) total += gam;
@@ -486,7 +485,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d) {
       for (; p < e; ++p) {
         const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
         if (__ldg(d.gene_of + t) != g) break;
-        D += masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24);
+        D += pair_sum(d.subsets, w);
         gam = d.gamma[t];
       }
       d.weights[run] = (D != 0.0) ? c * gam / total / D : 0.0;
@@ -499,12 +498,11 @@ __global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d) {
 //   u[p] = count[n] * (Gamma_r / sum_r' Gamma_r') * (I_t / S_r) / x_p
 //   x_p = sum_{h in mask_p} theta[t][h],  I_t = sum_h theta[t][h] (all h),  S_r = sum_{p in r, x_p != 0} I_t
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d) {
+__global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d, int64_t first_class) {
   if (d.ctrl[GBRS_CTRL_DONE]) return;
-  const double* __restrict__ th = theta_cur(d);
   const double* __restrict__ iso = d.iso + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+  for (int64_t n = first_class + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
     const double c = __ldg(d.count + n);
     double total = 0.0;
@@ -514,7 +512,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d) {
       for (; p < e; ++p) {
         const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
         if (__ldg(d.gene_of + t) != g) break;
-        if (masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24) != 0.0) S += iso[t];
+        if (pair_sum(d.subsets, w) != 0.0) S += iso[t];
         gam = d.gamma[t];
       }
       if (S != 0.0) total += gam;
@@ -526,15 +524,102 @@ __global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d) {
       for (; q < e; ++q) {
         const uint32_t w = __ldg(d.pairs + q), t = w & kLocusMask;
         if (__ldg(d.gene_of + t) != g) break;
-        if (masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24) != 0.0) S += iso[t];
+        if (pair_sum(d.subsets, w) != 0.0) S += iso[t];
         gam = d.gamma[t];
       }
       const double wg = (S != 0.0) ? c * gam / total / S : 0.0;
       for (; p < q; ++p) {
         const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
-        const double x = masked_sum8(th + (size_t) t * GBRS_HPAD, w >> 24);
+        const double x = pair_sum(d.subsets, w);
         d.weights[p] = (x != 0.0) ? wg * iso[t] / x : 0.0;
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fixed-width row passes for models 3 and 2 (classes with K <= GBRS_KMAX pairs, no row pointers): one thread per class,
+// all K pair words, masked sums (two subset-table loads each), gene ids and gene totals are fetched up front; the run
+// structure (pairs of one gene are adjacent) is resolved in registers with K^2 compares.  Same arithmetic as the
+// generic kernels above, which remain in use for the wide classes.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int K, int MODEL>
+__device__ __forceinline__ void row_class_m23(const gbrs_em_dev& d, const double* __restrict__ iso, int64_t n,
+                                              const uint32_t* __restrict__ pw, uint32_t pair0) {
+  uint32_t w[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) w[p] = __ldg(pw + p);
+  const double c = __ldg(d.count + n);
+  double x[K], gam[K], it[K];
+  int32_t g[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const uint32_t t = w[p] & kLocusMask;
+    const double* row = d.subsets + (size_t) t * 32;
+    x[p] = __ldg(row + ((w[p] >> 24) & 15u)) + __ldg(row + 16 + (w[p] >> 28));
+    g[p] = __ldg(d.gene_of + t);
+    gam[p] = d.gamma[t];
+    it[p] = (MODEL == 2) ? iso[t] : 0.0;
+  }
+  // per pair: the group sum of its run.  model 3: D = sum x; model 2: S = sum of isoform totals over alive pairs
+  double grp[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      const double term = (MODEL == 3) ? x[q] : ((x[q] != 0.0) ? it[q] : 0.0);
+      a += (g[q] == g[p]) ? term : 0.0;
+    }
+    grp[p] = a;
+  }
+  double total = 0.0;
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const bool start = (p == 0) || (g[p] != g[p - 1]);
+    total += (start && grp[p] != 0.0) ? gam[p] : 0.0;
+  }
+  if (MODEL == 3) {
+    uint32_t run = __ldg(d.runptr + n);
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+      const bool start = (p == 0) || (g[p] != g[p - 1]);
+      if (start) {
+        if (p > 0) ++run;
+        d.weights[run] = (grp[p] != 0.0) ? c * gam[p] / total / grp[p] : 0.0;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+      const double wg = (grp[p] != 0.0) ? c * gam[p] / total / grp[p] : 0.0;
+      d.weights[pair0 + p] = (x[p] != 0.0) ? wg * it[p] / x[p] : 0.0;
+    }
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kThreads) k_weights_m23_fixed(const __grid_constant__ gbrs_em_dev d) {
+  if (d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ iso = d.iso + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T;
+  const int64_t n_fixed = d.bucket_class0[GBRS_KMAX];
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  // classes are visited widest first (n_fixed - 1 down to 0): the expensive ones must not form the tail
+  for (int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; j < n_fixed; j += stride) {
+    const int64_t n = n_fixed - 1 - j;
+    int k = GBRS_KMAX;
+    while (n < d.bucket_class0[k - 1]) --k;
+    const uint32_t pair0 = (uint32_t) (d.bucket_pair0[k - 1] + (n - d.bucket_class0[k - 1]) * k);
+    const uint32_t* __restrict__ pw = d.pairs + pair0;
+    switch (k) {
+      case 1: row_class_m23<1, MODEL>(d, iso, n, pw, pair0); break;
+      case 2: row_class_m23<2, MODEL>(d, iso, n, pw, pair0); break;
+      case 3: row_class_m23<3, MODEL>(d, iso, n, pw, pair0); break;
+      case 4: row_class_m23<4, MODEL>(d, iso, n, pw, pair0); break;
+      case 5: row_class_m23<5, MODEL>(d, iso, n, pw, pair0); break;
+      case 6: row_class_m23<6, MODEL>(d, iso, n, pw, pair0); break;
+      case 7: row_class_m23<7, MODEL>(d, iso, n, pw, pair0); break;
+      default: row_class_m23<8, MODEL>(d, iso, n, pw, pair0); break;
     }
   }
 }
@@ -1272,8 +1357,19 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   if (d->n_classes > 0) {
     switch (model) {
       case 4: if (int rc4 = launch_row_m4<false>(d, s)) return rc4; break;
-      case 3: k_weights_m3<<<cg, kThreads, 0, s>>>(*d); break;
-      case 2: k_weights_m2<<<cg, kThreads, 0, s>>>(*d); break;
+      case 3:
+      case 2: {
+        const int64_t n_fixed = d->bucket_class0[GBRS_KMAX], n_long = d->n_classes - n_fixed;
+        if (n_fixed > 0) {
+          if (model == 3) k_weights_m23_fixed<3><<<resident_grid(k_weights_m23_fixed<3>, n_fixed), kThreads, 0, s>>>(*d);
+          else k_weights_m23_fixed<2><<<resident_grid(k_weights_m23_fixed<2>, n_fixed), kThreads, 0, s>>>(*d);
+        }
+        if (n_long > 0) {
+          if (model == 3) k_weights_m3<<<grid_for(n_long), kThreads, 0, s>>>(*d, n_fixed);
+          else k_weights_m2<<<grid_for(n_long), kThreads, 0, s>>>(*d, n_fixed);
+        }
+        break;
+      }
       default: k_weights_m1<<<cg, kThreads, 0, s>>>(*d); break;
     }
     GBRS_LAUNCH_CHECK("k_weights");

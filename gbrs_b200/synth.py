@@ -60,9 +60,11 @@ def _popcount8(x: np.ndarray) -> np.ndarray:
 
 
 def generate(T: int, N: int, H: int = 8, sample_index: int = 0, with_genotype: bool = False,
-             n_genes: int | None = None) -> SynthData:
+             n_genes: int | None = None, wide_frac: float = 0.0, wide_max: int = 24) -> SynthData:
     """Generate one sample.  `sample_index` shifts the seed (cohort mode shares gene_of / lengths by
-    drawing them from the base seed first)."""
+    drawing them from the base seed first).  `wide_frac` > 0 additionally makes that fraction of the classes
+    "wide" (9..wide_max loci, spread over a window of 4*wide_max loci) to exercise the long-class code paths; the
+    canonical benchmark shapes use wide_frac = 0."""
     if not (1 <= H <= 8):
         raise ValueError("synthetic generator supports 1..8 haplotypes")
     shared = np.random.default_rng(BASE_SEED)
@@ -83,6 +85,15 @@ def generate(T: int, N: int, H: int = 8, sample_index: int = 0, with_genotype: b
     first = np.zeros(slots, dtype=bool)
     first[np.cumsum(k) - k] = True
     off = rng.integers(0, 6, slots)
+    if wide_frac > 0.0:
+        wide = rng.random(N) < wide_frac
+        k_w = np.where(wide, rng.integers(9, wide_max + 1, N), k)
+        k = k_w.astype(np.int64)
+        slots = int(k.sum())
+        cls = np.repeat(np.arange(N, dtype=np.int64), k)
+        first = np.zeros(slots, dtype=bool)
+        first[np.cumsum(k) - k] = True
+        off = np.where(wide[cls], rng.integers(0, 4 * wide_max, slots), rng.integers(0, 6, slots))
     off[first] = 0
     loc = (base[cls] + off) % T
     key = np.unique(cls * T + loc)  # de-duplicate, sorted class-major then locus

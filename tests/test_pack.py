@@ -202,3 +202,14 @@ def test_packed_layout_reproduces_reference_model4(name):
         acc, theta = em_update_model4(p.arrays, p.info, d.T, theta, eff)
     assert hp.relerr(theta[:, :d.H].T, g["theta"]) < 1e-10
     assert hp.relerr(acc[:, :d.H].T, g["counts"]) < 1e-10
+
+
+def test_pack_wide_classes_go_to_the_long_bucket():
+    d = synth.generate(T=300, N=2000, H=8, sample_index=8, wide_frac=0.1)
+    p = PackedPattern(make_apm(d), gene_of=gene_index(d.T, d.groups()))
+    assert packed_signatures(p) == class_signatures(d)
+    bc = p.info["bucket_class0"]
+    rp = p.arrays["rowptr"].astype(np.int64)
+    widths = np.diff(rp)
+    assert bc[_lib.GBRS_KMAX] < p.info["n_classes"] and np.all(widths[bc[_lib.GBRS_KMAX]:] > _lib.GBRS_KMAX)
+    assert np.all(widths[:bc[_lib.GBRS_KMAX]] <= _lib.GBRS_KMAX) and p.info["max_pairs_per_class"] == widths.max()
