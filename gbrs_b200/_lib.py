@@ -54,7 +54,7 @@ class EmDev(C.Structure):
                 ("rowptr", C.c_void_p), ("pairs", C.c_void_p), ("count", C.c_void_p), ("runptr", C.c_void_p),
                 ("ent_cls", C.c_void_p), ("ent_pair", C.c_void_p), ("ent_run", C.c_void_p),
                 ("item_off", C.c_void_p), ("item_order", C.c_void_p), ("item_desc", C.c_void_p),
-                ("locus_order", C.c_void_p), ("locus_item_ptr", C.c_void_p),
+                ("locus_order", C.c_void_p), ("locus_desc", C.c_void_p), ("locus_item_ptr", C.c_void_p),
                 ("gene_of", C.c_void_p), ("gene_ptr", C.c_void_p), ("gene_loci", C.c_void_p),
                 ("theta", C.c_void_p), ("efflen", C.c_void_p), ("acc", C.c_void_p), ("iso", C.c_void_p),
                 ("weights", C.c_void_p), ("subsets", C.c_void_p), ("wit", C.c_void_p), ("part", C.c_void_p), ("gene_hap", C.c_void_p),

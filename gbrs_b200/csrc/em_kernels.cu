@@ -836,10 +836,16 @@ __global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, boo
     const int64_t g_in_round = (int64_t) (threadIdx.x >> 3) * gridDim.x + blockIdx.x;
     const int64_t slot = r * (stride >> 3) + g_in_round;
     const bool valid = slot < d.T;
-    const int64_t t = valid ? (int64_t) __ldg(d.locus_order + slot) : 0;
+    // one 16-byte descriptor (locus, first item, one-past-last item) instead of three dependent loads; theta and the
+    // effective length are requested before the item sums are walked so that their latency overlaps
+    uint4 ld = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) ld = __ldg(reinterpret_cast<const uint4*>(d.locus_desc) + slot);
+    const int64_t t = (int64_t) ld.x;
     const int64_t o = t * GBRS_HPAD + h;
-    uint32_t it = 0, e = 0;
-    if (valid) { it = __ldg(d.locus_item_ptr + t); e = __ldg(d.locus_item_ptr + t + 1); }
+    uint32_t it = ld.y;
+    const uint32_t e = ld.z;
+    const double th_o = (valid && !UNIT) ? th[o] : 1.0;
+    const double len_o = (valid && FUSE) ? d.efflen[o] : 1.0;
     double W = 0.0;
     for (; it + 3 < e; it += 4) {
       const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 1) * GBRS_HPAD + h];
@@ -849,14 +855,14 @@ __global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, boo
     for (; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
     double a = 0.0;
     if (valid) {
-      a = UNIT ? ((h < d.H) ? W : 0.0) : th[o] * W;
+      a = UNIT ? ((h < d.H) ? W : 0.0) : th_o * W;
       if (!FUSE && d.xchg_enabled) xchg_acc_local(d, d.xchg_rank)[o] = a;
       else d.acc[o] = a;
     }
     if (FUSE) {
       double v = 0.0;
       if (valid) {
-        v = fast_div(a, d.efflen[o]);
+        v = fast_div(a, len_o);
         dst[o] = v;
       }
       const double s = group8_sum(v);
@@ -1085,7 +1091,7 @@ int check_dev(const gbrs_em_dev* d, const char* who) {
   if (d->T <= 0 || d->H < 1 || d->H > GBRS_HPAD || (d->entry_bytes != 4 && d->entry_bytes != 8)) {
     gbrs_set_error(std::string(who) + ": bad descriptor shape"); return GBRS_E_ARG;
   }
-  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->item_order || !d->item_desc || !d->locus_order || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
+  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->item_order || !d->item_desc || !d->locus_order || !d->locus_desc || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
       !d->iso || !d->weights || !d->subsets || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
     gbrs_set_error(std::string(who) + ": null device buffer in descriptor"); return GBRS_E_ARG;
   }

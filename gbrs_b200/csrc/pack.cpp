@@ -13,6 +13,7 @@
 // every pair's mask with a per-locus byte; pairs and classes that become empty are dropped.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -29,7 +30,7 @@ void gbrs_set_error(const std::string& s);  // capi.cu
 struct gbrs_pack {
   gbrs_pack_info info{};
   int32_t T = 0;
-  std::vector<uint32_t> rowptr, pairs, runptr, item_off, item_order, item_desc, locus_item_ptr, locus_order, gene_ptr, gene_loci;
+  std::vector<uint32_t> rowptr, pairs, runptr, item_off, item_order, item_desc, locus_item_ptr, locus_order, locus_desc, gene_ptr, gene_loci;
   std::vector<int32_t> gene_of;
   std::vector<double> count;
   std::vector<uint8_t> ent_cls, ent_pair, ent_run;  // entry words, 4 or 8 bytes each
@@ -271,10 +272,12 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
 
     // ---- 6. column-pass work items ------------------------------------------------------------------------------
     // Each part (partial / full) of a locus is cut separately.  A part with up to 8 * item_len entries becomes short
-    // items (<= item_len entries, one aligned 8-lane group each); a deeper part becomes long items (<= 16 * item_len
+    // items (<= item_len entries, one aligned 8-lane group each); a deeper part becomes long items (<= 32 * item_len
     // entries, a whole warp each), so that the per-locus combine in k_locus_acc, which walks a locus' items serially,
     // stays short even for the deepest loci.
-    const int64_t long_len = 16 * (int64_t) item_len;
+    const char* lf_env = std::getenv("GBRS_LONG_FACTOR");  // tuning knob: long item = factor * item_len entries
+    const int64_t long_factor = lf_env ? std::max(8, std::atoi(lf_env)) : 32;
+    const int64_t long_len = long_factor * (int64_t) item_len;
     auto item_len_of = [&](int64_t len) -> int64_t {
       if (len <= 8 * (int64_t) item_len) return item_len;
       const int64_t n = (len + long_len - 1) / long_len;
@@ -322,13 +325,21 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
         P->item_desc[4 * i + 3] = item_full[idx[i]];
       }
     }
-    // (3) loci in descending item count: the per-locus combine starts with the deepest loci
+    // (3) loci in descending item count: the per-locus combine starts with the deepest loci.  locus_desc carries, per
+    // visiting slot, everything the combine needs in one 16-byte load: locus, first item, one-past-last item.
     {
       P->locus_order.resize((size_t) T);
       std::iota(P->locus_order.begin(), P->locus_order.end(), 0u);
       std::stable_sort(P->locus_order.begin(), P->locus_order.end(), [&](uint32_t x, uint32_t y) {
         return P->locus_item_ptr[x + 1] - P->locus_item_ptr[x] > P->locus_item_ptr[y + 1] - P->locus_item_ptr[y];
       });
+      P->locus_desc.assign((size_t) T * 4, 0);
+      for (int i = 0; i < T; ++i) {
+        const uint32_t t = P->locus_order[i];
+        P->locus_desc[4 * (size_t) i + 0] = t;
+        P->locus_desc[4 * (size_t) i + 1] = P->locus_item_ptr[t];
+        P->locus_desc[4 * (size_t) i + 2] = P->locus_item_ptr[t + 1];
+      }
     }
 
     // ---- 7. gene -> loci CSR ------------------------------------------------------------------------------------
@@ -386,6 +397,7 @@ extern "C" int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void**
   GBRS_ARR("item_order", p->item_order)
   GBRS_ARR("item_desc", p->item_desc)
   GBRS_ARR("locus_order", p->locus_order)
+  GBRS_ARR("locus_desc", p->locus_desc)
   GBRS_ARR("locus_item_ptr", p->locus_item_ptr)
   GBRS_ARR("gene_ptr", p->gene_ptr)
   GBRS_ARR("gene_loci", p->gene_loci)

@@ -33,7 +33,7 @@ ERR_LOG_CAP = 1 << 16
 
 _PACK_ARRAYS = {  # name -> numpy dtype (None = entry word, depends on entry_bytes)
     "rowptr": np.uint32, "pairs": np.uint32, "count": np.float64, "runptr": np.uint32,
-    "ent_cls": None, "ent_pair": None, "ent_run": None, "item_off": np.uint32, "item_order": np.uint32, "item_desc": np.uint32, "locus_order": np.uint32,
+    "ent_cls": None, "ent_pair": None, "ent_run": None, "item_off": np.uint32, "item_order": np.uint32, "item_desc": np.uint32, "locus_order": np.uint32, "locus_desc": np.uint32,
     "locus_item_ptr": np.uint32,
     "gene_ptr": np.uint32, "gene_loci": np.uint32, "gene_of": np.int32,
 }
@@ -190,7 +190,7 @@ class DevicePattern:
             d.bucket_class0[k] = i["bucket_class0"][k]
             d.bucket_pair0[k] = i["bucket_pair0"][k]
         for k in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "item_order",
-                  "item_desc", "locus_order", "locus_item_ptr"):
+                  "item_desc", "locus_order", "locus_desc", "locus_item_ptr"):
             setattr(d, k, self.dev[k].data_ptr())
         if self.packed.has_genes:
             for k in ("gene_of", "gene_ptr", "gene_loci"):

@@ -77,7 +77,7 @@ typedef struct {
   int64_t n_runs;      /* (class, gene) runs in this shard */
   int64_t n_items;     /* column-pass work items */
   int64_t n_entries;   /* locus-major entry words incl. padding (every item starts at a multiple of 4 entries) */
-  int64_t n_long_items;/* of which long (deep loci, up to 16 * item_len entries, processed by a whole warp) */
+  int64_t n_long_items;/* of which long (deep loci, up to 32 * item_len entries, processed by a whole warp) */
   int64_t nnz;         /* incidence entries in this shard (popcount over pair masks) */
   int64_t nnz_total;   /* incidence entries over all shards */
   int64_t n_classes_total;
@@ -101,7 +101,7 @@ int gbrs_pack_get_info(gbrs_pack_t p, gbrs_pack_info* info);
  *   "ent_cls" / "ent_pair" / "ent_run"  entry words [n_entries], locus-major (index | mask << (8*entry_bytes-8));
  *                                     padding words carry an empty mask and index n_classes / n_pairs / n_runs
  *   "item_off" uint32 [n_items+1]    "locus_item_ptr" uint32 [T+1]   "item_order" uint32 [n_items]
- *   "item_desc" uint32 [n_items][4]  "locus_order" uint32 [T]
+ *   "item_desc" uint32 [n_items][4]  "locus_order" uint32 [T]   "locus_desc" uint32 [T][4]
  *   "gene_ptr" uint32 [n_gene_ids+1] "gene_loci" uint32 [T]     "gene_of" int32 [T]
  */
 int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64_t* bytes);
@@ -139,6 +139,7 @@ typedef struct {
   const uint32_t* item_order;   /* [n_items] item ids in visiting order, bit 31 = full-mask item */
   const uint32_t* item_desc;    /* [n_items][4] per visiting slot: first entry, one-past-last entry, item id, flags */
   const uint32_t* locus_order;  /* [T] loci in descending item count */
+  const uint32_t* locus_desc;   /* [T][4] per visiting slot of locus_order: locus, first item, one-past-last item, 0 */
   const uint32_t* locus_item_ptr;
   const int32_t* gene_of;
   const uint32_t* gene_ptr;

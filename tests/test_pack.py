@@ -88,7 +88,7 @@ def test_pack_preserves_pattern(small):
     io, lip = a["item_off"].astype(np.int64), a["locus_item_ptr"].astype(np.int64)
     assert io[0] == 0 and io[-1] == p.info["n_entries"] and np.all(np.diff(io) > 0) and np.all(io % 4 == 0)
     lens = np.diff(io)
-    assert p.info["n_long_items"] == np.count_nonzero(lens > 64) and lens.max() <= 16 * 64
+    assert p.info["n_long_items"] == np.count_nonzero(lens > 64) and lens.max() <= 32 * 64
     locus_of_entry = pw & 0xFFFFFF
     for t in range(d.T):
         lo, hi = (io[lip[t]], io[lip[t + 1]]) if lip[t + 1] > lip[t] else (0, 0)
