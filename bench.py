@@ -41,8 +41,20 @@ METRIC = "em_alignment_nnz_per_s"
 UNIT = "nnz/s"
 
 
+_REAL_STDOUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -156,7 +168,7 @@ def run_reference_arm(args, wl):
             "iterations_per_s_at_full_size": rate / (nnz * wl["N"] / ncls),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -365,7 +377,7 @@ def run_gpu_arm(args, wl):
                 "iterations_per_s": K / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches_per_step * K, "clocks": clocks,
                 "pack_seconds": pat.packed.pack_seconds}
-        print(json.dumps(line), flush=True)
+        emit(line)
     # teardown: drop the captured graph (it holds NCCL work) before the communicator, and never hang on exit
     graph = None
     torch.cuda.synchronize(dev)
@@ -377,6 +389,12 @@ def run_gpu_arm(args, wl):
 
 
 def main():
+    # Keep stdout to the one JSON line: libraries (NCCL's version banner) write to fd 1, so fd 1 is pointed at stderr
+    # for the whole run and the line is written to the original stdout at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

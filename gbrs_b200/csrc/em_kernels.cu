@@ -213,6 +213,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ double2 ld_relaxed_sys_f64x2(const double* p) {
   double2 v;
   asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
@@ -254,8 +257,10 @@ __device__ __forceinline__ void xchg_signal_all(const gbrs_em_dev& d, int which,
     if (ticket == (int) gridDim.x - 1) {
       d.ctrl[ticket_slot] = 0;
       if (which == 1) d.ctrl[GBRS_CTRL_XEPOCH] = (int32_t) e;  // the exchange e is complete on this rank's side
+      // one system-scope fence, then the flags as plain system-scope stores issued back to back (a releasing store
+      // per peer would wait for the previous one to be performed: ~2 us each over NVLink)
       __threadfence_system();
-      for (int r = 0; r < d.n_ranks; ++r) st_release_sys(xchg_flags(d, r, which) + d.xchg_rank, e);
+      for (int r = 0; r < d.n_ranks; ++r) st_relaxed_sys_u32(xchg_flags(d, r, which) + d.xchg_rank, e);
     }
   }
 }
@@ -269,13 +274,22 @@ __global__ void __launch_bounds__(kThreads) k_xchg_reduce(const __grid_constant_
   const int64_t lo = per * d.xchg_rank, hi = lo + per < n2 ? lo + per : n2;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+    // all peer loads first (one NVLink round trip instead of n_ranks serial ones), then the sum in rank order: every
+    // element is summed exactly once, in one fixed order
+    double2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < d.n_ranks) v[r] = ld_relaxed_sys_f64x2(xchg_acc_local(d, r) + 2 * i);
     double2 s = make_double2(0.0, 0.0);
-    for (int r = 0; r < d.n_ranks; ++r) {  // rank order: every element is summed once, in one fixed order
-      const double2 v = ld_relaxed_sys_f64x2(xchg_acc_local(d, r) + 2 * i);
-      s.x += v.x;
-      s.y += v.y;
-    }
-    for (int r = 0; r < d.n_ranks; ++r) st_relaxed_sys_f64x2(xchg_acc_total(d, r) + 2 * i, s);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < d.n_ranks) {
+        s.x += v[r].x;
+        s.y += v[r].y;
+      }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < d.n_ranks) st_relaxed_sys_f64x2(xchg_acc_total(d, r) + 2 * i, s);
   }
   xchg_signal_all(d, 1, e, GBRS_CTRL_TICKET + 2);
 }
