@@ -333,14 +333,24 @@ def run_gpu_arm(args, wl):
         pat.host[k] = pat.host[k].pin_memory()
     Ke = K
     sync_all()
-    t0 = time.perf_counter()
-    pat.h2d_bytes = 0
-    pat.upload()
-    em.reset()
-    em.run(model=model, tol=0.0, max_iters=Ke, verbose=False)
-    counts = em.expected_read_counts()
-    torch.cuda.synchronize(dev)
-    t_e2e = time.perf_counter() - t0
+    def e2e_once():
+        t0 = time.perf_counter()
+        pat.h2d_bytes = 0
+        pat.upload()
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        em.reset()
+        t2 = time.perf_counter()
+        em.run(model=model, tol=0.0, max_iters=Ke, verbose=False)
+        t3 = time.perf_counter()
+        c = em.expected_read_counts()
+        torch.cuda.synchronize(dev)
+        t4 = time.perf_counter()
+        return t4 - t0, c, {"h2d_s": t1 - t0, "prepare_s": t2 - t1, "run_s": t3 - t2, "fetch_s": t4 - t3}
+
+    e2e_once()  # warm-up pass (first-use costs: pinned staging, graph instantiation paths), then the timed one
+    sync_all()
+    t_e2e, counts, e2e_parts = e2e_once()
     if world > 1:
         t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -350,7 +360,7 @@ def run_gpu_arm(args, wl):
     h2d = pat.h2d_bytes + 64 * T + 64 * T  # packed arrays + effective lengths (+ nothing else)
     d2h = 2 * 64 * T + 2 * 8 * wl["T"] * 8 + 8 * Ke
     e2e = {"value": nnz_total * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": d2h / Ke,
-           "seconds": t_e2e, "what": "H2D packed incidence (pinned) + prepare + run(%d updates) + D2H theta/counts/err "
+           "seconds": t_e2e, "parts": e2e_parts, "what": "H2D packed incidence (pinned) + prepare + run(%d updates) + D2H theta/counts/err "
                                      "log through EMfactory" % Ke}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------------
