@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_C", "libgbrs_em.so")
+LIB_PATH = os.environ.get("GBRS_LIB_PATH") or os.path.join(HERE, "_C", "libgbrs_em.so")  # override: tuning builds
 
 GBRS_HPAD = 8
 GBRS_KMAX = 8

@@ -38,6 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC,-fopenmp,-O3", "-Xptxas", "-v" if verbose else "-O3",
            "-I", os.path.join(ROOT, "include"), "-cudart", "static", "-o", LIB + ".tmp"] + SOURCES + ["-lgomp"]
+    if os.environ.get("GBRS_THREADS"):  # tuning experiments only
+        cmd.insert(1, "-DGBRS_THREADS=" + os.environ["GBRS_THREADS"])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

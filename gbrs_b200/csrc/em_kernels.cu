@@ -53,7 +53,10 @@ extern "C" int gbrs_abi_version(void) { return GBRS_EM_ABI_VERSION; }
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef GBRS_THREADS
+#define GBRS_THREADS 256
+#endif
+constexpr int kThreads = GBRS_THREADS;  // threads per block of every grid-stride kernel
 constexpr uint32_t kLocusMask = 0xFFFFFFu;
 
 int g_sm_count = 0;
@@ -775,7 +778,7 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
 // Warp work slots: slot < n_long_items -> the slot-th item of item_order (a long item, whole warp); otherwise four
 // short items.  item_order lists long items first, partial-mask items before full-mask ones, longest first.
 template <typename E, int VEC>
-__global__ void __launch_bounds__(kThreads, 4) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
+__global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
                                                              const E* __restrict__ ents, bool honour_done) {
   if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
   const int lane = threadIdx.x & 31;

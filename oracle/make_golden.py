@@ -140,6 +140,8 @@ def main():
         em_case(f"em_small_m{model}", 200, 3000, 8, model, False, 0.0)
         em_case(f"em_small_m{model}_diploid", 200, 3000, 8, model, True, 0.0)
         em_case(f"em_small_m{model}_pc", 200, 3000, 8, model, False, 0.5)
+    em_case("em_small_m4_h1", 150, 2000, 1, 4, False, 0.0)  # single haplotype: length file without _hap suffixes
+    em_case("em_small_m3_h1", 150, 2000, 1, 3, False, 0.25)
     em_case("em_small_m4_h2", 150, 2000, 2, 4, False, 0.0)
     em_case("em_small_m2_h3", 150, 2000, 3, 2, False, 0.0)
     em_case("em_small_m4_maxit5", 200, 3000, 8, 4, False, 0.0, max_iters=5)
