@@ -127,8 +127,9 @@ __device__ __forceinline__ void load8(const double* __restrict__ line, double (&
 __device__ __forceinline__ void masked_add8(double (&a)[8], double w, uint32_t m) {
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
-    const double one_or_zero = __hiloint2double(((m >> h) & 1u) ? 0x3FF00000 : 0, 0);
-    a[h] = fma(w, one_or_zero, a[h]);
+    // (m & 2^h) is 0 or 2^h; times (0x3FF00000 >> h) gives the high word of 0.0 or 1.0 in two integer instructions
+    const uint32_t hi = (m & (1u << h)) * (0x3FF00000u >> h);
+    a[h] = fma(w, __hiloint2double((int) hi, 0), a[h]);
   }
 }
 
@@ -389,13 +390,10 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
     if (n[u] < class_end) d.weights[n[u]] = fast_div(cnt[u], s[u]);
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 template <bool UNIT>
 __global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__ gbrs_em_dev d,
-                                                          const __grid_constant__ RowPlan plan, const bool prefetch) {
+                                                          const __grid_constant__ RowPlan plan) {
   if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
-  const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
   const int64_t total_units = plan.unit_end[GBRS_KMAX - 1];
   int i = 0;  // bucket index only ever advances along the warp's grid-stride walk
@@ -409,13 +407,6 @@ __global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__
     const int64_t c0 = d.bucket_class0[k - 1], c1 = d.bucket_class0[k], p0 = d.bucket_pair0[k - 1];
     const int cpu = 32 * unr_of(k);
     const int64_t class0 = c0 + (u - unit0) * cpu;
-    if (prefetch && u + nwarps < unit1) {
-      // pull the pair words and counts of this warp's next unit (same width) towards L2: cpu * k * 4 contiguous bytes
-      // of pair words and cpu * 8 bytes of counts, one 128-byte line per lane
-      const int64_t first = class0 + nwarps * cpu;
-      if (lane * 128 < cpu * k * 4) prefetch_l2(reinterpret_cast<const char*>(d.pairs + p0 + (first - c0) * k) + lane * 128);
-      if (lane * 128 < cpu * 8) prefetch_l2(reinterpret_cast<const char*>(d.count + first) + lane * 128);
-    }
     switch (k) {
       case 1: row_classes_m4<1, UNIT>(d, class0, c1, c0, p0); break;
       case 2: row_classes_m4<2, UNIT>(d, class0, c1, c0, p0); break;
@@ -1159,8 +1150,7 @@ int launch_row_m4(const gbrs_em_dev* d, cudaStream_t s) {
     plan.unit_end[i] = units;
   }
   if (units > 0) {
-    static const bool prefetch = std::getenv("GBRS_PREFETCH") != nullptr;  // measured: no gain on B200, off by default
-    k_weights_m4<UNIT><<<resident_grid(k_weights_m4<UNIT>, units * 32), kThreads, 0, s>>>(*d, plan, prefetch);
+    k_weights_m4<UNIT><<<resident_grid(k_weights_m4<UNIT>, units * 32), kThreads, 0, s>>>(*d, plan);
     GBRS_LAUNCH_CHECK("k_weights_m4");
   }
   const int64_t n_long = d->n_classes - d->bucket_class0[GBRS_KMAX];
@@ -1268,33 +1258,8 @@ extern "C" int gbrs_em_current_theta(const gbrs_em_dev* d, void* stream, double*
   return GBRS_OK;
 }
 
-// Keep the per-class weight vector (written by the row pass, gathered by the column pass) resident in L2: everything
-// else the two passes read is streamed once.  Best effort -- failures are ignored.
-static void pin_weights_in_l2(const gbrs_em_dev* d, cudaStream_t s) {
-  static const bool enabled = std::getenv("GBRS_NO_L2_PIN") == nullptr;
-  if (!enabled) return;
-  int dev = 0, max_persist = 0, max_window = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return;
-  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-  size_t bytes = (size_t) d->n_classes * sizeof(double);
-  if (max_persist <= 0 || max_window <= 0 || bytes == 0) return;
-  const size_t want = bytes < (size_t) max_persist ? bytes : (size_t) max_persist;
-  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-  cudaStreamAttrValue attr;
-  std::memset(&attr, 0, sizeof(attr));
-  attr.accessPolicyWindow.base_ptr = d->weights;
-  attr.accessPolicyWindow.num_bytes = bytes < (size_t) max_window ? bytes : (size_t) max_window;
-  attr.accessPolicyWindow.hitRatio = (float) ((double) want / (double) attr.accessPolicyWindow.num_bytes);
-  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
-  cudaGetLastError();
-}
-
 extern "C" int gbrs_em_run_begin(const gbrs_em_dev* d, double tol, int max_iters, void* stream) {
   if (int rc = check_dev(d, "gbrs_em_run_begin")) return rc;
-  pin_weights_in_l2(d, static_cast<cudaStream_t>(stream));
   if (max_iters < 0 || max_iters > d->max_iters_cap) {
     gbrs_set_error("gbrs_em_run_begin: max_iters exceeds the err_log capacity of the descriptor"); return GBRS_E_ARG;
   }

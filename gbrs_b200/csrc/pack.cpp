@@ -13,6 +13,7 @@
 // every pair's mask with a per-locus byte; pairs and classes that become empty are dropped.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -73,6 +74,11 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
   }
   const int item_len = in->item_len > 0 ? (in->item_len + 7) / 8 * 8 : 64;
 
+  const bool timing = std::getenv("GBRS_PACK_TIMING") != nullptr;
+  double t_last = omp_get_wtime();
+  auto lap = [&](const char* what) {
+    if (timing) { const double t = omp_get_wtime(); std::fprintf(stderr, "[pack] %-28s %8.1f ms\n", what, (t - t_last) * 1e3); t_last = t; }
+  };
   try {
     // ---- 1. merge the H columns of every locus into (class, mask) pairs, locus-major, all classes -----------------
     std::vector<int64_t> ub(T + 1, 0);  // upper bound offsets
@@ -111,6 +117,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     }
     if (bad) { gbrs_set_error("gbrs_pack_create: class index out of range"); return GBRS_E_ARG; }
 
+    lap("1 merge columns");
     // ---- 2. per-class pair / nnz counts, shard boundaries balanced by nnz -----------------------------------------
     std::vector<uint32_t> npair((size_t) N, 0), minloc((size_t) N, 0xFFFFFFFFu);
     std::vector<uint32_t> nz((size_t) N, 0);
@@ -141,6 +148,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       if (hi < lo) hi = lo;
     }
 
+    lap("2 class counts + shard");
     // ---- 3. order the shard's non-empty classes by (pairs capped at KMAX+1, smallest locus): stable counting sort ----
     // Equal-width classes are contiguous so the row pass needs no row pointers for them; within a width the classes are
     // ordered by smallest locus so that neighbouring classes touch neighbouring theta lines.
@@ -164,6 +172,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     for (int64_t c = lo; c < hi; ++c)
       if (npair[c]) new_id[c] = (uint32_t) bucket[(size_t) bucket_of(npair[c]) * T + minloc[c]]++;
 
+    lap("3 class order");
     auto* P = new gbrs_pack();
     P->T = T;
     P->rowptr.assign((size_t) n_classes + 1, 0);
@@ -175,6 +184,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       }
     for (int64_t n = 0; n < n_classes; ++n) P->rowptr[n + 1] += P->rowptr[n];
 
+    lap("3b rowptr/count");
     // ---- 4. class-major fill (loci ascending within a class), then order pairs by (gene, locus) and cut runs -----
     P->pairs.assign((size_t) n_pairs, 0);
     {
@@ -218,6 +228,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     for (int64_t n = 0; n < n_classes; ++n) P->runptr[n + 1] += P->runptr[n];
     const int64_t n_runs = P->runptr[n_classes];
 
+    lap("4 class-major fill + runs");
     // ---- 5. locus-major entries of this shard.  Within a locus: first the entries whose mask is partial, then the
     // entries hitting all H haplotypes ("full"), each part in ascending new class id.  Full entries need no per-haplotype
     // masking in the column pass (one add instead of eight masked ones) and are the commonest kind.
@@ -270,6 +281,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       }
     }
 
+    lap("5 locus-major entries");
     // ---- 6. column-pass work items ------------------------------------------------------------------------------
     // Each part (partial / full) of a locus is cut separately.  A part with up to 8 * item_len entries becomes short
     // items (<= item_len entries, one aligned 8-lane group each); a deeper part becomes long items (<= 32 * item_len
@@ -342,6 +354,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       }
     }
 
+    lap("6 items + orders");
     // ---- 7. gene -> loci CSR ------------------------------------------------------------------------------------
     P->gene_ptr.assign((size_t) n_gene_ids + 1, 0);
     for (int t = 0; t < T; ++t) ++P->gene_ptr[P->gene_of[t] + 1];
@@ -352,6 +365,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       for (int t = 0; t < T; ++t) P->gene_loci[cur[P->gene_of[t]]++] = (uint32_t) t;
     }
 
+    lap("7 gene csr");
     P->info.n_classes = n_classes;
     P->info.n_pairs = n_pairs;
     P->info.n_runs = n_runs;
