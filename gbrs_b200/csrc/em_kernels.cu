@@ -214,9 +214,6 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void st_relaxed_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -699,48 +696,52 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
   const double* __restrict__ wts = d.weights;
   const int lane = threadIdx.x & 31, lane8 = lane & 7, lanex = lane & (LANES - 1);
   double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (VEC == 1 && sizeof(E) == 4) {
+  if (VEC == 1) {
     // Items start at a multiple of 4 entries and are padded with empty words, so every lane fetches four consecutive
-    // entries per 128-bit load; two such loads and their eight weight gathers are in flight per lane before the adds.
-    // An out-of-range quad reads the item's first quad again with the masks stripped, which adds nothing.
+    // entries per step (one 128-bit load for 32-bit words, two for 64-bit words); two steps and their eight weight
+    // gathers are in flight per lane before the adds.  An out-of-range quad reads the item's first quad again with the
+    // masks stripped, which adds nothing.
     constexpr int CH = 2;
-    const uint32_t* __restrict__ e32 = reinterpret_cast<const uint32_t*>(ents);
     for (uint32_t p0 = b + 4 * lanex; p0 < e; p0 += 4 * LANES * CH) {
-      uint4 en[CH];
+      uint32_t msk[CH][4];
+      size_t idx[CH][4];
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
         const uint32_t p = p0 + 4 * LANES * q;
-        en[q] = __ldcs(reinterpret_cast<const uint4*>(e32 + (p < e ? p : b)));
-        if (p >= e) { en[q].x &= 0xFFFFFFu; en[q].y &= 0xFFFFFFu; en[q].z &= 0xFFFFFFu; en[q].w &= 0xFFFFFFu; }
+        const bool in = p < e;
+        const E* src = ents + (in ? p : b);
+        if (sizeof(E) == 4) {
+          const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { idx[q][i] = w4[i] & 0xFFFFFFu; msk[q][i] = in ? (w4[i] >> 24) : 0u; }
+        } else {
+          const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(src));
+          const ulonglong2 v1 = __ldcs(reinterpret_cast<const ulonglong2*>(src) + 1);
+          const unsigned long long w4[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            idx[q][i] = (size_t) (w4[i] & 0x00FFFFFFFFFFFFFFull);
+            msk[q][i] = in ? (uint32_t) (w4[i] >> 56) : 0u;
+          }
+        }
       }
       double w[CH][4];
 #pragma unroll
-      for (int q = 0; q < CH; ++q) {
-        w[q][0] = __ldg(wts + (en[q].x & 0xFFFFFFu));
-        w[q][1] = __ldg(wts + (en[q].y & 0xFFFFFFu));
-        w[q][2] = __ldg(wts + (en[q].z & 0xFFFFFFu));
-        w[q][3] = __ldg(wts + (en[q].w & 0xFFFFFFu));
-      }
+      for (int q = 0; q < CH; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[q][i] = __ldg(wts + idx[q][i]);
 #pragma unroll
       for (int q = 0; q < CH; ++q) {
         if (FULL) {
           // padding words (and re-read quads) must not count: their mask is empty
-          a[0] += ((en[q].x >> 24) ? w[q][0] : 0.0) + ((en[q].y >> 24) ? w[q][1] : 0.0);
-          a[0] += ((en[q].z >> 24) ? w[q][2] : 0.0) + ((en[q].w >> 24) ? w[q][3] : 0.0);
+          a[0] += (msk[q][0] ? w[q][0] : 0.0) + (msk[q][1] ? w[q][1] : 0.0);
+          a[0] += (msk[q][2] ? w[q][2] : 0.0) + (msk[q][3] ? w[q][3] : 0.0);
         } else {
-          masked_add8(a, w[q][0], en[q].x >> 24);
-          masked_add8(a, w[q][1], en[q].y >> 24);
-          masked_add8(a, w[q][2], en[q].z >> 24);
-          masked_add8(a, w[q][3], en[q].w >> 24);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) masked_add8(a, w[q][i], msk[q][i]);
         }
       }
-    }
-  } else if (VEC == 1) {
-    for (uint32_t p = b + lanex; p < e; p += LANES) {
-      const E ent = __ldcs(ents + p);
-      const double w = __ldg(wts + (size_t) (ent & IDX));
-      if (FULL) a[0] += (ent >> SH) ? w : 0.0;
-      else masked_add8(a, w, (uint32_t) (ent >> SH));
     }
   } else {
     for (uint32_t p = b + lanex; p < e; p += LANES) {

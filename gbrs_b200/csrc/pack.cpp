@@ -235,7 +235,10 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     // Every part is padded to a multiple of 4 entries with dummy words (empty mask, index = one past the last real
     // index, whose weight slot is kept at zero), so that items start 16-byte aligned and the column pass can fetch four
     // entries per load.
-    const int entry_bytes = std::max({n_classes, n_pairs, n_runs}) + 1 < (int64_t(1) << 24) ? 4 : 8;
+    // 32-bit entry words hold a 24-bit index; larger shards (> 16.7 M classes / pairs / runs) switch to 64-bit words.
+    // GBRS_FORCE_ENTRY64 forces the wide words on small inputs so that tests can exercise that path.
+    const bool force64 = std::getenv("GBRS_FORCE_ENTRY64") != nullptr;
+    const int entry_bytes = (!force64 && std::max({n_classes, n_pairs, n_runs}) + 1 < (int64_t(1) << 24)) ? 4 : 8;
     const uint32_t full_mask = (1u << H) - 1u;
     auto pad4 = [](int64_t x) { return (x + 3) / 4 * 4; };
     std::vector<int64_t> lcnt(T, 0), lpart(T, 0);

@@ -213,3 +213,13 @@ def test_pack_wide_classes_go_to_the_long_bucket():
     widths = np.diff(rp)
     assert bc[_lib.GBRS_KMAX] < p.info["n_classes"] and np.all(widths[bc[_lib.GBRS_KMAX]:] > _lib.GBRS_KMAX)
     assert np.all(widths[:bc[_lib.GBRS_KMAX]] <= _lib.GBRS_KMAX) and p.info["max_pairs_per_class"] == widths.max()
+
+
+def test_pack_wide_entry_words(monkeypatch):
+    monkeypatch.setenv("GBRS_FORCE_ENTRY64", "1")
+    d = synth.generate(T=60, N=500, H=8)
+    p = PackedPattern(make_apm(d))
+    assert p.info["entry_bytes"] == 8 and p.arrays["ent_cls"].dtype == np.uint64
+    idx, m = unpack_entries(p.arrays["ent_cls"], 8)
+    assert np.count_nonzero(m) == d.pairs and idx.max() == p.info["n_classes"]
+    assert packed_signatures(p) == class_signatures(d)
