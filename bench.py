@@ -35,6 +35,10 @@ WORKLOADS = {
     "c2": dict(T=80000, N=5_000_000, label="DO-mouse-scale quantify -M 4: 80k transcripts x 8 haplotypes x 5M classes"),
     "c1": dict(T=2000, N=200_000, label="config 1: 2k transcripts x 8 haplotypes x 200k classes"),
     "small": dict(T=8000, N=500_000, label="reduced: 8k x 8 x 500k (debug only)"),
+    # BASELINE config 4: diploid (-G) restriction, 20 M classes in total, row-sharded (STRONG scaling: N / world each)
+    "c4": dict(T=80000, N=20_000_000, diploid=True, strong=True,
+               label="diploid quantify -G -M 4: 80k transcripts x 2 of 8 haplotypes per locus x 20M classes, row-sharded"),
+    "c4small": dict(T=8000, N=2_000_000, diploid=True, strong=True, label="reduced diploid (debug only)"),
 }
 CPU_SAMPLE_CLASSES = 1_000_000
 METRIC = "em_alignment_nnz_per_s"
@@ -123,13 +127,15 @@ def measured_peaks():
 # --------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on a bounded sample
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(T, n_classes, steps, warmup, model=4):
+def cpu_port_rate(T, n_classes, steps, warmup, model=4, diploid=False):
     """nnz/s of the numpy restatement of the reference EM (oracle/em_oracle.py), single host thread."""
     from gbrs_b200 import synth
     from oracle import em_oracle as eo
 
-    d = synth.generate(T=T, N=n_classes, H=8)
+    d = synth.generate(T=T, N=n_classes, H=8, with_genotype=diploid)
     apm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    if diploid:
+        apm = eo.apply_genotype_mask(apm, synth.genotype_mask(d))
     eff = eo.effective_length_table(d.lengths)
     gene_of = eo.gene_index(d.T, d.groups()) if model != 4 else None
     keys = eo._Keys(apm, gene_of) if model != 4 else None
@@ -159,7 +165,7 @@ def run_reference_arm(args, wl):
         return
     ncls = min(CPU_SAMPLE_CLASSES, wl["N"])
     steps = max(1, min(args.steps, 10))
-    rate, s_per_step, nnz = cpu_port_rate(wl["T"], ncls, steps, min(args.warmup, 1), args.model)
+    rate, s_per_step, nnz = cpu_port_rate(wl["T"], ncls, steps, min(args.warmup, 1), args.model, bool(wl.get("diploid")))
     sample = f"{ncls} of {wl['N']} classes (nnz={nnz}), {steps} EM updates timed"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
@@ -199,10 +205,17 @@ def run_gpu_arm(args, wl):
 
     # ---- workload: every rank holds one `workload`-sized shard (weak scaling) ------------------------------------
     t0 = time.perf_counter()
-    d = synth.generate(T=wl["T"], N=wl["N"], H=8, sample_index=rank)
+    diploid, strong = bool(wl.get("diploid")), bool(wl.get("strong"))
+    n_local = wl["N"] // world if strong else wl["N"]
+    d = synth.generate(T=wl["T"], N=n_local, H=8, sample_index=rank, with_genotype=diploid)
     apm = synth.to_apm(d)
+    hapmask = None
+    if diploid:
+        import importlib
+
+        hapmask = importlib.import_module("gbrs_b200.quantify").hapmask_bytes(synth.genotype_mask(d))
     t_gen = time.perf_counter() - t0
-    em = EMfactory(apm, device=dev, shard="local" if world > 1 else None)
+    em = EMfactory(apm, device=dev, shard="local" if world > 1 else None, locus_hapmask=hapmask)
     em.target_lengths = synth.effective_lengths(d)  # same table prepare() would parse from a targets.info file
     t0 = time.perf_counter()
     em.prepare()  # gene tables + pack + upload + theta0
@@ -356,7 +369,8 @@ def run_gpu_arm(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     assert em.num_iters == Ke
-    assert abs(counts.sum() - (d.count.sum() if world == 1 else counts.sum())) < 1e-6 * counts.sum()
+    if world == 1 and not diploid:
+        assert abs(counts.sum() - d.count.sum()) < 1e-6 * counts.sum()
     h2d = pat.h2d_bytes + 64 * T + 64 * T  # packed arrays + effective lengths (+ nothing else)
     d2h = 2 * 64 * T + 2 * 8 * wl["T"] * 8 + 8 * Ke
     e2e = {"value": nnz_total * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": d2h / Ke,
@@ -365,7 +379,7 @@ def run_gpu_arm(args, wl):
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not diploid:
         ncls = min(CPU_SAMPLE_CLASSES, wl["N"])
         rate, s_per, nnz_s = cpu_port_rate(wl["T"], ncls, 5, 1, model)
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
@@ -375,8 +389,8 @@ def run_gpu_arm(args, wl):
     if rank == 0:
         launches_per_step = (4 if world == 1 else (6 if em.fused_exchange else 5)) + (1 if model != 4 else 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["label"], "model": model, "classes_per_gpu": Np, "pairs_per_gpu": Pp,
                            "nnz_per_gpu": nnz_local, "nnz_total": nnz_total, "loci": T, "haplotypes": 8,
                            "l2_policy": "inputs larger than L2 (packed incidence %.0f MB per GPU streams every step)"

@@ -826,7 +826,7 @@ __device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t 
 // `wit` is the *other* buffer: a single rank simply skips, a row-sharded rank recomputes the identical local numerator
 // from it (the in-place cross-rank sum that follows must always start from the local values).
 template <bool UNIT, bool FUSE>
-__global__ void __launch_bounds__(kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
+__global__ void __launch_bounds__(kThreads, 2048 / kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
   __shared__ double red[32];
   const bool done = !UNIT && d.ctrl[GBRS_CTRL_DONE];
   if (done && (honour_done || FUSE)) return;
@@ -1115,8 +1115,8 @@ inline int locus_grid(const gbrs_em_dev* d) {  // k_locus_update: one thread per
   int g = grid_for((int64_t) d->T * GBRS_HPAD, 8);
   return g > kHalfSlots ? kHalfSlots : g;
 }
-inline int acc_grid(const gbrs_em_dev* d) {  // k_locus_acc: one thread per (locus, haplotype slot)
-  int g = grid_for((int64_t) d->T * GBRS_HPAD, 6);
+inline int acc_grid(const gbrs_em_dev* d) {  // k_locus_acc: one thread per (locus, haplotype slot), 32 registers
+  int g = grid_for((int64_t) d->T * GBRS_HPAD, 2048 / kThreads);
   return g > kHalfSlots ? kHalfSlots : g;
 }
 inline int converge_grid(const gbrs_em_dev* d) {

@@ -255,13 +255,15 @@ class EMfactory:
     """A class that coordinates Expectation-Maximization (reference EMfactory.py:15-24)."""
 
     def __init__(self, alignments: APM, device=None, group=None, shard: bool | str | None = None, item_len: int = 0,
-                 poll_every: int = 4):
+                 poll_every: int = 4, locus_hapmask=None):
         """`alignments`: the incidence matrix.  Additions to the reference signature (all optional):
         `device` CUDA device; `group` a torch.distributed process group (or `shard=True` for the default group) over
         which the alignment classes are row-sharded -- every rank passes the same full matrix and packs only its own
         contiguous slice; `shard="local"` says the matrix passed in already is this rank's slice (each rank loaded
         different classes); `item_len` / `poll_every` are tuning knobs (column-pass work item size, iterations queued
-        between reads of the device-side stop flag)."""
+        between reads of the device-side stop flag); `locus_hapmask` (uint8 [T], bit h = haplotype h of the locus is
+        kept) applies the `-G` genotype restriction while packing, which is equivalent to -- and much cheaper than --
+        `alignments.multiply(gtmask, axis=2)` followed by `eliminate_zeros()` on the host matrices."""
         self.probability = alignments
         self._theta_host = None
         self._theta_dirty = False
@@ -271,6 +273,9 @@ class EMfactory:
         self._device = device
         self._group = group
         self._item_len = item_len or int(os.environ.get("GBRS_ITEM_LEN", "0"))
+        self._hapmask = None if locus_hapmask is None else np.ascontiguousarray(locus_hapmask, dtype=np.uint8)
+        if self._hapmask is not None and self._hapmask.shape != (alignments.num_loci,):
+            raise ValueError("locus_hapmask must hold one byte per locus")
         self._poll_every = poll_every
         self._pattern: DevicePattern | None = None
         self._gene_of = None
@@ -344,12 +349,13 @@ class EMfactory:
                     "stored values other than 1.0 (or explicit zeros) in the alignment matrix: call "
                     "eliminate_zeros() after masking; weighted (non-incidence) matrices are not supported")
             if self._presharded:
-                self._pattern = DevicePattern(p, gene_of=self._gene_of, device=self._device, item_len=self._item_len)
+                self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
+                                              item_len=self._item_len)
                 self._pattern.n_ranks = self.world
                 self._pattern._build_descriptor()
             else:
-                self._pattern = DevicePattern(p, gene_of=self._gene_of, device=self._device, shard_rank=self.rank,
-                                              shard_count=self.world, item_len=self._item_len)
+                self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
+                                              shard_rank=self.rank, shard_count=self.world, item_len=self._item_len)
             self._pattern.set_lengths(self.target_lengths)
             if self.world > 1:
                 self.fused_exchange = self._setup_fused_exchange(self._pattern)

@@ -36,6 +36,13 @@ def load_genotype_mask(aln_mat: AlignmentPropertyMatrix, genotype_file: str):
     return gtmask, gtcall_g, gtcall_t
 
 
+def hapmask_bytes(gtmask: np.ndarray) -> np.ndarray:
+    """H x T 0/1 genotype mask -> uint8 [T] with bit h set where haplotype h of the locus is kept."""
+    H = gtmask.shape[0]
+    bits = (np.asarray(gtmask) != 0).astype(np.uint8)
+    return (bits << np.arange(H, dtype=np.uint8)[:, None]).sum(axis=0).astype(np.uint8)
+
+
 def _write_reports(em_factory, outbase, alignment_file, group_file, report_group_counts, report_alignment_counts,
                    report_posterior, notes_t=None, notes_g=None):
     """The output section shared by `quantify` (gbrs/emase_utils.py:288-331) and `run` (emase/emase_utils.py:650-695)."""
@@ -116,20 +123,26 @@ def quantify(alignment_file: str, group_file: str = None, length_file: str = Non
 
     logger.info(f"Loading EMASE file: {alignment_file}")
     aln_mat = AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
+    locus_hapmask = None
 
     if genotype_file is not None:
         outbase = f"{outbase}.diploid"
         logger.info(f"Loading and processing genotype calls from: {genotype_file}")
         gtmask, gtcall_g, gtcall_t = load_genotype_mask(aln_mat, genotype_file)
-        aln_mat.multiply(gtmask, axis=2)
-        aln_mat.eliminate_zeros()
+        if report_posterior:
+            # the exported pattern must be the restricted one, as in the reference (emase_utils.py:271-273)
+            aln_mat.multiply(gtmask, axis=2)
+            aln_mat.eliminate_zeros()
+        else:
+            # same restriction applied while packing: one byte per locus, bit h = haplotype h survives
+            locus_hapmask = hapmask_bytes(gtmask)
     else:
         outbase = f"{outbase}.multiway"
         gtcall_g = None
         gtcall_t = None
 
     logger.info("Running EMASE")
-    em_factory = EMfactory(aln_mat, device=device, group=group)
+    em_factory = EMfactory(aln_mat, device=device, group=group, locus_hapmask=locus_hapmask)
     em_factory.prepare(pseudocount=pseudocount, lenfile=length_file)
     em_factory.run(model=multiread_model, tol=tolerance, max_iters=max_iters, verbose=True)
 

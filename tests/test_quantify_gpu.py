@@ -115,3 +115,25 @@ def test_cohort_mode_equals_individual_runs(tmp_path):
     # different samples give different answers (they share loci and lengths only)
     assert not np.array_equal(res[0]["theta"], res[1]["theta"])
     assert [r["iters"] for r in cohort.gather_results(res, 3)] == [res[i]["iters"] for i in samples]
+
+
+def test_diploid_fast_mask_path_equals_host_masking(tmp_path):
+    """`quantify -G` applies the genotype restriction while packing (one byte per locus); with `-w` it masks the host
+    matrices like the reference does (the exported pattern must be the restricted one).  Same tables either way."""
+    gdir = os.path.join(hp.GOLDEN, "quantify_diploid")
+    z = np.load(os.path.join(gdir, "input.npz"))
+    d = synth.generate(T=int(z["T"]), N=int(z["N"]), H=int(z["H"]), with_genotype=True)
+    aln = os.path.join(str(tmp_path), "aln.emase")
+    make_apm(d).save(aln)
+    outs = []
+    for posterior in (False, True):
+        outbase = os.path.join(str(tmp_path), f"o{int(posterior)}")
+        quantify(alignment_file=aln, group_file=os.path.join(gdir, "grp.tsv"), length_file=os.path.join(gdir, "len.tsv"),
+                 genotype_file=os.path.join(gdir, "gt.tsv"), outbase=outbase, multiread_model=4,
+                 report_posterior=posterior)
+        outs.append(read_table(f"{outbase}.diploid.isoforms.expected_read_counts"))
+    assert outs[0][1] == outs[1][1] and np.array_equal(outs[0][2], outs[1][2])
+    from gbrs_b200 import AlignmentPropertyMatrix
+
+    exported = AlignmentPropertyMatrix(h5file=os.path.join(str(tmp_path), "o1.diploid.posterior.h5"))
+    assert exported.nnz < make_apm(d).nnz  # the exported pattern is the restricted one
