@@ -12,6 +12,7 @@
 // The `-G` genotype restriction (src/gbrs/gbrs/emase_utils.py:247-273: multiply by gtmask + eliminate_zeros) is an AND of
 // every pair's mask with a per-locus byte; pairs and classes that become empty are dropped.
 #include <algorithm>
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -94,24 +95,55 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     for (int t = 0; t < T; ++t) {
       const uint32_t lm = in->locus_hapmask ? in->locus_hapmask[t] : 0xFFu;
       uint64_t* dst = tmp.data() + ub[t];
-      int64_t n = 0;
-      for (int h = 0; h < H; ++h) {
-        if (!((lm >> h) & 1u)) continue;
-        const int64_t b = in->indptr[h][t], e = in->indptr[h][t + 1];
-        for (int64_t i = b; i < e; ++i) {
-          if (in->values && in->values[h] && in->values[h][i] == 0.0) continue;
-          const int64_t c = index_at(in->indices[h], in->index_bytes, i);
-          if (c < 0 || c >= N) { bad = 1; continue; }
-          dst[n++] = ((uint64_t) c << 8) | (uint64_t) h;
+      // Fast path: every column is sorted by class id (what scipy / the EMASE writer produce) -> H-way merge, OR-ing
+      // the haplotype bits of equal classes.  Any disorder, explicit zero or bad index falls back to gather + sort.
+      int64_t m = 0;
+      bool merged = !(in->values);
+      if (merged) {
+        int64_t pos[GBRS_HPAD], end[GBRS_HPAD];
+        int nh = 0, hs[GBRS_HPAD];
+        for (int h = 0; h < H; ++h)
+          if ((lm >> h) & 1u) { pos[nh] = in->indptr[h][t]; end[nh] = in->indptr[h][t + 1]; hs[nh] = h; ++nh; }
+        int64_t last = -1;
+        while (merged) {
+          int64_t best = INT64_MAX;
+          for (int i = 0; i < nh; ++i)
+            if (pos[i] < end[i]) {
+              const int64_t c = index_at(in->indices[hs[i]], in->index_bytes, pos[i]);
+              if (c < best) best = c;
+            }
+          if (best == INT64_MAX) break;
+          if (best <= last || best < 0 || best >= N) { merged = false; break; }  // unsorted / duplicate / bad: redo slowly
+          uint64_t mask = 0;
+          for (int i = 0; i < nh; ++i)
+            if (pos[i] < end[i] && index_at(in->indices[hs[i]], in->index_bytes, pos[i]) == best) {
+              mask |= (uint64_t) 1 << hs[i];
+              ++pos[i];
+            }
+          dst[m++] = ((uint64_t) best << 8) | mask;
+          last = best;
         }
       }
-      std::sort(dst, dst + n);
-      int64_t m = 0;
-      for (int64_t i = 0; i < n;) {
-        const uint64_t c = dst[i] >> 8;
-        uint64_t mask = 0;
-        while (i < n && (dst[i] >> 8) == c) { mask |= (uint64_t) 1 << (dst[i] & 0xFF); ++i; }
-        dst[m++] = (c << 8) | mask;
+      if (!merged) {
+        int64_t n = 0;
+        for (int h = 0; h < H; ++h) {
+          if (!((lm >> h) & 1u)) continue;
+          const int64_t b = in->indptr[h][t], e = in->indptr[h][t + 1];
+          for (int64_t i = b; i < e; ++i) {
+            if (in->values && in->values[h] && in->values[h][i] == 0.0) continue;
+            const int64_t c = index_at(in->indices[h], in->index_bytes, i);
+            if (c < 0 || c >= N) { bad = 1; continue; }
+            dst[n++] = ((uint64_t) c << 8) | (uint64_t) h;
+          }
+        }
+        std::sort(dst, dst + n);
+        m = 0;
+        for (int64_t i = 0; i < n;) {
+          const uint64_t c = dst[i] >> 8;
+          uint64_t mask = 0;
+          while (i < n && (dst[i] >> 8) == c) { mask |= (uint64_t) 1 << (dst[i] & 0xFF); ++i; }
+          dst[m++] = (c << 8) | mask;
+        }
       }
       lcount[t] = m;
     }
@@ -119,17 +151,23 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
 
     lap("1 merge columns");
     // ---- 2. per-class pair / nnz counts, shard boundaries balanced by nnz -----------------------------------------
+    // (the scattered per-class updates are done by all threads with relaxed atomics: classes are hit in random order)
     std::vector<uint32_t> npair((size_t) N, 0), minloc((size_t) N, 0xFFFFFFFFu);
     std::vector<uint32_t> nz((size_t) N, 0);
+#pragma omp parallel for schedule(dynamic, 256)
     for (int t = 0; t < T; ++t) {
       const uint64_t* src = tmp.data() + ub[t];
       for (int64_t i = 0; i < lcount[t]; ++i) {
         const uint64_t c = src[i] >> 8;
-        if (npair[c]++ == 0) minloc[c] = (uint32_t) t;
-        nz[c] += (uint32_t) __builtin_popcountll(src[i] & 0xFF);
+        __atomic_fetch_add(&npair[c], 1u, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&nz[c], (uint32_t) __builtin_popcountll(src[i] & 0xFF), __ATOMIC_RELAXED);
+        uint32_t cur_min = __atomic_load_n(&minloc[c], __ATOMIC_RELAXED);
+        while ((uint32_t) t < cur_min &&
+               !__atomic_compare_exchange_n(&minloc[c], &cur_min, (uint32_t) t, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
       }
     }
     int64_t nnz_total = 0, nclass_total = 0;
+#pragma omp parallel for reduction(+ : nnz_total, nclass_total)
     for (int64_t c = 0; c < N; ++c) { nnz_total += nz[c]; nclass_total += npair[c] > 0; }
     // class c goes to shard floor(cum_before(c) * R / total)
     const int R = in->shard_count, rank = in->shard_rank;
@@ -177,6 +215,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     P->T = T;
     P->rowptr.assign((size_t) n_classes + 1, 0);
     P->count.assign((size_t) n_classes, 1.0);
+#pragma omp parallel for schedule(static)
     for (int64_t c = lo; c < hi; ++c)
       if (npair[c]) {
         P->rowptr[new_id[c] + 1] = npair[c];
@@ -188,17 +227,20 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     // ---- 4. class-major fill (loci ascending within a class), then order pairs by (gene, locus) and cut runs -----
     P->pairs.assign((size_t) n_pairs, 0);
     {
+      // all threads scatter; the slot inside a class is claimed atomically, the (gene, locus) sort below makes the
+      // final order independent of the claiming order
       std::vector<uint32_t> cur(P->rowptr.begin(), P->rowptr.end() - 1);
+#pragma omp parallel for schedule(dynamic, 256)
       for (int t = 0; t < T; ++t) {
         const uint64_t* src = tmp.data() + ub[t];
         for (int64_t i = 0; i < lcount[t]; ++i) {
           const uint32_t nid = new_id[src[i] >> 8];
           if (nid == 0xFFFFFFFFu) continue;
-          P->pairs[cur[nid]++] = (uint32_t) t | ((uint32_t)(src[i] & 0xFF) << 24);
+          const uint32_t slot = __atomic_fetch_add(&cur[nid], 1u, __ATOMIC_RELAXED);
+          P->pairs[slot] = (uint32_t) t | ((uint32_t)(src[i] & 0xFF) << 24);
         }
       }
     }
-    std::vector<uint64_t>().swap(tmp);
     P->gene_of.resize(T);
     for (int t = 0; t < T; ++t) {
       P->gene_of[t] = in->gene_of ? in->gene_of[t] : t;
@@ -206,6 +248,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     }
     const int32_t n_gene_ids = 1 + *std::max_element(P->gene_of.begin(), P->gene_of.end());
     P->runptr.assign((size_t) n_classes + 1, 0);
+    std::vector<uint32_t> run_in_class((size_t) n_pairs, 0);  // run number of a pair inside its class
     int max_k = 0;
 #pragma omp parallel for schedule(static) reduction(max : max_k)
     for (int64_t n = 0; n < n_classes; ++n) {
@@ -222,7 +265,11 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
         b[j + 1] = w;
       }
       uint32_t runs = k > 0 ? 1 : 0;
-      for (int i = 1; i < k; ++i) runs += go[b[i] & 0xFFFFFF] != go[b[i - 1] & 0xFFFFFF];
+      uint32_t* ric = run_in_class.data() + P->rowptr[n];
+      for (int i = 1; i < k; ++i) {
+        runs += go[b[i] & 0xFFFFFF] != go[b[i - 1] & 0xFFFFFF];
+        ric[i] = runs - 1;
+      }
       P->runptr[n + 1] = runs;
     }
     for (int64_t n = 0; n < n_classes; ++n) P->runptr[n + 1] += P->runptr[n];
@@ -242,9 +289,14 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     const uint32_t full_mask = (1u << H) - 1u;
     auto pad4 = [](int64_t x) { return (x + 3) / 4 * 4; };
     std::vector<int64_t> lcnt(T, 0), lpart(T, 0);
-    for (int64_t p = 0; p < n_pairs; ++p) {
-      ++lcnt[P->pairs[p] & 0xFFFFFF];
-      lpart[P->pairs[p] & 0xFFFFFF] += (P->pairs[p] >> 24) != full_mask;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int t = 0; t < T; ++t) {  // entries of this shard per locus, and how many of them have a partial mask
+      const uint64_t* src = tmp.data() + ub[t];
+      int64_t c_all = 0, c_part = 0;
+      for (int64_t i = 0; i < lcount[t]; ++i)
+        if (new_id[src[i] >> 8] != 0xFFFFFFFFu) { ++c_all; c_part += (src[i] & 0xFF) != full_mask; }
+      lcnt[t] = c_all;
+      lpart[t] = c_part;
     }
     // only deep loci are split into a partial and a full part; a shallow locus stays one (mixed) part, otherwise the
     // many tiny loci would double their item count for nothing
@@ -262,27 +314,48 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     P->ent_cls.assign((size_t) n_entries * entry_bytes, 0);
     P->ent_pair.assign((size_t) n_entries * entry_bytes, 0);
     P->ent_run.assign((size_t) n_entries * entry_bytes, 0);
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n_entries; ++i) {
       put_entry(P->ent_cls, entry_bytes, i, (uint64_t) n_classes, 0);
       put_entry(P->ent_pair, entry_bytes, i, (uint64_t) n_pairs, 0);
       put_entry(P->ent_run, entry_bytes, i, (uint64_t) n_runs, 0);
     }
     {
+      // The classes are walked in new order and every pair is appended to its locus' cursor, which yields ascending
+      // class ids inside a locus without sorting.  To do that with all threads, the loci are cut into contiguous
+      // ranges of about equal entry count; each thread walks ALL pair words (sequential, cheap) and keeps only the
+      // pairs whose locus falls into its own range, so no two threads ever touch the same cursor.
       std::vector<int64_t> cur_part(lptr.begin(), lptr.end() - 1), cur_full(T);
       for (int t = 0; t < T; ++t) cur_full[t] = lptr[t] + ppart[t];
-      const int32_t* go = P->gene_of.data();
-      for (int64_t n = 0; n < n_classes; ++n) {
-        uint64_t run = P->runptr[n];
-        for (uint32_t p = P->rowptr[n]; p < P->rowptr[n + 1]; ++p) {
-          const uint32_t w = P->pairs[p], t = w & 0xFFFFFF, m = w >> 24;
-          if (p > P->rowptr[n] && go[t] != go[P->pairs[p - 1] & 0xFFFFFF]) ++run;
-          const int64_t pos = (split[t] && m == full_mask) ? cur_full[t]++ : cur_part[t]++;
-          put_entry(P->ent_cls, entry_bytes, pos, (uint64_t) n, m);
-          put_entry(P->ent_pair, entry_bytes, pos, (uint64_t) p, m);
-          put_entry(P->ent_run, entry_bytes, pos, run, m);
+      int nt = 1;
+#ifdef _OPENMP
+      nt = omp_get_max_threads();
+#endif
+      std::vector<int> cut(nt + 1, T);
+      cut[0] = 0;
+      for (int k = 1, t = 0; k < nt; ++k) {
+        const int64_t want = n_entries * k / nt;
+        while (t < T && lptr[t] < want) ++t;
+        cut[k] = t;
+      }
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+      for (int k = 0; k < nt; ++k) {
+        const uint32_t t_lo = (uint32_t) cut[k], t_hi = (uint32_t) cut[k + 1];
+        if (t_lo >= t_hi) continue;
+        for (int64_t n = 0; n < n_classes; ++n) {
+          const uint32_t r0 = P->runptr[n];
+          for (uint32_t p = P->rowptr[n]; p < P->rowptr[n + 1]; ++p) {
+            const uint32_t w = P->pairs[p], t = w & 0xFFFFFF, m = w >> 24;
+            if (t < t_lo || t >= t_hi) continue;
+            const int64_t pos = (split[t] && m == full_mask) ? cur_full[t]++ : cur_part[t]++;
+            put_entry(P->ent_cls, entry_bytes, pos, (uint64_t) n, m);
+            put_entry(P->ent_pair, entry_bytes, pos, (uint64_t) p, m);
+            put_entry(P->ent_run, entry_bytes, pos, (uint64_t) r0 + run_in_class[p], m);
+          }
         }
       }
     }
+    std::vector<uint64_t>().swap(tmp);
 
     lap("5 locus-major entries");
     // ---- 6. column-pass work items ------------------------------------------------------------------------------
