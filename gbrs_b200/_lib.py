@@ -51,8 +51,7 @@ class EmDev(C.Structure):
                 ("n_entries", C.c_int64), ("n_long_items", C.c_int64), ("n_ranks", C.c_int32), ("max_iters_cap", C.c_int32),
                 ("bucket_class0", C.c_int64 * (GBRS_KMAX + 2)), ("bucket_pair0", C.c_int64 * (GBRS_KMAX + 2)),
                 ("xchg_enabled", C.c_int32), ("xchg_rank", C.c_int32), ("xchg_peer", C.c_void_p * 8),
-                ("rowptr", C.c_void_p), ("pairs", C.c_void_p), ("count", C.c_void_p), ("count32", C.c_void_p),
-                ("runptr", C.c_void_p),
+                ("rowptr", C.c_void_p), ("pairs", C.c_void_p), ("count", C.c_void_p), ("runptr", C.c_void_p),
                 ("ent_cls", C.c_void_p), ("ent_pair", C.c_void_p), ("ent_run", C.c_void_p),
                 ("item_off", C.c_void_p), ("item_order", C.c_void_p), ("item_desc", C.c_void_p),
                 ("locus_order", C.c_void_p), ("locus_desc", C.c_void_p), ("locus_item_ptr", C.c_void_p),

@@ -144,11 +144,6 @@ __device__ __forceinline__ double fast_div(double c, double s) {
   return fma(fma(-s, q, c), r, q);
 }
 
-// Class count: stored as fp32 when every count is an integer below 2^24 (lossless, halves that stream), else fp64.
-__device__ __forceinline__ double class_count(const gbrs_em_dev& d, int64_t n) {
-  return d.count32 ? (double) __ldcs(d.count32 + n) : __ldcs(d.count + n);
-}
-
 // Sum over the 8 lanes of an aligned lane group; every lane gets the total.  Fixed order => deterministic.
 __device__ __forceinline__ double group8_sum(double v) {
   v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
@@ -358,7 +353,7 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
     const uint32_t* __restrict__ pw = d.pairs + bucket_pair0 + (valid ? (n[u] - bucket_class0) : 0) * K;
 #pragma unroll
     for (int p = 0; p < K; ++p) w[u][p] = valid ? __ldcs(pw + p) : 0u;
-    cnt[u] = valid ? class_count(d, n[u]) : 0.0;
+    cnt[u] = valid ? __ldcs(d.count + n[u]) : 0.0;
   }
   double s[UNR];
   if (UNIT) {
@@ -435,7 +430,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m4_long(const gbrs_em_dev 
       if (UNIT) s += (double) __popc(w >> 24);
       else s += pair_sum(d.subsets, w);
     }
-    d.weights[n] = class_count(d, n) / s;
+    d.weights[n] = __ldg(d.count + n) / s;
   }
 }
 
@@ -473,7 +468,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d, in
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t n = first_class + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
-    const double c = class_count(d, n);
+    const double c = __ldg(d.count + n);
     double total = 0.0;
     // pass 1: sum of gene totals over the runs that are alive
     for (uint32_t p = b; p < e;) {
@@ -514,7 +509,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d, in
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t n = first_class + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
-    const double c = class_count(d, n);
+    const double c = __ldg(d.count + n);
     double total = 0.0;
     for (uint32_t p = b; p < e;) {
       const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
@@ -559,7 +554,7 @@ __device__ __forceinline__ void row_class_m23(const gbrs_em_dev& d, const double
   uint32_t w[K];
 #pragma unroll
   for (int p = 0; p < K; ++p) w[p] = __ldg(pw + p);
-  const double c = class_count(d, n);
+  const double c = __ldg(d.count + n);
   double x[K], gam[K], it[K];
   int32_t g[K];
 #pragma unroll
@@ -645,7 +640,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d) {
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
-    const double c = class_count(d, n);
+    const double c = __ldg(d.count + n);
     double total = 0.0;
     for (uint32_t p = b; p < e;) {
       const int32_t g = __ldg(d.gene_of + (__ldg(d.pairs + p) & kLocusMask));
@@ -1062,7 +1057,7 @@ __global__ void __launch_bounds__(kThreads) k_alignment_counts(const gbrs_em_dev
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = d.rowptr[n], e = d.rowptr[n + 1];
-    const double c = class_count(d, n);
+    const double c = d.count[n];
     if (!gene_level) {
       int nz = 0;
       for (uint32_t p = b; p < e; ++p) nz += __popc(d.pairs[p] >> 24);
@@ -1105,7 +1100,7 @@ int check_dev(const gbrs_em_dev* d, const char* who) {
   if (d->T <= 0 || d->H < 1 || d->H > GBRS_HPAD || (d->entry_bytes != 4 && d->entry_bytes != 8)) {
     gbrs_set_error(std::string(who) + ": bad descriptor shape"); return GBRS_E_ARG;
   }
-  if (!d->rowptr || !d->pairs || (!d->count && !d->count32) || !d->item_off || !d->item_order || !d->item_desc || !d->locus_order || !d->locus_desc || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
+  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->item_order || !d->item_desc || !d->locus_order || !d->locus_desc || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
       !d->iso || !d->weights || !d->subsets || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
     gbrs_set_error(std::string(who) + ": null device buffer in descriptor"); return GBRS_E_ARG;
   }

@@ -112,11 +112,6 @@ class PackedPattern:
                     self.arrays[name] = np.frombuffer(buf, dtype=dt).copy()
         finally:
             lib.gbrs_pack_free(handle)
-        # class counts travel as fp32 when that is lossless (integer valued, below 2^24): half the bytes of that stream
-        c = self.arrays["count"]
-        self.count_is_f32 = bool(c.size == 0 or (np.all(c == np.floor(c)) and c.min() >= 0 and c.max() < 2**24))
-        if self.count_is_f32:
-            self.arrays["count32"] = c.astype(np.float32)
         self.pack_seconds = time.perf_counter() - t0
         self.T, self.H, self.N = T, H, N
         self.has_genes = gene_of is not None
@@ -143,8 +138,6 @@ class DevicePattern:
         self.n_ranks = shard_count
         self.host = {}
         for k, a in packed.arrays.items():
-            if k == "count" and packed.count_is_f32:
-                continue  # the fp32 copy is shipped instead
             # torch has no uint32/uint64 arithmetic needs here: ship raw bytes
             t = torch.from_numpy(a.view(np.uint8))
             self.host[k] = t.pin_memory() if pin else t
@@ -196,9 +189,7 @@ class DevicePattern:
         for k in range(_lib.GBRS_KMAX + 2):
             d.bucket_class0[k] = i["bucket_class0"][k]
             d.bucket_pair0[k] = i["bucket_pair0"][k]
-        d.count = self.dev["count"].data_ptr() if "count" in self.dev else None
-        d.count32 = self.dev["count32"].data_ptr() if "count32" in self.dev else None
-        for k in ("rowptr", "pairs", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "item_order",
+        for k in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "item_order",
                   "item_desc", "locus_order", "locus_desc", "locus_item_ptr"):
             setattr(d, k, self.dev[k].data_ptr())
         if self.packed.has_genes:

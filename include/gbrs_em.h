@@ -130,8 +130,7 @@ typedef struct {
   /* packed incidence (read-only) */
   const uint32_t* rowptr;
   const uint32_t* pairs;
-  const double* count;     /* [n_classes] class counts ... */
-  const float* count32;    /* ... or the same as fp32 when that is lossless (all integers < 2^24); exactly one is set */
+  const double* count;
   const uint32_t* runptr;
   const void* ent_cls;
   const void* ent_pair;
