@@ -314,8 +314,9 @@ def run_gpu_arm(args, wl):
     Np, Pp, It, T = info["n_classes"], info["n_pairs"], info["n_items"], wl["T"]
     eb = info["entry_bytes"]
     widx = {4: Np, 3: info["n_runs"], 2: Pp, 1: 8 * info["n_runs"]}[model]
-    bytes_row = 4 * Pp + 4 * (Np + 1) + 8 * Np + 8 * widx + 64 * T
-    bytes_col = eb * Pp + 4 * (It + 1) + 8 * widx + 64 * It
+    Ee = info["n_entries"]
+    bytes_row = 4 * Pp + 8 * Np + 8 * widx + 256 * T  # pair words, counts, weights out, subset tables in
+    bytes_col = eb * Ee + 16 * It + 8 * widx + 64 * It  # entry words, item descriptors, weights in, item sums out
     bytes_iter = 4 * Pp + 4 * (Np + 1) + 8 * Np + 3 * 64 * T  # SURVEY 8(d), pair+mask layout, inputs once
     peak, peak_src = measured_peaks()
     if row_ms >= col_ms:
