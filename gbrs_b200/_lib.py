@@ -84,6 +84,9 @@ SYMBOLS = {
     "gbrs_em_run": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p,
                               C.POINTER(C.c_int32), C.c_void_p]),
     "gbrs_em_read_ctrl": (C.c_int, [C.POINTER(EmDev), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gbrs_write_table": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int64, C.c_void_p, C.c_int32,
+                                   C.POINTER(C.c_char_p), C.c_void_p, C.c_int32]),
+    "gbrs_format_double": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
     "gbrs_em_alignment_counts": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
 }

@@ -80,13 +80,43 @@ def group_conversion_matrix(num_loci: int, groups):
 
 def write_table_rows(fh, names, cntdata: np.ndarray, notes=None, order=None) -> None:
     """Rows `name<TAB>v0<TAB>v1...[<TAB>note]` with values formatted like the reference's `str(numpy.float64)`
-    (EMfactory.py:325-331, :370-380)."""
-    idx = range(len(names)) if order is None else order
-    cols = cntdata.shape[0]
-    for i in idx:
-        name = names[i]
-        vals = cntdata[:, i]
-        line = str(name) + "\t" + "\t".join(repr(float(vals[k])) for k in range(cols))
-        if notes is not None:
-            line += f"\t{notes[name]}"
-        fh.write(line + "\n")
+    (EMfactory.py:325-331, :370-380).  The formatting runs natively (libgbrs_em.so, all host threads): at 80k loci a
+    table is ~0.7 M numbers and the python loop took longer than the whole EM.  `fh` is an open text file positioned
+    after the header; the rows are appended to the same file."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    n = len(names)
+    data = np.ascontiguousarray(cntdata, dtype=np.float64)
+    if data.ndim != 2 or data.shape[1] != n:
+        raise ValueError("cntdata must be [columns][rows]")
+    c_names = (C.c_char_p * n)(*[str(x).encode() for x in names])
+    c_notes = None
+    if notes is not None:
+        c_notes = (C.c_char_p * n)(*[str(notes[x]).encode() for x in names])
+    c_order, n_rows = None, n
+    if order is not None:
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        c_order, n_rows = order.ctypes.data, int(order.shape[0])
+    fh.flush()
+    path = fh.name
+    # rows index `names` / `data` through `order`; n_rows of them are written, the arrays keep their full length
+    if c_order is not None and n_rows != n:
+        raise ValueError("order must be a permutation of the rows")
+    _lib.check(lib.gbrs_write_table(path.encode(), None, c_names, n, data.ctypes.data, data.shape[0], c_notes, c_order, 1))
+    fh.seek(0, 2)
+
+
+def py_float_str(x: float) -> str:
+    """The native formatter for one value (tests compare it with python's repr)."""
+    import ctypes as C
+
+    from . import _lib
+
+    buf = C.create_string_buffer(64)
+    n = _lib.load().gbrs_format_double(float(x), buf, 64)
+    if n < 0:
+        raise ValueError("formatting failed")
+    return buf.value.decode()

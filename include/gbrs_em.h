@@ -214,6 +214,15 @@ int gbrs_em_read_ctrl(const gbrs_em_dev* d, void* stream, int32_t* ctrl_host, do
 int gbrs_em_alignment_counts(const gbrs_em_dev* d, int gene_level, int32_t n_real_genes, double* aln_dev,
                              double* uniq_dev, double* locus_uniq_dev, void* stream);
 
+/* Report tables (EMfactory.report_read_counts / report_depths, EMfactory.py:289-380; APM.report_alignment_counts,
+ * AlignmentPropertyMatrix.py:442-459): rows `name<TAB>v0<TAB>v1...[<TAB>note]`, every value formatted exactly like
+ * python's str(numpy.float64).  `data` is [n_cols][n_rows] (the reference's `cntdata`), `order` an optional row
+ * permutation, `header` is written verbatim first (unless NULL).  Host only; rows are formatted by all host threads. */
+int gbrs_write_table(const char* path, const char* header, const char* const* names, int64_t n_rows, const double* data,
+                     int32_t n_cols, const char* const* notes, const int64_t* order, int32_t append);
+/* python repr of one double into `out` (NUL-terminated); returns the length or GBRS_E_ARG if `cap` is too small. */
+int gbrs_format_double(double x, char* out, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif
