@@ -326,18 +326,27 @@ class AlignmentPropertyMatrix:
             self.data[h].data = np.ones(self.data[h].nnz, dtype=self.data[h].dtype)
 
     # ------------------------------------------------------------------ alignment counts (device)
-    def _alignment_count_tables(self, gene_level=False, device=None):
+    def _alignment_count_tables(self, gene_level=False, device=None, pattern=None):
+        """(aln, uniq, locus_uniq) on the device.  `pattern`: an already packed + resident `DevicePattern` of THIS
+        (unmasked) matrix to reuse -- `quantify` passes the EM's own pattern for multiway runs, so that the matrix is
+        neither reloaded nor packed again; otherwise one pattern is packed on first use and kept."""
         from .emfactory import DevicePattern
 
-        gene_of = None
         n_real = 0
         if gene_level:
             if not (self.num_groups > 0 and self.groups is not None and self.gname is not None):
                 raise RuntimeError("No group information is available for bundling.")
-            gene_of = utils.gene_index(self.num_loci, self.groups)
             n_real = self.num_groups
-        pat = DevicePattern(self, gene_of=gene_of, device=device)
-        return pat.alignment_counts(gene_level=gene_level, n_real_genes=n_real)
+        if pattern is None:
+            pattern = getattr(self, "_count_pattern", None)
+            need_genes = self.num_groups > 0 and self.groups is not None
+            if pattern is None or (gene_level and not pattern.packed.has_genes):
+                gene_of = utils.gene_index(self.num_loci, self.groups) if need_genes else None
+                pattern = DevicePattern(self, gene_of=gene_of, device=device)
+                self._count_pattern = pattern
+        elif gene_level and not pattern.packed.has_genes:
+            raise RuntimeError("the supplied pattern was packed without gene information")
+        return pattern.alignment_counts(gene_level=gene_level, n_real_genes=n_real)
 
     def count_alignments(self):
         """H x T count-weighted alignment counts (AlignmentPropertyMatrix.py:436-440)."""
@@ -347,10 +356,10 @@ class AlignmentPropertyMatrix:
         aln, uniq, locus_uniq = self._alignment_count_tables()
         return locus_uniq if ignore_haplotype else uniq
 
-    def report_alignment_counts(self, filename, gene_level=False):
+    def report_alignment_counts(self, filename, gene_level=False, pattern=None):
         """AlignmentPropertyMatrix.report_alignment_counts (:442-459).  `gene_level=True` is what the reference
         obtains by `_bundle_inline(reset=True)` followed by this call (gbrs/emase_utils.py:327-331)."""
-        aln, uniq, locus_uniq = self._alignment_count_tables(gene_level=gene_level)
+        aln, uniq, locus_uniq = self._alignment_count_tables(gene_level=gene_level, pattern=pattern)
         names = self.gname if gene_level else self.lname
         cntdata = np.vstack((aln, uniq, locus_uniq[None, :]))
         with open(filename, "w") as fh:

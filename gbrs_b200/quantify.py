@@ -44,7 +44,7 @@ def hapmask_bytes(gtmask: np.ndarray) -> np.ndarray:
 
 
 def _write_reports(em_factory, outbase, alignment_file, group_file, report_group_counts, report_alignment_counts,
-                   report_posterior, notes_t=None, notes_g=None):
+                   report_posterior, notes_t=None, notes_g=None, unmasked=None, unmasked_pattern=None):
     """The output section shared by `quantify` (gbrs/emase_utils.py:288-331) and `run` (emase/emase_utils.py:650-695)."""
     logger.info(f"Generating isoform TPMs: {outbase}.isoforms.tpm")
     em_factory.report_depths(filename=f"{outbase}.isoforms.tpm", tpm=True, notes=notes_t)
@@ -59,13 +59,16 @@ def _write_reports(em_factory, outbase, alignment_file, group_file, report_group
         logger.info(f"Generating gene Read Counts: {outbase}.genes.expected_read_counts")
         em_factory.report_read_counts(filename=f"{outbase}.genes.expected_read_counts", grp_wise=True, notes=notes_g)
     if report_alignment_counts:
-        # the reference reloads the file, i.e. counts are taken on the *unmasked* matrix (gbrs/emase_utils.py:319)
-        alnmat = AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
+        # The reference reloads the file, i.e. counts are taken on the *unmasked* matrix (gbrs/emase_utils.py:319).
+        # Here the host matrix is still unmasked unless `-w` forced the in-place restriction, so it is reused; for a
+        # multiway run even the EM's packed, device-resident pattern is reused.
+        alnmat = unmasked if unmasked is not None else AlignmentPropertyMatrix(h5file=alignment_file, grpfile=group_file)
         logger.info(f"Generating isoform Alignment Counts: {outbase}.isoforms.alignment_counts")
-        alnmat.report_alignment_counts(filename=f"{outbase}.isoforms.alignment_counts")
+        alnmat.report_alignment_counts(filename=f"{outbase}.isoforms.alignment_counts", pattern=unmasked_pattern)
         if report_group_counts:
             logger.info(f"Generating gene Alignment Counts: {outbase}.genes.alignment_counts")
-            alnmat.report_alignment_counts(filename=f"{outbase}.genes.alignment_counts", gene_level=True)
+            alnmat.report_alignment_counts(filename=f"{outbase}.genes.alignment_counts", gene_level=True,
+                                           pattern=unmasked_pattern)
 
 
 def run(alignment_file: str, group_file: str = None, length_file: str = None, outbase: str = "emase",
@@ -88,8 +91,9 @@ def run(alignment_file: str, group_file: str = None, length_file: str = None, ou
     em_factory.prepare(pseudocount=pseudocount, lenfile=length_file, read_length=read_length)
     em_factory.run(model=multiread_model, tol=tolerance, max_iters=max_iters, verbose=True)
     if em_factory.rank == 0:
+        reuse_pattern = em_factory.world == 1 and em_factory._pattern.packed.has_genes
         _write_reports(em_factory, outbase, alignment_file, group_file, report_group_counts, report_alignment_counts,
-                       report_posterior)
+                       report_posterior, unmasked=aln_mat, unmasked_pattern=em_factory._pattern if reuse_pattern else None)
     logger.debug("Done")
 
 
@@ -147,6 +151,10 @@ def quantify(alignment_file: str, group_file: str = None, length_file: str = Non
     em_factory.run(model=multiread_model, tol=tolerance, max_iters=max_iters, verbose=True)
 
     if em_factory.rank == 0:
+        masked_on_host = genotype_file is not None and report_posterior
+        reuse_pattern = genotype_file is None and em_factory.world == 1 and em_factory._pattern.packed.has_genes
         _write_reports(em_factory, outbase, alignment_file, group_file, report_group_counts, report_alignment_counts,
-                       report_posterior, notes_t=gtcall_t, notes_g=gtcall_g)
+                       report_posterior, notes_t=gtcall_t, notes_g=gtcall_g,
+                       unmasked=None if masked_on_host else aln_mat,
+                       unmasked_pattern=em_factory._pattern if reuse_pattern else None)
     logger.debug("Done")
