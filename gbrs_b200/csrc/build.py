@@ -31,15 +31,24 @@ def is_stale() -> bool:
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    """`out`: alternative output path (tuning builds, loaded through GBRS_LIB_PATH)."""
+    if out is not None:
+        global LIB
+        saved, LIB = LIB, out
+        try:
+            return build(force=True, verbose=verbose)
+        finally:
+            LIB = saved
     if not force and not is_stale():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC,-fopenmp,-O3", "-Xptxas", "-v" if verbose else "-O3",
            "-I", os.path.join(ROOT, "include"), "-cudart", "static", "-o", LIB + ".tmp"] + SOURCES + ["-lgomp"]
-    if os.environ.get("GBRS_THREADS"):  # tuning experiments only
-        cmd.insert(1, "-DGBRS_THREADS=" + os.environ["GBRS_THREADS"])
+    for knob in ("GBRS_THREADS", "GBRS_COL_MINBLOCKS"):  # tuning experiments only
+        if os.environ.get(knob):
+            cmd.insert(1, f"-D{knob}=" + os.environ[knob])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -57,6 +57,9 @@ namespace {
 #define GBRS_THREADS 256
 #endif
 constexpr int kThreads = GBRS_THREADS;  // threads per block of every grid-stride kernel
+#ifndef GBRS_COL_MINBLOCKS
+#define GBRS_COL_MINBLOCKS 4  // resident blocks per SM the column pass is compiled for (64 registers at 256 threads)
+#endif
 constexpr uint32_t kLocusMask = 0xFFFFFFu;
 
 int g_sm_count = 0;
@@ -120,10 +123,13 @@ __device__ __forceinline__ void load8(const double* __restrict__ line, double (&
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = e.x; v[7] = e.y;
 }
 
-// a[h] += w for every haplotype slot h whose bit is set in m.  The column pass is bound by instruction issue; ptxas
-// turns both `if (bit) a += w` and `a += bit ? w : 0` (and even PTX-level predicated add.f64) into DADD + two 32-bit
-// selects per slot.  Multiplying by a 0.0 / 1.0 whose high word is selected from the bit is one select + one DFMA, and
-// fma(w, 1.0, a) == a + w exactly.
+// a[h] += w for every haplotype slot h whose bit is set in m.  ptxas turns both `if (bit) a += w` and
+// `a += bit ? w : 0` (and even PTX-level predicated add.f64) into DADD + two 32-bit selects per slot.  Multiplying by a
+// 0.0 / 1.0 whose high word is built from the bit costs LOP3 + IMAD + IMAD.MOV (zero low word) + DFMA, and
+// fma(w, 1.0, a) == a + w exactly.  Measured on B200 (C2, column pass, profiles/r1_column_pass_variants.txt): this form
+// 34.2 us; selecting both words of w with R2P predicates (3 instructions per slot, all on the ALU pipe) 41.6 us;
+// selecting only the high word (2 per slot, masked-out terms become denormals) 53.5 us.  Fewer instructions lose here
+// because the multiplier form spreads its work over the ALU, FMA and FP64 pipes.
 __device__ __forceinline__ void masked_add8(double (&a)[8], double w, uint32_t m) {
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
@@ -686,6 +692,52 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d) {
 // reference: APM.sum(axis=READ)  AlignmentPropertyMatrix.py:288-298 (count-weighted column reduce), without the
 // per-haplotype matrix copy.  VEC = 1: scalar weight per index; VEC = 8: one weight per haplotype (model 1).
 // ---------------------------------------------------------------------------------------------------------------------
+// CH steps of one lane of the column pass: step q covers the four entry words at p0 + 4 * LANES * q.  A step beyond the
+// item's end reads the item's first quad again with the masks stripped, which adds nothing.
+template <typename E, int LANES, bool FULL, int CH>
+__device__ __forceinline__ void column_steps(const E* __restrict__ ents, const double* __restrict__ wts, uint32_t b,
+                                             uint32_t e, uint32_t p0, double (&a)[8]) {
+  uint32_t msk[CH][4];
+  E idx[CH][4];
+#pragma unroll
+  for (int q = 0; q < CH; ++q) {
+    const uint32_t p = p0 + 4 * LANES * q;
+    const bool in = p < e;
+    const E* src = ents + (in ? p : b);
+    if (sizeof(E) == 4) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { idx[q][i] = w4[i] & 0xFFFFFFu; msk[q][i] = in ? (w4[i] >> 24) : 0u; }
+    } else {
+      const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(src));
+      const ulonglong2 v1 = __ldcs(reinterpret_cast<const ulonglong2*>(src) + 1);
+      const unsigned long long w4[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        idx[q][i] = w4[i] & 0x00FFFFFFFFFFFFFFull;
+        msk[q][i] = in ? (uint32_t) (w4[i] >> 56) : 0u;
+      }
+    }
+  }
+  double w[CH][4];
+#pragma unroll
+  for (int q = 0; q < CH; ++q)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[q][i] = __ldg(wts + idx[q][i]);
+#pragma unroll
+  for (int q = 0; q < CH; ++q) {
+    if (FULL) {
+      // padding words (and re-read quads) must not count: their mask is empty
+      a[0] += (msk[q][0] ? w[q][0] : 0.0) + (msk[q][1] ? w[q][1] : 0.0);
+      a[0] += (msk[q][2] ? w[q][2] : 0.0) + (msk[q][3] ? w[q][3] : 0.0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) masked_add8(a, w[q][i], msk[q][i]);
+    }
+  }
+}
+
 // LANES = 8: four short items per warp (one per aligned 8-lane group); LANES = 32: one long item per warp.
 // FULL: every entry of the item hits all H haplotypes -- a plain sum, broadcast to the H slots, no masking.
 template <typename E, int VEC, int LANES, bool FULL>
@@ -699,49 +751,13 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
   if (VEC == 1) {
     // Items start at a multiple of 4 entries and are padded with empty words, so every lane fetches four consecutive
     // entries per step (one 128-bit load for 32-bit words, two for 64-bit words); two steps and their eight weight
-    // gathers are in flight per lane before the adds.  An out-of-range quad reads the item's first quad again with the
-    // masks stripped, which adds nothing.
-    constexpr int CH = 2;
-    for (uint32_t p0 = b + 4 * lanex; p0 < e; p0 += 4 * LANES * CH) {
-      uint32_t msk[CH][4];
-      size_t idx[CH][4];
-#pragma unroll
-      for (int q = 0; q < CH; ++q) {
-        const uint32_t p = p0 + 4 * LANES * q;
-        const bool in = p < e;
-        const E* src = ents + (in ? p : b);
-        if (sizeof(E) == 4) {
-          const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src));
-          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { idx[q][i] = w4[i] & 0xFFFFFFu; msk[q][i] = in ? (w4[i] >> 24) : 0u; }
-        } else {
-          const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(src));
-          const ulonglong2 v1 = __ldcs(reinterpret_cast<const ulonglong2*>(src) + 1);
-          const unsigned long long w4[4] = {v0.x, v0.y, v1.x, v1.y};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            idx[q][i] = (size_t) (w4[i] & 0x00FFFFFFFFFFFFFFull);
-            msk[q][i] = in ? (uint32_t) (w4[i] >> 56) : 0u;
-          }
-        }
-      }
-      double w[CH][4];
-#pragma unroll
-      for (int q = 0; q < CH; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[q][i] = __ldg(wts + idx[q][i]);
-#pragma unroll
-      for (int q = 0; q < CH; ++q) {
-        if (FULL) {
-          // padding words (and re-read quads) must not count: their mask is empty
-          a[0] += (msk[q][0] ? w[q][0] : 0.0) + (msk[q][1] ? w[q][1] : 0.0);
-          a[0] += (msk[q][2] ? w[q][2] : 0.0) + (msk[q][3] ? w[q][3] : 0.0);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) masked_add8(a, w[q][i], msk[q][i]);
-        }
-      }
+    // gathers are in flight per lane before the adds.  When no item this warp is working on is longer than one step
+    // (most short items are: the shallow loci), a single step without the loop does.
+    const uint32_t longest = __reduce_max_sync(0xFFFFFFFFu, e - b);
+    if (longest <= 4u * LANES) {
+      column_steps<E, LANES, FULL, 1>(ents, wts, b, e, b + 4 * lanex, a);
+    } else {
+      for (uint32_t p0 = b + 4 * lanex; p0 < e; p0 += 4 * LANES * 2) column_steps<E, LANES, FULL, 2>(ents, wts, b, e, p0, a);
     }
   } else {
     for (uint32_t p = b + lanex; p < e; p += LANES) {
@@ -770,7 +786,7 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
 // Warp work slots: slot < n_long_items -> the slot-th item of item_order (a long item, whole warp); otherwise four
 // short items.  item_order lists long items first, partial-mask items before full-mask ones, longest first.
 template <typename E, int VEC>
-__global__ void __launch_bounds__(kThreads, 1024 / kThreads) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
+__global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
                                                              const E* __restrict__ ents, bool honour_done) {
   if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
   const int lane = threadIdx.x & 31;
@@ -826,7 +842,7 @@ __device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t 
 // `wit` is the *other* buffer: a single rank simply skips, a row-sharded rank recomputes the identical local numerator
 // from it (the in-place cross-rank sum that follows must always start from the local values).
 template <bool UNIT, bool FUSE>
-__global__ void __launch_bounds__(kThreads, 2048 / kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
+__global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
   __shared__ double red[32];
   const bool done = !UNIT && d.ctrl[GBRS_CTRL_DONE];
   if (done && (honour_done || FUSE)) return;
@@ -839,16 +855,23 @@ __global__ void __launch_bounds__(kThreads, 2048 / kThreads) k_locus_acc(const g
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   const int64_t rounds = (total + stride - 1) / stride;
   double mine = 0.0;
+  // deepest loci first, and consecutive entries of locus_order go to different blocks (the deep loci are few: spread
+  // them over all SMs instead of piling them into the first blocks).  One 16-byte descriptor per locus (locus, first
+  // item, one-past-last item) instead of three dependent loads; the descriptor of the NEXT round is requested before
+  // this round's work, so that only one memory latency per round (item sums / theta / length) stays exposed.
+  const int64_t g_in_round = (int64_t) (threadIdx.x >> 3) * gridDim.x + blockIdx.x;
+  const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.locus_desc);
+  uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+  if (g_in_round < d.T) nx = __ldg(descs + g_in_round);
   for (int64_t r = 0; r < rounds; ++r) {
-    // deepest loci first, and consecutive entries of locus_order go to different blocks (the deep loci are few: spread
-    // them over all SMs instead of piling them into the first blocks)
-    const int64_t g_in_round = (int64_t) (threadIdx.x >> 3) * gridDim.x + blockIdx.x;
     const int64_t slot = r * (stride >> 3) + g_in_round;
     const bool valid = slot < d.T;
-    // one 16-byte descriptor (locus, first item, one-past-last item) instead of three dependent loads; theta and the
-    // effective length are requested before the item sums are walked so that their latency overlaps
-    uint4 ld = make_uint4(0u, 0u, 0u, 0u);
-    if (valid) ld = __ldg(reinterpret_cast<const uint4*>(d.locus_desc) + slot);
+    const uint4 ld = nx;
+    {
+      const int64_t next = slot + (stride >> 3);
+      nx = make_uint4(0u, 0u, 0u, 0u);
+      if (r + 1 < rounds && next < d.T) nx = __ldg(descs + next);
+    }
     const int64_t t = (int64_t) ld.x;
     const int64_t o = t * GBRS_HPAD + h;
     uint32_t it = ld.y;
@@ -1115,8 +1138,8 @@ inline int locus_grid(const gbrs_em_dev* d) {  // k_locus_update: one thread per
   int g = grid_for((int64_t) d->T * GBRS_HPAD, 8);
   return g > kHalfSlots ? kHalfSlots : g;
 }
-inline int acc_grid(const gbrs_em_dev* d) {  // k_locus_acc: one thread per (locus, haplotype slot), 32 registers
-  int g = grid_for((int64_t) d->T * GBRS_HPAD, 2048 / kThreads);
+inline int acc_grid(const gbrs_em_dev* d) {  // k_locus_acc: one thread per (locus, haplotype slot), 40 registers
+  int g = grid_for((int64_t) d->T * GBRS_HPAD, 1536 / kThreads);
   return g > kHalfSlots ? kHalfSlots : g;
 }
 inline int converge_grid(const gbrs_em_dev* d) {

@@ -430,6 +430,41 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       }
     }
 
+    // ---- 6b. lane-interleaved entry order inside every work item ----------------------------------------------------
+    // The column pass gives every lane four consecutive entry words per 128-bit load (lane j of a LANES-wide group holds
+    // words 4j .. 4j+3 of a block of 4 * LANES words) and then gathers the weight of its i-th word in round i.  With the
+    // entries in plain ascending class order, the lanes of one gather round would be four entries apart and touch up
+    // to LANES different 128-byte lines of the weight vector; the gather rate is bound by lines per load instruction
+    // (L1 wavefronts), not by bytes.  So the ascending sequence is dealt round-robin instead: word 4j + i of a block
+    // holds its (i * nq + j)-th smallest entry (nq = quads in the block), which makes every gather round read LANES
+    // *consecutive* entries -- neighbouring classes, mostly the same one or two lines.
+    if (std::getenv("GBRS_NO_INTERLEAVE") == nullptr) {  // (knob for A/B measurements of this layout)
+      const int64_t nit = n_items;
+#pragma omp parallel
+      {
+        std::vector<uint64_t> buf(128);
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t it = 0; it < nit; ++it) {
+          const int64_t b = P->item_off[it], e = P->item_off[it + 1];
+          const int64_t B = (e - b > item_len) ? 128 : 32;  // long items: a warp; short items: an 8-lane group
+          for (int64_t k = b; k < e; k += B) {
+            const int64_t m = std::min<int64_t>(B, e - k), nq = m / 4;
+            for (std::vector<uint8_t>* arr : {&P->ent_cls, &P->ent_pair, &P->ent_run}) {
+              if (entry_bytes == 4) {
+                uint32_t* w = reinterpret_cast<uint32_t*>(arr->data()) + k;
+                for (int64_t r = 0; r < m; ++r) buf[r] = w[r];
+                for (int64_t r = 0; r < m; ++r) w[4 * (r % nq) + r / nq] = (uint32_t) buf[r];
+              } else {
+                uint64_t* w = reinterpret_cast<uint64_t*>(arr->data()) + k;
+                for (int64_t r = 0; r < m; ++r) buf[r] = w[r];
+                for (int64_t r = 0; r < m; ++r) w[4 * (r % nq) + r / nq] = buf[r];
+              }
+            }
+          }
+        }
+      }
+    }
+
     lap("6 items + orders");
     // ---- 7. gene -> loci CSR ------------------------------------------------------------------------------------
     P->gene_ptr.assign((size_t) n_gene_ids + 1, 0);

@@ -10,6 +10,20 @@ def unpack_entries(ent, entry_bytes):
     return (ent & np.uint64((1 << sh) - 1)).astype(np.int64), (ent >> np.uint64(sh)).astype(np.int64)
 
 
+def deinterleave(a, item_off, item_len=64):
+    """Undo the packer's lane-interleaved order inside every work item (step 6b of pack.cpp): word 4j + i of a block of
+    4 * LANES words holds the block's (i * nq + j)-th entry in ascending order, nq = quads in the block."""
+    out = a.copy()
+    for b, e in zip(item_off[:-1], item_off[1:]):
+        B = 128 if e - b > item_len else 32
+        for k in range(b, e, B):
+            m = min(B, e - k)
+            nq = m // 4
+            r = np.arange(m)
+            out[k + r] = a[k + 4 * (r % nq) + r // nq]
+    return out
+
+
 def bits(mask):
     return ((mask[:, None] >> np.arange(8)[None, :]) & 1).astype(np.float64)
 

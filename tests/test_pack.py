@@ -8,7 +8,7 @@ from gbrs_b200.emfactory import PackedPattern
 from gbrs_b200.utils import gene_index
 from oracle import em_oracle as eo
 from tests import helpers as hp
-from tests.packed_emulation import em_update_model4, unpack_entries
+from tests.packed_emulation import deinterleave, em_update_model4, unpack_entries
 
 
 def make_apm(d):
@@ -90,6 +90,10 @@ def test_pack_preserves_pattern(small):
     lens = np.diff(io)
     assert p.info["n_long_items"] == np.count_nonzero(lens > 64) and lens.max() <= 32 * 64
     locus_of_entry = pw & 0xFFFFFF
+    # inside an item the ascending sequence is dealt round-robin over the lanes; undo that before looking at the order
+    real_stored = real
+    idx_c, m_c, real = deinterleave(idx_c, io), deinterleave(m_c, io), deinterleave(real, io)
+    locus_of_entry = deinterleave(locus_of_entry, io)
     for t in range(d.T):
         lo, hi = (io[lip[t]], io[lip[t + 1]]) if lip[t + 1] > lip[t] else (0, 0)
         rl = real[lo:hi]
@@ -116,7 +120,7 @@ def test_pack_preserves_pattern(small):
     assert np.all(np.diff(key) >= 0) and np.all(np.diff(lens_o)[np.diff(key) == 0] <= 0)
     # runs: consecutive pairs of one class in the same gene
     g = gene_index(d.T, d.groups())[pw_locus(a)]
-    idx_p, idx_r = idx_p[real], idx_r[real]
+    idx_p, idx_r = idx_p[real_stored], idx_r[real_stored]
     runptr = a["runptr"].astype(np.int64)
     run_of_pair = np.zeros(p.info["n_pairs"], dtype=np.int64)
     for n in range(p.info["n_classes"]):
