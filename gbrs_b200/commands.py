@@ -1,5 +1,6 @@
 """`gbrs quantify` command line -- same flags as the reference (/root/reference/src/gbrs/gbrs/commands.py:108-150):
--i -g -L -G -o -M -p -m -t -a -w -v.  Errors are logged, not raised, and the process exits 0 (:146-150)."""
+-i -g -L -G -o -M -p -m -t -a -w -v, and `gbrs compress` (:76-105): -i (repeatable / comma separated) -o -c -v.
+Errors are logged, not raised, and the process exits 0 (:146-150)."""
 from __future__ import annotations
 
 import logging
@@ -51,6 +52,33 @@ def quantify(
             outbase=outbase, multiread_model=multiread_model, pseudocount=pseudocount, max_iters=max_iters,
             tolerance=tolerance, report_alignment_counts=report_alignment_counts, report_posterior=report_posterior)
     except Exception as e:  # reference policy: log and return
+        if logger.level == logging.DEBUG:
+            logger.exception(e)
+        else:
+            logger.error(e)
+
+
+@app.command(help="compress EMASE format alignment incidence matrix")
+def compress(
+    emase_files: Annotated[list[Path], typer.Option("-i", "--emase-file", exists=False, dir_okay=False, resolve_path=True, help='EMASE file to compress, can seperate files by "," or have multiple -i')],
+    output_file: Annotated[Path, typer.Option("-o", "--output", exists=False, dir_okay=False, writable=True, resolve_path=True, help="name of the compressed EMASE file")],
+    comp_lib: Annotated[str, typer.Option("-c", "--comp-lib", help="compression library to use")] = "zlib",
+    verbose: Annotated[int, typer.Option("-v", "--verbose", count=True, help="specify multiple times for more verbose output")] = 0,
+) -> None:
+    """Flag surface of the reference's `gbrs compress` (/root/reference/src/gbrs/gbrs/commands.py:76-105)."""
+    logger = utils.configure_logging("gbrs", verbose)
+    logger.debug("compress")
+    try:
+        # file shortcut: -i abc.h5 -i def.h5  ==  -i abc.h5,def.h5   (:86-91)
+        all_emase_files: list[str] = []
+        for x in emase_files:
+            all_emase_files.extend(str(x).split(","))
+        for f in all_emase_files:
+            if not Path(f).is_file():
+                raise FileNotFoundError(f"{f} does not exist or is not a file")
+        importlib.import_module(".compress", __package__).compress(
+            emase_files=all_emase_files, output_file=str(output_file), comp_lib=comp_lib)
+    except Exception as e:
         if logger.level == logging.DEBUG:
             logger.exception(e)
         else:

@@ -223,6 +223,22 @@ int gbrs_write_table(const char* path, const char* header, const char* const* na
 /* python repr of one double into `out` (NUL-terminated); returns the length or GBRS_E_ARG if `cap` is too small. */
 int gbrs_format_double(double x, char* out, int32_t cap);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * `gbrs compress`: equivalence classes of reads (src/gbrs/gbrs/emase_utils.py:46-72).  A read is a row of pair words
+ * (locus | hapmask << 24, ascending locus) in CSR form; reads with identical rows form one class, classes are numbered
+ * in order of first appearance (the reference's dict insertion order) and carry the sum of their reads' counts.
+ *   rowptr_dev [n_reads+1], pairs_dev [rowptr[n_reads]], count_dev [n_reads] or NULL (= all ones, :58-59)   inputs
+ *   class_of_read_dev [n_reads], first_read_dev [n_reads] (first n_classes valid: the read a class was first seen
+ *   at), class_count_dev [n_reads] (first n_classes valid)                                                  outputs
+ * `workspace_dev` must hold gbrs_ec_workspace_bytes(n_reads) bytes.  Grouping is by a seeded 64-bit hash followed by an
+ * exact comparison; if two different rows collide, *collisions_out is non-zero, the outputs are undefined and the
+ * caller repeats the call with another seed.  Synchronises the stream.  No CPU fallback. */
+int gbrs_ec_workspace_bytes(int64_t n_reads, int64_t* bytes);
+int gbrs_ec_build(int64_t n_reads, const uint32_t* rowptr_dev, const uint32_t* pairs_dev, const double* count_dev,
+                  uint64_t seed, uint32_t* class_of_read_dev, uint32_t* first_read_dev, double* class_count_dev,
+                  void* workspace_dev, int64_t workspace_bytes, void* stream, int64_t* n_classes_out,
+                  int64_t* collisions_out);
+
 #ifdef __cplusplus
 }
 #endif
