@@ -221,6 +221,8 @@ def run_gpu_arm(args, wl):
     em.prepare()  # gene tables + pack + upload + theta0
     t_first = time.perf_counter() - t0
     pat = em._pattern
+    if args.model != 4:
+        pat.ensure_full()  # the arrays only models 1-3 read are uploaded on demand
     lib, desc = pat.lib, pat.desc
     info = pat.info
     nnz_local = info["nnz"]

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -1123,7 +1124,10 @@ int check_dev(const gbrs_em_dev* d, const char* who) {
   if (d->T <= 0 || d->H < 1 || d->H > GBRS_HPAD || (d->entry_bytes != 4 && d->entry_bytes != 8)) {
     gbrs_set_error(std::string(who) + ": bad descriptor shape"); return GBRS_E_ARG;
   }
-  if (!d->rowptr || !d->pairs || !d->count || !d->item_off || !d->item_order || !d->item_desc || !d->locus_order || !d->locus_desc || !d->locus_item_ptr || !d->theta || !d->efflen || !d->acc ||
+  // Needed by every model.  rowptr / runptr / ent_pair / ent_run are read only by models 1-3, the wide-class row pass
+  // and the alignment counts (checked there): a caller that runs model 4 only need not make them resident.
+  // item_off / item_order / locus_order / locus_item_ptr describe the layout for the host; no kernel reads them.
+  if (!d->pairs || !d->count || !d->item_desc || !d->locus_desc || !d->theta || !d->efflen || !d->acc ||
       !d->iso || !d->weights || !d->subsets || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
     gbrs_set_error(std::string(who) + ": null device buffer in descriptor"); return GBRS_E_ARG;
   }
@@ -1179,6 +1183,7 @@ int launch_row_m4(const gbrs_em_dev* d, cudaStream_t s) {
   }
   const int64_t n_long = d->n_classes - d->bucket_class0[GBRS_KMAX];
   if (n_long > 0) {
+    if (!d->rowptr) { gbrs_set_error("row pass: classes wider than GBRS_KMAX need rowptr"); return GBRS_E_ARG; }
     k_weights_m4_long<UNIT><<<grid_for(n_long), kThreads, 0, s>>>(*d);
     GBRS_LAUNCH_CHECK("k_weights_m4_long");
   }
@@ -1360,6 +1365,10 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
       gbrs_set_error("Group information matrix is missing.");  // AlignmentPropertyMatrix.py:345-346
       return GBRS_E_ARG;
     }
+    if (!d->rowptr || !d->ent_pair || !d->ent_run) {
+      gbrs_set_error("models 1-3 need rowptr / ent_pair / ent_run in the descriptor");
+      return GBRS_E_ARG;
+    }
     k_gene_totals<<<grid_for((int64_t) d->n_gene_ids * 8), kThreads, 0, s>>>(*d);
     GBRS_LAUNCH_CHECK("k_gene_totals");
   }
@@ -1420,6 +1429,25 @@ extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
   return GBRS_OK;
 }
 
+namespace {
+struct GraphEntry { uint64_t key; cudaGraphExec_t exec; uint64_t stamp; };
+std::vector<GraphEntry> g_graph_cache;
+std::mutex g_graph_mutex;
+uint64_t g_graph_stamp = 0;
+
+uint64_t graph_key(const gbrs_em_dev* d, int model, int poll_every) {  // FNV-1a over the descriptor bytes
+  uint64_t h = 1469598103934665603ull;
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(d);
+  for (size_t i = 0; i < sizeof(gbrs_em_dev); ++i) h = (h ^ p[i]) * 1099511628211ull;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t extra[3] = {(uint64_t) model, (uint64_t) poll_every, (uint64_t) dev};
+  p = reinterpret_cast<const unsigned char*>(extra);
+  for (size_t i = 0; i < sizeof(extra); ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+}  // namespace
+
 extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_iters, int poll_every, void* stream,
                            int32_t* iters_out, double* errs_host) {
   if (int rc = check_dev(d, "gbrs_em_run")) return rc;
@@ -1444,24 +1472,41 @@ extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_
   int32_t ctrl[16];
   std::memset(ctrl, 0, sizeof(ctrl));
   if (!rc) rc = gbrs_em_read_ctrl(d, s, ctrl, nullptr);
-  cudaGraph_t graph = nullptr;
+  // The instantiated graph is kept across calls (capture + instantiation cost about as much as ten updates): it bakes
+  // the descriptor in by value, so it is keyed by the descriptor's bytes, the model and the poll interval.
   cudaGraphExec_t exec = nullptr;
   if (!rc && !ctrl[GBRS_CTRL_DONE] && use_graph) {
-    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      for (int i = 0; i < poll_every && !rc; ++i) {
-        rc = gbrs_em_launch_local(d, model, s);
-        if (!rc) rc = gbrs_em_launch_update(d, s);
-      }
-      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
-      if (rc || ce != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    const uint64_t key = graph_key(d, model, poll_every);
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    for (auto& e : g_graph_cache)
+      if (e.key == key) { exec = e.exec; e.stamp = ++g_graph_stamp; break; }
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        for (int i = 0; i < poll_every && !rc; ++i) {
+          rc = gbrs_em_launch_local(d, model, s);
+          if (!rc) rc = gbrs_em_launch_update(d, s);
+        }
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc || ce != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+          exec = nullptr;
+          cudaGetLastError();
+          if (!rc) rc = GBRS_OK;  // fall back to plain launches below
+        }
         if (graph) cudaGraphDestroy(graph);
-        graph = nullptr;
-        exec = nullptr;
+      } else {
         cudaGetLastError();
-        if (!rc) rc = GBRS_OK;  // fall back to plain launches below
       }
-    } else {
-      cudaGetLastError();
+      if (exec) {
+        if (g_graph_cache.size() >= 8) {  // drop the least recently used
+          size_t lru = 0;
+          for (size_t i = 1; i < g_graph_cache.size(); ++i)
+            if (g_graph_cache[i].stamp < g_graph_cache[lru].stamp) lru = i;
+          cudaGraphExecDestroy(g_graph_cache[lru].exec);
+          g_graph_cache.erase(g_graph_cache.begin() + lru);
+        }
+        g_graph_cache.push_back({key, exec, ++g_graph_stamp});
+      }
     }
   }
   while (!rc && !ctrl[GBRS_CTRL_DONE]) {
@@ -1483,8 +1528,6 @@ extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_
       rc = GBRS_E_CUDA;
     }
   }
-  if (exec) cudaGraphExecDestroy(exec);
-  if (graph) cudaGraphDestroy(graph);
   if (own) {
     cudaStreamSynchronize(own);
     cudaStreamDestroy(own);
@@ -1503,6 +1546,7 @@ extern "C" int gbrs_em_alignment_counts(const gbrs_em_dev* d, int gene_level, in
   if (int rc = check_dev(d, "gbrs_em_alignment_counts")) return rc;
   if (!aln_dev || !uniq_dev || !locus_uniq_dev) { gbrs_set_error("gbrs_em_alignment_counts: null output"); return GBRS_E_ARG; }
   if (gene_level && !d->gene_of) { gbrs_set_error("No group information is available for bundling."); return GBRS_E_ARG; }
+  if (!d->rowptr) { gbrs_set_error("gbrs_em_alignment_counts: rowptr missing from descriptor"); return GBRS_E_ARG; }
   if (d->n_classes == 0) return GBRS_OK;
   k_alignment_counts<<<grid_for(d->n_classes), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       *d, gene_level, n_real_genes, aln_dev, uniq_dev, locus_uniq_dev);

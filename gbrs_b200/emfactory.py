@@ -39,6 +39,13 @@ _PACK_ARRAYS = {  # name -> numpy dtype (None = entry word, depends on entry_byt
 }
 
 
+# Packed arrays only the row / column passes of models 1-3, the wide-class row pass and the alignment counts read: made
+# resident on first use (a model-4 run streams none of them).  The host-only ones describe the layout and are never
+# read by a kernel.
+_LAZY_ARRAYS = ("rowptr", "runptr", "ent_pair", "ent_run")
+_HOST_ONLY_ARRAYS = ("item_off", "item_order", "locus_order", "locus_item_ptr")
+
+
 def _torch():
     import torch
 
@@ -143,15 +150,25 @@ class DevicePattern:
             self.host[k] = t.pin_memory() if pin else t
         self.dev = {}
         self.h2d_bytes = 0
+        self.full = False
+        i = self.info
+        self._need_rowptr = i["bucket_class0"][_lib.GBRS_KMAX] < i["n_classes"]  # classes wider than GBRS_KMAX
         self.upload()
         self._alloc_state()
         self._build_descriptor()
 
     # -- device residency -------------------------------------------------------------------------------------------
-    def upload(self):
+    def upload(self, lazy=False):
+        """Host -> device copy of the packed arrays a model-4 run needs (`lazy=True`: of the remaining ones; once the
+        pattern is `full`, a plain upload() refreshes everything)."""
         torch = _torch()
         with torch.cuda.device(self.device):
             for k, t in self.host.items():
+                if k in _HOST_ONLY_ARRAYS:
+                    continue
+                is_lazy = k in _LAZY_ARRAYS and not (k == "rowptr" and self._need_rowptr)
+                if is_lazy != lazy and not (self.full and not lazy):
+                    continue
                 if t.numel() == 0:  # keep a valid (non-null) pointer for empty shards
                     self.dev[k] = torch.zeros(16, dtype=torch.uint8, device=self.device)
                 elif k in self.dev and self.dev[k].numel() == t.numel():
@@ -159,6 +176,13 @@ class DevicePattern:
                 else:
                     self.dev[k] = t.to(self.device, non_blocking=True)
                 self.h2d_bytes += t.numel()
+
+    def ensure_full(self):
+        """Make the arrays of models 1-3 / the alignment counts resident too (no-op once done)."""
+        if not self.full:
+            self.upload(lazy=True)
+            self.full = True
+            self._build_descriptor()
 
     def _alloc_state(self):
         torch = _torch()
@@ -180,7 +204,7 @@ class DevicePattern:
         self.ctrl = torch.zeros(16, dtype=torch.int32, device=dv)
 
     def _build_descriptor(self):
-        d = _lib.EmDev()
+        d = getattr(self, "desc", None) or _lib.EmDev()  # updated in place: callers may hold a reference
         i = self.info
         d.T, d.H, d.n_gene_ids, d.entry_bytes = self.T, self.H, i["n_gene_ids"], i["entry_bytes"]
         d.n_classes, d.n_pairs, d.n_runs, d.n_items = i["n_classes"], i["n_pairs"], i["n_runs"], i["n_items"]
@@ -191,7 +215,7 @@ class DevicePattern:
             d.bucket_pair0[k] = i["bucket_pair0"][k]
         for k in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_off", "item_order",
                   "item_desc", "locus_order", "locus_desc", "locus_item_ptr"):
-            setattr(d, k, self.dev[k].data_ptr())
+            setattr(d, k, self.dev[k].data_ptr() if k in self.dev else None)
         if self.packed.has_genes:
             for k in ("gene_of", "gene_ptr", "gene_loci"):
                 setattr(d, k, self.dev[k].data_ptr())
@@ -207,13 +231,30 @@ class DevicePattern:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # -- small conveniences -----------------------------------------------------------------------------------------
+    def _staging(self):
+        """One pinned [T][8] host buffer for the small state transfers (theta, lengths, numerator): pageable copies of
+        these 5 MB tables cost more than ten EM updates each."""
+        if getattr(self, "_stage", None) is None:
+            self._stage = _torch().empty((self.T, 8), dtype=_torch().float64).pin_memory()
+        return self._stage
+
+    def _fetch_T8(self, dev_tensor) -> np.ndarray:
+        """device [T][8] -> host H x T (contiguous copy).  The transpose is done on the device (a strided numpy copy of
+        these 640k doubles costs as much as ten EM updates), the transfer goes through the pinned staging buffer."""
+        st = self._staging().view(-1)[: self.H * self.T].view(self.H, self.T)
+        st.copy_(dev_tensor[:, : self.H].t(), non_blocking=True)
+        _torch().cuda.current_stream(self.device).synchronize()
+        return st.numpy().copy()
+
     def set_lengths(self, target_lengths_HT):
         """H x T effective lengths -> device [T][8] (1.0 in unused slots)."""
-        torch = _torch()
-        e = np.ones((self.T, 8), dtype=np.float64)
+        st = self._staging()
+        e = st.numpy()
+        e[:] = 1.0
         if target_lengths_HT is not None:
             e[:, : self.H] = np.asarray(target_lengths_HT, dtype=np.float64).T
-        self.efflen.copy_(torch.from_numpy(e))
+        self.efflen.copy_(st, non_blocking=True)
+        _torch().cuda.current_stream(self.device).synchronize()  # the staging buffer is reused
 
     def read_ctrl(self):
         ctrl = np.zeros(16, dtype=np.int32)
@@ -223,22 +264,23 @@ class DevicePattern:
 
     def current_theta_HT(self) -> np.ndarray:
         ctrl, _ = self.read_ctrl()
-        th = self.theta[int(ctrl[_lib.CTRL_PARITY])].cpu().numpy()
-        return np.ascontiguousarray(th[:, : self.H].T)
+        return self._fetch_T8(self.theta[int(ctrl[_lib.CTRL_PARITY])])
 
     def set_theta_HT(self, theta_HT):
-        torch = _torch()
-        t = np.zeros((self.T, 8), dtype=np.float64)
+        st = self._staging()
+        t = st.numpy()
+        t[:] = 0.0
         t[:, : self.H] = np.asarray(theta_HT, dtype=np.float64).T
-        staged = torch.from_numpy(t).to(self.device)
+        staged = st.to(self.device, non_blocking=True)
         _lib.check(self.lib.gbrs_em_set_theta(C.byref(self.desc), C.c_void_p(staged.data_ptr()), self.stream()))
         _torch().cuda.current_stream(self.device).synchronize()
 
     def acc_HT(self) -> np.ndarray:
-        return np.ascontiguousarray(self.acc.cpu().numpy()[:, : self.H].T)
+        return self._fetch_T8(self.acc)
 
     def alignment_counts(self, gene_level=False, n_real_genes=0):
         torch = _torch()
+        self.ensure_full()
         rows = n_real_genes if gene_level else self.T
         alloc = max(self.info["n_gene_ids"], rows) if gene_level else self.T
         aln = torch.zeros((alloc, 8), dtype=torch.float64, device=self.device)
@@ -490,6 +532,8 @@ class EMfactory:
         if model not in (1, 2, 3, 4):
             raise RuntimeError("The read normalization model should be 1, 2, 3, or 4.")
         pat = self._ensure_pattern()
+        if model != 4:
+            pat.ensure_full()
         self._sync_theta_to_device()
         _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), 0.0, 1, pat.stream()))
         _lib.check(pat.lib.gbrs_em_launch_local(C.byref(pat.desc), int(model), pat.stream()))
@@ -513,6 +557,8 @@ class EMfactory:
         if max_iters > ERR_LOG_CAP:
             raise ValueError(f"max_iters above {ERR_LOG_CAP} is not supported")
         pat = self._ensure_pattern()
+        if model != 4:
+            pat.ensure_full()
         self._sync_theta_to_device()
         if verbose:
             print("")

@@ -27,6 +27,8 @@ def run_sharded(d, model, R, tol=1e-4, max_iters=999):
     lib = pats[0].lib
     for p in pats:
         p.set_lengths(eff)
+        if model != 4:
+            p.ensure_full()  # the arrays only models 1-3 read are uploaded on demand
 
     def exchange():
         total = torch.zeros_like(pats[0].acc)
