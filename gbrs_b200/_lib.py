@@ -86,6 +86,8 @@ SYMBOLS = {
     "gbrs_em_read_ctrl": (C.c_int, [C.POINTER(EmDev), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gbrs_write_table": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int64, C.c_void_p, C.c_int32,
                                    C.POINTER(C.c_char_p), C.c_void_p, C.c_int32]),
+    "gbrs_parse_lengths": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int64, C.POINTER(C.c_char_p), C.c_int32,
+                                     C.c_double, C.c_void_p, C.POINTER(C.c_int64)]),
     "gbrs_format_double": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
     "gbrs_ec_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),
     "gbrs_ec_build": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,

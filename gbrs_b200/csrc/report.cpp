@@ -120,3 +120,72 @@ extern "C" int gbrs_write_table(const char* path, const char* header, const char
   if (!ok) { gbrs_set_error(std::string("gbrs_write_table: write failed for ") + path); return GBRS_E_ARG; }
   return GBRS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Length table of EMfactory.prepare (src/gbrs/emase/EMfactory.py:60-89): lines `locus_hap<TAB>length` (or
+// `locus<TAB>length` with one haplotype) -> out[locus][hap] = max(length - read_length + 1, 1).  The reference walks
+// the file in a python loop (about a second per 10^6 lines).  Only well-formed lines are handled here; at the first
+// line that is not (unknown name, key that does not split into exactly two parts at '_', anything python's float()
+// might still accept but strtod in the C locale does not take whole) the function stops and reports the line, and the
+// caller re-parses with the reference-style loop so that errors surface exactly as the reference raises them.
+// ---------------------------------------------------------------------------------------------------------------------
+#include <fstream>
+#include <iterator>
+#include <unordered_map>
+
+extern "C" int gbrs_parse_lengths(const char* path, const char* const* lnames, int64_t n_loci, const char* const* hnames,
+                                  int32_t n_haps, double read_length, double* out, int64_t* bad_line) {
+  if (!path || !lnames || !out || n_loci < 1 || n_haps < 1 || (n_haps > 1 && !hnames) || !bad_line) {
+    gbrs_set_error("gbrs_parse_lengths: bad argument"); return GBRS_E_ARG;
+  }
+  *bad_line = 0;
+  std::ifstream fh(path, std::ios::binary);
+  if (!fh) { gbrs_set_error(std::string("gbrs_parse_lengths: cannot open ") + path); return GBRS_E_ARG; }
+  std::string data((std::istreambuf_iterator<char>(fh)), std::istreambuf_iterator<char>());
+  std::unordered_map<std::string_view, int64_t> lid, hid;
+  lid.reserve((size_t) n_loci * 2);
+  for (int64_t i = 0; i < n_loci; ++i) lid[std::string_view(lnames[i])] = i;  // later duplicates win, like dict(zip(...))
+  for (int32_t h = 0; h < n_haps && hnames; ++h) hid[std::string_view(hnames[h])] = h;
+  for (int64_t i = 0; i < n_loci * n_haps; ++i) out[i] = 0.0;
+  const char* p = data.data();
+  const char* end = p + data.size();
+  int64_t line_no = 0;
+  auto is_space = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; };
+  while (p < end) {
+    ++line_no;
+    const char* eol = static_cast<const char*>(std::memchr(p, '\n', (size_t) (end - p)));
+    const char* next = eol ? eol + 1 : end;
+    const char* le = eol ? eol : end;
+    while (le > p && is_space(le[-1])) --le;  // curline.rstrip()
+    const char* tab = static_cast<const char*>(std::memchr(p, '\t', (size_t) (le - p)));
+    if (!tab) { *bad_line = line_no; return GBRS_OK; }
+    const char* v0 = tab + 1;
+    const char* v1 = static_cast<const char*>(std::memchr(v0, '\t', (size_t) (le - v0)));
+    if (!v1) v1 = le;
+    // the number: plain decimal / exponent notation only, consumed whole (surrounding blanks allowed, as float() does)
+    while (v0 < v1 && is_space(*v0)) ++v0;
+    while (v1 > v0 && is_space(v1[-1])) --v1;
+    double len = 0.0;
+    auto res = std::from_chars(v0, v1, len);
+    if (v0 == v1 || res.ec != std::errc() || res.ptr != v1) { *bad_line = line_no; return GBRS_OK; }
+    std::string_view key(p, (size_t) (tab - p));
+    int64_t li = -1, hi = 0;
+    if (n_haps > 1) {
+      const size_t us = key.find('_');
+      if (us == std::string_view::npos || key.find('_', us + 1) != std::string_view::npos) { *bad_line = line_no; return GBRS_OK; }
+      auto a = lid.find(key.substr(0, us));
+      auto b = hid.find(key.substr(us + 1));
+      if (a == lid.end() || b == hid.end()) { *bad_line = line_no; return GBRS_OK; }
+      li = a->second;
+      hi = b->second;
+    } else {
+      auto a = lid.find(key);
+      if (a == lid.end()) { *bad_line = line_no; return GBRS_OK; }
+      li = a->second;
+    }
+    const double eff = len - read_length + 1.0;
+    out[li * n_haps + hi] = eff > 1.0 ? eff : 1.0;  // max(float(item[1]) - read_length + 1.0, 1.0)
+    p = next;
+  }
+  return GBRS_OK;
+}

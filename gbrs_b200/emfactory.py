@@ -361,7 +361,40 @@ class EMfactory:
 
     # ---------------------------------------------------------------------------------------------------------------
     def _read_lengths(self, lenfile, read_length):
-        """EMfactory.prepare length handling (EMfactory.py:60-94)."""
+        """EMfactory.prepare length handling (EMfactory.py:60-94).  The reference walks the file line by line in
+        Python (seconds at 640k lines); the table is parsed in bulk here and the line loop is kept as the fallback for
+        anything unusual, so malformed files raise exactly what the reference raises."""
+        p = self.probability
+        tl = None
+        if p.num_haplotypes > 0:
+            try:
+                tl = self._read_lengths_bulk(lenfile, read_length)
+            except Exception:  # noqa: BLE001 - odd file: let the reference's loop decide what the error is
+                tl = None
+        if tl is None:
+            tl = self._read_lengths_loop(lenfile, read_length)
+        tl = tl.transpose()
+        if not np.all(tl > 0.0):
+            raise RuntimeError("There exist transcripts missing length information.")
+        return tl
+
+    def _read_lengths_bulk(self, lenfile, read_length):
+        """Native parser (gbrs_parse_lengths); None if it met a line it does not take as well-formed."""
+        p = self.probability
+        lib = _lib.load()
+        lnames = [str(x).encode() for x in p.lname]
+        hnames = [str(x).encode() for x in p.hname]
+        if len(set(lnames)) != len(lnames):
+            return None
+        c_l = (C.c_char_p * len(lnames))(*lnames)
+        c_h = (C.c_char_p * len(hnames))(*hnames)
+        tl = np.zeros((p.num_loci, p.num_haplotypes))
+        bad = C.c_int64(0)
+        _lib.check(lib.gbrs_parse_lengths(str(lenfile).encode(), c_l, p.num_loci, c_h, p.num_haplotypes,
+                                          float(read_length), tl.ctypes.data, C.byref(bad)))
+        return None if bad.value else tl
+
+    def _read_lengths_loop(self, lenfile, read_length):
         p = self.probability
         hid = dict(zip(p.hname, np.arange(len(p.hname))))
         tl = np.zeros((p.num_loci, p.num_haplotypes))
@@ -378,9 +411,6 @@ class EMfactory:
                     tl[p.lid[item[0]], 0] = max(float(item[1]) - read_length + 1.0, 1.0)
         else:
             raise RuntimeError("There is something wrong with your emase-format alignment file.")
-        tl = tl.transpose()
-        if not np.all(tl > 0.0):
-            raise RuntimeError("There exist transcripts missing length information.")
         return tl
 
     def _ensure_pattern(self):

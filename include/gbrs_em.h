@@ -220,6 +220,12 @@ int gbrs_em_alignment_counts(const gbrs_em_dev* d, int gene_level, int32_t n_rea
  * permutation, `header` is written verbatim first (unless NULL).  Host only; rows are formatted by all host threads. */
 int gbrs_write_table(const char* path, const char* header, const char* const* names, int64_t n_rows, const double* data,
                      int32_t n_cols, const char* const* notes, const int64_t* order, int32_t append);
+/* Length table of EMfactory.prepare (EMfactory.py:60-89): `locus_hap<TAB>length` lines (`locus<TAB>length` when
+ * n_haps == 1) -> out[locus * n_haps + hap] = max(length - read_length + 1, 1), zero where the file has no line.  Host
+ * only.  Stops at the first line it does not take as well-formed and returns its 1-based number in *bad_line (0 = the
+ * whole file was parsed); the caller then falls back to the reference's line loop, which raises the reference's error. */
+int gbrs_parse_lengths(const char* path, const char* const* lnames, int64_t n_loci, const char* const* hnames,
+                       int32_t n_haps, double read_length, double* out, int64_t* bad_line);
 /* python repr of one double into `out` (NUL-terminated); returns the length or GBRS_E_ARG if `cap` is too small. */
 int gbrs_format_double(double x, char* out, int32_t cap);
 
