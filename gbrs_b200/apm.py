@@ -19,6 +19,8 @@ PyTables is present and the name does not end in `.npz`).
 """
 from __future__ import annotations
 
+import os
+
 import copy
 from enum import IntEnum
 
@@ -135,26 +137,41 @@ class AlignmentPropertyMatrix:
         self.finalized = True
 
     def _load_npz(self, path, shallow, dtype):
+        """The `.npz` twin of the PyTables layout.  The per-haplotype arrays are inflated and turned into CSC matrices
+        by a pool of threads (zlib and numpy's fills release the GIL): at benchmark scale the single-threaded inflate
+        was the largest part of a whole `quantify` run."""
+        from concurrent.futures import ThreadPoolExecutor
+
         with np.load(path, allow_pickle=False) as z:
             T, H, N = (int(x) for x in z["shape"])
             self.shape = (T, H, N)
-            incidence_only = bool(z["incidence_only"]) if "incidence_only" in z.files else True
-            for h in range(H):
-                indptr = z[f"h{h}_indptr"]
-                indices = z[f"h{h}_indices"]
-                if not incidence_only and f"h{h}_data" in z.files:
-                    vals = z[f"h{h}_data"].astype(dtype)
-                else:
-                    vals = np.ones(indices.shape[0], dtype=dtype)
+            files = set(z.files)
+            incidence_only = bool(z["incidence_only"]) if "incidence_only" in files else True
+
+            def one(h):
+                with np.load(path, allow_pickle=False) as zz:  # a handle of its own: no shared file position
+                    indptr = zz[f"h{h}_indptr"]
+                    indices = zz[f"h{h}_indices"]
+                    if not incidence_only and f"h{h}_data" in files:
+                        vals = zz[f"h{h}_data"].astype(dtype)
+                    else:
+                        vals = np.ones(indices.shape[0], dtype=dtype)
                 idx_t = np.int64 if max(N, indices.shape[0]) >= 2**31 - 1 else np.int32
-                self.data.append(csc_matrix((vals, indices.astype(idx_t), indptr.astype(idx_t)), shape=(N, T)))
-            if "count" in z.files:
+                return csc_matrix((vals, indices.astype(idx_t), indptr.astype(idx_t)), shape=(N, T))
+
+            workers = max(1, min(H, os.cpu_count() or 1))
+            if workers > 1:
+                with ThreadPoolExecutor(max_workers=workers) as pool:
+                    self.data = list(pool.map(one, range(H)))
+            else:
+                self.data = [one(h) for h in range(H)]
+            if "count" in files:
                 self.count = z["count"].astype(np.float64)
             if not shallow:
                 self.hname = [str(x) for x in z["hname"]]
                 self.lname = [str(x) for x in z["lname"]]
                 self.lid = dict(zip(self.lname, np.arange(T)))
-                if "rname" in z.files:
+                if "rname" in files:
                     self.rname = z["rname"]
                     self.rid = dict(zip(self.rname, np.arange(N)))
 
