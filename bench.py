@@ -390,7 +390,7 @@ def run_gpu_arm(args, wl):
                          f"{s_per:.3f} s/update, host has {os.cpu_count()} logical cores (path is single-threaded)"}
 
     if rank == 0:
-        launches_per_step = (4 if world == 1 else (6 if em.fused_exchange else 5)) + (1 if model != 4 else 0)
+        launches_per_step = (4 if world == 1 else 5) + (1 if model != 4 else 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -399,7 +399,9 @@ def run_gpu_arm(args, wl):
                            "l2_policy": "inputs larger than L2 (packed incidence %.0f MB per GPU streams every step)"
                                         % (pat.packed.nbytes() / 1e6),
                            "exchange": "none" if world == 1 else (
-                               "fused two-shot all-reduce of T x 8 fp64 over NVLink peer memory inside the locus kernels"
+                               ("fused two-shot all-reduce of T x 8 fp64 inside the locus kernels: NVLS (multimem.ld_reduce / "
+                                "multimem.st on the NVSwitch multicast mapping)" if em.nvls_exchange else
+                                "fused two-shot all-reduce of T x 8 fp64 over NVLink peer memory inside the locus kernels")
                                if em.fused_exchange else "NCCL all-reduce of T x 8 fp64 per step")},
                 "iterations_per_s": K / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches_per_step * K, "clocks": clocks,

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("GBRS_LIB_PATH") or os.path.join(HERE, "_C", "libgbrs_
 GBRS_HPAD = 8
 GBRS_KMAX = 8
 GBRS_PART_SLOTS = 4096
+ABI_VERSION = 2
 CTRL_ITERS, CTRL_DONE, CTRL_ERROR, CTRL_PARITY, CTRL_MAX_ITERS, CTRL_PREPARED = range(6)
 SCAL_ERR, SCAL_SUM_PREV, SCAL_TARGET, SCAL_SUM_CUR = range(4)
 
@@ -50,7 +51,7 @@ class EmDev(C.Structure):
                 ("n_classes", C.c_int64), ("n_pairs", C.c_int64), ("n_runs", C.c_int64), ("n_items", C.c_int64),
                 ("n_entries", C.c_int64), ("n_long_items", C.c_int64), ("n_ranks", C.c_int32), ("max_iters_cap", C.c_int32),
                 ("bucket_class0", C.c_int64 * (GBRS_KMAX + 2)), ("bucket_pair0", C.c_int64 * (GBRS_KMAX + 2)),
-                ("xchg_enabled", C.c_int32), ("xchg_rank", C.c_int32), ("xchg_peer", C.c_void_p * 8),
+                ("xchg_enabled", C.c_int32), ("xchg_rank", C.c_int32), ("xchg_peer", C.c_void_p * 8), ("xchg_mc", C.c_void_p),
                 ("rowptr", C.c_void_p), ("pairs", C.c_void_p), ("count", C.c_void_p), ("runptr", C.c_void_p),
                 ("ent_cls", C.c_void_p), ("ent_pair", C.c_void_p), ("ent_run", C.c_void_p),
                 ("item_off", C.c_void_p), ("item_order", C.c_void_p), ("item_desc", C.c_void_p),
@@ -112,7 +113,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.gbrs_abi_version() != 1:
+        if lib.gbrs_abi_version() != ABI_VERSION:
             raise GbrsError("libgbrs_em.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

@@ -209,10 +209,13 @@ __device__ __forceinline__ const double* theta_cur(const gbrs_em_dev& d) {
 //     [0, 64T)   acc_local   this rank's local numerator (written by k_locus_acc)
 //     [64T,128T) acc_total   the numerator summed over ranks (written by the owners of each slice, k_xchg_reduce)
 //     then       ready[8], done[8]   u32 epoch flags, written remotely by the rank they are indexed by
+// `xchg_mc` (optional) is the NVSwitch multicast mapping of the same buffers.
 // Two-shot all-reduce inside our own kernels: k_locus_acc publishes acc_local and raises ready[me] = e on every peer;
 // k_xchg_reduce waits for all ready flags, sums ITS slice of the loci over the ranks in rank order with peer loads,
 // stores the total into every rank's acc_total with peer stores and raises done[me] = e everywhere; k_locus_update
-// waits for all done flags and carries on locally.  Each element is summed by exactly one rank, so all ranks see
+// waits for all done flags and carries on locally.  In an EM update the reduce step runs at the head of the
+// k_locus_update launch itself (k_locus_update<true, true>), and with a multicast mapping the switch does the adding
+// and the broadcasting (xchg_reduce_slice<true>).  Each element is summed by exactly one rank, so all ranks see
 // bit-identical totals and take identical stop decisions.  Waits are bounded: a missing peer raises the error flag
 // instead of hanging the GPU.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -273,32 +276,60 @@ __device__ __forceinline__ void xchg_signal_all(const gbrs_em_dev& d, int which,
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_xchg_reduce(const __grid_constant__ gbrs_em_dev d) {
-  const uint32_t e = (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH] + 1u;
-  xchg_wait_all(d, 0, e);
-  // this rank's slice of the T*8 numerator, in units of double2
+// In-switch reduction / multicast store on the NVSwitch multicast mapping of the symmetric buffers (NVLS): one load
+// returns the sum over all ranks of the addressed element, one store writes every rank's copy.
+__device__ __forceinline__ double multimem_ld_reduce_add(const double* mc) {
+  double v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(double* mc, double v) {
+  asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
+
+// This rank's slice of the T*8 numerator (in units of double2): summed over the ranks and stored into every rank's
+// acc_total.  NVLS = false: peer loads, all issued first (one NVLink round trip instead of n_ranks serial ones), then
+// the sum in rank order.  NVLS = true: the switch adds (multimem.ld_reduce) and broadcasts (multimem.st); a rank moves
+// 2 x 1/R of the numerator instead of 2 x (R-1)/R.  Either way every element is reduced by exactly one rank and the
+// same bits reach every rank, so all ranks take identical stop decisions.
+template <bool NVLS>
+__device__ __forceinline__ void xchg_reduce_slice(const gbrs_em_dev& d) {
   const int64_t n2 = (int64_t) d.T * GBRS_HPAD / 2;
   const int64_t per = (n2 + d.n_ranks - 1) / d.n_ranks;
   const int64_t lo = per * d.xchg_rank, hi = lo + per < n2 ? lo + per : n2;
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
   for (int64_t i = lo + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
-    // all peer loads first (one NVLink round trip instead of n_ranks serial ones), then the sum in rank order: every
-    // element is summed exactly once, in one fixed order
-    double2 v[8];
+    if (NVLS) {
+      double* mc_local = static_cast<double*>(d.xchg_mc);
+      double* mc_total = mc_local + (size_t) d.T * GBRS_HPAD;
+      const double x = multimem_ld_reduce_add(mc_local + 2 * i), y = multimem_ld_reduce_add(mc_local + 2 * i + 1);
+      multimem_st(mc_total + 2 * i, x);
+      multimem_st(mc_total + 2 * i + 1, y);
+    } else {
+      double2 v[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < d.n_ranks) v[r] = ld_relaxed_sys_f64x2(xchg_acc_local(d, r) + 2 * i);
-    double2 s = make_double2(0.0, 0.0);
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) v[r] = ld_relaxed_sys_f64x2(xchg_acc_local(d, r) + 2 * i);
+      double2 s = make_double2(0.0, 0.0);
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < d.n_ranks) {
-        s.x += v[r].x;
-        s.y += v[r].y;
-      }
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) {
+          s.x += v[r].x;
+          s.y += v[r].y;
+        }
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < d.n_ranks) st_relaxed_sys_f64x2(xchg_acc_total(d, r) + 2 * i, s);
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) st_relaxed_sys_f64x2(xchg_acc_total(d, r) + 2 * i, s);
+    }
   }
+}
+
+// stand-alone reduce (prepare): k_locus_update follows as a kernel of its own
+__global__ void __launch_bounds__(kThreads) k_xchg_reduce(const __grid_constant__ gbrs_em_dev d) {
+  const uint32_t e = (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH] + 1u;
+  xchg_wait_all(d, 0, e);
+  if (d.xchg_mc) xchg_reduce_slice<true>(d);
+  else xchg_reduce_slice<false>(d);
   xchg_signal_all(d, 1, e, GBRS_CTRL_TICKET + 2);
 }
 
@@ -916,13 +947,27 @@ __global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const g
 
 // theta' = acc / efflen (EMfactory.py:228-232), iso'[t] = sum_h theta'[t][h], block partial sums of iso'.
 // FROM_ACC = false: only (re)compute iso / partials of the current theta (after prepare / set_theta / pseudocount).
-template <bool FROM_ACC>
+// REDUCE (row-sharded EM updates with the fused exchange): the cross-rank reduction of this rank's slice runs at the
+// head of the same launch -- wait for every rank's local numerator, reduce + broadcast the slice, raise `done`, wait
+// for every rank's `done`, then update -- instead of a kernel of its own.  All blocks of the grid must be resident at
+// once (the launcher sizes the grid by the occupancy API): blocks waiting for `done` would otherwise keep blocks that
+// still have to reduce from ever starting.
+template <bool FROM_ACC, bool REDUCE = false>
 __global__ void __launch_bounds__(kThreads) k_locus_update(const __grid_constant__ gbrs_em_dev d) {
   __shared__ double red[32];
   const bool xchg = FROM_ACC && d.xchg_enabled;
-  // fused exchange: k_xchg_reduce (same stream, just before) has set XEPOCH to the epoch of this exchange; the totals are
-  // complete once every rank has raised its done flag for it
-  if (xchg) xchg_wait_all(d, 1, (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH]);
+  if (REDUCE) {
+    const uint32_t e = (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH] + 1u;  // every block reads it before the last one bumps it
+    xchg_wait_all(d, 0, e);
+    if (d.xchg_mc) xchg_reduce_slice<true>(d);
+    else xchg_reduce_slice<false>(d);
+    xchg_signal_all(d, 1, e, GBRS_CTRL_TICKET + 2);
+    xchg_wait_all(d, 1, e);
+  } else if (xchg) {
+    // fused exchange, two launches: k_xchg_reduce (same stream, just before) has set XEPOCH to the epoch of this
+    // exchange; the totals are complete once every rank has raised its done flag for it
+    xchg_wait_all(d, 1, (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH]);
+  }
   if (FROM_ACC && d.ctrl[GBRS_CTRL_DONE]) return;
   const int par = d.ctrl[GBRS_CTRL_PARITY];
   const double* __restrict__ src =
@@ -939,7 +984,7 @@ __global__ void __launch_bounds__(kThreads) k_locus_update(const __grid_constant
     double v = 0.0;
     const bool valid = i < total;
     if (valid) {
-      v = src[i];
+      v = xchg ? __ldcg(src + i) : src[i];  // totals written by peers: never through a stale L1 line
       if (FROM_ACC) {
         if (xchg) d.acc[i] = v;  // keep the summed numerator where the reports read it
         v = fast_div(v, d.efflen[i]);
@@ -1151,15 +1196,20 @@ inline int converge_grid(const gbrs_em_dev* d) {
   return g < 1 ? 1 : (g > 128 ? 128 : g);
 }
 
-// Fused NVLink exchange (descriptor flag); otherwise the caller all-reduces `acc` between the two halves of an update.
-int launch_exchange(const gbrs_em_dev* d, cudaStream_t s) {
-  if (!d->xchg_enabled) return GBRS_OK;
+int check_exchange(const gbrs_em_dev* d) {
   if (d->n_ranks < 2 || d->n_ranks > 8 || d->xchg_rank < 0 || d->xchg_rank >= d->n_ranks) {
     gbrs_set_error("fused exchange: 2..8 ranks and a valid rank index are required");
     return GBRS_E_ARG;
   }
   for (int r = 0; r < d->n_ranks; ++r)
     if (!d->xchg_peer[r]) { gbrs_set_error("fused exchange: null peer buffer"); return GBRS_E_ARG; }
+  return GBRS_OK;
+}
+
+// Fused NVLink exchange (descriptor flag); otherwise the caller all-reduces `acc` between the two halves of an update.
+int launch_exchange(const gbrs_em_dev* d, cudaStream_t s) {
+  if (!d->xchg_enabled) return GBRS_OK;
+  if (int rc = check_exchange(d)) return rc;
   const int64_t slice = ((int64_t) d->T * GBRS_HPAD / 2 + d->n_ranks - 1) / d->n_ranks;
   k_xchg_reduce<<<resident_grid(k_xchg_reduce, slice), kThreads, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_xchg_reduce");
@@ -1420,8 +1470,17 @@ extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
   int nparts = acc_grid(d);  // single rank: k_locus_acc already produced theta', iso' and the partial sums
   if (d->n_ranks > 1) {
     nparts = locus_grid(d);
-    if (int rc = launch_exchange(d, s)) return rc;
-    k_locus_update<true><<<nparts, kThreads, 0, s>>>(*d);
+    static const bool two_launches = std::getenv("GBRS_XCHG_SPLIT") != nullptr;  // A/B knob: reduce as its own kernel
+    if (d->xchg_enabled && !two_launches) {
+      if (int rc = check_exchange(d)) return rc;
+      // all blocks resident at once (see k_locus_update<true, true>)
+      const int cap = resident_grid(k_locus_update<true, true>, (int64_t) d->T * GBRS_HPAD);
+      if (nparts > cap) nparts = cap;
+      k_locus_update<true, true><<<nparts, kThreads, 0, s>>>(*d);
+    } else {
+      if (int rc = launch_exchange(d, s)) return rc;
+      k_locus_update<true><<<nparts, kThreads, 0, s>>>(*d);
+    }
     GBRS_LAUNCH_CHECK("k_locus_update");
   }
   k_converge<false><<<converge_grid(d), kThreads, 0, s>>>(*d, nparts);

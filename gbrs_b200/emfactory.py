@@ -326,6 +326,7 @@ class EMfactory:
         self.err_history = np.zeros(0)
         self.rank, self.world = 0, 1
         self.fused_exchange = False
+        self.nvls_exchange = False
         if shard is None:
             shard = group is not None
         self._presharded = shard == "local"
@@ -448,11 +449,15 @@ class EMfactory:
         torch = _torch()
         import torch.distributed as dist
 
-        if self.world < 2 or self.world > 8 or os.environ.get("GBRS_XCHG", "fused") != "fused":
+        # fused / p2p: peer loads and stores | nvls: in-switch reduction where the box has a multicast mapping | nccl:
+        # plain all-reduce.  NVLS is opt-in: a multimem f64 access moves 8 bytes per request (no vector form for f64) and
+        # measured slower than peer loads both on 2 ranks (47.8 vs 20.9 us per exchange) and on 8 (44.1 vs 36.5 us),
+        # although it moves 2/R of the numerator per rank instead of 2(R-1)/R.
+        mode = os.environ.get("GBRS_XCHG", "fused")
+        if self.world < 2 or self.world > 8 or mode not in ("fused", "nvls", "p2p"):
             return False
-        if dist.get_backend(self._group) != "nccl":
-            return False
-        ok, buf, hdl = 1, None, None
+        use_mc = mode == "nvls"
+        ok, buf, hdl, mc = 1, None, None, 0
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
@@ -463,16 +468,20 @@ class EMfactory:
             ptrs = list(hdl.buffer_ptrs)
             if len(ptrs) != self.world or any(int(p) == 0 for p in ptrs):
                 ok = 0
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if use_mc else 0
         except Exception as e:  # noqa: BLE001 - any failure means "use NCCL"
             logger.info(f"fused NVLink exchange unavailable ({e}); using the NCCL all-reduce")
             ok = 0
-        flag = torch.tensor([ok], dtype=torch.int32, device=pat.device)
+        # every rank must take the same path: fused only if all could map the buffers, NVLS only if all have the multicast
+        flag = torch.tensor([ok, 1 if (ok and mc) else 0], dtype=torch.int32, device=pat.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self._group)  # also orders the zero-fill before first use
         torch.cuda.synchronize(pat.device)
-        if int(flag.item()) != 1:
+        if int(flag[0].item()) != 1:
             return False
+        self.nvls_exchange = bool(int(flag[1].item()))
         pat._xchg = (buf, hdl)
         pat.desc.xchg_enabled = 1
+        pat.desc.xchg_mc = mc if self.nvls_exchange else None
         pat.desc.xchg_rank = self.rank
         for r in range(self.world):
             pat.desc.xchg_peer[r] = int(ptrs[r])

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GBRS_EM_ABI_VERSION 1
+#define GBRS_EM_ABI_VERSION 2
 #define GBRS_HPAD 8 /* haplotype slots per locus line */
 #define GBRS_KMAX 8 /* classes with up to this many (class, locus) pairs take the fixed-width row pass */
 
@@ -127,6 +127,9 @@ typedef struct {
   int32_t xchg_enabled;
   int32_t xchg_rank;
   void* xchg_peer[8];
+  void* xchg_mc;       /* optional: NVSwitch multicast mapping of the same symmetric buffers (NVLS); with it the
+                          cross-rank sum is one multimem.ld_reduce + one multimem.st per element instead of peer
+                          loads from / stores to every rank.  NULL = peer loads and stores */
   /* packed incidence (read-only) */
   const uint32_t* rowptr;
   const uint32_t* pairs;

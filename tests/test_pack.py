@@ -50,7 +50,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.gbrs_abi_version() == 1
+    assert lib.gbrs_abi_version() == _lib.ABI_VERSION
 
 
 def test_pack_preserves_pattern(small):
