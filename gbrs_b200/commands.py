@@ -1,5 +1,6 @@
 """`gbrs quantify` command line -- same flags as the reference (/root/reference/src/gbrs/gbrs/commands.py:108-150):
--i -g -L -G -o -M -p -m -t -a -w -v, and `gbrs compress` (:76-105): -i (repeatable / comma separated) -o -c -v.
+-i -g -L -G -o -M -p -m -t -a -w -v, `gbrs compress` (:76-105): -i (repeatable / comma separated) -o -c -v, and
+`gbrs stencil` (:343-370): -i -G -g -o -v.
 Errors are logged, not raised, and the process exits 0 (:146-150)."""
 from __future__ import annotations
 
@@ -78,6 +79,28 @@ def compress(
                 raise FileNotFoundError(f"{f} does not exist or is not a file")
         importlib.import_module(".compress", __package__).compress(
             emase_files=all_emase_files, output_file=str(output_file), comp_lib=comp_lib)
+    except Exception as e:
+        if logger.level == logging.DEBUG:
+            logger.exception(e)
+        else:
+            logger.error(e)
+
+
+@app.command(help="apply genotype calls to multi-way alignment incidence matrix")
+def stencil(
+    alignment_file: Annotated[Path, typer.Option("-i", "--alignment-file", exists=True, dir_okay=False, resolve_path=True, help="alignment incidence file (h5)")],
+    genotype_file: Annotated[Path, typer.Option("-G", "--genotype", exists=True, dir_okay=False, resolve_path=True, help="genotype calls by GBRS (tsv)")],
+    group_file: Annotated[Path, typer.Option("-g", "--group-file", exists=True, dir_okay=False, resolve_path=True, help="gene ID to isoform ID mapping info (tsv)")] = None,
+    output_file: Annotated[Path, typer.Option("-o", "--output", exists=False, dir_okay=False, writable=True, resolve_path=True, help="genotyped version of alignment incidence file (h5)")] = None,
+    verbose: Annotated[int, typer.Option("-v", "--verbose", count=True, help="specify multiple times for more verbose output")] = 0,
+) -> None:
+    """Flag surface of the reference's `gbrs stencil` (/root/reference/src/gbrs/gbrs/commands.py:343-370)."""
+    logger = utils.configure_logging("gbrs", verbose)
+    logger.debug("stencil")
+    try:
+        importlib.import_module(".stencil", __package__).stencil(
+            alignment_file=str(alignment_file), genotype_file=str(genotype_file),
+            group_file=str(group_file) if group_file else None, output_file=str(output_file) if output_file else None)
     except Exception as e:
         if logger.level == logging.DEBUG:
             logger.exception(e)
