@@ -18,7 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "gbrs_em.h"
@@ -29,13 +31,37 @@
 
 void gbrs_set_error(const std::string& s);  // capi.cu
 
+// Large work arrays: allocation without the value-initialising pass of std::vector (a single thread touching hundreds
+// of megabytes page by page cost more than any packing stage); whatever needs a defined start value is filled by all
+// threads (par_fill), which also spreads the first touch of the pages.
+template <typename T>
+struct noinit_alloc : std::allocator<T> {
+  template <typename U> struct rebind { using other = noinit_alloc<U>; };
+  noinit_alloc() = default;
+  template <typename U> noinit_alloc(const noinit_alloc<U>&) {}
+  template <typename U, typename... A> void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new (static_cast<void*>(p)) U;  // default-init: no write
+    else ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+  }
+};
+template <typename T> using bigvec = std::vector<T, noinit_alloc<T>>;
+
+template <typename V, typename T>
+void par_fill(V& v, size_t n, T value) {
+  v.resize(n);
+  auto* p = v.data();
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t) n; ++i) p[i] = value;
+}
+
 struct gbrs_pack {
   gbrs_pack_info info{};
   int32_t T = 0;
-  std::vector<uint32_t> rowptr, pairs, runptr, item_off, item_order, item_desc, locus_item_ptr, locus_order, locus_desc, gene_ptr, gene_loci;
+  bigvec<uint32_t> rowptr, pairs, runptr;
+  std::vector<uint32_t> item_off, item_order, item_desc, locus_item_ptr, locus_order, locus_desc, gene_ptr, gene_loci;
   std::vector<int32_t> gene_of;
-  std::vector<double> count;
-  std::vector<uint8_t> ent_cls, ent_pair, ent_run;  // entry words, 4 or 8 bytes each
+  bigvec<double> count;
+  bigvec<uint8_t> ent_cls, ent_pair, ent_run;  // entry words, 4 or 8 bytes each
 };
 
 namespace {
@@ -44,7 +70,7 @@ inline int64_t index_at(const void* base, int bytes, int64_t i) {
   return bytes == 4 ? (int64_t) static_cast<const int32_t*>(base)[i] : static_cast<const int64_t*>(base)[i];
 }
 
-inline void put_entry(std::vector<uint8_t>& v, int bytes, int64_t pos, uint64_t idx, uint32_t mask) {
+inline void put_entry(bigvec<uint8_t>& v, int bytes, int64_t pos, uint64_t idx, uint32_t mask) {
   if (bytes == 4) {
     reinterpret_cast<uint32_t*>(v.data())[pos] = (uint32_t) idx | (mask << 24);
   } else {
@@ -88,7 +114,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       for (int h = 0; h < H; ++h) s += in->indptr[h][t + 1] - in->indptr[h][t];
       ub[t + 1] = ub[t] + s;
     }
-    std::vector<uint64_t> tmp((size_t) ub[T]);  // class << 8 | mask
+    bigvec<uint64_t> tmp((size_t) ub[T]);  // class << 8 | mask; every locus writes (and later reads) only its own prefix
     std::vector<int64_t> lcount(T, 0);
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 64)
@@ -151,19 +177,33 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
 
     lap("1 merge columns");
     // ---- 2. per-class pair / nnz counts, shard boundaries balanced by nnz -----------------------------------------
-    // (the scattered per-class updates are done by all threads with relaxed atomics: classes are hit in random order)
-    std::vector<uint32_t> npair((size_t) N, 0), minloc((size_t) N, 0xFFFFFFFFu);
-    std::vector<uint32_t> nz((size_t) N, 0);
-#pragma omp parallel for schedule(dynamic, 256)
-    for (int t = 0; t < T; ++t) {
-      const uint64_t* src = tmp.data() + ub[t];
-      for (int64_t i = 0; i < lcount[t]; ++i) {
-        const uint64_t c = src[i] >> 8;
-        __atomic_fetch_add(&npair[c], 1u, __ATOMIC_RELAXED);
-        __atomic_fetch_add(&nz[c], (uint32_t) __builtin_popcountll(src[i] & 0xFF), __ATOMIC_RELAXED);
-        uint32_t cur_min = __atomic_load_n(&minloc[c], __ATOMIC_RELAXED);
-        while ((uint32_t) t < cur_min &&
-               !__atomic_compare_exchange_n(&minloc[c], &cur_min, (uint32_t) t, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    // Every thread owns a contiguous range of class ids and walks ALL merged entries (a sequential scan of the
+    // locus-major list), keeping only the entries of its own classes: no atomics, and the loci come by in ascending
+    // order, so the first locus seen for a class is its smallest one.
+    bigvec<uint32_t> npair, minloc, nz;
+    par_fill(npair, (size_t) N, 0u);
+    par_fill(minloc, (size_t) N, 0xFFFFFFFFu);
+    par_fill(nz, (size_t) N, 0u);
+    {
+      int nt = 1;
+#ifdef _OPENMP
+      nt = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+      for (int k = 0; k < nt; ++k) {
+        const uint64_t c_lo = (uint64_t) (N * k / nt), c_hi = (uint64_t) (N * (k + 1) / nt);
+        if (c_lo >= c_hi) continue;
+        for (int t = 0; t < T; ++t) {
+          const uint64_t* src = tmp.data() + ub[t];
+          const int64_t m = lcount[t];
+          for (int64_t i = 0; i < m; ++i) {
+            const uint64_t c = src[i] >> 8;
+            if (c < c_lo || c >= c_hi) continue;
+            ++npair[c];
+            nz[c] += (uint32_t) __builtin_popcountll(src[i] & 0xFF);
+            if (minloc[c] == 0xFFFFFFFFu) minloc[c] = (uint32_t) t;
+          }
+        }
       }
     }
     int64_t nnz_total = 0, nclass_total = 0;
@@ -206,15 +246,16 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     if (n_pairs >= (int64_t(1) << 32)) { gbrs_set_error("gbrs_pack_create: more than 2^32 pairs in one shard"); return GBRS_E_LIMIT; }
     for (size_t i = 0; i < (size_t) NB * T; ++i) bucket[i + 1] += bucket[i];
     for (int b = 0; b < NB; ++b) { bclass[b + 1] += bclass[b]; bpair[b + 1] += bpair[b]; }
-    std::vector<uint32_t> new_id((size_t) N, 0xFFFFFFFFu);
+    bigvec<uint32_t> new_id;
+    par_fill(new_id, (size_t) N, 0xFFFFFFFFu);
     for (int64_t c = lo; c < hi; ++c)
       if (npair[c]) new_id[c] = (uint32_t) bucket[(size_t) bucket_of(npair[c]) * T + minloc[c]]++;
 
     lap("3 class order");
     auto* P = new gbrs_pack();
     P->T = T;
-    P->rowptr.assign((size_t) n_classes + 1, 0);
-    P->count.assign((size_t) n_classes, 1.0);
+    par_fill(P->rowptr, (size_t) n_classes + 1, 0u);
+    par_fill(P->count, (size_t) n_classes, 1.0);
 #pragma omp parallel for schedule(static)
     for (int64_t c = lo; c < hi; ++c)
       if (npair[c]) {
@@ -225,11 +266,11 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
 
     lap("3b rowptr/count");
     // ---- 4. class-major fill (loci ascending within a class), then order pairs by (gene, locus) and cut runs -----
-    P->pairs.assign((size_t) n_pairs, 0);
+    P->pairs.resize((size_t) n_pairs);  // every slot is claimed exactly once below
     {
       // all threads scatter; the slot inside a class is claimed atomically, the (gene, locus) sort below makes the
       // final order independent of the claiming order
-      std::vector<uint32_t> cur(P->rowptr.begin(), P->rowptr.end() - 1);
+      bigvec<uint32_t> cur(P->rowptr.begin(), P->rowptr.end() - 1);
 #pragma omp parallel for schedule(dynamic, 256)
       for (int t = 0; t < T; ++t) {
         const uint64_t* src = tmp.data() + ub[t];
@@ -247,8 +288,9 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       if (P->gene_of[t] < 0) { delete P; gbrs_set_error("gbrs_pack_create: negative gene id"); return GBRS_E_ARG; }
     }
     const int32_t n_gene_ids = 1 + *std::max_element(P->gene_of.begin(), P->gene_of.end());
-    P->runptr.assign((size_t) n_classes + 1, 0);
-    std::vector<uint32_t> run_in_class((size_t) n_pairs, 0);  // run number of a pair inside its class
+    P->runptr.resize((size_t) n_classes + 1);  // [0] set here, [n + 1] by the loop below
+    P->runptr[0] = 0;
+    bigvec<uint32_t> run_in_class((size_t) n_pairs);  // run number of a pair inside its class (written for every pair)
     int max_k = 0;
 #pragma omp parallel for schedule(static) reduction(max : max_k)
     for (int64_t n = 0; n < n_classes; ++n) {
@@ -266,6 +308,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       }
       uint32_t runs = k > 0 ? 1 : 0;
       uint32_t* ric = run_in_class.data() + P->rowptr[n];
+      if (k > 0) ric[0] = 0;
       for (int i = 1; i < k; ++i) {
         runs += go[b[i] & 0xFFFFFF] != go[b[i - 1] & 0xFFFFFF];
         ric[i] = runs - 1;
@@ -311,9 +354,9 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     }
     const int64_t n_entries = lptr[T];
     if (n_entries >= (int64_t(1) << 32)) { delete P; gbrs_set_error("gbrs_pack_create: more than 2^32 entries in one shard"); return GBRS_E_LIMIT; }
-    P->ent_cls.assign((size_t) n_entries * entry_bytes, 0);
-    P->ent_pair.assign((size_t) n_entries * entry_bytes, 0);
-    P->ent_run.assign((size_t) n_entries * entry_bytes, 0);
+    P->ent_cls.resize((size_t) n_entries * entry_bytes);
+    P->ent_pair.resize((size_t) n_entries * entry_bytes);
+    P->ent_run.resize((size_t) n_entries * entry_bytes);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n_entries; ++i) {
       put_entry(P->ent_cls, entry_bytes, i, (uint64_t) n_classes, 0);
@@ -321,41 +364,40 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
       put_entry(P->ent_run, entry_bytes, i, (uint64_t) n_runs, 0);
     }
     {
-      // The classes are walked in new order and every pair is appended to its locus' cursor, which yields ascending
-      // class ids inside a locus without sorting.  To do that with all threads, the loci are cut into contiguous
-      // ranges of about equal entry count; each thread walks ALL pair words (sequential, cheap) and keeps only the
-      // pairs whose locus falls into its own range, so no two threads ever touch the same cursor.
-      std::vector<int64_t> cur_part(lptr.begin(), lptr.end() - 1), cur_full(T);
-      for (int t = 0; t < T; ++t) cur_full[t] = lptr[t] + ppart[t];
-      int nt = 1;
-#ifdef _OPENMP
-      nt = omp_get_max_threads();
-#endif
-      std::vector<int> cut(nt + 1, T);
-      cut[0] = 0;
-      for (int k = 1, t = 0; k < nt; ++k) {
-        const int64_t want = n_entries * k / nt;
-        while (t < T && lptr[t] < want) ++t;
-        cut[k] = t;
-      }
-#pragma omp parallel for schedule(static, 1) num_threads(nt)
-      for (int k = 0; k < nt; ++k) {
-        const uint32_t t_lo = (uint32_t) cut[k], t_hi = (uint32_t) cut[k + 1];
-        if (t_lo >= t_hi) continue;
-        for (int64_t n = 0; n < n_classes; ++n) {
-          const uint32_t r0 = P->runptr[n];
-          for (uint32_t p = P->rowptr[n]; p < P->rowptr[n + 1]; ++p) {
-            const uint32_t w = P->pairs[p], t = w & 0xFFFFFF, m = w >> 24;
-            if (t < t_lo || t >= t_hi) continue;
-            const int64_t pos = (split[t] && m == full_mask) ? cur_full[t]++ : cur_part[t]++;
+      // Every locus is filled by one thread from its merged column (step 1): the surviving (class, mask) entries are
+      // ordered by NEW class id (within a split locus: partial masks first), and the pair word of each entry is looked
+      // up in its class row (a handful of words), which gives its pair index and run.  The writes of a locus are
+      // sequential; loci are handed out dynamically, the few very deep ones first would not matter at this grain.
+#pragma omp parallel
+      {
+        std::vector<uint64_t> keys;
+#pragma omp for schedule(dynamic, 64)
+        for (int t = 0; t < T; ++t) {
+          if (lcnt[t] == 0) continue;
+          const uint64_t* src = tmp.data() + ub[t];
+          keys.clear();
+          for (int64_t i = 0; i < lcount[t]; ++i) {
+            const uint32_t nid = new_id[src[i] >> 8];
+            if (nid == 0xFFFFFFFFu) continue;
+            const uint64_t m = src[i] & 0xFF;
+            const uint64_t part = (split[t] && m == full_mask) ? 1 : 0;  // full-mask entries of a deep locus go last
+            keys.push_back((part << 40) | ((uint64_t) nid << 8) | m);
+          }
+          std::sort(keys.begin(), keys.end());
+          int64_t pos_part = lptr[t], pos_full = lptr[t] + ppart[t];
+          for (const uint64_t k : keys) {
+            const uint32_t n = (uint32_t) ((k >> 8) & 0xFFFFFFFFu), m = (uint32_t) (k & 0xFF);
+            uint32_t p = P->rowptr[n];
+            while ((P->pairs[p] & 0xFFFFFF) != (uint32_t) t) ++p;  // the class does hit this locus
+            const int64_t pos = (k >> 40) ? pos_full++ : pos_part++;
             put_entry(P->ent_cls, entry_bytes, pos, (uint64_t) n, m);
             put_entry(P->ent_pair, entry_bytes, pos, (uint64_t) p, m);
-            put_entry(P->ent_run, entry_bytes, pos, (uint64_t) r0 + run_in_class[p], m);
+            put_entry(P->ent_run, entry_bytes, pos, (uint64_t) P->runptr[n] + run_in_class[p], m);
           }
         }
       }
     }
-    std::vector<uint64_t>().swap(tmp);
+    bigvec<uint64_t>().swap(tmp);
 
     lap("5 locus-major entries");
     // ---- 6. column-pass work items ------------------------------------------------------------------------------
@@ -449,7 +491,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
           const int64_t B = (e - b > item_len) ? 128 : 32;  // long items: a warp; short items: an 8-lane group
           for (int64_t k = b; k < e; k += B) {
             const int64_t m = std::min<int64_t>(B, e - k), nq = m / 4;
-            for (std::vector<uint8_t>* arr : {&P->ent_cls, &P->ent_pair, &P->ent_run}) {
+            for (bigvec<uint8_t>* arr : {&P->ent_cls, &P->ent_pair, &P->ent_run}) {
               if (entry_bytes == 4) {
                 uint32_t* w = reinterpret_cast<uint32_t*>(arr->data()) + k;
                 for (int64_t r = 0; r < m; ++r) buf[r] = w[r];

@@ -61,8 +61,24 @@ def _require_cuda(device=None):
     return torch.device(device)
 
 
+class _PackHandle:
+    """Owns one gbrs_pack_t; the numpy views handed out by PackedPattern keep it alive through their ctypes buffers."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def __del__(self):
+        if self.handle is not None and self.lib is not None:
+            try:
+                self.lib.gbrs_pack_free(self.handle)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self.handle = None
+
+
 class PackedPattern:
-    """Host result of gbrs_pack_create for one row shard (numpy views are copied out, the C object is freed)."""
+    """Host result of gbrs_pack_create for one row shard.  The arrays are views into the packer's own memory (no copy
+    of the few hundred megabytes); every view keeps the C object alive for as long as it is referenced."""
 
     def __init__(self, apm: APM, gene_of=None, hapmask=None, shard_rank=0, shard_count=1, item_len=0):
         lib = _lib.load()
@@ -100,7 +116,8 @@ class PackedPattern:
         handle = C.c_void_p()
         t0 = time.perf_counter()
         _lib.check(lib.gbrs_pack_create(C.byref(inp), C.byref(handle)))
-        try:
+        owner = _PackHandle(lib, handle)
+        if True:
             info = _lib.PackInfo()
             _lib.check(lib.gbrs_pack_get_info(handle, C.byref(info)))
             self.info = {f: getattr(info, f) for f, _ in _lib.PackInfo._fields_}
@@ -116,9 +133,10 @@ class PackedPattern:
                     self.arrays[name] = np.zeros(0, dtype=dt)
                 else:
                     buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
-                    self.arrays[name] = np.frombuffer(buf, dtype=dt).copy()
-        finally:
-            lib.gbrs_pack_free(handle)
+                    buf._gbrs_owner = owner  # the view's base: keeps the packer's memory alive
+                    a = np.frombuffer(buf, dtype=dt)
+                    self.arrays[name] = a
+        self._owner = owner
         self.pack_seconds = time.perf_counter() - t0
         self.T, self.H, self.N = T, H, N
         self.has_genes = gene_of is not None
