@@ -90,6 +90,9 @@ SYMBOLS = {
     "gbrs_parse_lengths": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int64, C.POINTER(C.c_char_p), C.c_int32,
                                      C.c_double, C.c_void_p, C.POINTER(C.c_int64)]),
     "gbrs_format_double": (C.c_int, [C.c_double, C.c_char_p, C.c_int32]),
+    "gbrs_rows_create": (C.c_int, [C.POINTER(PackInput), C.POINTER(C.c_void_p)]),
+    "gbrs_rows_get": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "gbrs_rows_free": (C.c_int, [C.c_void_p]),
     "gbrs_ec_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_int64)]),
     "gbrs_ec_build": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64),

@@ -8,8 +8,8 @@ insertion order, :72, :92) and written as a compressed-EMASE incidence matrix wi
 
 The reference builds a Python string per read and a dict; here the grouping runs on the GPU through the C ABI
 (`gbrs_ec_build`, gbrs_b200/csrc/ec_kernels.cu: hash, radix sort, exact comparison, first-appearance numbering).  The
-host side only re-lays the H per-haplotype sparse matrices as one row of (locus | mask << 24) words per read and
-expands the representative rows back into H CSC matrices.  There is no CPU fallback.
+host side only re-lays the H per-haplotype sparse matrices as one row of (locus | mask << 24) words per read
+(`gbrs_rows_create`, native and threaded) and expands the representative rows back into H CSC matrices.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -28,32 +28,38 @@ _SEEDS = (0x243F6A8885A308D3, 0x13198A2E03707344, 0xA4093822299F31D0, 0x082EFA98
 
 def read_rows(mats, T: int, H: int):
     """H sparse matrices (reads x loci) -> CSR of pair words per read: rowptr [n+1] (int64), words [pairs] (uint32,
-    locus | hapmask << 24, ascending locus inside a read).  Stored zeros are not alignments and are dropped."""
+    locus | hapmask << 24, ascending locus inside a read).  Stored zeros are not alignments and are dropped.  Native
+    (gbrs_rows_create: threaded merge + transposition); the result is copied out and the C object freed."""
     if H > _lib.GBRS_HPAD:
         raise NotImplementedError("more than 8 haplotypes is not supported by the packed mask layout")
     if T >= (1 << 24):
         raise NotImplementedError("more than 2^24 loci is not supported by the packed pair words")
+    lib = _lib.load()
     n = mats[0].shape[0]
-    keys, bits = [], []
-    for h, m in enumerate(mats):
-        coo = m.tocoo()
-        nz = coo.data != 0
-        keys.append(coo.row[nz].astype(np.int64) * T + coo.col[nz].astype(np.int64))
-        bits.append(np.full(int(nz.sum()), 1 << h, dtype=np.uint32))
-    keys = np.concatenate(keys) if keys else np.zeros(0, dtype=np.int64)
-    bits = np.concatenate(bits) if bits else np.zeros(0, dtype=np.uint32)
-    order = np.argsort(keys, kind="stable")
-    keys, bits = keys[order], bits[order]
-    if keys.size:
-        starts = np.flatnonzero(np.concatenate(([True], keys[1:] != keys[:-1])))
-        mask = np.bitwise_or.reduceat(bits, starts)
-        keys = keys[starts]
-    else:
-        mask = bits
-    read, locus = keys // T, keys % T
-    words = (locus.astype(np.uint32) | (mask.astype(np.uint32) << np.uint32(24))).astype(np.uint32)
-    rowptr = np.zeros(n + 1, dtype=np.int64)
-    rowptr[1:] = np.cumsum(np.bincount(read, minlength=n))
+    csc = [m if m.format == "csc" else m.tocsc() for m in mats]
+    indptr = [np.ascontiguousarray(m.indptr, dtype=np.int64) for m in csc]
+    wide = any(m.indices.dtype.itemsize == 8 for m in csc)
+    indices = [np.ascontiguousarray(m.indices, dtype=np.int64 if wide else np.int32) for m in csc]
+    values = [np.ascontiguousarray(m.data, dtype=np.float64) for m in csc]
+    inp = _lib.PackInput()
+    inp.T, inp.H, inp.N = T, H, n
+    inp.indptr = (C.c_void_p * H)(*[a.ctypes.data for a in indptr])
+    inp.indices = (C.c_void_p * H)(*[a.ctypes.data for a in indices])
+    inp.values = (C.c_void_p * H)(*[a.ctypes.data for a in values])
+    inp.index_bytes = 8 if wide else 4
+    inp.shard_rank, inp.shard_count = 0, 1
+    handle = C.c_void_p()
+    _lib.check(lib.gbrs_rows_create(C.byref(inp), C.byref(handle)))
+    try:
+        p_rowptr, p_words, n_words = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(lib.gbrs_rows_get(handle, C.byref(p_rowptr), C.byref(p_words), C.byref(n_words)))
+        rowptr = np.frombuffer((C.c_int64 * (n + 1)).from_address(p_rowptr.value), dtype=np.int64).copy()
+        if n_words.value:
+            words = np.frombuffer((C.c_uint32 * n_words.value).from_address(p_words.value), dtype=np.uint32).copy()
+        else:
+            words = np.zeros(0, dtype=np.uint32)
+    finally:
+        lib.gbrs_rows_free(handle)
     return rowptr, words
 
 

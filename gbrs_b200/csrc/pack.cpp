@@ -578,3 +578,117 @@ extern "C" int gbrs_pack_free(gbrs_pack_t p) {
   delete p;
   return GBRS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Read rows for `gbrs compress` (src/gbrs/gbrs/emase_utils.py:52-71): H x CSC(reads x loci)  ->  one row of
+// (locus | hapmask << 24) words per read, ascending locus inside a read.  The reference converts every matrix to CSR
+// and walks the reads in python; this is the packer's merge (step 1 above) followed by a transposition: every thread
+// owns a contiguous range of reads, scans the merged locus-major list in ascending locus order and appends to its own
+// reads, so the rows come out sorted without atomics.  Stored zeros are not alignments.
+// ---------------------------------------------------------------------------------------------------------------------
+struct gbrs_rows {
+  bigvec<int64_t> rowptr;
+  bigvec<uint32_t> words;
+};
+
+extern "C" int gbrs_rows_create(const gbrs_pack_input* in, gbrs_rows_t* out) {
+  if (!in || !out) { gbrs_set_error("gbrs_rows_create: null argument"); return GBRS_E_ARG; }
+  const int T = in->T, H = in->H;
+  const int64_t N = in->N;
+  if (T <= 0 || N < 0 || H <= 0 || !in->indptr || !in->indices || (in->index_bytes != 4 && in->index_bytes != 8)) {
+    gbrs_set_error("gbrs_rows_create: bad shape / index width"); return GBRS_E_ARG;
+  }
+  if (H > GBRS_HPAD) { gbrs_set_error("gbrs_rows_create: more than 8 haplotypes is not supported by the mask layout"); return GBRS_E_LIMIT; }
+  if (T >= (1 << 24)) { gbrs_set_error("gbrs_rows_create: T must be < 2^24"); return GBRS_E_LIMIT; }
+  try {
+    // per locus: (read << 8 | mask), reads ascending (gather + sort: the columns of a read-level file are small)
+    std::vector<int64_t> ub(T + 1, 0);
+    for (int t = 0; t < T; ++t) {
+      int64_t s = 0;
+      for (int h = 0; h < H; ++h) {
+        if (!in->indptr[h] || in->indptr[h][t + 1] < in->indptr[h][t]) { gbrs_set_error("gbrs_rows_create: bad CSC arrays"); return GBRS_E_ARG; }
+        s += in->indptr[h][t + 1] - in->indptr[h][t];
+      }
+      ub[t + 1] = ub[t] + s;
+    }
+    bigvec<uint64_t> tmp((size_t) ub[T]);
+    std::vector<int64_t> lcount(T, 0);
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int t = 0; t < T; ++t) {
+      uint64_t* dst = tmp.data() + ub[t];
+      int64_t n = 0;
+      for (int h = 0; h < H; ++h) {
+        const int64_t b = in->indptr[h][t], e = in->indptr[h][t + 1];
+        for (int64_t i = b; i < e; ++i) {
+          if (in->values && in->values[h] && in->values[h][i] == 0.0) continue;
+          const int64_t r = index_at(in->indices[h], in->index_bytes, i);
+          if (r < 0 || r >= N) { bad = 1; continue; }
+          dst[n++] = ((uint64_t) r << 8) | (uint64_t) h;
+        }
+      }
+      std::sort(dst, dst + n);
+      int64_t m = 0;
+      for (int64_t i = 0; i < n;) {
+        const uint64_t r = dst[i] >> 8;
+        uint64_t mask = 0;
+        while (i < n && (dst[i] >> 8) == r) { mask |= (uint64_t) 1 << (dst[i] & 0xFF); ++i; }
+        dst[m++] = (r << 8) | mask;
+      }
+      lcount[t] = m;
+    }
+    if (bad) { gbrs_set_error("gbrs_rows_create: read index out of range"); return GBRS_E_ARG; }
+    auto* R = new gbrs_rows();
+    par_fill(R->rowptr, (size_t) N + 1, (int64_t) 0);
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    // pairs per read (read-range ownership), prefix sum, then the fill with the same ownership
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+    for (int k = 0; k < nt; ++k) {
+      const uint64_t r_lo = (uint64_t) (N * k / nt), r_hi = (uint64_t) (N * (k + 1) / nt);
+      if (r_lo >= r_hi) continue;
+      for (int t = 0; t < T; ++t) {
+        const uint64_t* src = tmp.data() + ub[t];
+        for (int64_t i = 0; i < lcount[t]; ++i) {
+          const uint64_t r = src[i] >> 8;
+          if (r >= r_lo && r < r_hi) ++R->rowptr[r + 1];
+        }
+      }
+    }
+    for (int64_t r = 0; r < N; ++r) R->rowptr[r + 1] += R->rowptr[r];
+    R->words.resize((size_t) R->rowptr[N]);
+    bigvec<int64_t> cur(R->rowptr.begin(), R->rowptr.end() - 1);
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+    for (int k = 0; k < nt; ++k) {
+      const uint64_t r_lo = (uint64_t) (N * k / nt), r_hi = (uint64_t) (N * (k + 1) / nt);
+      if (r_lo >= r_hi) continue;
+      for (int t = 0; t < T; ++t) {
+        const uint64_t* src = tmp.data() + ub[t];
+        for (int64_t i = 0; i < lcount[t]; ++i) {
+          const uint64_t r = src[i] >> 8;
+          if (r >= r_lo && r < r_hi) R->words[cur[r]++] = (uint32_t) t | ((uint32_t) (src[i] & 0xFF) << 24);
+        }
+      }
+    }
+    *out = R;
+    return GBRS_OK;
+  } catch (const std::bad_alloc&) {
+    gbrs_set_error("gbrs_rows_create: out of host memory");
+    return GBRS_E_NOMEM;
+  }
+}
+
+extern "C" int gbrs_rows_get(gbrs_rows_t r, const int64_t** rowptr, const uint32_t** words, int64_t* n_words) {
+  if (!r || !rowptr || !words || !n_words) { gbrs_set_error("gbrs_rows_get: null argument"); return GBRS_E_ARG; }
+  *rowptr = r->rowptr.data();
+  *words = r->words.data();
+  *n_words = (int64_t) r->words.size();
+  return GBRS_OK;
+}
+
+extern "C" int gbrs_rows_free(gbrs_rows_t r) {
+  delete r;
+  return GBRS_OK;
+}

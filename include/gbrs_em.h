@@ -232,6 +232,15 @@ int gbrs_parse_lengths(const char* path, const char* const* lnames, int64_t n_lo
 /* python repr of one double into `out` (NUL-terminated); returns the length or GBRS_E_ARG if `cap` is too small. */
 int gbrs_format_double(double x, char* out, int32_t cap);
 
+/* Host side of `gbrs compress` (src/gbrs/gbrs/emase_utils.py:52-71): H x CSC(reads x loci) -> one row of pair words
+ * (locus | hapmask << 24, ascending locus) per read, CSR form.  Uses T, H, N, indptr, indices, index_bytes and values of
+ * the gbrs_pack_input struct -- stored zeros are dropped; the other fields are ignored.  rowptr [N+1] (int64) and words stay valid
+ * until gbrs_rows_free. */
+typedef struct gbrs_rows* gbrs_rows_t;
+int gbrs_rows_create(const gbrs_pack_input* in, gbrs_rows_t* out);
+int gbrs_rows_get(gbrs_rows_t r, const int64_t** rowptr, const uint32_t** words, int64_t* n_words);
+int gbrs_rows_free(gbrs_rows_t r);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * `gbrs compress`: equivalence classes of reads (src/gbrs/gbrs/emase_utils.py:46-72).  A read is a row of pair words
  * (locus | hapmask << 24, ascending locus) in CSR form; reads with identical rows form one class, classes are numbered
