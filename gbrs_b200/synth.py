@@ -191,3 +191,122 @@ def genotype_mask(d: SynthData) -> np.ndarray:
         for c in d.genotype[g]:
             gm[hid[c], tids] = 1.0
     return gm
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# inputs of `gbrs reconstruct` (the step after quantify: gene-level TPM -> diplotype per gene along each chromosome)
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class SynthReconstruct:
+    """Logical content of the files `reconstruct` reads (reference src/gbrs/gbrs/gbrs_utils.py:382-470): chromosome
+    list (`ref.fa.fai`), genes in genome order per chromosome (`ref.gene_pos.ordered.npz`), log transition matrices
+    per chromosome (`tranprob.*.npz`, [steps][S][S]), alignment specificity per gene (`avecs.npz`, H x H) and the
+    gene-level TPM table of one sample (`*.genes.tpm`)."""
+    hname: tuple
+    chroms: list  # chromosome names in fai order (may include names without genes / transition matrices)
+    chrlen: dict  # name -> length (only written to the fai file)
+    genes: dict  # chrom -> list of gene ids in genome order
+    gpos: dict  # chrom -> list of int positions
+    tprob: dict  # chrom -> float64 [steps][S][S] log transition probabilities
+    avecs: dict  # gene id -> float64 [H][H]
+    expr: dict  # gene id -> float64 [H] (dict order = row order of the TPM file)
+    truth: dict  # chrom -> int array, the diplotype index the expression was simulated from
+
+    @property
+    def H(self) -> int:
+        return len(self.hname)
+
+    @property
+    def S(self) -> int:
+        return self.H * (self.H + 1) // 2
+
+
+def diplotype_pairs(H: int) -> list:
+    """(i, j), i <= j, in itertools.combinations_with_replacement order (reference gbrs_utils.py:452-454)."""
+    return [(i, j) for i in range(H) for j in range(i, H)]
+
+
+def generate_reconstruct(genes_per_chrom=(40, 25, 33), H: int = 8, sample_index: int = 0, extra_tprob_step=(),
+                         frac_low: float = 0.15, frac_no_avec: float = 0.1, switch_rate: float = 0.03,
+                         empty_chrom: bool = True) -> SynthReconstruct:
+    """One sample.  Chromosomes are named 1, 2, ... and X (last).  `extra_tprob_step`: chromosome names whose
+    transition file carries as many matrices as genes (the legacy layout the reference's back-trace special-cases,
+    gbrs_utils.py:585-588) instead of genes - 1.  `frac_low` genes are expressed below any sensible threshold (null
+    emission), `frac_no_avec` genes have no alignment-specificity entry (naive emission)."""
+    shared = np.random.default_rng(BASE_SEED + 7919)
+    rng = np.random.default_rng(BASE_SEED + 104729 + sample_index)
+    hname = HAPLOTYPES[:H]
+    dip = diplotype_pairs(H)
+    S = len(dip)
+    names = [str(i + 1) for i in range(len(genes_per_chrom) - 1)] + ["X"] if len(genes_per_chrom) > 1 else ["1"]
+    chroms, chrlen, genes, gpos, tprob, avecs, expr, truth = [], {}, {}, {}, {}, {}, {}, {}
+    gcount = 0
+    for c, n in zip(names, genes_per_chrom):
+        chroms.append(c)
+        pos = np.sort(shared.integers(1000, 1000 + 40000 * max(n, 1), n))
+        chrlen[c] = int(pos[-1] + 5000) if n else 5000
+        genes[c] = [f"ENSG{gcount + i:08d}" for i in range(n)]
+        gcount += n
+        gpos[c] = [int(p) for p in pos]
+        steps = n if c in extra_tprob_step else max(n - 1, 0)
+        r = shared.uniform(0.002, 0.08, steps)  # probability of leaving the current diplotype
+        q = shared.dirichlet(np.ones(S) * 0.5, size=(steps, S))
+        p = (1.0 - r)[:, None, None] * np.eye(S)[None] + r[:, None, None] * q
+        tprob[c] = np.log(p / p.sum(axis=2, keepdims=True))
+        for g in genes[c]:
+            if shared.random() >= frac_no_avec:
+                a = np.eye(H) + shared.gamma(0.3, 0.08, (H, H))  # mostly specific, some cross-alignment
+                avecs[g] = a / np.linalg.norm(a, axis=1, keepdims=True)
+        # sample-specific: diplotype path and expression
+        state = np.zeros(n, dtype=np.int64)
+        if n:
+            state[0] = rng.integers(0, S)
+            for i in range(1, n):
+                state[i] = rng.integers(0, S) if rng.random() < switch_rate else state[i - 1]
+        truth[c] = state
+        for i, g in enumerate(genes[c]):
+            a = avecs.get(g, np.eye(H))
+            h1, h2 = dip[state[i]]
+            level = rng.lognormal(2.5, 1.2)
+            if rng.random() < frac_low:
+                level = rng.uniform(0.0, 0.5)
+            w = rng.beta(8, 8)
+            v = level * (w * a[h1] + (1 - w) * a[h2]) * rng.lognormal(0.0, 0.15, H)
+            expr[g] = np.round(v, 6)
+    if empty_chrom:  # a chromosome of the fai file without genes or transition matrices (e.g. Y, MT): skipped
+        chroms.append("MT")
+        chrlen["MT"] = 16299
+    # the TPM table also lists genes that are on no chromosome of the gene-position file
+    for i in range(3):
+        expr[f"ENSGX{i:07d}"] = np.round(rng.gamma(1.0, 3.0, H), 6)
+    return SynthReconstruct(hname=hname, chroms=chroms, chrlen=chrlen, genes=genes, gpos=gpos, tprob=tprob, avecs=avecs,
+                            expr=expr, truth=truth)
+
+
+def write_reconstruct_files(d: SynthReconstruct, directory: str, prefix: str = "") -> dict:
+    """Write the five input files in the reference's formats; returns their paths (`data_dir` is what $GBRS_DATA must
+    point at for `ref.fa.fai`)."""
+    import os
+
+    paths = {"data_dir": directory,
+             "fai": os.path.join(directory, "ref.fa.fai"),
+             "gpos": os.path.join(directory, prefix + "ref.gene_pos.ordered.npz"),
+             "tprob": os.path.join(directory, prefix + "tranprob.npz"),
+             "avecs": os.path.join(directory, prefix + "avecs.npz"),
+             "expr": os.path.join(directory, prefix + "sample.genes.tpm")}
+    with open(paths["fai"], "w") as fh:
+        off = 0
+        for c in d.chroms:
+            fh.write(f"{c}\t{d.chrlen[c]}\t{off + len(c) + 2}\t60\t61\n")
+            off += d.chrlen[c]
+    # get_transition_prob saves lists of (gene id, position) tuples: numpy makes them [n][2] string arrays
+    # (gbrs_utils.py:262-265)
+    np.savez_compressed(paths["gpos"], **{c: np.array([(g, p) for g, p in zip(d.genes[c], d.gpos[c])])
+                                          for c in d.genes if len(d.genes[c])})
+    np.savez_compressed(paths["tprob"], **{c: d.tprob[c] for c in d.tprob if len(d.genes[c])})
+    np.savez_compressed(paths["avecs"], **d.avecs)
+    with open(paths["expr"], "w") as fh:
+        fh.write("locus\t" + "\t".join(d.hname) + "\ttotal\n")
+        for g, v in d.expr.items():
+            fh.write(g + "\t" + "\t".join(repr(float(x)) for x in v) + "\t" + repr(float(v.sum())) + "\n")
+    return paths
