@@ -62,6 +62,11 @@ class EmDev(C.Structure):
                 ("gamma", C.c_void_p), ("err_log", C.c_void_p), ("scal", C.c_void_p), ("ctrl", C.c_void_p)]
 
 
+class HmmChain(C.Structure):
+    _fields_ = [("gene0", C.c_int64), ("tprob0", C.c_int64), ("n_genes", C.c_int32), ("n_steps", C.c_int32),
+                ("state0", C.c_int64)]
+
+
 # every symbol include/gbrs_em.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "gbrs_last_error": (C.c_char_p, []),
@@ -99,6 +104,10 @@ SYMBOLS = {
                                 C.POINTER(C.c_int64)]),
     "gbrs_em_alignment_counts": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
+    "gbrs_hmm_emission": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                    C.c_double, C.c_void_p, C.c_void_p]),
+    "gbrs_hmm_run": (C.c_int, [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

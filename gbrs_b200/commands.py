@@ -1,6 +1,6 @@
 """`gbrs quantify` command line -- same flags as the reference (/root/reference/src/gbrs/gbrs/commands.py:108-150):
--i -g -L -G -o -M -p -m -t -a -w -v, `gbrs compress` (:76-105): -i (repeatable / comma separated) -o -c -v, and
-`gbrs stencil` (:343-370): -i -G -g -o -v.
+-i -g -L -G -o -M -p -m -t -a -w -v, `gbrs compress` (:76-105): -i (repeatable / comma separated) -o -c -v,
+`gbrs stencil` (:343-370): -i -G -g -o -v, and `gbrs reconstruct` (:153-183): -e -t -x -g -c -s -o -v.
 Errors are logged, not raised, and the process exits 0 (:146-150)."""
 from __future__ import annotations
 
@@ -101,6 +101,32 @@ def stencil(
         importlib.import_module(".stencil", __package__).stencil(
             alignment_file=str(alignment_file), genotype_file=str(genotype_file),
             group_file=str(group_file) if group_file else None, output_file=str(output_file) if output_file else None)
+    except Exception as e:
+        if logger.level == logging.DEBUG:
+            logger.exception(e)
+        else:
+            logger.error(e)
+
+
+@app.command(help="reconstruct the genome based upon gene-level TPM quantities")
+def reconstruct(
+    expression_file: Annotated[Path, typer.Option("-e", "--expr-file", exists=True, dir_okay=False, resolve_path=True, help="file containing gene-level TPM quantities")],
+    tprob_file: Annotated[Path, typer.Option("-t", "--tprob-file", exists=True, dir_okay=False, resolve_path=True, help="transition probabilities file")],
+    avec_file: Annotated[Path, typer.Option("-x", "--avec-file", exists=True, dir_okay=False, resolve_path=True, help="alignment specificity file")] = None,
+    gpos_file: Annotated[Path, typer.Option("-g", "--gpos-file", exists=True, dir_okay=False, resolve_path=True, help="meta information for genes (chrom, id, location)")] = None,
+    expr_threshold: Annotated[float, typer.Option("-c", "--expr-threshold")] = 1.5,
+    sigma: Annotated[float, typer.Option("-s", "--sigma")] = 0.12,
+    outbase: Annotated[str, typer.Option("-o", "--outbase", help="basename of all the generated output files")] = None,
+    verbose: Annotated[int, typer.Option("-v", "--verbose", count=True, help="specify multiple times for more verbose output")] = 0,
+) -> None:
+    """Flag surface of the reference's `gbrs reconstruct` (/root/reference/src/gbrs/gbrs/commands.py:153-183)."""
+    logger = utils.configure_logging("gbrs", verbose)
+    logger.debug("reconstruct")
+    try:
+        importlib.import_module(".reconstruct", __package__).reconstruct(
+            expression_file=str(expression_file), tprob_file=str(tprob_file),
+            avec_file=str(avec_file) if avec_file else None, gpos_file=str(gpos_file) if gpos_file else None,
+            expr_threshold=expr_threshold, sigma=sigma, outbase=outbase)
     except Exception as e:
         if logger.level == logging.DEBUG:
             logger.exception(e)

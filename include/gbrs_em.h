@@ -257,6 +257,44 @@ int gbrs_ec_build(int64_t n_reads, const uint32_t* rowptr_dev, const uint32_t* p
                   void* workspace_dev, int64_t workspace_bytes, void* stream, int64_t* n_classes_out,
                   int64_t* collisions_out);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * `gbrs reconstruct`: diplotype HMM along the genes of every chromosome (src/gbrs/gbrs/gbrs_utils.py:382-609).
+ * S = H (H + 1) / 2 diplotypes in itertools.combinations_with_replacement order (:452-454).  All tables are gene-major
+ * ([gene][S]): the chains of one call -- chromosomes of one sample, or of all samples of a cohort -- are laid one after
+ * the other along the gene axis and described by `gbrs_hmm_chain` records.  No CPU fallback.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* Emission log-probabilities (gbrs_utils.py:462-488; get_genotype_probability :80-100, unit_vector :63-67):
+ *   expr_dev       [n_genes][H]  gene-level TPM per haplotype
+ *   avec_dev       [n_avec][H][H] alignment-specificity matrices; avec_index_dev [n_genes] = row of the gene's matrix
+ *                  or -1 (no entry: naive vectors eye + 1e-4 and sigma 0.45, :472-483)
+ *   init_dev       [S] null-model log-probabilities (:462-469), used for genes whose TPM sum is below expr_threshold
+ *   eprob_dev      [n_genes][S]  out */
+int gbrs_hmm_emission(int64_t n_genes, int32_t H, const double* expr_dev, const double* avec_dev,
+                      const int32_t* avec_index_dev, const double* init_dev, double expr_threshold, double sigma,
+                      double* eprob_dev, void* stream);
+
+typedef struct {
+  int64_t gene0;    /* first gene row of the chain in eprob / alpha / scaler / gamma / delta / backptr */
+  int64_t tprob0;   /* index of the chain's first S x S matrix in tprob_dev (chains of different samples may share) */
+  int32_t n_genes;  /* >= 1 */
+  int32_t n_steps;  /* matrices the transition file holds for this chromosome: n_genes - 1, or >= n_genes (legacy
+                       files; the back-trace then also uses matrix n_genes - 1, gbrs_utils.py:585-590) */
+  int64_t state0;   /* first slot of the chain in states_dev; it fills min(n_genes, n_steps) + 1 slots */
+} gbrs_hmm_chain;
+
+/* Scaled forward pass (:498-523), backward pass (:527-548), posterior (:552-558), Viterbi scores (:565-575) and the
+ * back-trace (:578-594) of every chain; one thread block per chain.
+ *   tprob_dev   [.][S][S] log transition matrices as stored in the file (tprob[i][k][j]: towards state k of gene i+1
+ *               from state j of gene i)
+ *   alpha_dev   [genes][S], scaler_dev [genes]   out: normalised forward log-probabilities and -log normaliser
+ *   gamma_dev   [genes][S]   out: posterior (the reference's genoprobs, transposed)
+ *   delta_dev   [genes][S]   out: Viterbi scores;  backptr_dev [genes][S] bytes: work space
+ *   states_dev  out: per chain the states of genes 0 .. m-1 (m = min(n_genes, n_steps): the genes that get a genotype
+ *               call) followed by the arg-max state of the last gene -- the reference's `viterbi_states` list */
+int gbrs_hmm_run(int32_t n_chains, const gbrs_hmm_chain* chains_dev, int32_t H, const double* init_dev,
+                 const double* eprob_dev, const double* tprob_dev, double* alpha_dev, double* scaler_dev,
+                 double* gamma_dev, double* delta_dev, uint8_t* backptr_dev, int32_t* states_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
