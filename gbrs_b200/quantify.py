@@ -17,22 +17,41 @@ logger = utils.get_logger("gbrs")
 
 
 def load_genotype_mask(aln_mat: AlignmentPropertyMatrix, genotype_file: str):
-    """Genotype TSV -> (gtmask H x T, gtcall_g, gtcall_t)   (emase_utils.py:240-269)."""
+    """Genotype TSV -> (gtmask H x T, gtcall_g, gtcall_t)   (emase_utils.py:240-269).  The reference sets the mask gene
+    by gene (a meshgrid assignment and a loop over the gene's transcripts per line: a second at 32k genes); here the
+    lines are parsed in the same order with the same look-ups -- an unknown gene or haplotype letter raises the same
+    KeyError -- and the mask and the transcript notes are then filled in bulk."""
     hid = dict(zip(aln_mat.hname, np.arange(aln_mat.num_haplotypes)))
     gid = dict(zip(aln_mat.gname, np.arange(len(aln_mat.gname))))
     gtmask = np.zeros((aln_mat.num_haplotypes, aln_mat.num_loci))
     gtcall_g = dict.fromkeys(aln_mat.gname)
     gtcall_t = dict.fromkeys(aln_mat.lname)
+    genes, calls, haps = [], [], []
     with open(genotype_file) as fh:
         for curline in dropwhile(utils.is_comment, fh):
             item = curline.rstrip().split("\t")
             g, gt = item[:2]
             gtcall_g[g] = gt
-            hid2set = np.array([hid[c] for c in gt])
-            tid2set = np.array(aln_mat.groups[gid[g]])
-            gtmask[tuple(np.meshgrid(hid2set, tid2set))] = 1.0
-            for t in tid2set:
-                gtcall_t[aln_mat.lname[t]] = gt
+            haps.append([hid[c] for c in gt])
+            genes.append(gid[g])
+            calls.append(gt)
+    if not genes:
+        return gtmask, gtcall_g, gtcall_t
+    groups = aln_mat.groups
+    size = np.fromiter((len(groups[g]) for g in genes), dtype=np.int64, count=len(genes))
+    loci = np.fromiter((t for g in genes for t in groups[g]), dtype=np.int64, count=int(size.sum()))
+    line_of = np.repeat(np.arange(len(genes)), size)
+    width = max(len(h) for h in haps)
+    hap_tab = np.full((len(genes), max(width, 1)), -1, dtype=np.int64)
+    for i, h in enumerate(haps):
+        hap_tab[i, : len(h)] = h
+    for k in range(width):
+        h = hap_tab[line_of, k]
+        ok = h >= 0
+        gtmask[h[ok], loci[ok]] = 1.0
+    lname = aln_mat.lname
+    for t, i in zip(loci.tolist(), line_of.tolist()):  # later lines win, as in the reference's loop
+        gtcall_t[lname[t]] = calls[i]
     return gtmask, gtcall_g, gtcall_t
 
 

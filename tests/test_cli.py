@@ -74,6 +74,39 @@ def test_genotype_mask_matches_reference_semantics(tmp_path):
     assert apm.is_pure_incidence() and apm.nnz < before
 
 
+def test_genotype_mask_odd_files_follow_the_reference_loop(tmp_path):
+    """Comment lines, extra columns, a gene listed twice, one- and three-letter calls, genes missing from the file
+    (fully masked out), an unknown gene (KeyError): against the reference's line loop (gbrs/emase_utils.py:247-269)."""
+    d = synth.generate(T=300, N=200, H=8, with_genotype=True)
+    apm = synth.to_apm(d)
+    gt = tmp_path / "gt.tsv"
+    with open(gt, "w") as fh:
+        fh.write("#Gene_ID\tDiplotype\n# another comment\n")
+        for g, call in enumerate(d.genotype):
+            if g % 7 != 3:
+                fh.write(f"{d.gname[g]}\t{call}\tignored\n")
+        fh.write(f"{d.gname[5]}\tH\n{d.gname[6]}\tABC\n")
+    hid = {h: i for i, h in enumerate(apm.hname)}
+    gid = {g: i for i, g in enumerate(apm.gname)}
+    want, want_g, want_t = np.zeros((8, d.T)), dict.fromkeys(apm.gname), dict.fromkeys(apm.lname)
+    for line in open(gt):
+        if line.startswith("#"):
+            continue
+        g, call = line.rstrip().split("\t")[:2]
+        want_g[g] = call
+        for t in apm.groups[gid[g]]:
+            want_t[apm.lname[t]] = call
+            for c in call:
+                want[hid[c], t] = 1.0
+    gtmask, gtcall_g, gtcall_t = qmod.load_genotype_mask(apm, str(gt))
+    assert np.array_equal(gtmask, want) and gtcall_g == want_g and gtcall_t == want_t
+    assert gtcall_g[d.gname[3]] is None and gtmask[:, apm.groups[3]].sum() == 0
+    with open(gt, "a") as fh:
+        fh.write("NOPE\tAB\n")
+    with pytest.raises(KeyError):
+        qmod.load_genotype_mask(apm, str(gt))
+
+
 def test_apm_npz_roundtrip_and_groups(tmp_path):
     d = synth.generate(T=30, N=150, H=4)
     apm = synth.to_apm(d)
