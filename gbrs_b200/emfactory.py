@@ -116,26 +116,24 @@ class PackedPattern:
         handle = C.c_void_p()
         t0 = time.perf_counter()
         _lib.check(lib.gbrs_pack_create(C.byref(inp), C.byref(handle)))
-        owner = _PackHandle(lib, handle)
-        if True:
-            info = _lib.PackInfo()
-            _lib.check(lib.gbrs_pack_get_info(handle, C.byref(info)))
-            self.info = {f: getattr(info, f) for f, _ in _lib.PackInfo._fields_}
-            self.info["bucket_class0"] = list(info.bucket_class0)
-            self.info["bucket_pair0"] = list(info.bucket_pair0)
-            self.arrays = {}
-            entry_t = np.uint32 if info.entry_bytes == 4 else np.uint64
-            for name, dt in _PACK_ARRAYS.items():
-                ptr, nbytes = C.c_void_p(), C.c_int64()
-                _lib.check(lib.gbrs_pack_get_array(handle, name.encode(), C.byref(ptr), C.byref(nbytes)))
-                dt = entry_t if dt is None else dt
-                if nbytes.value == 0:
-                    self.arrays[name] = np.zeros(0, dtype=dt)
-                else:
-                    buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
-                    buf._gbrs_owner = owner  # the view's base: keeps the packer's memory alive
-                    a = np.frombuffer(buf, dtype=dt)
-                    self.arrays[name] = a
+        owner = _PackHandle(lib, handle)  # frees the C object when the last view is gone (also if a call below fails)
+        info = _lib.PackInfo()
+        _lib.check(lib.gbrs_pack_get_info(handle, C.byref(info)))
+        self.info = {f: getattr(info, f) for f, _ in _lib.PackInfo._fields_}
+        self.info["bucket_class0"] = list(info.bucket_class0)
+        self.info["bucket_pair0"] = list(info.bucket_pair0)
+        self.arrays = {}
+        entry_t = np.uint32 if info.entry_bytes == 4 else np.uint64
+        for name, dt in _PACK_ARRAYS.items():
+            ptr, nbytes = C.c_void_p(), C.c_int64()
+            _lib.check(lib.gbrs_pack_get_array(handle, name.encode(), C.byref(ptr), C.byref(nbytes)))
+            dt = entry_t if dt is None else dt
+            if nbytes.value == 0:
+                self.arrays[name] = np.zeros(0, dtype=dt)
+            else:
+                buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
+                buf._gbrs_owner = owner  # the view's base: keeps the packer's memory alive
+                self.arrays[name] = np.frombuffer(buf, dtype=dt)
         self._owner = owner
         self.pack_seconds = time.perf_counter() - t0
         self.T, self.H, self.N = T, H, N
@@ -264,15 +262,25 @@ class DevicePattern:
         _torch().cuda.current_stream(self.device).synchronize()
         return st.numpy().copy()
 
+    def _sync(self):
+        _torch().cuda.current_stream(self.device).synchronize()
+
     def set_lengths(self, target_lengths_HT):
-        """H x T effective lengths -> device [T][8] (1.0 in unused slots)."""
+        """H x T effective lengths -> device [T][8] (1.0 in unused slots).  `EMfactory._read_lengths` hands over the
+        transpose of a [T][H] table, so for H = 8 the fill of the pinned staging buffer is one contiguous copy."""
+        torch = _torch()
+        if target_lengths_HT is None:
+            self.efflen.fill_(1.0)
+            return
         st = self._staging()
-        e = st.numpy()
-        e[:] = 1.0
-        if target_lengths_HT is not None:
-            e[:, : self.H] = np.asarray(target_lengths_HT, dtype=np.float64).T
+        src = np.asarray(target_lengths_HT, dtype=np.float64)
+        if src.shape != (self.H, self.T):
+            raise ValueError(f"effective lengths must be {self.H} x {self.T}, got {src.shape}")
+        if self.H < 8:
+            st[:, self.H:] = 1.0
+        st[:, : self.H].copy_(torch.from_numpy(src.T if src.T.flags.c_contiguous else np.ascontiguousarray(src.T)))
         self.efflen.copy_(st, non_blocking=True)
-        _torch().cuda.current_stream(self.device).synchronize()  # the staging buffer is reused
+        self._sync()  # the staging buffer is reused
 
     def read_ctrl(self):
         ctrl = np.zeros(16, dtype=np.int32)
@@ -566,8 +574,10 @@ class EMfactory:
 
     def reset(self, pseudocount: float = 0.0) -> None:
         """EMfactory.reset (EMfactory.py:113-138): theta0 from the incidence pattern."""
+        fresh = self._pattern is None
         pat = self._ensure_pattern()
-        pat.set_lengths(self.target_lengths)
+        if not fresh:  # a new pattern has just been given the lengths
+            pat.set_lengths(self.target_lengths)
         _lib.check(pat.lib.gbrs_em_prepare_local(C.byref(pat.desc), pat.stream()))
         self._exchange(pat)
         _lib.check(pat.lib.gbrs_em_prepare_finish(C.byref(pat.desc), float(pseudocount), pat.stream()))
