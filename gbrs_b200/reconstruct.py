@@ -104,6 +104,11 @@ class HmmPlan:
     def chain_of(self, sample: int, chrom_index: int):
         return self.chains[sample * len(self.chroms) + chrom_index]
 
+    def launch_order(self) -> np.ndarray:
+        """The chain records longest first: blocks are scheduled in index order and chromosomes differ several-fold in
+        gene count, so the long chains must not start last.  Records carry their own offsets; the order is free."""
+        return np.ascontiguousarray(self.chains[np.argsort(-self.chains["n_genes"].astype(np.int64), kind="stable")])
+
 
 def build_plan(chrom_names, gene_order, tprob, avecs, expr_list, num_haps) -> HmmPlan:
     """`chrom_names`: fai order; `gene_order`: chrom -> gene ids; `tprob`: mapping chrom -> [steps][S][S] (an NpzFile or a
@@ -185,7 +190,7 @@ def run_plan_on_device(plan: HmmPlan, expr_threshold: float, sigma: float, devic
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         d_expr, d_aidx, d_avecs, d_init = up(plan.expr), up(plan.avec_index), up(plan.avecs), up(plan.init)
-        d_tprob, d_chains = up(plan.tprob), up(plan.chains)
+        d_tprob, d_chains = up(plan.tprob), up(plan.launch_order())
         eprob = torch.empty((max(G, 1), S), dtype=f64, device=dev)
         alpha = torch.empty((max(G, 1), S), dtype=f64, device=dev)
         gamma = torch.empty((max(G, 1), S), dtype=f64, device=dev)

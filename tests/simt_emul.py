@@ -75,7 +75,7 @@ def run_emission(plan, expr_threshold, sigma, grid=None, lib=None):
 def run_chains(plan, eprob, grid=None, lib=None):
     lib = lib or load()
     G, S = plan.expr.shape[0], plan.S
-    chains, init = np.ascontiguousarray(plan.chains), np.ascontiguousarray(plan.init)
+    chains, init = plan.launch_order(), np.ascontiguousarray(plan.init)
     tprob, eprob = np.ascontiguousarray(plan.tprob), np.ascontiguousarray(eprob)
     out = {k: np.full((G, S), np.nan) for k in ("alpha", "gamma", "delta")}
     out["scaler"] = np.full(G, np.nan)

@@ -66,7 +66,8 @@ def main():
         def up(a):
             return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
 
-        d = {k: up(getattr(plan, k)) for k in ("expr", "avec_index", "avecs", "init", "tprob", "chains")}
+        d = {k: up(getattr(plan, k)) for k in ("expr", "avec_index", "avecs", "init", "tprob")}
+        d["chains"] = up(plan.launch_order())
         buf = {k: torch.empty((G, S), dtype=torch.float64, device=dev) for k in ("eprob", "alpha", "gamma", "delta")}
         scaler = torch.empty(G, dtype=torch.float64, device=dev)
         backptr = torch.zeros((G, S), dtype=torch.uint8, device=dev)
