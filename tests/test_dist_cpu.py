@@ -65,3 +65,68 @@ def test_two_rank_gloo_sharded_update(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
+
+
+COHORT_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["GBRS_ROOT"])
+import numpy as np, torch.distributed as dist
+from gbrs_b200 import reconstruct as rc, synth
+from tests import simt_emul
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+tmp = os.environ["GBRS_TMP"]
+# the device step is replaced by the emulated kernels (CPU box); everything else is the product's N > 1 path
+rc.run_plan_on_device = lambda plan, t, s, device=None, keep_work=False: simt_emul.run_plan_emulated(plan, t, s)
+os.environ["GBRS_DATA"] = tmp
+files = [os.path.join(tmp, f"s{i}.sample.genes.tpm") for i in range(5)]
+os.makedirs(os.path.join(tmp, f"rank{rank}"), exist_ok=True)
+outs = [os.path.join(tmp, f"rank{rank}", f"out{i}") for i in range(5)]   # per-rank directory: who wrote what is visible
+rc.reconstruct_cohort(files, os.path.join(tmp, "s0.tranprob.npz"), avec_file=os.path.join(tmp, "s0.avecs.npz"),
+                      gpos_file=os.path.join(tmp, "s0.ref.gene_pos.ordered.npz"), outbases=outs)
+mine = [i for i in range(5) if i % world == rank]
+for i in range(5):
+    assert os.path.exists(outs[i] + ".genotypes.tsv") == (i in mine)   # a rank handles its own samples only
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok", mine)
+'''
+
+
+def test_two_rank_gloo_reconstruct_cohort(tmp_path):
+    """N > 1 path of `reconstruct_cohort`: replicas only -- samples dealt round-robin over the ranks, no collective.
+    Two gloo ranks (device step = emulated kernels); together they must produce every sample's files, equal to the
+    oracle's."""
+    import shutil
+
+    import numpy as np
+
+    if shutil.which("g++") is None:
+        pytest.skip("g++ is needed to build the SIMT emulation")
+    from gbrs_b200 import synth
+    from oracle import reconstruct_oracle as ro
+    from tests import reconstruct_checks as chk
+    from tests import simt_emul
+
+    simt_emul.build()  # once, before the ranks race for it
+    kw = dict(genes_per_chrom=(14, 6), H=4)
+    samples = [synth.generate_reconstruct(sample_index=i, **kw) for i in range(5)]
+    for i, d in enumerate(samples):
+        synth.write_reconstruct_files(d, str(tmp_path), prefix=f"s{i}.")
+    script = tmp_path / "worker.py"
+    script.write_text(COHORT_WORKER)
+    env = dict(os.environ, GBRS_ROOT=ROOT, GBRS_TMP=str(tmp_path), MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2
+    d0 = samples[0]
+    for i, d in enumerate(samples):
+        want = ro.reconstruct_tables(d0.chroms, d0.genes, d0.tprob, d0.avecs, d.expr, d0.hname, 1.5, 0.12)
+        base = tmp_path / f"rank{i % 2}"
+        assert open(base / f"out{i}.genotypes.tsv").read() == chk.tsv_of(want["gtcall"])
+        gp = np.load(base / f"out{i}.genoprobs.npz")
+        for c in want["gamma"]:
+            np.testing.assert_allclose(gp[c], want["gamma"][c], rtol=chk.RTOL, atol=1e-300)
