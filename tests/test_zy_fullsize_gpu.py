@@ -1,0 +1,82 @@
+"""Size-independent properties of the EM at BASELINE.json's full single-GPU size (configs[1]: 80k transcripts x 8
+haplotypes x 5M alignment classes, model 4), where the oracle is too slow to be the checker:
+  * every class' responsibilities sum to one  ->  expected counts add up to the class counts, in prepare() and after
+    every update;
+  * expected counts are finite, non-negative, and zero wherever a (locus, haplotype) has no alignment;
+  * theta = counts / effective length (the M-step, EMfactory.py:228-232);
+  * the result does not depend on the order of the alignment classes (a random relabelling of the 5M classes);
+  * the result does not depend on row-sharding (two shards on one GPU, numerators summed by hand).
+The run is cut at a fixed number of updates (tol = 0) so that both sides of a comparison do the same work.
+
+Named to run after the parity tests of the EM (first executed on a device by the round-end driver)."""
+import numpy as np
+import pytest
+
+from gbrs_b200 import synth
+from tests import helpers as hp
+
+UPDATES = 12
+
+
+def relabel_classes(d, seed=5):
+    """The same alignment classes under a random permutation of their ids."""
+    perm = np.random.default_rng(seed).permutation(d.N)
+    new_cls = perm[d.pair_class]
+    order = np.argsort(new_cls, kind="stable")  # pairs stay locus-sorted inside a class
+    count = np.empty_like(d.count)
+    count[perm] = d.count
+    d2 = synth.SynthData(T=d.T, H=d.H, N=d.N, pair_class=new_cls[order], pair_locus=d.pair_locus[order],
+                         pair_mask=d.pair_mask[order], count=count, gene_of=d.gene_of, lengths=d.lengths, hname=d.hname)
+    d2.lname, d2.gname = d.lname, d.gname
+    return d2
+
+
+def test_relabelling_keeps_the_problem():
+    """CPU check of the helper: the oracle gives the same answer for the relabelled input."""
+    d = synth.generate(T=60, N=900, H=8, sample_index=2)
+    d2 = relabel_classes(d)
+    assert not np.array_equal(d.count, d2.count) and d2.nnz == d.nnz and np.all(np.diff(d2.pair_class) >= 0)
+    a, b = hp.oracle_run(d, 4), hp.oracle_run(d2, 4)
+    assert a["iters"] == b["iters"] and hp.relerr(a["counts"], b["counts"]) < 1e-12
+
+
+def run_fixed(d, eff):
+    from gbrs_b200.emfactory import EMfactory
+
+    em = EMfactory(synth.to_apm(d))
+    em.target_lengths = eff
+    em.prepare()
+    theta0 = em.get_allelic_expression()
+    em.run(model=4, tol=0.0, max_iters=UPDATES, verbose=False)
+    assert em.num_iters == UPDATES
+    return theta0, em.get_allelic_expression(), em.expected_read_counts().copy(), em.err_history.copy()
+
+
+@pytest.mark.gpu
+def test_full_size_properties_model4():
+    from tests.test_sharded_gpu import run_sharded
+
+    d = synth.generate(T=80_000, N=5_000_000, H=8)
+    eff = synth.effective_lengths(d)
+    total = d.count.sum()
+    theta0, theta, counts, errs = run_fixed(d, eff)
+    # conservation: prepare() distributes every class' count over its alignments, every E-step over its posterior
+    assert abs((theta0 * eff).sum() - total) < 1e-9 * total
+    assert abs(counts.sum() - total) < 1e-9 * total
+    assert np.isfinite(counts).all() and counts.min() >= 0.0 and np.isfinite(errs).all() and errs.min() >= 0.0
+    # support: no alignment, no expression
+    support = np.zeros((d.H, d.T), dtype=bool)
+    for h in range(d.H):
+        support[h, d.pair_locus[((d.pair_mask >> h) & 1).astype(bool)]] = True
+    assert not counts[~support].any() and not theta[~support].any()
+    assert (counts[support] > 0).mean() > 0.99  # and (almost) every aligned slot keeps some
+    # M-step: theta = counts / effective length
+    assert hp.relerr(theta * eff, counts) < 1e-12
+    # order of the classes is irrelevant
+    _, theta_p, counts_p, errs_p = run_fixed(relabel_classes(d), eff)
+    assert hp.relerr(counts_p, counts) < 1e-10 and hp.relerr(theta_p, theta) < 1e-10
+    np.testing.assert_allclose(errs_p, errs, rtol=1e-8)
+    # row-sharding is irrelevant
+    s = run_sharded(d, 4, 2, tol=0.0, max_iters=UPDATES)
+    assert s["iters"] == UPDATES
+    assert hp.relerr(s["counts"], counts) < 1e-10 and hp.relerr(s["theta"], theta) < 1e-10
