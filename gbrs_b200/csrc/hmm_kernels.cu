@@ -7,13 +7,17 @@
 // chromosomes x the samples of a cohort) and over the S target states inside a step:
 //   k_hmm_emission<H>   one thread per gene: squared distances between the unit expression vector and the unit
 //                        specificity vector of every diplotype, gaussian kernel, normalisation, log
-//   k_hmm_chain<H>      one 64-thread block per chain, thread k owns diplotype k.  The S x S log transition matrix of
-//                        the next step is staged into (double-buffered, odd-stride) shared memory with cp.async while
-//                        the current step computes, so a step costs S exp() per thread plus two block barriers; the
-//                        Viterbi scores and back-pointers share the forward pass' matrix, the posterior is formed in
-//                        the backward pass, the back-trace walks byte back-pointers staged through shared memory.
-// HBM traffic per chain = its transition matrices twice (forward, backward): 2 * 8 * S^2 bytes per gene (20.7 KB at
-// S = 36; matrices are shared by the samples of a cohort and stay L2-resident across them).
+//   k_hmm_exp           transition matrices into the probability domain, once per matrix (they are shared by the
+//                        samples of a cohort): the forward / backward recursions then are multiply-adds
+//   k_hmm_chain<H>      two 64-thread blocks per chain, thread k owns diplotype k.  Block 0: scaled forward pass,
+//                        backward pass and posterior on the probability-domain matrices -- per gene S multiply-adds,
+//                        one log and one exp per thread and two block barriers (the reference's formulation costs S
+//                        exp per state and gene).  Block 1: Viterbi scores, byte back-pointers and the back-trace on
+//                        the log matrices (additions and comparisons only).  The S x S matrix of the next step is
+//                        staged into double-buffered, odd-stride shared memory with cp.async while the current step
+//                        computes.
+// HBM traffic per chain = its matrices three times (forward, backward, Viterbi): 3 * 8 * S^2 bytes per gene (31 KB at
+// S = 36); the chains of all samples on one chromosome are launched next to each other, so they share it through L2.
 // Sums run in the reference's order where it is defined (python `sum` = left to right, numpy reductions over the
 // first axis = row by row); exp / log are CUDA's (<= 1 ulp), so values agree with numpy to ~1e-14, not bitwise.  Given
 // the same emission values the Viterbi scores and path are bit-exact (additions and comparisons only).
@@ -148,168 +152,194 @@ __device__ __forceinline__ void stage_matrix(double* __restrict__ dst, const dou
   __pipeline_commit();
 }
 
+// Transition matrices in the probability domain: out = exp(in), once per matrix, shared by every chain that walks it.
+__global__ void __launch_bounds__(kEmitThreads) k_hmm_exp(int64_t n, const double* __restrict__ in,
+                                                          double* __restrict__ out) {
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = exp(in[i]);
+}
+
+// One block per (chain, role).  Role 0: scaled forward pass, backward pass and posterior, on the probability-domain
+// matrices (a step is a 36-term multiply-add per thread plus one exp and one log, instead of 36 exp).  Role 1: Viterbi
+// scores, back-pointers and back-trace on the log matrices (additions and comparisons only: bit-exact).  The two roles
+// of a chain are independent and run side by side.
 template <int H>
 __global__ void __launch_bounds__(kChainThreads) k_hmm_chain(int32_t n_chains, const gbrs_hmm_chain* __restrict__ chains,
                                                              const double* __restrict__ init,
                                                              const double* __restrict__ eprob,
                                                              const double* __restrict__ tprob,
+                                                             const double* __restrict__ tlin,
                                                              double* __restrict__ alpha, double* __restrict__ scaler,
                                                              double* __restrict__ gamma, double* __restrict__ delta,
                                                              uint8_t* __restrict__ backptr, int32_t* __restrict__ states) {
   constexpr int S = H * (H + 1) / 2;
   constexpr int SP = S | 1;  // odd row stride: row- and column-wise walks of the staged matrix are bank-conflict free
-  __shared__ double tp[2][S * SP];
-  __shared__ double a_s[kChainThreads];   // normalised forward values of the previous gene / beta of the next gene
-  __shared__ double d_s[kChainThreads];   // Viterbi scores of the previous gene / emission of the next gene
-  __shared__ double x_s[kChainThreads];   // exp() terms of the column being normalised
-  __shared__ uint8_t bp_s[kTraceRows * S];
+  __shared__ double tp[2][S * SP];          // the staged matrix of the current / the next step
+  __shared__ double a_s[kChainThreads];     // role 0: exp(alpha) of the previous gene / backward terms of the next gene
+  __shared__ double x_s[kChainThreads];     // role 0: terms of the column being normalised
+  __shared__ double d_s[2][kChainThreads];  // role 1: Viterbi scores of the previous / the current gene
+  __shared__ uint8_t bp_s[kTraceRows * S];  // role 1: back-pointer rows of one back-trace round
 
   const int k = threadIdx.x;
   const bool on = k < S;
-  for (int chain = blockIdx.x; chain < n_chains; chain += gridDim.x) {
-    const gbrs_hmm_chain ch = chains[chain];
+  for (int work = blockIdx.x; work < 2 * n_chains; work += gridDim.x) {
+    const gbrs_hmm_chain ch = chains[work >> 1];
     const int n = ch.n_genes, n_steps = ch.n_steps;
     const double* e_c = eprob + ch.gene0 * S;
-    const double* t_c = tprob + ch.tprob0 * (int64_t) (S * S);
-    double* al_c = alpha + ch.gene0 * S;
-    double* sc_c = scaler + ch.gene0;
-    double* ga_c = gamma + ch.gene0 * S;
-    double* de_c = delta + ch.gene0 * S;
-    uint8_t* bp_c = backptr + ch.gene0 * S;
-    __syncthreads();  // shared memory of the previous chain is no longer read
+    __syncthreads();  // shared memory of the previous work item is no longer read
 
-    // ---------------- forward + Viterbi scores (gbrs_utils.py:498-523, :565-575) ----------------
-    if (n > 1) stage_matrix<S, SP>(tp[0], t_c, k);
-    {
-      const double v = on ? init[k] + e_c[k] : 0.0;  // alpha[:, 0] = delta[:, 0] = init_vec + eprob[first gene]
-      x_s[k] = on ? exp(v) : 0.0;
-      __syncthreads();
-      double sum = 0.0;
-      for (int j = 0; j < S; ++j) sum += x_s[j];
-      const double norm = log(sum);
-      if (on) {
-        a_s[k] = v - norm;
-        d_s[k] = v;
-        al_c[k] = v - norm;
-        de_c[k] = v;
+    if ((work & 1) == 0) {
+      // ---------------- forward (gbrs_utils.py:498-523) ----------------
+      // alpha[k, i] = log(sum_j exp(alpha[j, i-1] + tprob[i-1][k][j]) + tiny) + eprob[i][k], then normalised;
+      // here sum_j P[k][j] * a[j] with P = exp(tprob) and a = exp(alpha[:, i-1]) (= the normalised terms kept from the
+      // previous step).
+      const double* p_c = tlin + ch.tprob0 * (int64_t) (S * S);
+      double* al_c = alpha + ch.gene0 * S;
+      double* sc_c = scaler + ch.gene0;
+      double* ga_c = gamma + ch.gene0 * S;
+      if (n > 1) stage_matrix<S, SP>(tp[0], p_c, k);
+      {
+        const double v = on ? init[k] + e_c[k] : 0.0;  // alpha[:, 0] = init_vec + eprob[first gene]
+        const double x = on ? exp(v) : 0.0;
+        x_s[k] = x;
+        __syncthreads();
+        double sum = 0.0;
+        for (int j = 0; j < S; ++j) sum += x_s[j];
+        const double norm = log(sum);
+        if (on) al_c[k] = v - norm;
+        if (k == 0) sc_c[0] = -norm;
+        a_s[k] = x / sum;
       }
-      if (k == 0) sc_c[0] = -norm;
-    }
-    int cur = 0;
-    for (int i = 1; i < n; ++i) {
-      __pipeline_wait_prior(0);
-      __syncthreads();  // matrix i-1 is in tp[cur]; a_s / d_s of gene i-1 are complete; x_s may be rewritten
-      if (i + 1 < n) stage_matrix<S, SP>(tp[cur ^ 1], t_c + (int64_t) i * (S * S), k);
-      double raw = 0.0, dnew = 0.0;
-      if (on) {
-        const double e = e_c[(int64_t) i * S + k];
-        const double* row = tp[cur] + k * SP;  // tprob[i-1][k][:]
-        double acc = 0.0, best = 0.0;
+      int cur = 0;
+      for (int i = 1; i < n; ++i) {
+        __pipeline_wait_prior(0);
+        __syncthreads();  // matrix i-1 is in tp[cur]; a_s of gene i-1 is complete; x_s may be rewritten
+        if (i + 1 < n) stage_matrix<S, SP>(tp[cur ^ 1], p_c + (int64_t) i * (S * S), k);
+        double raw = 0.0, x = 0.0;
+        if (on) {
+          const double e = e_c[(int64_t) i * S + k];
+          const double* row = tp[cur] + k * SP;  // P[i-1][k][:]
+          double acc = 0.0;
+          for (int j = 0; j < S; ++j) acc += row[j] * a_s[j];
+          raw = log(acc + tiny()) + e;
+          x = exp(raw);
+        }
+        x_s[k] = x;
+        __syncthreads();  // all reads of a_s done, x_s complete
+        double sum = 0.0;
+        for (int j = 0; j < S; ++j) sum += x_s[j];
+        const double norm = log(sum);
+        a_s[k] = x / sum;
+        if (on) al_c[(int64_t) i * S + k] = raw - norm;
+        if (k == 0) sc_c[i] = -norm;
+        cur ^= 1;
+      }
+
+      // ---------------- backward + posterior (gbrs_utils.py:527-558) ----------------
+      // beta[k, i] = log(sum_j exp(tprob[i][j][k] + beta[j, i+1] + eprob[i+1][j] + scaler[i])) = log(sum_j P[j][k] b[j])
+      // with b[j] = exp((beta[j, i+1] + eprob[i+1][j]) + scaler[i]), computed by thread j as soon as it has beta[j, i+1].
+      __syncthreads();  // forward reads of tp / a_s are over; scaler and alpha written by this block are visible
+      if (n > 1) stage_matrix<S, SP>(tp[0], p_c + (int64_t) (n - 2) * (S * S), k);
+      {
+        const double b = sc_c[n - 1];  // beta[:, -1] = alpha_scaler[-1]
+        const double g = on ? exp(al_c[(int64_t) (n - 1) * S + k] + b) : 0.0;
+        x_s[k] = g;
+        a_s[k] = (on && n > 1) ? exp((b + e_c[(int64_t) (n - 1) * S + k]) + sc_c[n - 2]) : 0.0;
+        __syncthreads();
+        double sum = 0.0;
+        for (int j = 0; j < S; ++j) sum += x_s[j];
+        if (on) ga_c[(int64_t) (n - 1) * S + k] = g / sum;
+      }
+      cur = 0;
+      for (int i = n - 2; i >= 0; --i) {
+        __pipeline_wait_prior(0);
+        __syncthreads();  // matrix i in tp[cur]; a_s = b terms of gene i+1; x_s may be rewritten
+        if (i > 0) stage_matrix<S, SP>(tp[cur ^ 1], p_c + (int64_t) (i - 1) * (S * S), k);
+        double bnew = 0.0, g = 0.0;
+        if (on) {
+          const double* col = tp[cur] + k;  // P[i][:, k]
+          double acc = 0.0;
+          for (int j = 0; j < S; ++j) acc += col[j * SP] * a_s[j];
+          bnew = log(acc);
+          g = exp(al_c[(int64_t) i * S + k] + bnew);
+        }
+        x_s[k] = g;
+        __syncthreads();  // all reads of a_s done, x_s complete
+        double sum = 0.0;
+        for (int j = 0; j < S; ++j) sum += x_s[j];
+        if (on) {
+          ga_c[(int64_t) i * S + k] = g / sum;
+          if (i > 0) a_s[k] = exp((bnew + e_c[(int64_t) i * S + k]) + sc_c[i - 1]);
+        }
+        cur ^= 1;
+      }
+    } else {
+      // ---------------- Viterbi scores and back-pointers (gbrs_utils.py:565-575, :589) ----------------
+      const double* t_c = tprob + ch.tprob0 * (int64_t) (S * S);
+      double* de_c = delta + ch.gene0 * S;
+      uint8_t* bp_c = backptr + ch.gene0 * S;
+      if (n > 1) stage_matrix<S, SP>(tp[0], t_c, k);
+      {
+        const double v = on ? init[k] + e_c[k] : 0.0;  // delta[:, 0] = init_vec + eprob[first gene]
+        d_s[0][k] = v;
+        if (on) de_c[k] = v;
+      }
+      int cur = 0, dc = 0;
+      for (int i = 1; i < n; ++i) {
+        __pipeline_wait_prior(0);
+        __syncthreads();  // matrix i-1 is in tp[cur]; d_s[dc] of gene i-1 is complete; d_s[dc ^ 1] is free
+        if (i + 1 < n) stage_matrix<S, SP>(tp[cur ^ 1], t_c + (int64_t) i * (S * S), k);
+        if (on) {
+          const double e = e_c[(int64_t) i * S + k];
+          const double* row = tp[cur] + k * SP;  // tprob[i-1][k][:]
+          double best = 0.0;
+          int arg = 0;
+          for (int j = 0; j < S; ++j) {
+            const double v = d_s[dc][j] + row[j];
+            if (j == 0 || v > best) { best = v; arg = j; }  // first maximum, as numpy's max / argmax
+          }
+          const double dnew = best + e;
+          d_s[dc ^ 1][k] = dnew;
+          de_c[(int64_t) i * S + k] = dnew;
+          bp_c[(int64_t) (i - 1) * S + k] = (uint8_t) arg;  // = argmax_j(delta[j, i-1] + tprob[i-1][k][j])
+        }
+        cur ^= 1;
+        dc ^= 1;
+      }
+      __syncthreads();  // d_s[dc] holds the scores of the last gene
+      // Legacy transition files carry one matrix per gene: the reference's back-trace then starts at the last gene
+      // with that extra matrix (gbrs_utils.py:585-590).
+      const int n_called = n < n_steps ? n : n_steps;
+      if (n_called == n && on) {
+        const double* row = t_c + (int64_t) (n - 1) * (S * S) + k * S;
+        double best = 0.0;
         int arg = 0;
         for (int j = 0; j < S; ++j) {
-          const double t = row[j];
-          acc += exp(a_s[j] + t);
-          const double v = d_s[j] + t;
-          if (j == 0 || v > best) { best = v; arg = j; }  // first maximum, as numpy's max / argmax
+          const double v = d_s[dc][j] + row[j];
+          if (j == 0 || v > best) { best = v; arg = j; }
         }
-        raw = log(acc + tiny()) + e;
-        dnew = best + e;
-        bp_c[(int64_t) (i - 1) * S + k] = (uint8_t) arg;  // = argmax_j(delta[j, i-1] + tprob[i-1][k][j]) (:589)
-        x_s[k] = exp(raw);
+        bp_c[(int64_t) (n - 1) * S + k] = (uint8_t) arg;
       }
-      __syncthreads();  // all reads of a_s / d_s done, x_s complete
-      double sum = 0.0;
-      for (int j = 0; j < S; ++j) sum += x_s[j];
-      const double norm = log(sum);
-      if (on) {
-        a_s[k] = raw - norm;
-        d_s[k] = dnew;
-        al_c[(int64_t) i * S + k] = raw - norm;
-        de_c[(int64_t) i * S + k] = dnew;
-      }
-      if (k == 0) sc_c[i] = -norm;
-      cur ^= 1;
-    }
-    __syncthreads();  // d_s holds the scores of the last gene
-    // Legacy transition files carry one matrix per gene: the reference's back-trace then starts at the last gene with
-    // that extra matrix (gbrs_utils.py:585-590).
-    const int n_called = n < n_steps ? n : n_steps;
-    if (n_called == n && on) {
-      const double* row = t_c + (int64_t) (n - 1) * (S * S) + k * S;
-      double best = 0.0;
-      int arg = 0;
-      for (int j = 0; j < S; ++j) {
-        const double v = d_s[j] + row[j];
-        if (j == 0 || v > best) { best = v; arg = j; }
-      }
-      bp_c[(int64_t) (n - 1) * S + k] = (uint8_t) arg;
-    }
-
-    // ---------------- backward + posterior (gbrs_utils.py:527-558) ----------------
-    __syncthreads();  // d_s is reused below: the extra step above has read it
-    int last_state = 0;
-    if (k == 0) {  // arg-max of the last gene's scores: where the back-trace starts (:581)
-      double best = d_s[0];
-      for (int j = 1; j < S; ++j)
-        if (d_s[j] > best) { best = d_s[j]; last_state = j; }
-    }
-    __syncthreads();
-    if (n > 1) stage_matrix<S, SP>(tp[0], t_c + (int64_t) (n - 2) * (S * S), k);
-    {
-      const double b = sc_c[n - 1];  // beta[:, -1] = alpha_scaler[-1]
-      const double g = on ? exp(al_c[(int64_t) (n - 1) * S + k] + b) : 0.0;
-      x_s[k] = g;
-      if (on) {
-        a_s[k] = b;
-        d_s[k] = e_c[(int64_t) (n - 1) * S + k];
-      }
-      __syncthreads();
-      double sum = 0.0;
-      for (int j = 0; j < S; ++j) sum += x_s[j];
-      if (on) ga_c[(int64_t) (n - 1) * S + k] = g / sum;
-    }
-    cur = 0;
-    for (int i = n - 2; i >= 0; --i) {
-      __pipeline_wait_prior(0);
-      __syncthreads();  // matrix i in tp[cur]; a_s = beta of gene i+1, d_s = emission of gene i+1; x_s may be rewritten
-      if (i > 0) stage_matrix<S, SP>(tp[cur ^ 1], t_c + (int64_t) (i - 1) * (S * S), k);
-      double bnew = 0.0, g = 0.0, enew = 0.0;
-      if (on) {
-        const double sc = sc_c[i];
-        const double al = al_c[(int64_t) i * S + k];
-        enew = e_c[(int64_t) i * S + k];
-        const double* col = tp[cur] + k;  // tprob[i][:, k]
-        double acc = 0.0;
-        for (int j = 0; j < S; ++j) acc += exp(((col[j * SP] + a_s[j]) + d_s[j]) + sc);
-        bnew = log(acc);
-        g = exp(al + bnew);
-        x_s[k] = g;
-      }
-      __syncthreads();
-      double sum = 0.0;
-      for (int j = 0; j < S; ++j) sum += x_s[j];
-      if (on) {
-        ga_c[(int64_t) i * S + k] = g / sum;
-        a_s[k] = bnew;
-        d_s[k] = enew;
-      }
-      cur ^= 1;
-    }
-
-    // ---------------- back-trace (gbrs_utils.py:578-594) ----------------
-    // states[n_called] = arg-max of the last gene, states[i] = backptr[i][states[i + 1]] for i = n_called-1 .. 0
-    int32_t* st_c = states + ch.state0;
-    int sid = last_state;
-    if (k == 0) st_c[n_called] = sid;
-    for (int hi = n_called; hi > 0; hi -= kTraceRows) {
-      const int lo = hi > kTraceRows ? hi - kTraceRows : 0;
-      __syncthreads();  // back-pointers written by this block are visible; bp_s of the previous round is done with
-      for (int e = k; e < (hi - lo) * S; e += kChainThreads) bp_s[e] = bp_c[(int64_t) lo * S + e];
-      __syncthreads();
+      // ---------------- back-trace (gbrs_utils.py:578-594) ----------------
+      // states[n_called] = arg-max of the last gene, states[i] = backptr[i][states[i + 1]] for i = n_called-1 .. 0
+      int32_t* st_c = states + ch.state0;
+      int sid = 0;
       if (k == 0) {
-        for (int i = hi - 1; i >= lo; --i) {
-          sid = bp_s[(i - lo) * S + sid];
-          st_c[i] = sid;
+        double best = d_s[dc][0];
+        for (int j = 1; j < S; ++j)
+          if (d_s[dc][j] > best) { best = d_s[dc][j]; sid = j; }
+        st_c[n_called] = sid;
+      }
+      for (int hi = n_called; hi > 0; hi -= kTraceRows) {
+        const int lo = hi > kTraceRows ? hi - kTraceRows : 0;
+        __syncthreads();  // back-pointers written by this block are visible; bp_s of the previous round is done with
+        for (int e = k; e < (hi - lo) * S; e += kChainThreads) bp_s[e] = bp_c[(int64_t) lo * S + e];
+        __syncthreads();
+        if (k == 0) {
+          for (int i = hi - 1; i >= lo; --i) {
+            sid = bp_s[(i - lo) * S + sid];
+            st_c[i] = sid;
+          }
         }
       }
     }
@@ -329,10 +359,10 @@ int launch_emission(int64_t n, const double* expr, const double* avec, const int
 
 template <int H>
 int launch_chain(int32_t n_chains, const gbrs_hmm_chain* chains, const double* init, const double* eprob,
-                 const double* tprob, double* alpha, double* scaler, double* gamma, double* delta, uint8_t* backptr,
-                 int32_t* states, cudaStream_t s) {
-  k_hmm_chain<H><<<n_chains, kChainThreads, 0, s>>>(n_chains, chains, init, eprob, tprob, alpha, scaler, gamma, delta,
-                                                    backptr, states);
+                 const double* tprob, const double* tlin, double* alpha, double* scaler, double* gamma, double* delta,
+                 uint8_t* backptr, int32_t* states, cudaStream_t s) {
+  k_hmm_chain<H><<<2 * n_chains, kChainThreads, 0, s>>>(n_chains, chains, init, eprob, tprob, tlin, alpha, scaler, gamma,
+                                                        delta, backptr, states);
   HMM_CUDA(cudaGetLastError());
   return GBRS_OK;
 }
@@ -375,18 +405,25 @@ extern "C" int gbrs_hmm_emission(int64_t n_genes, int32_t H, const double* expr_
 }
 
 extern "C" int gbrs_hmm_run(int32_t n_chains, const gbrs_hmm_chain* chains_dev, int32_t H, const double* init_dev,
-                            const double* eprob_dev, const double* tprob_dev, double* alpha_dev, double* scaler_dev,
-                            double* gamma_dev, double* delta_dev, uint8_t* backptr_dev, int32_t* states_dev,
-                            void* stream) {
-  if (n_chains < 0 || H < 1 || H > GBRS_HPAD) { gbrs_set_error("gbrs_hmm_run: bad argument"); return GBRS_E_ARG; }
+                            const double* eprob_dev, const double* tprob_dev, int64_t n_matrices, double* tprob_lin_dev,
+                            double* alpha_dev, double* scaler_dev, double* gamma_dev, double* delta_dev,
+                            uint8_t* backptr_dev, int32_t* states_dev, void* stream) {
+  if (n_chains < 0 || n_matrices < 0 || H < 1 || H > GBRS_HPAD) { gbrs_set_error("gbrs_hmm_run: bad argument"); return GBRS_E_ARG; }
   if (int rc = hmm_device("gbrs_hmm_run")) return rc;
   if (n_chains == 0) return GBRS_OK;
   if (!chains_dev || !init_dev || !eprob_dev || !alpha_dev || !scaler_dev || !gamma_dev || !delta_dev || !backptr_dev ||
-      !states_dev) {
+      !states_dev || (n_matrices > 0 && (!tprob_dev || !tprob_lin_dev))) {
     gbrs_set_error("gbrs_hmm_run: null device buffer"); return GBRS_E_ARG;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  HMM_DISPATCH(H, launch_chain, n_chains, chains_dev, init_dev, eprob_dev, tprob_dev, alpha_dev, scaler_dev, gamma_dev,
-                                delta_dev, backptr_dev, states_dev, s);
+  const int64_t n_elem = n_matrices * (int64_t) (H * (H + 1) / 2) * (H * (H + 1) / 2);
+  if (n_elem > 0) {
+    int64_t b = (n_elem + kEmitThreads - 1) / kEmitThreads;
+    if (b > 148 * 16) b = 148 * 16;
+    k_hmm_exp<<<(int) b, kEmitThreads, 0, s>>>(n_elem, tprob_dev, tprob_lin_dev);
+    HMM_CUDA(cudaGetLastError());
+  }
+  HMM_DISPATCH(H, launch_chain, n_chains, chains_dev, init_dev, eprob_dev, tprob_dev, tprob_lin_dev, alpha_dev, scaler_dev,
+               gamma_dev, delta_dev, backptr_dev, states_dev, s);
 }
 #endif  // GBRS_SIMT_EMULATION

@@ -196,14 +196,16 @@ def run_plan_on_device(plan: HmmPlan, expr_threshold: float, sigma: float, devic
         gamma = torch.empty((max(G, 1), S), dtype=f64, device=dev)
         delta = torch.empty((max(G, 1), S), dtype=f64, device=dev)
         scaler = torch.empty(max(G, 1), dtype=f64, device=dev)
+        n_mat = int(plan.tprob.shape[0])
+        tlin = torch.empty(max(n_mat * S * S, 1), dtype=f64, device=dev)
         backptr = torch.zeros((max(G, 1), S), dtype=torch.uint8, device=dev)
         states = torch.zeros(max(plan.n_states_out, 1), dtype=torch.int32, device=dev)
         _lib.check(lib.gbrs_hmm_emission(G, plan.H, d_expr.data_ptr(), d_avecs.data_ptr(), d_aidx.data_ptr(),
                                          d_init.data_ptr(), float(expr_threshold), float(sigma), eprob.data_ptr(),
                                          stream))
         _lib.check(lib.gbrs_hmm_run(len(plan.chains), d_chains.data_ptr(), plan.H, d_init.data_ptr(), eprob.data_ptr(),
-                                    d_tprob.data_ptr(), alpha.data_ptr(), scaler.data_ptr(), gamma.data_ptr(),
-                                    delta.data_ptr(), backptr.data_ptr(), states.data_ptr(), stream))
+                                    d_tprob.data_ptr(), n_mat, tlin.data_ptr(), alpha.data_ptr(), scaler.data_ptr(),
+                                    gamma.data_ptr(), delta.data_ptr(), backptr.data_ptr(), states.data_ptr(), stream))
         out = {"gamma": gamma[:G].cpu().numpy(), "states": states[: plan.n_states_out].cpu().numpy()}
         if keep_work:
             out.update(eprob=eprob[:G].cpu().numpy(), alpha=alpha[:G].cpu().numpy(), scaler=scaler[:G].cpu().numpy(),

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GBRS_EM_ABI_VERSION 2
+#define GBRS_EM_ABI_VERSION 3
 #define GBRS_HPAD 8 /* haplotype slots per locus line */
 #define GBRS_KMAX 8 /* classes with up to this many (class, locus) pairs take the fixed-width row pass */
 
@@ -283,17 +283,20 @@ typedef struct {
 } gbrs_hmm_chain;
 
 /* Scaled forward pass (:498-523), backward pass (:527-548), posterior (:552-558), Viterbi scores (:565-575) and the
- * back-trace (:578-594) of every chain; one thread block per chain.
- *   tprob_dev   [.][S][S] log transition matrices as stored in the file (tprob[i][k][j]: towards state k of gene i+1
- *               from state j of gene i)
+ * back-trace (:578-594) of every chain; two thread blocks per chain (forward / backward / posterior on exp(tprob),
+ * Viterbi on tprob).
+ *   tprob_dev     [n_matrices][S][S] log transition matrices as stored in the file (tprob[i][k][j]: towards state k of
+ *                 gene i+1 from state j of gene i)
+ *   tprob_lin_dev [n_matrices][S][S] work space: receives exp(tprob), computed once per call
  *   alpha_dev   [genes][S], scaler_dev [genes]   out: normalised forward log-probabilities and -log normaliser
  *   gamma_dev   [genes][S]   out: posterior (the reference's genoprobs, transposed)
  *   delta_dev   [genes][S]   out: Viterbi scores;  backptr_dev [genes][S] bytes: work space
  *   states_dev  out: per chain the states of genes 0 .. m-1 (m = min(n_genes, n_steps): the genes that get a genotype
  *               call) followed by the arg-max state of the last gene -- the reference's `viterbi_states` list */
 int gbrs_hmm_run(int32_t n_chains, const gbrs_hmm_chain* chains_dev, int32_t H, const double* init_dev,
-                 const double* eprob_dev, const double* tprob_dev, double* alpha_dev, double* scaler_dev,
-                 double* gamma_dev, double* delta_dev, uint8_t* backptr_dev, int32_t* states_dev, void* stream);
+                 const double* eprob_dev, const double* tprob_dev, int64_t n_matrices, double* tprob_lin_dev,
+                 double* alpha_dev, double* scaler_dev, double* gamma_dev, double* delta_dev, uint8_t* backptr_dev,
+                 int32_t* states_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,10 +29,14 @@ extern "C" int emul_hmm_emission(int64_t n_genes, int32_t H, const double* expr,
 }
 
 extern "C" int emul_hmm_run(int32_t n_chains, const gbrs_hmm_chain* chains, int32_t H, const double* init,
-                            const double* eprob, const double* tprob, double* alpha, double* scaler, double* gamma,
-                            double* delta, uint8_t* backptr, int32_t* states, int32_t grid) {
+                            const double* eprob, const double* tprob, int64_t n_matrices, double* tlin, double* alpha,
+                            double* scaler, double* gamma, double* delta, uint8_t* backptr, int32_t* states,
+                            int32_t grid) {
+  const int64_t n_elem = n_matrices * (int64_t) (H * (H + 1) / 2) * (H * (H + 1) / 2);
+  if (n_elem > 0) simt_launch(3, kEmitThreads, [=] { k_hmm_exp(n_elem, tprob, tlin); });
   EMUL_DISPATCH(H, simt_launch(grid, kChainThreads, [=] {
-                  k_hmm_chain<HH>(n_chains, chains, init, eprob, tprob, alpha, scaler, gamma, delta, backptr, states);
+                  k_hmm_chain<HH>(n_chains, chains, init, eprob, tprob, tlin, alpha, scaler, gamma, delta, backptr,
+                                  states);
                 }));
   return 0;
 }

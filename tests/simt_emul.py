@@ -18,7 +18,7 @@ OUT_DIR = os.path.join(HERE, "simt", "_build")
 
 EMISSION_ARGS = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                  C.c_void_p, C.c_int32]
-RUN_ARGS = [C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 9 + [C.c_int32]
+RUN_ARGS = [C.c_int32, C.c_void_p, C.c_int32] + [C.c_void_p] * 3 + [C.c_int64] + [C.c_void_p] * 7 + [C.c_int32]
 
 
 def build(tsan: bool = False) -> str:
@@ -81,9 +81,10 @@ def run_chains(plan, eprob, grid=None, lib=None):
     out["scaler"] = np.full(G, np.nan)
     backptr = np.full((G, S), 255, dtype=np.uint8)
     states = np.full(plan.n_states_out, -1, dtype=np.int32)
-    lib.emul_hmm_run(len(chains), _ptr(chains), plan.H, _ptr(init), _ptr(eprob), _ptr(tprob), _ptr(out["alpha"]),
-                     _ptr(out["scaler"]), _ptr(out["gamma"]), _ptr(out["delta"]), _ptr(backptr), _ptr(states),
-                     grid or len(chains))
+    tlin = np.full(tprob.shape, np.nan)
+    lib.emul_hmm_run(len(chains), _ptr(chains), plan.H, _ptr(init), _ptr(eprob), _ptr(tprob), tprob.shape[0], _ptr(tlin),
+                     _ptr(out["alpha"]), _ptr(out["scaler"]), _ptr(out["gamma"]), _ptr(out["delta"]), _ptr(backptr),
+                     _ptr(states), grid or 2 * len(chains))
     out["states"], out["backptr"], out["eprob"] = states, backptr, eprob
     return out
 

@@ -80,7 +80,7 @@ def test_there_is_no_cpu_fallback(files, monkeypatch):
     with pytest.raises(_lib.GbrsCudaError):
         rc.reconstruct(expression_file=p["expr"], tprob_file=p["tprob"], avec_file=p["avecs"], gpos_file=p["gpos"])
     lib = _lib.load()
-    assert lib.gbrs_hmm_run(1, None, 8, None, None, None, None, None, None, None, None, None, None) == _lib.GBRS_E_CUDA
+    assert lib.gbrs_hmm_run(1, None, 8, None, None, None, 0, None, None, None, None, None, None, None, None) == _lib.GBRS_E_CUDA
     assert lib.gbrs_hmm_emission(1, 8, None, None, None, None, 1.5, 0.12, None, None) == _lib.GBRS_E_CUDA
     assert lib.gbrs_hmm_emission(1, 9, None, None, None, None, 1.5, 0.12, None, None) == _lib.GBRS_E_ARG
 

@@ -6,7 +6,7 @@ reference's per-gene numpy loop: `python -m tests.time_reconstruct_oracle`.)
 
 Device time = CUDA events on the launch stream around the emission kernel + the chain kernel, tables resident;
 `e2e` adds the upload of expression / transition tables and the download of posterior and states.  Algorithmic bytes of
-the chain kernel: every transition matrix twice (forward, backward) per sample + emission, forward, posterior, score and
+the chain kernel: every transition matrix three times (forward, backward, Viterbi) per sample + emission, forward, posterior, score and
 back-pointer tables once each; in a cohort the matrices are shared, so DRAM traffic should stay near one copy of them
 (they fit the 126 MB L2 only per chromosome, not as a whole: 25k x 10 KB = 259 MB)."""
 from __future__ import annotations
@@ -69,6 +69,8 @@ def main():
         d["chains"] = up(plan.launch_order())
         buf = {k: torch.empty((G, S), dtype=torch.float64, device=dev) for k in ("eprob", "alpha", "gamma", "delta")}
         scaler = torch.empty(G, dtype=torch.float64, device=dev)
+        n_mat = int(plan.tprob.shape[0])
+        tlin = torch.empty(max(n_mat * S * S, 1), dtype=torch.float64, device=dev)
         backptr = torch.zeros((G, S), dtype=torch.uint8, device=dev)
         states = torch.zeros(plan.n_states_out, dtype=torch.int32, device=dev)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -80,7 +82,8 @@ def main():
                                              d["init"].data_ptr(), 1.5, 0.12, buf["eprob"].data_ptr(), stream))
             ev[1].record()
             _lib.check(lib.gbrs_hmm_run(len(plan.chains), d["chains"].data_ptr(), 8, d["init"].data_ptr(),
-                                        buf["eprob"].data_ptr(), d["tprob"].data_ptr(), buf["alpha"].data_ptr(),
+                                        buf["eprob"].data_ptr(), d["tprob"].data_ptr(), n_mat, tlin.data_ptr(),
+                                        buf["alpha"].data_ptr(),
                                         scaler.data_ptr(), buf["gamma"].data_ptr(), buf["delta"].data_ptr(),
                                         backptr.data_ptr(), states.data_ptr(), stream))
             ev[2].record()
@@ -92,7 +95,7 @@ def main():
         steps = G
         mat_bytes = 8 * S * S * int(sum(len(base.tprob[c]) for c in plan.chroms))
         table_bytes = G * S * (8 * 4 + 8 + 2) + 8 * G  # eprob r, alpha w+r, gamma w, delta w, backptr w+r, scaler
-        algo = 2 * mat_bytes * n_s + table_bytes
+        algo = 3 * mat_bytes * n_s + 2 * mat_bytes + table_bytes  # forward, backward, Viterbi per sample + exp once
         out[label] = {"samples": n_s, "chains": int(len(plan.chains)), "emission_ms": ms_e, "chain_ms": ms_c,
                       "value": steps / ((ms_e + ms_c) * 1e-3), "e2e_seconds": float(np.median(e2e)),
                       "first_call_seconds": first, "e2e_value": steps / float(np.median(e2e)),
