@@ -49,6 +49,17 @@ def test_emulated_other_haplotype_counts(H):
     chk.check_against_oracle(plan, res, d, [d.expr], 1.0, 0.15)
 
 
+@pytest.mark.parametrize("H,sigma", chk.STRESS)
+def test_emulated_forbidden_transitions_and_underflowing_emissions(H, sigma):
+    d = chk.stress_case(H)
+    plan = chk.plan_of(d)
+    with np.errstate(all="ignore"):
+        res = simt_emul.run_plan_emulated(plan, 1.5, sigma)
+        assert res["eprob"].min() < -700.0 or sigma > 0.1  # the floor is really reached
+        assert np.isfinite(res["gamma"]).all()
+        chk.check_against_oracle(plan, res, d, [d.expr], 1.5, sigma)
+
+
 def test_kernels_are_race_free_under_thread_sanitizer():
     """The emulation built with -fsanitize=thread: every pair of shared / global memory accesses of the kernels that
     is not ordered by a barrier is reported.  Runs in a subprocess (the sanitizer runtime has to be loaded first)."""

@@ -45,6 +45,16 @@ def test_gpu_other_haplotype_counts(H):
     chk.check_against_oracle(plan, res, d, [d.expr], 1.0, 0.15)
 
 
+@pytest.mark.parametrize("H,sigma", chk.STRESS)
+def test_gpu_forbidden_transitions_and_underflowing_emissions(H, sigma):
+    d = chk.stress_case(H)
+    plan = chk.plan_of(d)
+    res = rc.run_plan_on_device(plan, 1.5, sigma, keep_work=True)
+    assert np.isfinite(res["gamma"]).all()
+    with np.errstate(all="ignore"):
+        chk.check_against_oracle(plan, res, d, [d.expr], 1.5, sigma)
+
+
 def test_gpu_reconstruct_files_match_reference(tmp_path, monkeypatch):
     """File to file through `reconstruct()`: the three output files against the reference's."""
     z, d, thr, sigma = chk.load_case("reconstruct_h8")
