@@ -282,8 +282,6 @@ def reconstruct_cohort(expression_files, tprob_file: str, avec_file: str = None,
     logger.info(f"Sigma: {sigma}")
     logger.info("Loading chromosome information")
     chrlens = get_chromosome_info(data_dir)
-    logger.info(f"Loading alignment specificity: {avec_file}")
-    avecs = np.load(avec_file)
     logger.info(f"Loading gene meta data: {gpos_file}")
     gene_order = read_gene_order(gpos_file)
     haplotypes, tables = None, []
@@ -297,8 +295,14 @@ def reconstruct_cohort(expression_files, tprob_file: str, avec_file: str = None,
     if not tables:
         return
     genotypes = [h1 + h2 for h1, h2 in combinations_with_replacement(haplotypes, 2)]
+    # the chromosomes of the fai file that the transition file has (gbrs_utils.py:501), then only the alignment
+    # specificity of their genes: members are read in bulk (utils.read_npz_members) instead of one np.load item at a time
     logger.info(f"Loading transition probabilities: {tprob_file}")
-    tprob = np.load(tprob_file)
+    wanted_chroms = set(chrlens.keys())
+    tprob = utils.read_npz_members(tprob_file, lambda name: name in wanted_chroms)
+    logger.info(f"Loading alignment specificity: {avec_file}")
+    wanted_genes = set(g for c in tprob for g in gene_order.get(c, ()))
+    avecs = utils.read_npz_members(avec_file, lambda name: name in wanted_genes)
     plan = build_plan(list(chrlens.keys()), gene_order, tprob, avecs, tables, len(haplotypes))
     logger.info("Getting forward-backward probability and running Viterbi on the GPU")
     result = run_plan_on_device(plan, expr_threshold, sigma, device=device)

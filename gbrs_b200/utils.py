@@ -120,3 +120,74 @@ def py_float_str(x: float) -> str:
     if n < 0:
         raise ValueError("formatting failed")
     return buf.value.decode()
+
+
+def read_npz_members(path: str, names=None, workers: int | None = None) -> dict:
+    """name -> array for members of an `.npz` file, without numpy's per-member overhead.  `names`: a list of member
+    names (KeyError for one the file lacks), a predicate on the member name, or None for all members.
+
+    `np.load(path)[name]` opens the member, parses its header with `ast.literal_eval` and inflates it, one member at a
+    time: ~0.15 ms for each of the 22k small matrices of an alignment-specificity file and 2.4 s of single-threaded zlib
+    for the 20 large matrices of a transition file.  Here large members are dealt over a pool of threads (zlib releases
+    the GIL), every thread with a zip handle of its own; small members are interpreter-bound and stay on one thread.  A
+    header is parsed only when its bytes differ from the previous member's (same dtype and shape: the common case).
+    Fortran-ordered and object arrays fall back to numpy."""
+    import io
+    import zipfile
+    from concurrent.futures import ThreadPoolExecutor
+
+    def load_chunk(chunk, zf):
+        out = {}
+        last_hdr, last_meta = None, None
+        for name in chunk:
+            raw = zf.read(name + ".npy")
+            if raw[:6] != b"\x93NUMPY":
+                raise ValueError(f"{path}: member {name} is not an .npy array")
+            major = raw[6]
+            if major == 1:
+                hlen, off = int.from_bytes(raw[8:10], "little"), 10
+            elif major == 2:
+                hlen, off = int.from_bytes(raw[8:12], "little"), 12
+            else:  # format 3 (utf-8 field names) and anything newer: numpy's own reader
+                out[name] = np.load(io.BytesIO(raw), allow_pickle=False)
+                continue
+            hdr = raw[off: off + hlen]
+            if hdr != last_hdr:
+                fh = io.BytesIO(raw)
+                np.lib.format.read_magic(fh)
+                shape, fortran, dtype = (np.lib.format.read_array_header_1_0(fh) if major == 1
+                                         else np.lib.format.read_array_header_2_0(fh))
+                last_hdr, last_meta = hdr, (shape, fortran, dtype)
+            shape, fortran, dtype = last_meta
+            if fortran or dtype.hasobject:
+                out[name] = np.load(io.BytesIO(raw), allow_pickle=False)
+            else:
+                out[name] = np.frombuffer(raw, dtype=dtype, offset=off + hlen,
+                                          count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+        return out
+
+    def load_chunk_own_handle(chunk):
+        with zipfile.ZipFile(path) as zf:
+            return load_chunk(chunk, zf)
+
+    with zipfile.ZipFile(path) as zf0:
+        if names is None or callable(names):
+            have = [n[:-4] for n in zf0.namelist() if n.endswith(".npy")]
+            want = have if names is None else [n for n in have if names(n)]
+        else:
+            want = list(names)
+        if not want:
+            return {}
+        if workers is None:
+            # small members are interpreter-bound (zip bookkeeping, not zlib): threads would only fight over the GIL
+            # and re-read the zip directory once each
+            small = os.path.getsize(path) / max(len(zf0.namelist()), 1) < (1 << 18)
+            workers = 1 if small else (os.cpu_count() or 1)
+        workers = max(1, min(workers, 16, len(want)))
+        if workers == 1:
+            return load_chunk(want, zf0)
+    merged = {}
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        for part in pool.map(load_chunk_own_handle, [want[w::workers] for w in range(workers)]):
+            merged.update(part)
+    return {n: merged[n] for n in want}

@@ -116,3 +116,32 @@ def test_cli_flags_defaults_and_error_policy(tmp_path, monkeypatch, caplog):
     assert seen["expr_threshold"] == 1.5 and seen["sigma"] == 0.12 and seen["outbase"] is None
     assert seen["avec_file"] is None and seen["gpos_file"] is None and seen["expression_file"] == str(e)
     assert runner.invoke(commands.app, ["reconstruct", "-e", str(tmp_path / "nope"), "-t", str(t)]).exit_code != 0
+
+
+def test_bulk_npz_reader_equals_numpy(tmp_path):
+    """utils.read_npz_members against np.load on every kind of member the workflow meets: many small matrices, large
+    3-D arrays (threaded path), string tables, Fortran order, a format-3 header; selection by list and by predicate."""
+    from gbrs_b200 import utils
+
+    rng = np.random.default_rng(0)
+    small = {f"G{i:05d}": rng.random((8, 8)) for i in range(300)}
+    small["odd_shape"] = rng.random((3, 5))
+    small["ints"] = np.arange(7, dtype=np.int32)
+    small["fortran"] = np.asfortranarray(rng.random((4, 6)))
+    small["strings"] = np.array([("ENSG1", "100"), ("ENSG2", "250")])
+    small["utf8_field"] = np.zeros(2, dtype=[("\u00e9", "<f8")])  # npy format 3: numpy's own reader
+    p1 = tmp_path / "small.npz"
+    np.savez_compressed(p1, **small)
+    big = {str(c): rng.random((40, 36, 36)) for c in range(6)}
+    p2 = tmp_path / "big.npz"
+    np.savez_compressed(p2, **big)
+    for path, ref, workers in ((p1, small, None), (p2, big, 4), (p2, big, 1)):
+        got = utils.read_npz_members(str(path), None, workers=workers)
+        assert list(got) == list(ref)
+        for k, v in ref.items():
+            assert got[k].dtype == v.dtype and got[k].shape == v.shape and np.array_equal(got[k], v), k
+    assert list(utils.read_npz_members(str(p2), ["3", "1"])) == ["3", "1"]
+    assert sorted(utils.read_npz_members(str(p1), lambda n: n.startswith("G0000"))) == [f"G0000{i}" for i in range(10)]
+    assert utils.read_npz_members(str(p1), lambda n: False) == {}
+    with pytest.raises(KeyError):
+        utils.read_npz_members(str(p2), ["nope"])
