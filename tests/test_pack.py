@@ -227,3 +227,49 @@ def test_pack_wide_entry_words(monkeypatch):
     idx, m = unpack_entries(p.arrays["ent_cls"], 8)
     assert np.count_nonzero(m) == d.pairs and idx.max() == p.info["n_classes"]
     assert packed_signatures(p) == class_signatures(d)
+
+
+_DIGEST = r'''
+import sys, hashlib, json, os
+sys.path.insert(0, os.environ["GBRS_ROOT"])
+import numpy as np
+from gbrs_b200 import synth, utils
+from gbrs_b200.compress import read_rows
+from gbrs_b200.emfactory import PackedPattern
+from gbrs_b200.quantify import hapmask_bytes
+h = hashlib.sha256()
+for kw, shard, item_len, mask in ((dict(T=900, N=60000, H=8), (0, 1), 0, False),
+                                  (dict(T=400, N=30000, H=8, wide_frac=0.05), (1, 3), 8, False),
+                                  (dict(T=700, N=40000, H=8, with_genotype=True), (0, 1), 0, True),
+                                  (dict(T=300, N=20000, H=3, sample_index=2), (0, 2), 0, False)):
+    d = synth.generate(**kw)
+    hm = hapmask_bytes(synth.genotype_mask(d)) if mask else None
+    p = PackedPattern(synth.to_apm(d), gene_of=utils.gene_index(d.T, d.groups()), hapmask=hm, shard_rank=shard[0],
+                      shard_count=shard[1], item_len=item_len)
+    for k in sorted(p.arrays):
+        h.update(k.encode()); h.update(np.ascontiguousarray(p.arrays[k]).tobytes())
+    h.update(json.dumps(p.info, sort_keys=True).encode())
+    rowptr, words = read_rows(synth.to_csc_list(d), d.T, d.H)
+    h.update(rowptr.tobytes()); h.update(words.tobytes())
+print(h.hexdigest())
+'''
+
+
+def test_packer_and_row_builder_do_not_depend_on_the_thread_count(tmp_path):
+    """The threaded host packer (gbrs_pack_create) and read-row builder (gbrs_rows_create) split their work by class /
+    locus / read ranges: every array must come out bit-identical with 1, 3 and 13 OpenMP threads (13 oversubscribes
+    the test machine, which is what shakes out ordering assumptions)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "digest.py"
+    script.write_text(_DIGEST)
+    seen = set()
+    for threads in ("1", "3", "13"):
+        env = dict(os.environ, GBRS_ROOT=root, OMP_NUM_THREADS=threads)
+        res = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        seen.add(res.stdout.strip())
+    assert len(seen) == 1, seen
