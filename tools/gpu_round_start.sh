@@ -38,3 +38,13 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_hm
 ncu -i $out/${tag}_hmm_chain.ncu-rep --page raw --csv > $out/${tag}_hmm_chain_raw.csv 2>/dev/null
 python profiles/ncu_extract.py $out/${tag}_hmm_chain_raw.csv > $out/${tag}_hmm_chain_summary.txt 2>&1
 tail -30 $out/${tag}_hmm_chain_summary.txt
+
+echo "== compute-sanitizer (memcheck, then racecheck) on small runs: smoke() and the reconstruct golden cases"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py --smoke \
+  > $out/${tag}_memcheck_smoke.log 2>&1; echo "memcheck smoke rc=$?"; tail -3 $out/${tag}_memcheck_smoke.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_reconstruct_gpu.py -m gpu -q \
+  -k "golden or other_haplotype" > $out/${tag}_memcheck_reconstruct.log 2>&1; echo "memcheck reconstruct rc=$?"
+tail -3 $out/${tag}_memcheck_reconstruct.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_zz_reconstruct_gpu.py -m gpu -q \
+  -k "golden" > $out/${tag}_racecheck_reconstruct.log 2>&1; echo "racecheck reconstruct rc=$?"
+tail -3 $out/${tag}_racecheck_reconstruct.log
