@@ -169,22 +169,25 @@ def test_without_pytables_an_hdf5_file_is_refused_with_a_pointer_to_the_converte
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/gbrs/emase"), reason="needs the reference sources")
-def test_hdf5_calls_are_interchangeable_with_the_reference(tmp_path):
+def test_hdf5_calls_are_interchangeable_with_the_reference(tmp_path, monkeypatch):
     """Both directions through ONE stand-in `tables`: the reference writes / we read, we write / the reference reads."""
     from oracle import ref_harness as rh
 
-    ref = rh.load_reference()  # registers the oracle's pickle-backed `tables` and imports the reference with it
+    # load_reference() registers the oracle's pickle-backed `tables` for good; keep that out of the other tests
+    monkeypatch.setitem(sys.modules, "tables", rh._fake_tables_module())
+    ref = rh.load_reference()  # imports the reference with a stand-in `tables` (its modules keep their own binding)
     d = synth.generate(T=30, N=200, H=8, sample_index=3)
     theirs = rh.build_reference_apm(d)
     f1 = str(tmp_path / "by_reference.h5")
     theirs.save(h5file=f1)
+    monkeypatch.setitem(sys.modules, "tables", ref.apm_mod.tables)  # the module the reference itself is bound to
     ours = APM()
     ours._load_hdf5(f1, "/", "/", False, float)  # the stand-in's files carry no HDF5 signature: call the branch directly
     ours.num_loci, ours.num_haplotypes, ours.num_reads = ours.shape
     same(ours, synth.to_apm(d))
     f2 = str(tmp_path / "by_us.h5")
     mine = synth.to_apm(d)
-    mine._save_hdf5(sys.modules["tables"], f2, None, "uint32", float, True, "zlib", False)
+    mine._save_hdf5(ref.apm_mod.tables, f2, None, "uint32", float, True, "zlib", False)
     back = ref.APM(h5file=f2)
     assert tuple(back.shape) == (30, 8, 200) and list(back.hname) == list(d.hname) and list(back.lname) == list(d.lname)
     assert np.array_equal(back.count, d.count)
