@@ -131,3 +131,43 @@ def test_cli_compress(tmp_path):
     # a missing input is logged, not raised (commands.py:101-105)
     res = CliRunner().invoke(app, ["compress", "-i", os.path.join(str(tmp_path), "nope.h5"), "-o", out + "2"])
     assert res.exit_code == 0 and not os.path.exists(out + "2")
+
+
+def _dict_grouping(rowptr, words, count=None, device=None):
+    """Test-only stand-in for the device step (`equivalence_classes`): the same contract from a python dict."""
+    n = len(rowptr) - 1
+    seen, cls, first, ccount = {}, np.zeros(n, np.uint32), [], []
+    for r in range(n):
+        key = words[rowptr[r]:rowptr[r + 1]].tobytes()
+        c = seen.setdefault(key, len(seen))
+        if c == len(first):
+            first.append(r)
+            ccount.append(0.0)
+        cls[r] = c
+        ccount[c] += 1.0 if count is None else float(count[r])
+    return cls, np.array(first, dtype=np.uint32), np.array(ccount)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_compress_workflow_on_cpu_with_the_device_step_replaced(name, tmp_path, monkeypatch):
+    """Everything of `compress` around the GPU grouping -- reading several files in order, read rows, counts,
+    representative rows back into matrices, the output file, the CLI -- against the reference-written goldens."""
+    from typer.testing import CliRunner
+
+    from gbrs_b200.commands import app
+
+    monkeypatch.setattr(cz, "equivalence_classes", _dict_grouping)
+    T, H, files, want, want_count = load_case(name)
+    paths = write_inputs(tmp_path, files, T, H)
+    out = os.path.join(str(tmp_path), "out.npz")
+    cz.compress(paths, out)
+    res = AlignmentPropertyMatrix(h5file=out)
+    assert res.shape == (T, H, len(want_count)) and np.array_equal(res.count, want_count)
+    assert all(same_pattern(res.data[h], want[h]) for h in range(H))
+    out2 = os.path.join(str(tmp_path), "cli.npz")
+    args = ["compress", "-o", out2]
+    for p in paths:
+        args += ["-i", p]
+    assert CliRunner().invoke(app, args).exit_code == 0
+    got = AlignmentPropertyMatrix(h5file=out2)
+    assert np.array_equal(got.count, want_count) and all(same_pattern(got.data[h], want[h]) for h in range(H))
