@@ -56,7 +56,10 @@ def gene_index(num_loci: int, groups) -> np.ndarray:
         flat = np.fromiter((t for x in groups for t in x), dtype=np.int64, count=int(sizes.sum()))
         gid = np.repeat(np.arange(n_groups, dtype=np.int64), sizes)
         if flat.size and np.unique(flat).size != flat.size:
-            raise NotImplementedError("a transcript listed in more than one gene group is not supported")
+            # a locus repeated inside one group is harmless (the reference assigns 1.0 twice); in two groups it is not
+            pairs = np.unique(np.stack((flat, gid)), axis=1)
+            if np.unique(pairs[0]).size != pairs.shape[1]:
+                raise NotImplementedError("a transcript listed in more than one gene group is not supported")
         g[flat] = gid
     free = np.flatnonzero(g < 0)
     g[free] = n_groups + np.arange(free.size)

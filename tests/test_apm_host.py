@@ -118,3 +118,25 @@ def test_host_container_equals_the_reference_container(data, monkeypatch):
     assert tuple(co.shape) == tuple(ct.shape) and list(co.lname) == list(ct.lname)
     for h in range(d.H):
         assert (sp.csc_matrix(co.data[h]) != sp.csc_matrix(ct.data[h])).nnz == 0
+
+
+def test_group_tables_follow_the_reference_loop():
+    """`grp_conv_mat[groups[i], i] = 1.0` (EMfactory.py:42-47) and the gene id per locus the kernels use instead of
+    `t2t_mat`; loci outside every group get ids of their own past the real genes."""
+    from gbrs_b200 import utils
+
+    groups = [[0, 3], [5], [], [1, 2, 2]]  # an empty group and a repeated locus
+    T = 8
+    want = np.zeros((T, len(groups)))
+    for i, g in enumerate(groups):
+        want[g, i] = 1.0
+    m = utils.group_conversion_matrix(T, groups)
+    assert m.format == "csc" and np.array_equal(m.toarray(), want)
+    g = utils.gene_index(T, groups)
+    assert g.dtype == np.int32 and list(g[[0, 3, 5, 1, 2]]) == [0, 0, 1, 3, 3]
+    assert sorted(g[[4, 6, 7]]) == [4, 5, 6] and len(set(g[[4, 6, 7]])) == 3
+    with pytest.raises(NotImplementedError, match="more than one gene"):
+        utils.gene_index(T, [[0, 1], [1, 2]])
+    log = utils.configure_logging("gbrs-test", 2)
+    assert log.level == 10 and utils.configure_logging("gbrs-test", 1).level == 20 and len(log.handlers) == 1
+    assert utils.configure_logging("gbrs-test", 0).level == 30 and not log.propagate
