@@ -266,8 +266,10 @@ class DevicePattern:
         _torch().cuda.current_stream(self.device).synchronize()
 
     def set_lengths(self, target_lengths_HT):
-        """H x T effective lengths -> device [T][8] (1.0 in unused slots).  `EMfactory._read_lengths` hands over the
-        transpose of a [T][H] table, so for H = 8 the fill of the pinned staging buffer is one contiguous copy."""
+        """H x T effective lengths -> device [T][8] (1.0 in unused slots).  The pinned staging buffer is always filled
+        by ONE contiguous copy: `EMfactory._read_lengths` hands over the transpose of a [T][H] table (already the device
+        layout); a C-contiguous H x T table goes up as it is and is transposed on the device (a strided host copy of
+        these 640k doubles costs more than ten EM updates)."""
         torch = _torch()
         if target_lengths_HT is None:
             self.efflen.fill_(1.0)
@@ -276,10 +278,18 @@ class DevicePattern:
         src = np.asarray(target_lengths_HT, dtype=np.float64)
         if src.shape != (self.H, self.T):
             raise ValueError(f"effective lengths must be {self.H} x {self.T}, got {src.shape}")
-        if self.H < 8:
-            st[:, self.H:] = 1.0
-        st[:, : self.H].copy_(torch.from_numpy(src.T if src.T.flags.c_contiguous else np.ascontiguousarray(src.T)))
-        self.efflen.copy_(st, non_blocking=True)
+        if src.T.flags.c_contiguous:  # [T][H] in memory
+            if self.H < 8:
+                st[:, self.H:] = 1.0
+            st[:, : self.H].copy_(torch.from_numpy(src.T))
+            self.efflen.copy_(st, non_blocking=True)
+        else:
+            flat = st.view(-1)[: self.H * self.T].view(self.H, self.T)
+            flat.copy_(torch.from_numpy(np.ascontiguousarray(src)))
+            on_dev = flat.to(self.device, non_blocking=True)
+            if self.H < 8:
+                self.efflen[:, self.H:] = 1.0
+            self.efflen[:, : self.H].copy_(on_dev.t())
         self._sync()  # the staging buffer is reused
 
     def read_ctrl(self):

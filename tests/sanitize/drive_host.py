@@ -50,7 +50,11 @@ for kw, shard, item_len, mask in CASES:
         assert EMfactory._read_lengths(em, lf, 100).shape == (d.H, d.T)
         with open(os.path.join(tmp, "t.tsv"), "w") as fh:
             utils.write_table_rows(fh, apm.lname, np.random.rand(d.H + 1, d.T), notes=None, order=np.arange(d.T)[::-1])
+    keep = p.arrays["pairs"]  # a view into the packer's memory must keep it alive (use-after-free otherwise)
     del p, q
+    import gc
+    gc.collect()
+    assert int(keep.astype(np.int64).sum()) >= 0
 empty = APM.from_csc([sp.csc_matrix((4, 6)) for _ in range(2)], ["A", "B"], [f"t{i}" for i in range(6)], count=np.ones(4))
 assert PackedPattern(empty).info["n_classes"] == 0
 buf = C.create_string_buffer(64)

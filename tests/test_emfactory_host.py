@@ -1,0 +1,58 @@
+"""Host-side pieces of gbrs_b200.emfactory that need no device: the staging of the effective-length table (run on a
+stand-in object carrying CPU tensors) and the lifetime of the packer's memory behind the zero-copy array views."""
+import gc
+
+import numpy as np
+import torch
+
+from gbrs_b200 import synth, utils
+from gbrs_b200.emfactory import DevicePattern, PackedPattern
+
+
+class _Stub:
+    """What DevicePattern.set_lengths touches, on the CPU."""
+    device = "cpu"
+
+    def __init__(self, T, H):
+        self.T, self.H = T, H
+        self.efflen = torch.full((T, 8), -7.0, dtype=torch.float64)
+        self._stage = torch.full((T, 8), -9.0, dtype=torch.float64)
+
+    def _staging(self):
+        return self._stage
+
+    def _sync(self):
+        pass
+
+
+def test_set_lengths_accepts_every_layout():
+    T = 50
+    for H in (1, 3, 8):
+        tl = (np.random.default_rng(H).random((T, H)) + 1).transpose()  # as EMfactory._read_lengths returns it
+        for src in (tl, np.ascontiguousarray(tl), tl.tolist(), np.asfortranarray(tl), tl.astype(np.float32)):
+            s = _Stub(T, H)
+            DevicePattern.set_lengths(s, src)
+            want = np.ones((T, 8))
+            want[:, :H] = np.asarray(src, dtype=np.float64).T
+            assert np.array_equal(s.efflen.numpy(), want)
+        s = _Stub(T, H)
+        DevicePattern.set_lengths(s, None)
+        assert (s.efflen == 1.0).all()
+        try:
+            DevicePattern.set_lengths(_Stub(T, H), np.ones((H + 1, T)))
+            raise AssertionError("a table of the wrong shape must be refused")
+        except ValueError:
+            pass
+
+
+def test_packed_arrays_outlive_the_pattern_object():
+    d = synth.generate(T=200, N=5000, H=8)
+    p = PackedPattern(synth.to_apm(d), gene_of=utils.gene_index(d.T, d.groups()))
+    pairs, count = p.arrays["pairs"], p.arrays["count"]
+    want = (int(pairs.astype(np.int64).sum()), float(count.sum()))
+    assert pairs.base is not None and not pairs.flags.owndata  # a view into the packer's memory, not a copy
+    del p
+    gc.collect()
+    junk = [np.ones(1 << 16) for _ in range(8)]  # churn the allocator
+    assert (int(pairs.astype(np.int64).sum()), float(count.sum())) == want and len(junk) == 8
+    assert float(count.sum()) == float(d.count.sum())
