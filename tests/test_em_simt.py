@@ -1,0 +1,172 @@
+"""The EM library itself -- kernels, launchers and C ABI of gbrs_b200/csrc/em_kernels.cu -- executed on the CPU through
+the host SIMT shim (tests/simt_em.py: the source is rewritten mechanically, `<<<>>>` launches become thread-per-CUDA-thread
+launches, the CUDA runtime is a stand-in) against the golden vectors of the reference: identical iteration counts,
+theta / counts / error trajectory as on the GPU.  A check of the kernel CODE on machines without a GPU -- not a product
+path: the package cannot load this library, and the product's entry points fail without a CUDA device.
+
+By default a subset of the golden cases runs (one OS thread per CUDA thread is slow: 4-30 s per case); set
+GBRS_SIMT_ALL=1 for all of them."""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gbrs_b200 import synth
+from gbrs_b200.quantify import hapmask_bytes
+from oracle import em_oracle as eo
+from tests import helpers as hp
+from tests import simt_em
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ is needed to build the SIMT emulation")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = [n for n in hp.golden_em_cases() if n.startswith("em_small")]
+DEFAULT = ["em_small_m4", "em_small_m4_diploid", "em_small_m4_maxit5", "em_small_m4_pc", "em_small_m1_diploid",
+           "em_small_m2_h3", "em_small_m3_h1"]
+CASES = SMALL if os.environ.get("GBRS_SIMT_ALL") else DEFAULT
+
+
+def pattern_for(g, d, **kw):
+    hm = hapmask_bytes(g["gtmask"]) if g["masked"] else None
+    return simt_em.HostPattern(synth.to_apm(d), gene_of=eo.gene_index(d.T, d.groups()), hapmask=hm, **kw)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_library_matches_reference_golden(name):
+    g = hp.load_golden(name)
+    d = hp.synth_from_golden(g)
+    pat = pattern_for(g, d)
+    theta0 = pat.prepare(eo.effective_length_table(d.lengths), g["pseudocount"])
+    assert hp.relerr(theta0, g["theta0"]) < 1e-12
+    out = pat.run(g["model"], g["tol"], g["max_iters"])
+    assert out["iters"] == g["iters"]
+    np.testing.assert_allclose(out["errs"], g["errs"], rtol=1e-7, atol=1e-7)
+    assert hp.relerr(out["theta"], g["theta"]) < 1e-12 and hp.relerr(out["counts"], g["counts"]) < 1e-12
+    assert abs(out["counts"].sum() - g["counts"].sum()) < 1e-9 * g["counts"].sum()
+
+
+def test_emulated_wide_classes_short_items_and_alignment_counts():
+    """Classes wider than GBRS_KMAX (row-pointer paths), 8-entry work items (many items per locus, long items), one
+    update of every model against the oracle, and the alignment-count kernel (bit-exact) at locus and gene level."""
+    d = synth.generate(T=120, N=1500, H=8, sample_index=9, wide_frac=0.08)
+    gene_of = eo.gene_index(d.T, d.groups())
+    pat = simt_em.HostPattern(synth.to_apm(d), gene_of=gene_of, item_len=8)
+    assert pat.info["max_pairs_per_class"] > 8 and pat.info["n_long_items"] > 0
+    eff = eo.effective_length_table(d.lengths)
+    theta = pat.prepare(eff)
+    oapm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    assert hp.relerr(theta, eo.prepare(oapm, eff, 0.0)) < 1e-12
+    for model in (4, 3, 2, 1):
+        want = eo.sum_read(oapm, eo.e_step(oapm, theta, model, gene_of))
+        out = pat.run(model, tol=0.0, max_iters=1)
+        assert out["iters"] == 1 and hp.relerr(out["counts"], want) < 1e-12
+        theta = out["theta"]
+        assert hp.relerr(theta, want / eff) < 1e-12
+    aln, uniq, lu = pat.alignment_counts()
+    want = eo.alignment_counts(oapm)
+    assert np.array_equal(aln, want["aln"]) and np.array_equal(uniq, want["uniq"]) and np.array_equal(lu, want["locus_uniq"])
+    groups = d.groups()
+    aln, uniq, lu = pat.alignment_counts(gene_level=True, n_real_genes=len(groups))
+    want = eo.alignment_counts(eo.bundle(oapm, groups))
+    assert np.array_equal(aln, want["aln"]) and np.array_equal(uniq, want["uniq"]) and np.array_equal(lu, want["locus_uniq"])
+
+
+def test_emulated_zero_normaliser_is_reported():
+    """theta = 0 on every alignment of a class -> 0/0 in the E-step: GBRS_E_NUMERIC (the reference raises
+    FloatingPointError under np.seterr(all='raise'))."""
+    d = synth.generate(T=40, N=300, H=4, sample_index=1)
+    pat = simt_em.HostPattern(synth.to_apm(d))
+    pat.prepare(None)
+    zero = np.zeros((d.T, 8))
+    pat.check(pat.lib.gbrs_em_set_theta(pat.desc, zero.ctypes.data, None))
+    with pytest.raises(FloatingPointError):
+        pat.run(4, tol=1e-4, max_iters=5)
+
+
+def test_em_kernels_are_race_free_under_thread_sanitizer():
+    """Five model-4 updates and one update of models 1-3 under ThreadSanitizer (intra-block ordering: blocks run one
+    after the other in the emulation, so races between blocks are out of its reach)."""
+    try:
+        lib = simt_em.build(tsan=True)
+    except RuntimeError as e:
+        pytest.skip(f"ThreadSanitizer build unavailable: {e}")
+    rt = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("libtsan.so not found")
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np
+from gbrs_b200 import synth
+from oracle import em_oracle as eo
+from tests import simt_em
+simt_em._emul[False] = simt_em.load(tsan=True)
+d = synth.generate(T=60, N=500, H=8, sample_index=3, wide_frac=0.05)
+pat = simt_em.HostPattern(synth.to_apm(d), gene_of=eo.gene_index(d.T, d.groups()), item_len=8)
+pat.prepare(eo.effective_length_table(d.lengths), 0.5)
+out = pat.run(4, tol=0.0, max_iters=5)
+for model in (3, 2, 1):
+    out = pat.run(model, tol=0.0, max_iters=1)
+assert np.isfinite(out["theta"]).all()
+pat.alignment_counts()
+print("TSAN-RUN-OK")
+"""
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0",
+               OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=1500)
+    if "TSAN-RUN-OK" not in res.stdout:
+        pytest.skip("the sanitizer run did not complete here: " + res.stderr[-400:])
+    assert "ThreadSanitizer: data race" not in res.stderr, res.stderr[-4000:]
+
+
+@pytest.mark.parametrize("model,R", [(4, 2), (2, 3)])
+def test_emulated_row_shards_equal_the_unsharded_run(model, R):
+    """The N > 1 compute path (gbrs_em_launch_local -> sum of the numerators over the shards -> gbrs_em_launch_update,
+    every shard taking the same stop decision) on the emulated library: R shards, exchange by hand, against the
+    single-shard run and the oracle.  Mirrors tests/test_sharded_gpu.py."""
+    import ctypes as C
+
+    from gbrs_b200 import _lib
+
+    d = synth.generate(T=100, N=1200, H=8, sample_index=7)
+    gene_of = eo.gene_index(d.T, d.groups())
+    eff = eo.effective_length_table(d.lengths)
+    apm = synth.to_apm(d)
+    whole = simt_em.HostPattern(apm, gene_of=gene_of)
+    whole.prepare(eff)
+    ref = whole.run(model, tol=1e-3, max_iters=60)
+    pats = [simt_em.HostPattern(apm, gene_of=gene_of, shard_rank=r, shard_count=R) for r in range(R)]
+    assert sum(p.info["nnz"] for p in pats) == d.nnz
+    lib = pats[0].lib
+
+    def exchange():
+        total = sum(p.acc for p in pats)
+        for p in pats:
+            p.acc[:] = total
+
+    for p in pats:
+        p.efflen[:, : d.H] = eff.T
+        p.check(lib.gbrs_em_prepare_local(C.byref(p.desc), None))
+    exchange()
+    for p in pats:
+        p.check(lib.gbrs_em_prepare_finish(C.byref(p.desc), 0.0, None))
+        p.check(lib.gbrs_em_run_begin(C.byref(p.desc), 1e-3, 60, None))
+    for it in range(1, 62):
+        for p in pats:
+            p.check(lib.gbrs_em_launch_local(C.byref(p.desc), model, None))
+        exchange()
+        for p in pats:
+            p.check(lib.gbrs_em_launch_update(C.byref(p.desc), None))
+        done = {int(p.ctrl[_lib.CTRL_DONE]) for p in pats}
+        assert len(done) == 1  # every shard takes the same decision
+        if done == {1}:
+            break
+    assert it == ref["iters"] == int(pats[0].ctrl[_lib.CTRL_ITERS])
+    for p in pats:
+        assert np.array_equal(p.current_theta(), pats[0].current_theta())
+    assert hp.relerr(pats[0].current_theta(), ref["theta"]) < 1e-12
+    assert hp.relerr(pats[0].acc[:, : d.H].T, ref["counts"]) < 1e-12
+    o = hp.oracle_run(d, model, tol=1e-3, max_iters=60)
+    assert o["iters"] == it and hp.relerr(ref["counts"], o["counts"]) < 1e-12
