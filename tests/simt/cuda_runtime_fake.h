@@ -4,6 +4,7 @@
 // return a small constant so that the persistent grids stay a handful of blocks.
 #pragma once
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "simt_shim.h"
@@ -26,7 +27,11 @@ enum { cudaStreamNonBlocking = 1, cudaStreamCaptureModeThreadLocal = 1, cudaDevA
 inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "not supported by the host SIMT shim"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* dev) { *dev = 0; return cudaSuccess; }
-inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return cudaSuccess; }  // "2 SMs"
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) {  // the SM count: 2, or $GBRS_SIMT_SMS
+  const char* e = std::getenv("GBRS_SIMT_SMS");
+  *v = e && std::atoi(e) > 0 ? std::atoi(e) : 2;
+  return cudaSuccess;
+}
 template <class K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t) { std::memset(dst, v, n); return cudaSuccess; }
@@ -51,9 +56,13 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSucces
 // `kernel<<<grid, block, 0, stream>>>(args)` is rewritten (tests/simt_em.py) to SIMT_LAUNCH(grid, block, kernel(args))
 // (variadic: template argument lists of the kernel name carry top-level commas)
 #define SIMT_LAUNCH(grid, block, ...) simt_launch((unsigned) (grid), (unsigned) (block), [=] { __VA_ARGS__; })
-// inline PTX (system-scope loads / stores and multimem of the multi-GPU exchange) has no host meaning: those paths need
-// peer GPUs and are not exercised by the emulation
+// Inline PTX of the multi-GPU exchange.  The system-scope flag accesses become C++ atomics (the flag store is issued
+// after a system fence in the kernel: a release store here), the system-scope f64x2 accesses plain accesses (the flags
+// order them), so that ranks emulated as concurrently running library instances exchange through shared host memory;
+// the NVSwitch multimem instructions have no host meaning and trap.
 #define SIMT_PTX_UNSUPPORTED() __builtin_trap()
+inline unsigned simt_ld_acquire_u32(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void simt_st_release_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 // rcp.approx.ftz.f64: a reciprocal good to ~20 bits (the seed of fast_div's Newton steps) -- modelled as the exact
 // reciprocal with the low 32 mantissa bits cleared, so that the refinement steps have real work to do
 inline double simt_rcp_approx(double s) {

@@ -170,3 +170,100 @@ def test_emulated_row_shards_equal_the_unsharded_run(model, R):
     assert hp.relerr(pats[0].acc[:, : d.H].T, ref["counts"]) < 1e-12
     o = hp.oracle_run(d, model, tol=1e-3, max_iters=60)
     assert o["iters"] == it and hp.relerr(ref["counts"], o["counts"]) < 1e-12
+
+
+def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1):
+    """R ranks = R private instances of the emulated library running at the same time in R host threads, their
+    symmetric exchange buffers in shared host memory: the fused NVLink exchange (k_locus_acc publishes and raises
+    `ready`, the reduce step sums a slice with peer loads and raises `done`, the update waits for it) runs for real.
+    One SM / one resident block per kernel ($GBRS_SIMT_SMS=1): the reduce + update launch needs all its blocks
+    resident at once, and the emulation runs the blocks of a launch one after the other."""
+    import ctypes as C
+    import threading
+
+    from gbrs_b200 import _lib
+
+    os.environ["GBRS_SIMT_SMS"] = "1"
+    try:
+        gene_of = eo.gene_index(d.T, d.groups())
+        eff = eo.effective_length_table(d.lengths)
+        apm = synth.to_apm(d)
+        pats = [simt_em.HostPattern(apm, gene_of=gene_of, shard_rank=r, shard_count=R,
+                                    lib=simt_em.load_instance(f"rank{r}", tsan)) for r in range(R)]
+        bufs = [np.zeros(2 * 8 * d.T + 16) for _ in range(R)]
+        for r, p in enumerate(pats):
+            p.efflen[:, : d.H] = eff.T
+            p.desc.xchg_enabled, p.desc.xchg_rank, p.desc.xchg_mc = 1, r, None
+            for q in range(R):
+                p.desc.xchg_peer[q] = bufs[q].ctypes.data
+        errors, iters = [], [0] * R
+
+        def rank_main(r):
+            p = pats[r]
+            try:
+                p.check(p.lib.gbrs_em_prepare_local(C.byref(p.desc), None))
+                p.check(p.lib.gbrs_em_prepare_finish(C.byref(p.desc), 0.0, None))
+                p.check(p.lib.gbrs_em_run_begin(C.byref(p.desc), tol, max_iters, None))
+                while not p.ctrl[_lib.CTRL_DONE]:
+                    for _ in range(poll):  # updates queued after the stop are no-ops, as in the product's graph replay
+                        p.check(p.lib.gbrs_em_launch_local(C.byref(p.desc), model, None))
+                        p.check(p.lib.gbrs_em_launch_update(C.byref(p.desc), None))
+                    assert p.ctrl[_lib.CTRL_ERROR] == 0, int(p.ctrl[_lib.CTRL_ERROR])
+                iters[r] = int(p.ctrl[_lib.CTRL_ITERS])
+            except BaseException as e:  # noqa: BLE001 - reported by the main thread
+                errors.append((r, repr(e)))
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(R)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=900)
+        assert not errors, errors
+        assert not any(t.is_alive() for t in threads)
+        return pats, iters
+    finally:
+        os.environ.pop("GBRS_SIMT_SMS", None)
+
+
+@pytest.mark.parametrize("R,model", [(2, 4), (3, 2)])
+def test_emulated_fused_exchange_between_concurrent_ranks(R, model):
+    d = synth.generate(T=70, N=900, H=8, sample_index=12)
+    pats, iters = _run_fused_ranks(d, model, R, 1e-3, 60, poll=2)
+    o = hp.oracle_run(d, model, tol=1e-3, max_iters=60)
+    assert iters == [o["iters"]] * R
+    for p in pats:  # bit-identical on every rank: each element of the numerator is summed by exactly one rank
+        assert np.array_equal(p.current_theta(), pats[0].current_theta())
+        assert np.array_equal(p.acc, pats[0].acc)
+    assert hp.relerr(pats[0].current_theta(), o["theta"]) < 1e-12
+    assert hp.relerr(pats[0].acc[:, : d.H].T, o["counts"]) < 1e-12
+
+
+def test_fused_exchange_is_race_free_under_thread_sanitizer():
+    """Two and three concurrent ranks under ThreadSanitizer: every access to a peer's numerator must be ordered by the
+    ready / done flags (with the flag store weakened to a relaxed store the sanitizer reports the peer loads)."""
+    try:
+        simt_em.build(tsan=True)
+    except RuntimeError as e:
+        pytest.skip(f"ThreadSanitizer build unavailable: {e}")
+    rt = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("libtsan.so not found")
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np
+from gbrs_b200 import synth
+from tests.test_em_simt import _run_fused_ranks
+d = synth.generate(T=40, N=400, H=8, sample_index=12)
+pats, iters = _run_fused_ranks(d, 4, 2, 0.0, 4, tsan=True)
+assert iters == [4, 4] and np.array_equal(pats[0].current_theta(), pats[1].current_theta())
+pats, iters = _run_fused_ranks(d, 1, 3, 0.0, 2, tsan=True)
+assert iters == [2, 2, 2]
+print("TSAN-RUN-OK")
+"""
+    env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0",
+               OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=1500)
+    if "TSAN-RUN-OK" not in res.stdout:
+        pytest.skip("the sanitizer run did not complete here: " + res.stderr[-400:])
+    assert "ThreadSanitizer: data race" not in res.stderr, res.stderr[-4000:]
