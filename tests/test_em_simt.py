@@ -267,3 +267,23 @@ print("TSAN-RUN-OK")
     if "TSAN-RUN-OK" not in res.stdout:
         pytest.skip("the sanitizer run did not complete here: " + res.stderr[-400:])
     assert "ThreadSanitizer: data race" not in res.stderr, res.stderr[-4000:]
+
+
+@pytest.mark.parametrize("knob", ["GBRS_FORCE_ENTRY64", "GBRS_NO_INTERLEAVE"])
+def test_emulated_alternative_layouts(knob, monkeypatch):
+    """64-bit locus-major entry words (what shards beyond 2^24 classes use) and the plain ascending entry order inside
+    work items: one update of every model on the forced layout against the oracle."""
+    monkeypatch.setenv(knob, "1")
+    d = synth.generate(T=90, N=1000, H=8, sample_index=13, wide_frac=0.04)
+    gene_of = eo.gene_index(d.T, d.groups())
+    pat = simt_em.HostPattern(synth.to_apm(d), gene_of=gene_of, item_len=8)
+    assert pat.info["entry_bytes"] == (8 if knob == "GBRS_FORCE_ENTRY64" else 4)
+    eff = eo.effective_length_table(d.lengths)
+    theta = pat.prepare(eff)
+    oapm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    assert hp.relerr(theta, eo.prepare(oapm, eff, 0.0)) < 1e-12
+    for model in (4, 3, 2, 1):
+        want = eo.sum_read(oapm, eo.e_step(oapm, theta, model, gene_of))
+        out = pat.run(model, tol=0.0, max_iters=1)
+        assert hp.relerr(out["counts"], want) < 1e-12
+        theta = out["theta"]
