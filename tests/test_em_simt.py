@@ -287,3 +287,79 @@ def test_emulated_alternative_layouts(knob, monkeypatch):
         out = pat.run(model, tol=0.0, max_iters=1)
         assert hp.relerr(out["counts"], want) < 1e-12
         theta = out["theta"]
+
+
+def _random_problem(rng):
+    """A small problem of arbitrary shape: 1-44 loci, 1-8 haplotypes, 1-260 classes (some wide, some with count 0),
+    random haplotype masks, random contiguous genes."""
+    T, H, N = int(rng.integers(1, 45)), int(rng.integers(1, 9)), int(rng.integers(1, 260))
+    kmax = int(rng.choice([1, 2, 4, 12, 30]))
+    k = np.minimum(1 + rng.poisson(rng.uniform(0.2, 3.0), N), min(kmax, T)).astype(np.int64)
+    cls = np.repeat(np.arange(N), k)
+    key = np.unique(cls * T + rng.integers(0, T, cls.size))
+    full = (1 << H) - 1
+    mask = np.where(rng.random(key.size) < 0.4, full, rng.integers(1, full + 1, key.size)).astype(np.uint8)
+    count = rng.integers(0 if rng.random() < 0.3 else 1, 9, N).astype(np.float64)
+    _, gene_of = np.unique(np.sort(rng.integers(0, int(rng.integers(1, T + 1)), T)), return_inverse=True)
+    d = synth.SynthData(T=T, H=H, N=N, pair_class=key // T, pair_locus=key % T, pair_mask=mask, count=count,
+                        gene_of=gene_of.astype(np.int64), lengths=rng.integers(50, 4000, size=(T, H)).astype(np.float64),
+                        hname=synth.HAPLOTYPES[:H])
+    d.lname = [f"T{t:04d}" for t in range(T)]
+    d.gname = [f"G{g:04d}" for g in range(int(gene_of.max()) + 1)]
+    return d
+
+
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_emulated_library_on_random_shapes(seed):
+    """Seeded sample of the fuzz run that was done by hand over 440 problems (no failure): arbitrary small shapes, loci
+    outside every gene, 1-3 row shards, 8-entry items, pseudocount, three models per problem, alignment counts."""
+    import ctypes as C
+
+    rng = np.random.default_rng(seed)
+    d = _random_problem(rng)
+    if d.count.sum() == 0:
+        d.count[0] = 1.0
+    groups = d.groups()
+    if rng.random() < 0.3 and len(groups) > 1:  # a gene missing from the group file: its loci are on their own
+        groups.pop(int(rng.integers(0, len(groups))))
+    gene_of = eo.gene_index(d.T, groups)
+    item_len, R = int(rng.choice([0, 8])), int(rng.choice([1, 1, 2, 3]))
+    apm = synth.to_apm(d)
+    eff = eo.effective_length_table(d.lengths)
+    oapm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    pats = [simt_em.HostPattern(apm, gene_of=gene_of, item_len=item_len, shard_rank=r, shard_count=R) for r in range(R)]
+    lib = pats[0].lib
+
+    def exchange():
+        total = sum(p.acc for p in pats)
+        for p in pats:
+            p.acc[:] = total
+
+    for p in pats:
+        p.efflen[:, : d.H] = eff.T
+        p.check(lib.gbrs_em_prepare_local(C.byref(p.desc), None))
+    exchange()
+    pseudocount = float(rng.choice([0.0, 0.0, 0.7]))
+    for p in pats:
+        p.check(lib.gbrs_em_prepare_finish(C.byref(p.desc), pseudocount, None))
+    theta = pats[0].current_theta()
+    assert hp.relerr(theta, eo.prepare(oapm, eff, pseudocount)) < 1e-11
+    for model in (int(m) for m in rng.permutation([1, 2, 3, 4])[:3]):
+        with np.errstate(all="ignore"):
+            want = eo.sum_read(oapm, eo.e_step(oapm, theta, model, gene_of))
+        if not np.isfinite(want).all():
+            break
+        for p in pats:
+            p.check(lib.gbrs_em_run_begin(C.byref(p.desc), 0.0, 1, None))
+            p.check(lib.gbrs_em_launch_local(C.byref(p.desc), model, None))
+        exchange()
+        for p in pats:
+            p.check(lib.gbrs_em_launch_update(C.byref(p.desc), None))
+            assert int(p.ctrl[2]) == 0
+        assert hp.relerr(pats[0].acc[:, : d.H].T, want) < 1e-11
+        theta = pats[0].current_theta()
+        assert hp.relerr(theta, want / eff) < 1e-11
+    if R == 1:
+        aln, uniq, lu = pats[0].alignment_counts()
+        want = eo.alignment_counts(oapm)
+        assert np.array_equal(aln, want["aln"]) and np.array_equal(uniq, want["uniq"]) and np.array_equal(lu, want["locus_uniq"])
