@@ -171,3 +171,55 @@ def test_compress_workflow_on_cpu_with_the_device_step_replaced(name, tmp_path, 
     assert CliRunner().invoke(app, args).exit_code == 0
     got = AlignmentPropertyMatrix(h5file=out2)
     assert np.array_equal(got.count, want_count) and all(same_pattern(got.data[h], want[h]) for h in range(H))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_emulated_ec_kernels_match_reference_golden(name, tmp_path, monkeypatch):
+    """The GPU grouping code itself (ec_kernels.cu: hashing, exact comparison of sorted neighbours, first-appearance
+    numbering, class counts, launcher, C ABI) on the host SIMT shim -- the CUB sort / scan calls served by a stable sort
+    and a loop -- behind the unchanged `compress` workflow, against the goldens written by the reference."""
+    import shutil
+
+    if shutil.which("g++") is None:
+        pytest.skip("g++ is needed to build the SIMT emulation")
+    from tests import simt_em
+
+    monkeypatch.setattr(cz, "equivalence_classes", simt_em.emulated_equivalence_classes)
+    T, H, files, want, want_count = load_case(name)
+    out = os.path.join(str(tmp_path), "out.npz")
+    cz.compress(write_inputs(tmp_path, files, T, H), out)
+    res = AlignmentPropertyMatrix(h5file=out)
+    assert res.shape == (T, H, len(want_count)) and np.array_equal(res.count, want_count)
+    assert all(same_pattern(res.data[h], want[h]) for h in range(H))
+
+
+def test_emulated_ec_kernels_match_oracle_and_edge_cases():
+    import shutil
+
+    if shutil.which("g++") is None:
+        pytest.skip("g++ is needed to build the SIMT emulation")
+    from tests import simt_em
+
+    files = [make_reads(seed=21, T=300, H=8, n_classes=900, n_reads=5000, with_count=True, empty_reads=7),
+             make_reads(seed=22, T=300, H=8, n_classes=900, n_reads=3000, with_count=False)]
+    rps, ws, cs, base = [], [], [], 0
+    for mats, count in files:
+        rp, w = cz.read_rows(mats, 300, 8)
+        rps.append(rp[1:] + base if rps else rp)
+        base += int(rp[-1])
+        ws.append(w)
+        cs.append(np.ones(mats[0].shape[0]) if count is None else count)
+    rowptr, words, count = np.concatenate(rps), np.concatenate(ws), np.concatenate(cs)
+    cls, first, ccount = simt_em.emulated_equivalence_classes(rowptr, words, count)
+    want_mats, want_count = co.compress(files)
+    assert len(first) == len(want_count) and np.array_equal(ccount, want_count)
+    got = cz.class_matrices(rowptr, words, first, 300, 8)
+    assert all(same_pattern(got[h], want_mats[h]) for h in range(8))
+    assert np.all(np.diff(first.astype(np.int64)) > 0) and np.array_equal(cls[first], np.arange(len(first)))
+    for mats, cnt, n_ec in [([sp.csc_matrix((5, 4)) for _ in range(2)], None, 1),
+                            ([sp.csc_matrix(np.array([[0, 1.0, 0, 1.0]])) for _ in range(2)], np.array([3.0]), 1),
+                            ([sp.csc_matrix(np.tile(np.array([[1.0, 0, 0, 1.0]]), (6, 1))) for _ in range(2)], None, 1)]:
+        rp, w = cz.read_rows(mats, 4, 2)
+        c, f, cc = simt_em.emulated_equivalence_classes(rp, w, cnt)
+        _, wc = co.compress([(mats, cnt)])
+        assert len(f) == n_ec == len(wc) and np.array_equal(cc, wc) and f[0] == 0 and np.all(c == 0)
