@@ -674,11 +674,11 @@ __global__ void __launch_bounds__(kThreads) k_weights_m23_fixed(const __grid_con
 //   u[r][h] = count[n] * (Gamma_r / sum_r' Gamma_r') * (hg[g][h] / Hs_r) / Dh_r[h]
 //   Dh_r[h] = sum_{p in r, h in mask_p} theta[t_p][h],  Hs_r = sum_{h: Dh_r[h] != 0} hg[g][h],  hg = gene_hap
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d) {
+__global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d, int64_t first_class) {
   if (d.ctrl[GBRS_CTRL_DONE]) return;
   const double* __restrict__ th = theta_cur(d);
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  for (int64_t n = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
+  for (int64_t n = first_class + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < d.n_classes; n += stride) {
     const uint32_t b = __ldg(d.rowptr + n), e = __ldg(d.rowptr + n + 1);
     const double c = __ldg(d.count + n);
     double total = 0.0;
@@ -716,6 +716,91 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d) {
       double* out = d.weights + (size_t) run * GBRS_HPAD;
 #pragma unroll
       for (int h = 0; h < 8; ++h) out[h] = (Dh[h] != 0.0) ? wg * hg[h] / Dh[h] : 0.0;
+    }
+  }
+}
+
+// Model 1 for classes of 1..GBRS_KMAX pairs, eight lanes per class (opt-in: GBRS_M1_FIXED, not yet measured).  Lane h of a
+// group owns haplotype h: the theta line of a pair and the gene's per-haplotype totals are read as one 64-byte access
+// per group, the eight weights of a run are written as one 64-byte line, the class needs no row pointer (width bucket
+// addressing) and no data-dependent loop.  Every warp-level collective is executed unconditionally by all 32 lanes
+// (the four classes of a warp have different run structures): results are selected by predicate afterwards.
+template <int K>
+__device__ __forceinline__ void row_class_m1(const gbrs_em_dev& d, const double* __restrict__ th, int64_t n, bool valid,
+                                             int h, int lane) {
+  const uint32_t pair0 = (uint32_t) (d.bucket_pair0[K - 1] + (n - d.bucket_class0[K - 1]) * K);
+  const uint32_t* __restrict__ pw = d.pairs + pair0;
+  uint32_t w[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) w[p] = __ldg(pw + p);
+  const double c = __ldg(d.count + n);
+  int32_t g[K];
+  double gam[K], x[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const uint32_t t = w[p] & kLocusMask;
+    g[p] = __ldg(d.gene_of + t);
+    gam[p] = d.gamma[t];
+    x[p] = ((w[p] >> (24 + h)) & 1u) ? th[(size_t) t * GBRS_HPAD + h] : 0.0;
+  }
+  // Dh of the run each pair belongs to, for this lane's haplotype (members added in pair order)
+  double Dh[K], hg[K], Hs[K];
+  bool any[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    double a = 0.0;
+#pragma unroll
+    for (int q = 0; q < K; ++q) a += (g[q] == g[p]) ? x[q] : 0.0;
+    Dh[p] = a;
+    const bool nz = a != 0.0;
+    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, nz);
+    any[p] = ((bits >> (lane & 24)) & 0xFFu) != 0u;  // some haplotype of the run is alive
+    hg[p] = __ldg(d.gene_hap + (size_t) g[p] * GBRS_HPAD + h);
+    Hs[p] = group8_sum(nz ? hg[p] : 0.0);
+  }
+  double total = 0.0;
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const bool start = (p == 0) || (g[p] != g[p - 1]);
+    total += (start && any[p]) ? gam[p] : 0.0;
+  }
+  uint32_t run = __ldg(d.runptr + n);
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const bool start = (p == 0) || (g[p] != g[p - 1]);
+    if (start) {
+      if (p > 0) ++run;
+      if (valid) {
+        const double wg = (Hs[p] != 0.0) ? c * gam[p] / total / Hs[p] : 0.0;
+        d.weights[(size_t) run * GBRS_HPAD + h] = (Dh[p] != 0.0) ? wg * hg[p] / Dh[p] : 0.0;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_weights_m1_fixed(const __grid_constant__ gbrs_em_dev d) {
+  if (d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ th = theta_cur(d);
+  const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
+  const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  for (int k = GBRS_KMAX; k >= 1; --k) {  // widest first; k and the loop bounds are uniform over the warp
+    const int64_t c0 = d.bucket_class0[k - 1], c1 = d.bucket_class0[k];
+    const int64_t units = (c1 - c0 + 3) >> 2;  // four classes per warp
+    for (int64_t u = warp; u < units; u += n_warps) {
+      int64_t n = c0 + 4 * u + grp;
+      const bool valid = n < c1;
+      if (!valid) n = c1 - 1;  // idle group at the end of a bucket: recomputes the last class, stores nothing
+      switch (k) {
+        case 1: row_class_m1<1>(d, th, n, valid, h, lane); break;
+        case 2: row_class_m1<2>(d, th, n, valid, h, lane); break;
+        case 3: row_class_m1<3>(d, th, n, valid, h, lane); break;
+        case 4: row_class_m1<4>(d, th, n, valid, h, lane); break;
+        case 5: row_class_m1<5>(d, th, n, valid, h, lane); break;
+        case 6: row_class_m1<6>(d, th, n, valid, h, lane); break;
+        case 7: row_class_m1<7>(d, th, n, valid, h, lane); break;
+        default: row_class_m1<8>(d, th, n, valid, h, lane); break;
+      }
     }
   }
 }
@@ -1443,7 +1528,14 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
         }
         break;
       }
-      default: k_weights_m1<<<cg, kThreads, 0, s>>>(*d); break;
+      default: {
+        // GBRS_M1_FIXED: eight lanes per class for the classes of up to GBRS_KMAX pairs (parity-tested, not yet timed)
+        static const bool m1_fixed = std::getenv("GBRS_M1_FIXED") != nullptr;
+        const int64_t n_fixed = m1_fixed ? d->bucket_class0[GBRS_KMAX] : 0, n_long = d->n_classes - n_fixed;
+        if (n_fixed > 0) k_weights_m1_fixed<<<resident_grid(k_weights_m1_fixed, n_fixed * 8), kThreads, 0, s>>>(*d);
+        if (n_long > 0) k_weights_m1<<<grid_for(n_long), kThreads, 0, s>>>(*d, n_fixed);
+        break;
+      }
     }
     GBRS_LAUNCH_CHECK("k_weights");
   }
