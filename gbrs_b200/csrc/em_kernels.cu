@@ -778,31 +778,32 @@ __device__ __forceinline__ void row_class_m1(const gbrs_em_dev& d, const double*
   }
 }
 
+// one launch per width K: narrow classes (the bulk) are not compiled for the register needs of the widest
+template <int K>
 __global__ void __launch_bounds__(kThreads) k_weights_m1_fixed(const __grid_constant__ gbrs_em_dev d) {
   if (d.ctrl[GBRS_CTRL_DONE]) return;
   const double* __restrict__ th = theta_cur(d);
   const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
   const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
-  for (int k = GBRS_KMAX; k >= 1; --k) {  // widest first; k and the loop bounds are uniform over the warp
-    const int64_t c0 = d.bucket_class0[k - 1], c1 = d.bucket_class0[k];
-    const int64_t units = (c1 - c0 + 3) >> 2;  // four classes per warp
-    for (int64_t u = warp; u < units; u += n_warps) {
-      int64_t n = c0 + 4 * u + grp;
-      const bool valid = n < c1;
-      if (!valid) n = c1 - 1;  // idle group at the end of a bucket: recomputes the last class, stores nothing
-      switch (k) {
-        case 1: row_class_m1<1>(d, th, n, valid, h, lane); break;
-        case 2: row_class_m1<2>(d, th, n, valid, h, lane); break;
-        case 3: row_class_m1<3>(d, th, n, valid, h, lane); break;
-        case 4: row_class_m1<4>(d, th, n, valid, h, lane); break;
-        case 5: row_class_m1<5>(d, th, n, valid, h, lane); break;
-        case 6: row_class_m1<6>(d, th, n, valid, h, lane); break;
-        case 7: row_class_m1<7>(d, th, n, valid, h, lane); break;
-        default: row_class_m1<8>(d, th, n, valid, h, lane); break;
-      }
-    }
+  const int64_t c0 = d.bucket_class0[K - 1], c1 = d.bucket_class0[K];
+  const int64_t units = (c1 - c0 + 3) >> 2;  // four classes per warp; the loop bounds are uniform over the warp
+  for (int64_t u = warp; u < units; u += n_warps) {
+    int64_t n = c0 + 4 * u + grp;
+    const bool valid = n < c1;
+    if (!valid) n = c1 - 1;  // idle group at the end of the bucket: recomputes the last class, stores nothing
+    row_class_m1<K>(d, th, n, valid, h, lane);
   }
+}
+
+template <int K>
+int launch_m1_fixed(const gbrs_em_dev* d, cudaStream_t s) {
+  const int64_t n = d->bucket_class0[K] - d->bucket_class0[K - 1];
+  if (n > 0) {
+    k_weights_m1_fixed<K><<<resident_grid(k_weights_m1_fixed<K>, n * 8), kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_weights_m1_fixed");
+  }
+  return GBRS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1532,7 +1533,17 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
         // GBRS_M1_FIXED: eight lanes per class for the classes of up to GBRS_KMAX pairs (parity-tested, not yet timed)
         static const bool m1_fixed = std::getenv("GBRS_M1_FIXED") != nullptr;
         const int64_t n_fixed = m1_fixed ? d->bucket_class0[GBRS_KMAX] : 0, n_long = d->n_classes - n_fixed;
-        if (n_fixed > 0) k_weights_m1_fixed<<<resident_grid(k_weights_m1_fixed, n_fixed * 8), kThreads, 0, s>>>(*d);
+        if (n_fixed > 0) {  // widest first
+          int r8 = launch_m1_fixed<8>(d, s);
+          if (!r8) r8 = launch_m1_fixed<7>(d, s);
+          if (!r8) r8 = launch_m1_fixed<6>(d, s);
+          if (!r8) r8 = launch_m1_fixed<5>(d, s);
+          if (!r8) r8 = launch_m1_fixed<4>(d, s);
+          if (!r8) r8 = launch_m1_fixed<3>(d, s);
+          if (!r8) r8 = launch_m1_fixed<2>(d, s);
+          if (!r8) r8 = launch_m1_fixed<1>(d, s);
+          if (r8) return r8;
+        }
         if (n_long > 0) k_weights_m1<<<grid_for(n_long), kThreads, 0, s>>>(*d, n_fixed);
         break;
       }
