@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of a round: everything that has to be (re-)confirmed on a device, in one gpurun invocation.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_round_start.sh r2'
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/gpu_round_start.sh r2'   (about 20 minutes of box time)
 # Writes into gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/ afterwards.
 # Order: tests first (the `reconstruct` kernels had their first device run pending at the end of round 1), then the
 # bench lines WITHOUT a profiler, only then the ncu passes of the same commands.
