@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("GBRS_LIB_PATH") or os.path.join(HERE, "_C", "libgbrs_
 GBRS_HPAD = 8
 GBRS_KMAX = 8
 GBRS_PART_SLOTS = 4096
-ABI_VERSION = 3
+ABI_VERSION = 4
 CTRL_ITERS, CTRL_DONE, CTRL_ERROR, CTRL_PARITY, CTRL_MAX_ITERS, CTRL_PREPARED = range(6)
 SCAL_ERR, SCAL_SUM_PREV, SCAL_TARGET, SCAL_SUM_CUR = range(4)
 
@@ -62,6 +62,9 @@ class EmDev(C.Structure):
                 ("gamma", C.c_void_p), ("err_log", C.c_void_p), ("scal", C.c_void_p), ("ctrl", C.c_void_p)]
 
 
+POLL_CB = C.CFUNCTYPE(None, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_void_p)
+
+
 class HmmChain(C.Structure):
     _fields_ = [("gene0", C.c_int64), ("tprob0", C.c_int64), ("n_genes", C.c_int32), ("n_steps", C.c_int32),
                 ("state0", C.c_int64)]
@@ -81,6 +84,7 @@ SYMBOLS = {
     "gbrs_em_current_theta": (C.c_int, [C.POINTER(EmDev), C.c_void_p, C.POINTER(C.c_void_p)]),
     "gbrs_em_run_begin": (C.c_int, [C.POINTER(EmDev), C.c_double, C.c_int, C.c_void_p]),
     "gbrs_em_launch_local": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_void_p]),
+    "gbrs_em_launch_estep": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_void_p]),
     "gbrs_em_launch_update": (C.c_int, [C.POINTER(EmDev), C.c_void_p]),
     "gbrs_prof_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "gbrs_em_launch_local_profiled": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_void_p, C.c_void_p]),
@@ -89,6 +93,8 @@ SYMBOLS = {
     "gbrs_prof_free": (C.c_int, [C.c_void_p]),
     "gbrs_em_run": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p,
                               C.POINTER(C.c_int32), C.c_void_p]),
+    "gbrs_em_run_cb": (C.c_int, [C.POINTER(EmDev), C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p,
+                                 C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gbrs_em_read_ctrl": (C.c_int, [C.POINTER(EmDev), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gbrs_write_table": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int64, C.c_void_p, C.c_int32,
                                    C.POINTER(C.c_char_p), C.c_void_p, C.c_int32]),

@@ -1479,10 +1479,20 @@ extern "C" int gbrs_prof_free(gbrs_prof_t p) {
   return GBRS_OK;
 }
 
-static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs_prof* prof);
+static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs_prof* prof, bool estep_only = false);
 
 extern "C" int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* stream) {
   return launch_local_impl(d, model, stream, nullptr);
+}
+
+// E-step alone (EMfactory.update_probability_at_read_level, EMfactory.py:146-212): the numerator sum_n c[n] P[n,t,h] of
+// this rank's shard goes to `acc` and NOTHING else changes -- no theta', no isoform totals, no subset tables, no exchange
+// flags -- so it may be called any number of times between updates, exactly like the reference's method.
+extern "C" int gbrs_em_launch_estep(const gbrs_em_dev* d, int model, void* stream) {
+  if (!d) { gbrs_set_error("gbrs_em_launch_estep: null descriptor"); return GBRS_E_ARG; }
+  gbrs_em_dev plain = *d;
+  plain.xchg_enabled = 0;  // the caller sums `acc` over ranks (if any) itself
+  return launch_local_impl(&plain, model, stream, nullptr, true);
 }
 
 extern "C" int gbrs_em_launch_local_profiled(const gbrs_em_dev* d, int model, void* stream, gbrs_prof_t prof) {
@@ -1490,13 +1500,13 @@ extern "C" int gbrs_em_launch_local_profiled(const gbrs_em_dev* d, int model, vo
   return launch_local_impl(d, model, stream, prof);
 }
 
-static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs_prof* prof) {
+static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs_prof* prof, bool estep_only) {
   if (int rc = check_dev(d, "gbrs_em_launch_local")) return rc;
   if (model < 1 || model > 4) {
     gbrs_set_error("The read normalization model should be 1, 2, 3, or 4."); return GBRS_E_ARG;  // EMfactory.py:209-212
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool honour_done = d->n_ranks <= 1;
+  const bool honour_done = d->n_ranks <= 1 && !estep_only;
   int rc = GBRS_OK;
   if (model != 4) {
     if (!d->gene_of || !d->gene_ptr || !d->gene_loci || !d->gene_hap || !d->gamma || !d->runptr) {
@@ -1559,7 +1569,7 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   }
   if (rc) return rc;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[2], s));
-  if (d->n_ranks <= 1) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(*d, true);
+  if (d->n_ranks <= 1 && !estep_only) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(*d, true);
   else k_locus_acc<false, false><<<acc_grid(d), kThreads, 0, s>>>(*d, false);
   GBRS_LAUNCH_CHECK("k_locus_acc");
   if (ev) {
@@ -1614,6 +1624,11 @@ uint64_t graph_key(const gbrs_em_dev* d, int model, int poll_every) {  // FNV-1a
 
 extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_iters, int poll_every, void* stream,
                            int32_t* iters_out, double* errs_host) {
+  return gbrs_em_run_cb(d, model, tol, max_iters, poll_every, stream, iters_out, errs_host, nullptr, nullptr);
+}
+
+extern "C" int gbrs_em_run_cb(const gbrs_em_dev* d, int model, double tol, int max_iters, int poll_every, void* stream,
+                              int32_t* iters_out, double* errs_host, gbrs_poll_cb on_poll, void* user) {
   if (int rc = check_dev(d, "gbrs_em_run")) return rc;
   if (d->n_ranks > 1) {
     gbrs_set_error("gbrs_em_run: row-sharded runs interleave the exchange step; drive launch_local / launch_update");
@@ -1673,6 +1688,8 @@ extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_
       }
     }
   }
+  int reported = 0;
+  std::vector<double> poll_buf;
   while (!rc && !ctrl[GBRS_CTRL_DONE]) {
     if (exec) {
       if (cudaGraphLaunch(exec, s) != cudaSuccess) { gbrs_set_error("cudaGraphLaunch failed"); rc = GBRS_E_CUDA; break; }
@@ -1683,6 +1700,20 @@ extern "C" int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_
       }
     }
     if (!rc) rc = gbrs_em_read_ctrl(d, s, ctrl, nullptr);
+    if (!rc && on_poll && ctrl[GBRS_CTRL_ITERS] > reported) {
+      // progress rows as they happen (the reference prints one line per iteration, EMfactory.py:280-287)
+      const int n_new = ctrl[GBRS_CTRL_ITERS] - reported;
+      poll_buf.resize((size_t) n_new);
+      if (cudaMemcpyAsync(poll_buf.data(), d->err_log + reported, sizeof(double) * (size_t) n_new, cudaMemcpyDeviceToHost, s) !=
+              cudaSuccess ||
+          cudaStreamSynchronize(s) != cudaSuccess) {
+        gbrs_set_error("copying the error log failed");
+        rc = GBRS_E_CUDA;
+        break;
+      }
+      on_poll(reported, n_new, poll_buf.data(), user);
+      reported = ctrl[GBRS_CTRL_ITERS];
+    }
   }
   if (!rc && errs_host && ctrl[GBRS_CTRL_ITERS] > 0) {
     if (cudaMemcpyAsync(errs_host, d->err_log, sizeof(double) * (size_t) ctrl[GBRS_CTRL_ITERS], cudaMemcpyDeviceToHost, s) !=

@@ -523,7 +523,7 @@ class EMfactory:
             pat.desc.xchg_peer[r] = int(ptrs[r])
         return True
 
-    def _run_sharded(self, pat, model, tol, max_iters):
+    def _run_sharded(self, pat, model, tol, max_iters, on_poll=None):
         """Row-sharded loop: `poll_every` updates (local passes -> all-reduce of the numerator -> update + stop test)
         are captured once into a CUDA graph and replayed until the device-side stop flag is read back as set.  Every rank
         sees the same all-reduced numerator, hence the same error and the same decision, so no second collective is
@@ -551,12 +551,16 @@ class EMfactory:
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=side):
                     body()
+            reported = 0
             while not ctrl[_lib.CTRL_DONE]:
                 if graph is not None:
                     graph.replay()
                 else:
                     body()
                 ctrl, _ = pat.read_ctrl()
+                if on_poll is not None and ctrl[_lib.CTRL_ITERS] > reported:
+                    on_poll(reported, pat.err_log[reported:int(ctrl[_lib.CTRL_ITERS])].cpu().numpy())
+                    reported = int(ctrl[_lib.CTRL_ITERS])
         torch.cuda.current_stream(pat.device).wait_stream(side)
         side.synchronize()
         return ctrl
@@ -592,8 +596,7 @@ class EMfactory:
         self._exchange(pat)
         _lib.check(pat.lib.gbrs_em_prepare_finish(C.byref(pat.desc), float(pseudocount), pat.stream()))
         ctrl, _ = pat.read_ctrl()
-        if ctrl[_lib.CTRL_ERROR]:
-            raise FloatingPointError("non-finite initial expression estimate")
+        self._raise_on_ctrl_error(ctrl, "the initial expression estimate")
         self._fetch_theta()
         self._counts_host = None
         self.num_iters = 0
@@ -605,7 +608,24 @@ class EMfactory:
 
     def update_probability_at_read_level(self, model: int = 3) -> None:
         """E-step (EMfactory.py:146-212).  On the device the posterior is implicit: this queues the row pass and
-        the column reduce for `model`, leaving the count-weighted numerator sum_n c[n] P[n,t,h] in `acc`."""
+        the column reduce for `model`, leaving the count-weighted numerator sum_n c[n] P[n,t,h] in `acc` -- and nothing
+        else: like the reference's method it can be called repeatedly and does not move theta."""
+        if model not in (1, 2, 3, 4):
+            raise RuntimeError("The read normalization model should be 1, 2, 3, or 4.")
+        pat = self._ensure_pattern()
+        if model != 4:
+            pat.ensure_full()
+        self._sync_theta_to_device()
+        _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), 0.0, 1, pat.stream()))
+        _lib.check(pat.lib.gbrs_em_launch_estep(C.byref(pat.desc), int(model), pat.stream()))
+        if self.world > 1:  # the stand-alone E-step never uses the fused exchange (it must not touch its flags)
+            import torch.distributed as dist
+
+            dist.all_reduce(pat.acc, op=dist.ReduceOp.SUM, group=self._group)
+        self._counts_host = None
+
+    def update_allelic_expression(self, model: int = 3) -> None:
+        """A single EM step (EMfactory.py:214-232): E-step, then theta = numerator / effective length."""
         if model not in (1, 2, 3, 4):
             raise RuntimeError("The read normalization model should be 1, 2, 3, or 4.")
         pat = self._ensure_pattern()
@@ -615,17 +635,20 @@ class EMfactory:
         _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), 0.0, 1, pat.stream()))
         _lib.check(pat.lib.gbrs_em_launch_local(C.byref(pat.desc), int(model), pat.stream()))
         self._exchange(pat)
-        self._counts_host = None
-
-    def update_allelic_expression(self, model: int = 3) -> None:
-        """A single EM step (EMfactory.py:214-232)."""
-        self.update_probability_at_read_level(model)
-        pat = self._pattern
         _lib.check(pat.lib.gbrs_em_launch_update(C.byref(pat.desc), pat.stream()))
         ctrl, _ = pat.read_ctrl()
-        if ctrl[_lib.CTRL_ERROR]:
-            raise FloatingPointError("non-finite value in the EM update (zero normaliser or overflow)")
+        self._raise_on_ctrl_error(ctrl)
         self._fetch_theta()
+        self._counts_host = None
+
+    @staticmethod
+    def _raise_on_ctrl_error(ctrl, what="the EM update"):
+        """Device error flag -> the exception the reference (or the exchange) would raise."""
+        err = int(ctrl[_lib.CTRL_ERROR])
+        if err == 3:
+            raise _lib.GbrsError("fused NVLink exchange timed out waiting for a peer rank")
+        if err:
+            raise FloatingPointError(f"non-finite value in {what} (zero normaliser or overflow)")
 
     def run(self, model: int, tol: float = 0.001, max_iters: int = 999, verbose: bool = True) -> None:
         """Runs EM iterations (EMfactory.py:234-287); the stop test runs on the device."""
@@ -637,33 +660,36 @@ class EMfactory:
         if model != 4:
             pat.ensure_full()
         self._sync_theta_to_device()
-        if verbose:
+        show = verbose and self.rank == 0  # one table, from rank 0 (a sharded run would print it world times)
+        if show:
             print("")
             print("Iter No  Time (hh:mm:ss)    Total change (TPM)  ")
             print("-------  ---------------  ----------------------")
         time0 = time.time()
+
+        def print_rows(first, errs):
+            # one row per iteration as the polls come back, stamped with the time of that poll (EMfactory.py:280-287)
+            delmin, sec = divmod(int(time.time() - time0), 60)
+            h, m = divmod(delmin, 60)
+            for i, e in enumerate(errs):
+                print(" %5d      %4d:%02d:%02d     %9.1f / 1000000" % (first + i + 1, h, m, sec, e), flush=True)
+
         if self.world == 1:
             iters = C.c_int32(0)
             errs = np.zeros(max(max_iters, 1), dtype=np.float64)
-            rc = pat.lib.gbrs_em_run(C.byref(pat.desc), int(model), float(tol), int(max_iters), int(self._poll_every),
-                                     pat.stream(), C.byref(iters), errs.ctypes.data)
+            cb = _lib.POLL_CB(lambda first, n, p, _u: print_rows(first, [p[i] for i in range(n)])) if show else None
+            rc = pat.lib.gbrs_em_run_cb(C.byref(pat.desc), int(model), float(tol), int(max_iters), int(self._poll_every),
+                                        pat.stream(), C.byref(iters), errs.ctypes.data,
+                                        C.cast(cb, C.c_void_p) if cb is not None else None, None)
             _lib.check(rc)
             n = int(iters.value)
             self.err_history = errs[:n].copy()
         else:
-            ctrl = self._run_sharded(pat, int(model), float(tol), int(max_iters))
-            if ctrl[_lib.CTRL_ERROR] == 3:
-                raise _lib.GbrsError("fused NVLink exchange timed out waiting for a peer rank")
-            if ctrl[_lib.CTRL_ERROR]:
-                raise FloatingPointError("non-finite value in the EM update (zero normaliser or overflow)")
+            ctrl = self._run_sharded(pat, int(model), float(tol), int(max_iters), on_poll=print_rows if show else None)
+            self._raise_on_ctrl_error(ctrl)
             n = int(ctrl[_lib.CTRL_ITERS])
             self.err_history = pat.err_log[:n].cpu().numpy()
         self.num_iters = n
-        if verbose:
-            delmin, s = divmod(int(time.time() - time0), 60)
-            h, m = divmod(delmin, 60)
-            for i, e in enumerate(self.err_history):
-                print(" %5d      %4d:%02d:%02d     %9.1f / 1000000" % (i + 1, h, m, s, e))
         self._fetch_theta()
         self._counts_host = None
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GBRS_EM_ABI_VERSION 3
+#define GBRS_EM_ABI_VERSION 4
 #define GBRS_HPAD 8 /* haplotype slots per locus line */
 #define GBRS_KMAX 8 /* classes with up to this many (class, locus) pairs take the fixed-width row pass */
 
@@ -188,6 +188,10 @@ int gbrs_em_run_begin(const gbrs_em_dev* d, double tol, int max_iters, void* str
  * EMfactory.py:146-212, with normalize_reads AlignmentPropertyMatrix.py:305-370 and multiply Sparse3DMatrix.py:314-377)
  * and the count-weighted column reduce (APM.sum(READ), AlignmentPropertyMatrix.py:288-298) into `acc`. */
 int gbrs_em_launch_local(const gbrs_em_dev* d, int model, void* stream);
+/* The E-step alone, EMfactory.update_probability_at_read_level (EMfactory.py:146-212): same passes as
+ * gbrs_em_launch_local, but ONLY `acc` (this rank's numerator) is written -- theta, the isoform totals, the subset tables
+ * and the exchange flags stay as they are, so the call can be repeated or followed by a full update. */
+int gbrs_em_launch_estep(const gbrs_em_dev* d, int model, void* stream);
 /* Second half (after `acc` holds the sum over all shards): theta' = acc / efflen (EMfactory.py:228-232), TPM-scaled
  * isoform-total L1 change and the stop test (EMfactory.py:267-279), entirely on the device. */
 int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream);
@@ -206,6 +210,12 @@ int gbrs_prof_free(gbrs_prof_t p);
  * iterations performed and copies their err_sum values into errs_host[0..iters) (may be NULL). */
 int gbrs_em_run(const gbrs_em_dev* d, int model, double tol, int max_iters, int poll_every, void* stream,
                 int32_t* iters_out, double* errs_host);
+
+/* Same, reporting progress: after every poll `on_poll(first_iter, n_new, errs_new, user)` is called with the err_sum values
+ * of the iterations finished since the previous poll (the reference prints its table row by row, EMfactory.py:280-287). */
+typedef void (*gbrs_poll_cb)(int32_t first_iter, int32_t n_new, const double* errs_new, void* user);
+int gbrs_em_run_cb(const gbrs_em_dev* d, int model, double tol, int max_iters, int poll_every, void* stream,
+                   int32_t* iters_out, double* errs_host, gbrs_poll_cb on_poll, void* user);
 
 /* Read the control block (synchronises the stream): ctrl_host[16], scal_host[8]. */
 int gbrs_em_read_ctrl(const gbrs_em_dev* d, void* stream, int32_t* ctrl_host, double* scal_host);

@@ -73,6 +73,30 @@ def test_emulated_wide_classes_short_items_and_alignment_counts():
     assert np.array_equal(aln, want["aln"]) and np.array_equal(uniq, want["uniq"]) and np.array_equal(lu, want["locus_uniq"])
 
 
+def test_emulated_standalone_estep_does_not_move_the_state():
+    """update_probability_at_read_level semantics (EMfactory.py:146-212): the E-step alone leaves only the numerator
+    behind.  Two stand-alone E-steps followed by a full update must give exactly what one update gives."""
+    import ctypes as C
+
+    d = synth.generate(T=60, N=600, H=8, sample_index=5)
+    eff = eo.effective_length_table(d.lengths)
+    oapm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    gene_of = eo.gene_index(d.T, d.groups())
+    for model in (4, 2):
+        pat = simt_em.HostPattern(synth.to_apm(d), gene_of=gene_of)
+        theta = pat.prepare(eff)
+        want_counts = eo.sum_read(oapm, eo.e_step(oapm, theta, model, gene_of))
+        for _ in range(2):
+            pat.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), 0.0, 1, None))
+            pat.check(pat.lib.gbrs_em_launch_estep(C.byref(pat.desc), model, None))
+            assert hp.relerr(pat.acc[:, : pat.H].T, want_counts) < 1e-12
+            assert np.array_equal(pat.current_theta(), theta)  # theta did not move
+        out = pat.run(model, tol=0.0, max_iters=2)
+        t1 = want_counts / eff
+        t2 = eo.sum_read(oapm, eo.e_step(oapm, t1, model, gene_of)) / eff
+        assert out["iters"] == 2 and hp.relerr(out["theta"], t2) < 1e-12
+
+
 def test_emulated_zero_normaliser_is_reported():
     """theta = 0 on every alignment of a class -> 0/0 in the E-step: GBRS_E_NUMERIC (the reference raises
     FloatingPointError under np.seterr(all='raise'))."""

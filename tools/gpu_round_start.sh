@@ -10,6 +10,9 @@ mkdir -p $out
 cd "${GRAFT_REPO_ROOT:-.}"
 export PYTHONUNBUFFERED=1
 
+echo "== M-step scatter microbenchmark (atomics vs the gather formulation)"
+timeout 300 ./tools/ubench/mstep_scatter > $out/${tag}_ubench_mstep_scatter.txt 2>&1; echo "ubench rc=$?"; cat $out/${tag}_ubench_mstep_scatter.txt
+
 echo "== pytest -m gpu"
 timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -5 $out/${tag}_pytest_gpu.log
