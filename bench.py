@@ -321,7 +321,14 @@ def run_gpu_arm(args, wl):
     bytes_col = eb * Ee + 16 * It + 8 * widx + 64 * It  # entry words, item descriptors, weights in, item sums out
     bytes_iter = 4 * Pp + 4 * (Np + 1) + 8 * Np + 3 * 64 * T  # SURVEY 8(d), pair+mask layout, inputs once
     peak, peak_src = measured_peaks()
-    if row_ms >= col_ms:
+    tiled = pat.tiled is not None and model == 4
+    if tiled:
+        ti = pat.tiled.info
+        # the fused tile kernel: every tile blob once, the subset-table rows of its loci in, one 64-byte partial per
+        # (tile, locus) slot out
+        bytes_tile = ti["blob_bytes"] + 16 * ti["n_tiles"] + (256 + 64) * ti["n_slots"]
+        dom, dom_ms, dom_bytes = "k_tile_em (fused E-step + column reduce over tiles)", row_ms, bytes_tile
+    elif row_ms >= col_ms:
         dom, dom_ms, dom_bytes = "k_weights_m%d (row pass)" % model, row_ms, bytes_row
     else:
         dom, dom_ms, dom_bytes = "k_column_reduce (column pass)", col_ms, bytes_col
@@ -337,7 +344,7 @@ def run_gpu_arm(args, wl):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
                 "share_of_step": dom_ms / (ms / K),
-                "per_kernel_ms": {"row_pass": row_ms, "column_pass": col_ms, "locus_acc": acc_ms,
+                "per_kernel_ms": {("tile_pass" if tiled else "row_pass"): row_ms, "column_pass": col_ms, "locus_acc": acc_ms,
                                   "rest_of_step": max(ms / K - row_ms - col_ms - acc_ms, 0.0)},
                 "iteration": {"algorithmic_bytes": bytes_iter, "achieved": bytes_iter / (ms / K * 1e-3) / 1e9,
                               "frac": bytes_iter / (ms / K * 1e-3) / 1e9 / peak,
@@ -390,14 +397,17 @@ def run_gpu_arm(args, wl):
                          f"{s_per:.3f} s/update, host has {os.cpu_count()} logical cores (path is single-threaded)"}
 
     if rank == 0:
-        launches_per_step = (4 if world == 1 else 5) + (1 if model != 4 else 0)
+        launches_per_step = ((3 if tiled else 4) if world == 1 else (4 if tiled else 5)) + (1 if model != 4 else 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["label"], "model": model, "classes_per_gpu": Np, "pairs_per_gpu": Pp,
                            "nnz_per_gpu": nnz_local, "nnz_total": nnz_total, "loci": T, "haplotypes": 8,
+                           "layout": ("tiles: %d tiles, %.1f MB of blobs, %d partial slots" % (
+                               pat.tiled.info["n_tiles"], pat.tiled.info["blob_bytes"] / 1e6, pat.tiled.info["n_slots"]))
+                           if tiled else "two-pass: class-major + locus-major copies",
                            "l2_policy": "inputs larger than L2 (packed incidence %.0f MB per GPU streams every step)"
-                                        % (pat.packed.nbytes() / 1e6),
+                                        % ((pat.tiled.nbytes() if tiled else pat.packed.nbytes()) / 1e6),
                            "exchange": "none" if world == 1 else (
                                ("fused two-shot all-reduce of T x 8 fp64 inside the locus kernels: NVLS (multimem.ld_reduce / "
                                 "multimem.st on the NVSwitch multicast mapping)" if em.nvls_exchange else

@@ -46,6 +46,26 @@ class PackInfo(C.Structure):
                 ("bucket_pair0", C.c_int64 * (GBRS_KMAX + 2))]
 
 
+class TilesParams(C.Structure):
+    _fields_ = [("max_classes", C.c_int32), ("max_loci", C.c_int32), ("max_pairs", C.c_int32),
+                ("max_entries", C.c_int32), ("max_items", C.c_int32), ("item_len", C.c_int32)]
+
+
+class TilesInfo(C.Structure):
+    _fields_ = [("n_tiles", C.c_int64), ("n_slots", C.c_int64), ("blob_bytes", C.c_int64), ("n_entries", C.c_int64),
+                ("n_items", C.c_int64), ("n_pairs", C.c_int64), ("n_classes", C.c_int64),
+                ("max_classes", C.c_int32), ("max_loci", C.c_int32), ("max_items", C.c_int32),
+                ("max_part_a_bytes", C.c_int32), ("max_part_b_bytes", C.c_int32), ("max_planes", C.c_int32),
+                ("max_slots_per_locus", C.c_int32), ("item_len", C.c_int32)]
+
+
+# blob header words (include/gbrs_em.h)
+(TH_CLASSES, TH_LOCI, TH_PLANES, TH_PAIRS, TH_ENTRIES, TH_ITEMS, TH_OFF_LOCI, TH_OFF_SLOTS, TH_OFF_NPLANE, TH_OFF_COUNT,
+ TH_OFF_PAIRS, TH_A_BYTES, TH_B_BYTES, TH_OFF_ENTS, TH_FLAGS) = range(15)
+TH_WORDS = 16
+CTRL_TILE_NEXT = 13
+
+
 class EmDev(C.Structure):
     _fields_ = [("T", C.c_int32), ("H", C.c_int32), ("n_gene_ids", C.c_int32), ("entry_bytes", C.c_int32),
                 ("n_classes", C.c_int64), ("n_pairs", C.c_int64), ("n_runs", C.c_int64), ("n_items", C.c_int64),
@@ -57,6 +77,10 @@ class EmDev(C.Structure):
                 ("item_off", C.c_void_p), ("item_order", C.c_void_p), ("item_desc", C.c_void_p),
                 ("locus_order", C.c_void_p), ("locus_desc", C.c_void_p), ("locus_item_ptr", C.c_void_p),
                 ("gene_of", C.c_void_p), ("gene_ptr", C.c_void_p), ("gene_loci", C.c_void_p),
+                ("tile_blob", C.c_void_p), ("tile_desc", C.c_void_p), ("tile_locus_desc", C.c_void_p),
+                ("tile_partial", C.c_void_p), ("n_tiles", C.c_int64), ("n_tile_slots", C.c_int64),
+                ("tile_max_classes", C.c_int32), ("tile_max_loci", C.c_int32), ("tile_max_items", C.c_int32),
+                ("tile_max_a_bytes", C.c_int32), ("tile_max_b_bytes", C.c_int32), ("tile_reserved", C.c_int32),
                 ("theta", C.c_void_p), ("efflen", C.c_void_p), ("acc", C.c_void_p), ("iso", C.c_void_p),
                 ("weights", C.c_void_p), ("subsets", C.c_void_p), ("wit", C.c_void_p), ("part", C.c_void_p), ("gene_hap", C.c_void_p),
                 ("gamma", C.c_void_p), ("err_log", C.c_void_p), ("scal", C.c_void_p), ("ctrl", C.c_void_p)]
@@ -78,6 +102,10 @@ SYMBOLS = {
     "gbrs_pack_get_info": (C.c_int, [C.c_void_p, C.POINTER(PackInfo)]),
     "gbrs_pack_get_array": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "gbrs_pack_free": (C.c_int, [C.c_void_p]),
+    "gbrs_tiles_create": (C.c_int, [C.c_void_p, C.POINTER(TilesParams), C.POINTER(C.c_void_p)]),
+    "gbrs_tiles_get_info": (C.c_int, [C.c_void_p, C.POINTER(TilesInfo)]),
+    "gbrs_tiles_get_array": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "gbrs_tiles_free": (C.c_int, [C.c_void_p]),
     "gbrs_em_prepare_local": (C.c_int, [C.POINTER(EmDev), C.c_void_p]),
     "gbrs_em_prepare_finish": (C.c_int, [C.POINTER(EmDev), C.c_double, C.c_void_p]),
     "gbrs_em_set_theta": (C.c_int, [C.POINTER(EmDev), C.c_void_p, C.c_void_p]),

@@ -940,6 +940,232 @@ __global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused model-4 update over TILES (include/gbrs_em.h, tile_pack.cpp): E-step weights and the count-weighted column
+// reduce of a contiguous range of classes without leaving the SM.
+//   reference: normalize_reads(READ) AlignmentPropertyMatrix.py:335-342 + sum(READ) :288-298 (and the theta multiply of
+//   EMfactory.py:204-208), i.e. everything between two theta updates except the division by the effective length.
+// One thread block walks tiles handed out by a device-side work counter (costliest first).  Per tile:
+//   stage   part A (locus list, counts, pair planes) and part B (the tile's locus-major copy) arrive in shared memory by
+//           two bulk copies (cp.async.bulk + mbarrier complete_tx); the copy of the NEXT tile's part A is issued as soon
+//           as phase 1 is through with the buffer, part B after phase 2 -- loads run under the compute of the other phases
+//   phase 0 subset-sum table rows of the tile's loci -> shared (UNIT / prepare(): popcounts, so the normaliser is nnz)
+//   phase 1 one thread per class: s = sum over its pair words of tab[l][m & 15] + tab[l][16 + (m >> 4)];  w = count / s
+//   phase 2 one thread per work item (<= 16 local class ids of one (locus, nibble bucket)): isum = sum of w[id]
+//   phase 3 one thread per (local locus, haplotype): the bucket sums that contain the haplotype, items in order ->
+//           one 64-byte partial per (tile, locus) slot; k_locus_acc adds a locus' slots in slot order.
+// No atomics on the data path and a fixed summation order everywhere: bit-reproducible.  The per-haplotype masking of
+// the two-pass column pass (4 instructions per (entry, haplotype)) is replaced by bucket sums: a partial mask costs one
+// add per non-zero nibble, and the 15 + 15 + 1 bucket sums of a locus are expanded to haplotypes once per tile.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef GBRS_TILE_THREADS
+#define GBRS_TILE_THREADS 256
+#endif
+constexpr int kTileThreads = GBRS_TILE_THREADS;
+constexpr int kTabStride = 33;  // doubles per locus row of the shared subset table (odd: rows start on different banks)
+
+struct TileSmem {  // byte offsets into dynamic shared memory; identical on host and device
+  uint32_t buf_a, buf_b, w, tab, krange, slots, misc, total;
+};
+__host__ __device__ inline TileSmem tile_smem_layout(const gbrs_em_dev& d) {
+  auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
+  TileSmem L;
+  uint32_t o = 0;
+  L.buf_a = o; o = up(o + (uint32_t) d.tile_max_a_bytes);
+  L.buf_b = o; o = up(o + (uint32_t) d.tile_max_b_bytes);
+  L.w = o; o = up(o + 8u * (uint32_t) (d.tile_max_classes + 1));
+  const uint32_t tab = 8u * (uint32_t) (kTabStride * d.tile_max_loci), isum = 8u * (uint32_t) d.tile_max_items;
+  L.tab = o; o = up(o + (tab > isum ? tab : isum));  // the table (phases 0-1) and the item sums (phases 2-3) share it
+  L.krange = o; o = up(o + 4u * 32u * (uint32_t) d.tile_max_loci);
+  L.slots = o; o = up(o + 4u * (uint32_t) d.tile_max_loci);
+  L.misc = o; o += 64;  // two mbarriers, the next tile index
+  L.total = o;
+  return L;
+}
+
+#ifdef GBRS_SIMT_EMULATION
+// host SIMT shim (tests/simt): the barrier word counts completed phases; the bulk copy is a memcpy by the issuing thread
+__device__ __forceinline__ void tile_mbar_init(uint64_t* bar) { __atomic_store_n(bar, 0ull, __ATOMIC_RELEASE); }
+__device__ __forceinline__ void tile_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  std::memcpy(dst, src, bytes);
+  __atomic_fetch_add(bar, 1ull, __ATOMIC_RELEASE);
+}
+__device__ __forceinline__ void tile_mbar_wait(uint64_t* bar, uint32_t parity) {
+  while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull) == parity) sched_yield();
+}
+#else
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tile_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+// arm the barrier with the byte count, then start the copy that completes it (global -> shared, bulk / TMA engine)
+__device__ __forceinline__ void tile_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tile_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tTILE_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TILE_DONE;\n\t"
+      "bra TILE_WAIT;\n\tTILE_DONE:\n\t}" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
+
+template <bool UNIT>
+__global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant__ gbrs_em_dev d) {
+#ifdef GBRS_SIMT_EMULATION
+  static unsigned char smem[232448] __attribute__((aligned(128)));
+#else
+  extern __shared__ __align__(128) unsigned char smem[];
+#endif
+  if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
+  const TileSmem L = tile_smem_layout(d);
+  unsigned char* const buf_a = smem + L.buf_a;
+  unsigned char* const buf_b = smem + L.buf_b;
+  double* const w = reinterpret_cast<double*>(smem + L.w);
+  double* const tab = reinterpret_cast<double*>(smem + L.tab);
+  double* const isum = tab;
+  uint16_t* const krange = reinterpret_cast<uint16_t*>(smem + L.krange);  // [key][2]: first item, one past the last
+  uint32_t* const slot_of = reinterpret_cast<uint32_t*>(smem + L.slots);
+  uint64_t* const bar_a = reinterpret_cast<uint64_t*>(smem + L.misc);
+  uint64_t* const bar_b = bar_a + 1;
+  int* const s_next = reinterpret_cast<int*>(bar_a + 2);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int n_tiles = (int) d.n_tiles;
+  const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.tile_desc);
+
+  if (tid == 0) {
+    tile_mbar_init(bar_a);
+    tile_mbar_init(bar_b);
+#ifndef GBRS_SIMT_EMULATION
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
+  }
+  __syncthreads();
+  int cur = *s_next;
+  if (cur >= n_tiles) return;
+  if (tid == 0) {
+    const uint4 td = __ldg(descs + cur);
+    const unsigned char* src = d.tile_blob + (size_t) td.x * 16;
+    tile_bulk_load(buf_a, src, td.y, bar_a);
+    tile_bulk_load(buf_b, src + td.y, td.z, bar_b);
+  }
+  uint32_t phase = 0;
+  for (;;) {
+    tile_mbar_wait(bar_a, phase);
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(buf_a);
+    const int nc = (int) hdr[GBRS_TH_CLASSES], nl = (int) hdr[GBRS_TH_LOCI], n_planes = (int) hdr[GBRS_TH_PLANES];
+    const int n_items = (int) hdr[GBRS_TH_ITEMS];
+    const uint32_t full = hdr[GBRS_TH_FLAGS], off_ents = hdr[GBRS_TH_OFF_ENTS];
+    const uint32_t* loci = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_LOCI]);
+    const uint32_t* slots = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_SLOTS]);
+    const uint16_t* nplane = reinterpret_cast<const uint16_t*>(buf_a + hdr[GBRS_TH_OFF_NPLANE]);
+    const double* cnt = reinterpret_cast<const double*>(buf_a + hdr[GBRS_TH_OFF_COUNT]);
+    const uint16_t* pw = reinterpret_cast<const uint16_t*>(buf_a + hdr[GBRS_TH_OFF_PAIRS]);
+
+    // ---- phase 0: table rows, key ranges, slots; claim the next tile ---------------------------------------------
+    if (tid == 0) *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
+    for (int i = tid; i < nl * 32; i += nthr) {
+      const int l = i >> 5, sl = i & 31;
+      tab[l * kTabStride + sl] = UNIT ? (double) __popc(sl & 15) : __ldg(d.subsets + (size_t) loci[l] * 32 + sl);
+      reinterpret_cast<uint32_t*>(krange)[i] = 0u;
+    }
+    for (int l = tid; l < nl; l += nthr) slot_of[l] = slots[l];
+    __syncthreads();
+    const int nxt = *s_next;
+
+    // ---- phase 1: class weights ----------------------------------------------------------------------------------------
+    constexpr int CPT = 4;  // classes per thread and round, interleaved for instruction-level parallelism
+    for (int base = 0; base < nc; base += CPT * nthr) {
+      double s[CPT];
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) s[u] = 0.0;
+      uint32_t off = 0;
+      for (int p = 0; p < n_planes; ++p) {
+        const int np = (int) nplane[p];
+        if (base + tid >= np) break;  // classes are sorted by width: none of this thread's classes has a pair p
+        uint32_t wd[CPT];
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) {
+          const int j = base + u * nthr + tid;
+          wd[u] = j < np ? (uint32_t) pw[off + j] : 0u;  // local locus 0 with an empty mask adds exactly 0.0
+        }
+#pragma unroll
+        for (int u = 0; u < CPT; ++u) {
+          const double* row = tab + (wd[u] >> 8) * kTabStride;
+          s[u] += row[wd[u] & 15u] + row[16 + ((wd[u] >> 4) & 15u)];
+        }
+        off += (uint32_t) np;
+      }
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) {
+        const int j = base + u * nthr + tid;
+        if (j < nc) w[j] = fast_div(cnt[j], s[u]);
+      }
+    }
+    __syncthreads();  // part A and the table are no longer read
+    if (tid == 0 && nxt < n_tiles) {
+      const uint4 td = __ldg(descs + nxt);
+      tile_bulk_load(buf_a, d.tile_blob + (size_t) td.x * 16, td.y, bar_a);
+    }
+
+    // ---- phase 2: item sums ----------------------------------------------------------------------------------------------
+    tile_mbar_wait(bar_b, phase);
+    {
+      const uint32_t* items = reinterpret_cast<const uint32_t*>(buf_b);
+      const uint16_t* ents = reinterpret_cast<const uint16_t*>(buf_b + off_ents);
+      for (int it = tid; it < n_items; it += nthr) {
+        const uint32_t word = items[it];
+        const uint32_t start = word & 0xFFFFu, len = ((word >> 16) & 15u) + 1u, key = word >> 20;
+        const uint16_t* e = ents + start;
+        double a0 = 0.0, a1 = 0.0;
+        uint32_t i = 0;
+        for (; i + 1 < len; i += 2) {
+          a0 += w[e[i]];
+          a1 += w[e[i + 1]];
+        }
+        if (i < len) a0 += w[e[i]];
+        const uint32_t prev = it > 0 ? items[it - 1] >> 20 : 0xFFFFFFFFu;
+        const uint32_t next = it + 1 < n_items ? items[it + 1] >> 20 : 0xFFFFFFFFu;
+        if (prev != key) krange[2 * key] = (uint16_t) it;
+        if (next != key) krange[2 * key + 1] = (uint16_t) (it + 1);
+        isum[it] = a0 + a1;  // (the table is dead: every thread passed the barrier after phase 1)
+      }
+    }
+    __syncthreads();  // part B is no longer read
+    if (tid == 0 && nxt < n_tiles) {
+      const uint4 td = __ldg(descs + nxt);
+      tile_bulk_load(buf_b, d.tile_blob + (size_t) td.x * 16 + td.y, td.z, bar_b);
+    }
+
+    // ---- phase 3: bucket sums -> haplotypes -> the tile's slots -------------------------------------------------------
+    for (int q = tid; q < nl * 8; q += nthr) {
+      const int l = q >> 3, h = q & 7;
+      const uint32_t* kr = reinterpret_cast<const uint32_t*>(krange) + l * 32;
+      auto seg = [&](int bucket) {
+        const uint32_t r = kr[bucket];
+        double a = 0.0;
+        for (uint32_t i = r & 0xFFFFu; i < (r >> 16); ++i) a += isum[i];
+        return a;
+      };
+      double W = ((full >> h) & 1u) ? seg(0) : 0.0;
+      const int half = (h >> 2) * 16, bit = 1 << (h & 3);
+#pragma unroll
+      for (int v = 1; v < 16; ++v)
+        if (v & bit) W += seg(half + v);
+      d.tile_partial[(size_t) slot_of[l] * GBRS_HPAD + h] = W;
+    }
+    __syncthreads();  // item sums, key ranges and slots are free for the next tile
+    if (nxt >= n_tiles) break;
+    cur = nxt;
+    phase ^= 1u;
+  }
+}
+
 // Subset-sum table rows of one locus from the 8 lanes holding its theta' (same sums, same order as k_subset_tables):
 // lane h fills slots [4h, 4h + 4) = half (h >> 2), masks 4 * (h & 3) + q, q = 0..3 (bits 0, 1 enumerate; bits 2, 3
 // are fixed by h & 3).  All 32 lanes must call (warp shuffles).
@@ -964,6 +1190,7 @@ __device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t 
 template <bool UNIT, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
   __shared__ double red[32];
+  if (blockIdx.x == 0 && threadIdx.x == 0) d.ctrl[GBRS_CTRL_TILE_NEXT] = 0;  // work counter of the next k_tile_em launch
   const bool done = !UNIT && d.ctrl[GBRS_CTRL_DONE];
   if (done && (honour_done || FUSE)) return;
   const int par = d.ctrl[GBRS_CTRL_PARITY];
@@ -1176,6 +1403,7 @@ __global__ void k_reset_ctrl(const gbrs_em_dev d) {
     d.ctrl[GBRS_CTRL_MAX_ITERS] = 0;
     d.ctrl[GBRS_CTRL_PREPARED] = 1;
     d.ctrl[GBRS_CTRL_TICKET] = 0;
+    d.ctrl[GBRS_CTRL_TILE_NEXT] = 0;
   }
 }
 
@@ -1252,6 +1480,15 @@ __global__ void __launch_bounds__(kThreads) k_alignment_counts(const gbrs_em_dev
   }
 }
 
+// arrays of the two-pass (row pass + column pass) kernels: all models without a tile layout, models 1-3 always
+int check_twopass(const gbrs_em_dev* d, const char* who) {
+  if (!d->pairs || !d->count || !d->item_desc || !d->locus_desc || !d->weights || !d->wit) {
+    gbrs_set_error(std::string(who) + ": the two-pass kernels need pairs / count / item_desc / locus_desc / weights / wit");
+    return GBRS_E_ARG;
+  }
+  return GBRS_OK;
+}
+
 int check_dev(const gbrs_em_dev* d, const char* who) {
   if (!d) { gbrs_set_error(std::string(who) + ": null descriptor"); return GBRS_E_ARG; }
   if (d->T <= 0 || d->H < 1 || d->H > GBRS_HPAD || (d->entry_bytes != 4 && d->entry_bytes != 8)) {
@@ -1260,9 +1497,15 @@ int check_dev(const gbrs_em_dev* d, const char* who) {
   // Needed by every model.  rowptr / runptr / ent_pair / ent_run are read only by models 1-3, the wide-class row pass
   // and the alignment counts (checked there): a caller that runs model 4 only need not make them resident.
   // item_off / item_order / locus_order / locus_item_ptr describe the layout for the host; no kernel reads them.
-  if (!d->pairs || !d->count || !d->item_desc || !d->locus_desc || !d->theta || !d->efflen || !d->acc ||
-      !d->iso || !d->weights || !d->subsets || !d->wit || !d->part || !d->err_log || !d->scal || !d->ctrl) {
+  if (!d->theta || !d->efflen || !d->acc || !d->iso || !d->subsets || !d->part || !d->err_log || !d->scal || !d->ctrl) {
     gbrs_set_error(std::string(who) + ": null device buffer in descriptor"); return GBRS_E_ARG;
+  }
+  if (d->tile_blob) {  // fused model-4 path: the tile arrays must be complete
+    if (!d->tile_desc || !d->tile_locus_desc || !d->tile_partial || d->n_tiles < 0 || d->tile_max_loci < 0) {
+      gbrs_set_error(std::string(who) + ": incomplete tile layout in descriptor"); return GBRS_E_ARG;
+    }
+  } else if (int rc = check_twopass(d, who)) {
+    return rc;
   }
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {
@@ -1344,6 +1587,44 @@ int launch_column(const gbrs_em_dev* d, const void* ents, bool honour_done, cuda
   return GBRS_OK;
 }
 
+// fused model-4 / prepare pass over the tile layout
+template <bool UNIT>
+int launch_tiles(const gbrs_em_dev* d, cudaStream_t s) {
+  if (d->n_tiles <= 0) return GBRS_OK;
+  const TileSmem L = tile_smem_layout(*d);
+  if (L.total > 227u * 1024u) { gbrs_set_error("tile kernel: tile caps exceed the shared memory of an SM"); return GBRS_E_LIMIT; }
+  static uint32_t attr_set = 0;  // per instantiation
+  static std::unordered_map<uint32_t, int> occ_cache;
+  if (L.total > attr_set) {
+    GBRS_CUDA(cudaFuncSetAttribute(k_tile_em<UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.total));
+    attr_set = L.total;
+  }
+  int occ;
+  auto it = occ_cache.find(L.total);
+  if (it == occ_cache.end()) {
+    occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_em<UNIT>, kTileThreads, (size_t) L.total) != cudaSuccess || occ < 1) occ = 1;
+    occ_cache[L.total] = occ;
+  } else {
+    occ = it->second;
+  }
+  int64_t grid = (int64_t) sm_count() * occ;
+  if (grid > d->n_tiles) grid = d->n_tiles;
+  k_tile_em<UNIT><<<(int) grid, kTileThreads, L.total, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_tile_em");
+  return GBRS_OK;
+}
+
+// the locus kernel reads a locus' partial sums from consecutive slots: item sums of the column pass, or tile partials
+inline gbrs_em_dev locus_view(const gbrs_em_dev* d, bool tiles) {
+  gbrs_em_dev v = *d;
+  if (tiles) {
+    v.wit = d->tile_partial;
+    v.locus_desc = d->tile_locus_desc;
+  }
+  return v;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1354,9 +1635,15 @@ extern "C" int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   k_reset_ctrl<<<1, 32, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_reset_ctrl");
-  if (int rc = launch_row_m4<true>(d, s)) return rc;
-  if (int rc = launch_column<1>(d, d->ent_cls, false, s)) return rc;
-  k_locus_acc<true, false><<<acc_grid(d), kThreads, 0, s>>>(*d, false);
+  const bool tiles = d->tile_blob != nullptr;
+  if (tiles) {
+    if (int rc = launch_tiles<true>(d, s)) return rc;
+  } else {
+    if (int rc = launch_row_m4<true>(d, s)) return rc;
+    if (int rc = launch_column<1>(d, d->ent_cls, false, s)) return rc;
+  }
+  const gbrs_em_dev lv = locus_view(d, tiles);
+  k_locus_acc<true, false><<<acc_grid(d), kThreads, 0, s>>>(lv, false);
   GBRS_LAUNCH_CHECK("k_locus_acc<unit>");
   return GBRS_OK;
 }
@@ -1507,7 +1794,10 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool honour_done = d->n_ranks <= 1 && !estep_only;
+  const bool tiles = model == 4 && d->tile_blob != nullptr;
   int rc = GBRS_OK;
+  if (!tiles && d->tile_blob)
+    if (int rc2 = check_twopass(d, "gbrs_em_launch_local")) return rc2;
   if (model != 4) {
     if (!d->gene_of || !d->gene_ptr || !d->gene_loci || !d->gene_hap || !d->gamma || !d->runptr) {
       gbrs_set_error("Group information matrix is missing.");  // AlignmentPropertyMatrix.py:345-346
@@ -1523,7 +1813,9 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   const int cg = grid_for(d->n_classes);
   cudaEvent_t* ev = prof ? &prof->ev[(size_t) prof->used * 4] : nullptr;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[0], s));
-  if (d->n_classes > 0) {
+  if (tiles) {
+    if (int rct = launch_tiles<false>(d, s)) return rct;
+  } else if (d->n_classes > 0) {
     switch (model) {
       case 4: if (int rc4 = launch_row_m4<false>(d, s)) return rc4; break;
       case 3:
@@ -1561,7 +1853,7 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
     GBRS_LAUNCH_CHECK("k_weights");
   }
   if (ev) GBRS_CUDA(cudaEventRecord(ev[1], s));
-  switch (model) {
+  if (!tiles) switch (model) {
     case 4: rc = launch_column<1>(d, d->ent_cls, honour_done, s); break;
     case 3: rc = launch_column<1>(d, d->ent_run, honour_done, s); break;
     case 2: rc = launch_column<1>(d, d->ent_pair, honour_done, s); break;
@@ -1569,8 +1861,9 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   }
   if (rc) return rc;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[2], s));
-  if (d->n_ranks <= 1 && !estep_only) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(*d, true);
-  else k_locus_acc<false, false><<<acc_grid(d), kThreads, 0, s>>>(*d, false);
+  const gbrs_em_dev lv = locus_view(d, tiles);
+  if (d->n_ranks <= 1 && !estep_only) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(lv, true);
+  else k_locus_acc<false, false><<<acc_grid(d), kThreads, 0, s>>>(lv, false);
   GBRS_LAUNCH_CHECK("k_locus_acc");
   if (ev) {
     GBRS_CUDA(cudaEventRecord(ev[3], s));

@@ -46,6 +46,20 @@ _LAZY_ARRAYS = ("rowptr", "runptr", "ent_pair", "ent_run")
 _HOST_ONLY_ARRAYS = ("item_off", "item_order", "locus_order", "locus_item_ptr")
 
 
+_TILE_ARRAYS = ("tile_blob", "tile_desc", "tile_locus_desc")
+_GENE_ARRAYS = ("gene_ptr", "gene_loci", "gene_of")
+
+
+def _tile_params_from_env():
+    """GBRS_TILE_PARAMS="max_classes=1024,max_loci=64,..." (tuning / test knob); default: the builder's defaults."""
+    out = {}
+    for item in os.environ.get("GBRS_TILE_PARAMS", "").split(","):
+        if "=" in item:
+            k, v = item.split("=", 1)
+            out[k.strip()] = int(v)
+    return out
+
+
 def _torch():
     import torch
 
@@ -144,11 +158,59 @@ class PackedPattern:
         return int(sum(a.nbytes for a in self.arrays.values()))
 
 
+class _TilesHandle:
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def __del__(self):
+        if self.handle is not None and self.lib is not None:
+            try:
+                self.lib.gbrs_tiles_free(self.handle)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self.handle = None
+
+
+class TiledPattern:
+    """Host result of gbrs_tiles_create: the tile blobs of the fused model-4 update (include/gbrs_em.h).  Views into the
+    builder's memory, like PackedPattern."""
+
+    def __init__(self, packed: PackedPattern, **params):
+        lib = _lib.load()
+        prm = _lib.TilesParams()
+        for k, v in params.items():
+            setattr(prm, k, int(v))
+        handle = C.c_void_p()
+        t0 = time.perf_counter()
+        _lib.check(lib.gbrs_tiles_create(packed._owner.handle, C.byref(prm), C.byref(handle)))
+        owner = _TilesHandle(lib, handle)
+        info = _lib.TilesInfo()
+        _lib.check(lib.gbrs_tiles_get_info(handle, C.byref(info)))
+        self.info = {f: getattr(info, f) for f, _ in _lib.TilesInfo._fields_}
+        self.arrays = {}
+        for name, dt in (("blob", np.uint8), ("tile_desc", np.uint32), ("locus_desc", np.uint32)):
+            ptr, nbytes = C.c_void_p(), C.c_int64()
+            _lib.check(lib.gbrs_tiles_get_array(handle, name.encode(), C.byref(ptr), C.byref(nbytes)))
+            if nbytes.value == 0:
+                self.arrays[name] = np.zeros(0, dtype=dt)
+            else:
+                buf = (C.c_uint8 * nbytes.value).from_address(ptr.value)
+                buf._gbrs_owner = owner
+                self.arrays[name] = np.frombuffer(buf, dtype=dt)
+        self._owner = owner
+        self.build_seconds = time.perf_counter() - t0
+
+    def nbytes(self) -> int:
+        return int(sum(a.nbytes for a in self.arrays.values()))
+
+
 class DevicePattern:
     """Packed incidence + state vectors resident on one GPU, and the `gbrs_em_dev` descriptor pointing at them."""
 
     def __init__(self, apm: APM = None, gene_of=None, hapmask=None, device=None, shard_rank=0, shard_count=1,
-                 item_len=0, packed: PackedPattern = None, pin=False):
+                 item_len=0, packed: PackedPattern = None, pin=False, tiles=None, tile_params=None):
+        """`tiles`: build the tile layout of the fused model-4 update (default: yes, unless GBRS_NO_TILES is set or a
+        class is too wide for a tile -- then the two-pass kernels serve model 4 as well)."""
         torch = _torch()
         self.device = _require_cuda(device)
         self.lib = _lib.load()
@@ -159,8 +221,20 @@ class DevicePattern:
         self.info = packed.info
         self.T, self.H = packed.T, packed.H
         self.n_ranks = shard_count
+        if tiles is None:
+            tiles = os.environ.get("GBRS_NO_TILES") is None
+        self.tiled = None
+        if tiles:
+            try:
+                self.tiled = TiledPattern(packed, **(tile_params or _tile_params_from_env()))
+            except NotImplementedError as e:  # GBRS_E_LIMIT: a class wider than a tile
+                logger.info(f"tile layout not used ({e}); model 4 runs on the two-pass kernels")
         self.host = {}
-        for k, a in packed.arrays.items():
+        arrays = dict(packed.arrays)
+        if self.tiled is not None:
+            arrays.update(tile_blob=self.tiled.arrays["blob"], tile_desc=self.tiled.arrays["tile_desc"],
+                          tile_locus_desc=self.tiled.arrays["locus_desc"])
+        for k, a in arrays.items():
             # torch has no uint32/uint64 arithmetic needs here: ship raw bytes
             t = torch.from_numpy(a.view(np.uint8))
             self.host[k] = t.pin_memory() if pin else t
@@ -182,7 +256,7 @@ class DevicePattern:
             for k, t in self.host.items():
                 if k in _HOST_ONLY_ARRAYS:
                     continue
-                is_lazy = k in _LAZY_ARRAYS and not (k == "rowptr" and self._need_rowptr)
+                is_lazy = self._is_lazy(k)
                 if is_lazy != lazy and not (self.full and not lazy):
                     continue
                 if t.numel() == 0:  # keep a valid (non-null) pointer for empty shards
@@ -193,11 +267,26 @@ class DevicePattern:
                     self.dev[k] = t.to(self.device, non_blocking=True)
                 self.h2d_bytes += t.numel()
 
+    def _is_lazy(self, k):
+        """Arrays a model-4 run does not read stay on the host until a model-1-3 update or an alignment-count call asks
+        for them.  With the tile layout that is every array of the two-pass kernels."""
+        if k in _TILE_ARRAYS or k in _GENE_ARRAYS:
+            return False
+        if self.tiled is not None:
+            return True
+        return k in _LAZY_ARRAYS and not (k == "rowptr" and self._need_rowptr)
+
     def ensure_full(self):
         """Make the arrays of models 1-3 / the alignment counts resident too (no-op once done)."""
         if not self.full:
             self.upload(lazy=True)
             self.full = True
+            if self.tiled is not None:  # work arrays of the two-pass kernels were placeholders
+                torch = _torch()
+                i = self.info
+                nw = max(i["n_classes"], i["n_pairs"], 8 * i["n_runs"] if self.packed.has_genes else 0, 1) + 8
+                self.weights = torch.zeros(nw, dtype=torch.float64, device=self.device)
+                self.wit = torch.zeros((max(i["n_items"], 1), 8), dtype=torch.float64, device=self.device)
             self._build_descriptor()
 
     def _alloc_state(self):
@@ -205,13 +294,17 @@ class DevicePattern:
         T, dv, f64 = self.T, self.device, torch.float64
         i = self.info
         nw = max(i["n_classes"], i["n_pairs"], 8 * i["n_runs"] if self.packed.has_genes else 0, 1) + 8
+        n_wit = max(i["n_items"], 1)
+        if self.tiled is not None:  # two-pass work arrays are allocated by ensure_full()
+            nw, n_wit = 8, 1
+            self.tile_partial = torch.zeros((max(self.tiled.info["n_slots"], 1), 8), dtype=f64, device=dv)
         self.theta = torch.zeros((2, T, 8), dtype=f64, device=dv)
         self.efflen = torch.ones((T, 8), dtype=f64, device=dv)
         self.acc = torch.zeros((T, 8), dtype=f64, device=dv)
         self.iso = torch.zeros((2, T), dtype=f64, device=dv)
         self.weights = torch.zeros(nw, dtype=f64, device=dv)  # trailing slots stay zero (read by padding entries)
         self.subsets = torch.zeros((T, 32), dtype=f64, device=dv)
-        self.wit = torch.zeros((max(i["n_items"], 1), 8), dtype=f64, device=dv)
+        self.wit = torch.zeros((n_wit, 8), dtype=f64, device=dv)
         self.part = torch.zeros(_lib.GBRS_PART_SLOTS, dtype=f64, device=dv)
         self.gene_hap = torch.zeros((max(i["n_gene_ids"], 1), 8), dtype=f64, device=dv)
         self.gamma = torch.zeros(T, dtype=f64, device=dv)
@@ -240,6 +333,17 @@ class DevicePattern:
             d.gene_of = d.gene_ptr = d.gene_loci = d.gene_hap = d.gamma = None
         for k in ("theta", "efflen", "acc", "iso", "weights", "subsets", "wit", "part", "err_log", "scal", "ctrl"):
             setattr(d, k, getattr(self, k).data_ptr())
+        if self.tiled is not None:
+            ti = self.tiled.info
+            for k in _TILE_ARRAYS:
+                setattr(d, k, self.dev[k].data_ptr())
+            d.tile_partial = self.tile_partial.data_ptr()
+            d.n_tiles, d.n_tile_slots = ti["n_tiles"], ti["n_slots"]
+            d.tile_max_classes, d.tile_max_loci, d.tile_max_items = ti["max_classes"], ti["max_loci"], ti["max_items"]
+            d.tile_max_a_bytes, d.tile_max_b_bytes = ti["max_part_a_bytes"], ti["max_part_b_bytes"]
+        else:
+            d.tile_blob = d.tile_desc = d.tile_locus_desc = d.tile_partial = None
+            d.n_tiles = d.n_tile_slots = 0
         self.desc = d
 
     def stream(self):

@@ -108,6 +108,62 @@ int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64
 int gbrs_pack_free(gbrs_pack_t p);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Tile layout of the fused model-4 update: the classes of a shard, ordered by their smallest
+ * locus, are cut into TILES (contiguous class ranges that touch at most `max_loci` distinct loci).  Everything a tile
+ * needs is one contiguous blob, staged into shared memory with two bulk copies:
+ *   part A  header, the tile's locus list + output slots, class counts, pair words as 16-bit (local locus | mask),
+ *           laid out in "planes" (plane p = the p-th pair of every class that has one; classes sorted by width)
+ *   part B  the tile's own locus-major copy for the M-step: 16-bit local class ids grouped by (local locus, nibble
+ *           bucket) and cut into work items of at most `item_len` ids
+ * The kernel computes the class weights (E-step) into shared memory and reduces them per (locus, haplotype) without
+ * leaving the SM -- no weight vector, no second full-size copy and no atomics; every tile writes one 64-byte partial
+ * per locus it touches into its own slot, and the locus kernel sums a locus' slots in a fixed order (bit-reproducible).
+ * Replaces, for model 4 / prepare: normalize_reads(READ) + sum(READ), AlignmentPropertyMatrix.py:288-298, 335-342.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct gbrs_tiles* gbrs_tiles_t;
+
+typedef struct {   /* 0 = default */
+  int32_t max_classes;  /* classes per tile                  (default 1024, at most 2048)           */
+  int32_t max_loci;     /* distinct loci per tile            (default 64, at most 128)              */
+  int32_t max_pairs;    /* pair words per tile               (default 3072)                         */
+  int32_t max_entries;  /* M-step entries per tile           (default 4608, at most 65535)          */
+  int32_t max_items;    /* M-step work items per tile        (default 1536)                         */
+  int32_t item_len;     /* entries per work item             (default 16, at most 16)               */
+} gbrs_tiles_params;
+
+typedef struct {
+  int64_t n_tiles;
+  int64_t n_slots;       /* 64-byte partial-sum slots = sum over tiles of their locus count */
+  int64_t blob_bytes;
+  int64_t n_entries, n_items, n_pairs, n_classes;
+  /* actual maxima over the tiles: the kernel sizes its shared memory from these */
+  int32_t max_classes, max_loci, max_items, max_part_a_bytes, max_part_b_bytes, max_planes;
+  int32_t max_slots_per_locus;
+  int32_t item_len;
+} gbrs_tiles_info;
+
+/* Builds the tile layout from a packed shard.  GBRS_E_LIMIT if a class touches more than `max_loci` loci (the caller
+ * then stays on the two-pass kernels). */
+int gbrs_tiles_create(gbrs_pack_t p, const gbrs_tiles_params* params, gbrs_tiles_t* out);
+int gbrs_tiles_get_info(gbrs_tiles_t t, gbrs_tiles_info* info);
+/* Borrowed host pointers (valid until gbrs_tiles_free):
+ *   "blob"        bytes  [blob_bytes]      the tile blobs, each starting at a multiple of 128 bytes
+ *   "tile_desc"   uint32 [n_tiles][4]      per VISITING slot (costliest tile first): blob offset / 16, part A bytes,
+ *                                          part B bytes, tile id
+ *   "locus_desc"  uint32 [T][4]            per visiting slot (most slots first): locus, first slot, one-past-last slot, 0 */
+int gbrs_tiles_get_array(gbrs_tiles_t t, const char* name, const void** ptr, int64_t* bytes);
+int gbrs_tiles_free(gbrs_tiles_t t);
+
+/* Blob header: 16 uint32 words at the start of part A (byte offsets are relative to the start of part A). */
+enum { GBRS_TH_CLASSES = 0, GBRS_TH_LOCI = 1, GBRS_TH_PLANES = 2, GBRS_TH_PAIRS = 3, GBRS_TH_ENTRIES = 4,
+       GBRS_TH_ITEMS = 5, GBRS_TH_OFF_LOCI = 6, GBRS_TH_OFF_SLOTS = 7, GBRS_TH_OFF_NPLANE = 8, GBRS_TH_OFF_COUNT = 9,
+       GBRS_TH_OFF_PAIRS = 10, GBRS_TH_A_BYTES = 11, GBRS_TH_B_BYTES = 12, GBRS_TH_OFF_ENTS = 13 /* in part B; items at 0 */,
+       GBRS_TH_FLAGS = 14, GBRS_TH_WORDS = 16 };
+/* M-step work item word: first entry (16 bits) | (entries - 1) << 16 (4 bits) | key << 20 (12 bits),
+ * key = local locus * 32 + bucket; bucket 0 = the pair hits all H haplotypes, 1..15 = value of the low mask nibble,
+ * 17..31 = 16 + value of the high mask nibble (a partial mask contributes one entry per non-zero nibble). */
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Device descriptor: every pointer is a device pointer into a caller-owned buffer.
  * ---------------------------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -147,6 +203,13 @@ typedef struct {
   const int32_t* gene_of;
   const uint32_t* gene_ptr;
   const uint32_t* gene_loci;
+  /* tile layout of the fused model-4 update (all NULL / 0: the two-pass kernels are used) */
+  const uint8_t* tile_blob;
+  const uint32_t* tile_desc;       /* [n_tiles][4] */
+  const uint32_t* tile_locus_desc; /* [T][4] */
+  double* tile_partial;            /* [n_slots][8] per-(tile, locus) partial sums */
+  int64_t n_tiles, n_tile_slots;
+  int32_t tile_max_classes, tile_max_loci, tile_max_items, tile_max_a_bytes, tile_max_b_bytes, tile_reserved;
   /* state */
   double* theta;    /* [2][T][8] ping-pong allelic expression */
   double* efflen;   /* [T][8] effective lengths (1.0 where unused / no length file) */
@@ -166,7 +229,8 @@ typedef struct {
 
 #define GBRS_PART_SLOTS 4096 /* [0, 2048): block partial sums of the isoform totals; [2048, 4096): of the error */
 enum { GBRS_CTRL_ITERS = 0, GBRS_CTRL_DONE = 1, GBRS_CTRL_ERROR = 2, GBRS_CTRL_PARITY = 3, GBRS_CTRL_MAX_ITERS = 4,
-       GBRS_CTRL_PREPARED = 5, GBRS_CTRL_TICKET = 8 /* 8, 9, 10: block tickets */, GBRS_CTRL_XEPOCH = 12 };
+       GBRS_CTRL_PREPARED = 5, GBRS_CTRL_TICKET = 8 /* 8, 9, 10: block tickets */, GBRS_CTRL_XEPOCH = 12,
+       GBRS_CTRL_TILE_NEXT = 13 /* work counter of the tile kernel, zeroed by the locus kernel */ };
 enum { GBRS_SCAL_ERR = 0, GBRS_SCAL_SUM_PREV = 1, GBRS_SCAL_TARGET = 2, GBRS_SCAL_SUM_CUR = 3 };
 
 /* theta0 from the incidence alone.  EMfactory.prepare numeric part (EMfactory.py:95-111) / EMfactory.reset (:113-138).

@@ -9,6 +9,8 @@
 
 #include "simt_shim.h"
 
+#define GBRS_SIMT_EMULATION 1  // em_kernels.cu: host stand-ins for the bulk-copy / mbarrier PTX, static "dynamic" smem
+
 using std::isfinite;
 using std::isnan;
 using std::isinf;
@@ -32,6 +34,8 @@ inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) {  // the SM count: 
   *v = e && std::atoi(e) > 0 ? std::atoi(e) : 2;
   return cudaSuccess;
 }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class K> inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
 template <class K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t) { std::memset(dst, v, n); return cudaSuccess; }

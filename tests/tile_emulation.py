@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE ONLY -- a numpy walk over the TILE layout (include/gbrs_em.h, built by gbrs_b200/csrc/tile_pack.cpp)
+doing, tile by tile, exactly what the fused model-4 kernel does: class weights from the pair planes, per-(locus, bucket)
+sums from the tile's locus-major copy, expansion of the nibble buckets to haplotypes, partial sums into slots, and the
+per-locus sum over slots.  It checks the LAYOUT (every array the kernel reads) on machines without a GPU."""
+from __future__ import annotations
+
+import numpy as np
+
+from gbrs_b200 import _lib
+
+
+def _u32(blob, off, n):
+    return blob[off:off + 4 * n].view(np.uint32)
+
+
+def tile_views(blob, desc_row):
+    a0 = int(desc_row[0]) * 16
+    hdr = _u32(blob, a0, _lib.TH_WORDS)
+    nc, nl, npl, npairs = (int(hdr[k]) for k in (_lib.TH_CLASSES, _lib.TH_LOCI, _lib.TH_PLANES, _lib.TH_PAIRS))
+    ne, ni = int(hdr[_lib.TH_ENTRIES]), int(hdr[_lib.TH_ITEMS])
+    assert int(hdr[_lib.TH_A_BYTES]) == int(desc_row[1]) and int(hdr[_lib.TH_B_BYTES]) == int(desc_row[2])
+    b0 = a0 + int(hdr[_lib.TH_A_BYTES])
+    v = dict(n_classes=nc, n_loci=nl, n_planes=npl, n_pairs=npairs, n_entries=ne, n_items=ni, full=int(hdr[_lib.TH_FLAGS]))
+    v["loci"] = _u32(blob, a0 + int(hdr[_lib.TH_OFF_LOCI]), nl)
+    v["slots"] = _u32(blob, a0 + int(hdr[_lib.TH_OFF_SLOTS]), nl)
+    o = a0 + int(hdr[_lib.TH_OFF_NPLANE])
+    v["nplane"] = blob[o:o + 2 * npl].view(np.uint16)
+    o = a0 + int(hdr[_lib.TH_OFF_COUNT])
+    v["count"] = blob[o:o + 8 * nc].view(np.float64)
+    o = a0 + int(hdr[_lib.TH_OFF_PAIRS])
+    v["pairs"] = blob[o:o + 2 * npairs].view(np.uint16)
+    v["items"] = _u32(blob, b0, ni)
+    o = b0 + int(hdr[_lib.TH_OFF_ENTS])
+    v["ents"] = blob[o:o + 2 * ne].view(np.uint16)
+    return v
+
+
+def numerator_W(tiled, theta_T8, T, unit=False):
+    """W[t][h] = sum over classes hitting (t, h) of count / normaliser, through the tile layout.  theta_T8: [T][8]."""
+    blob, desc = tiled.arrays["blob"], tiled.arrays["tile_desc"].reshape(-1, 4)
+    partial = np.zeros((tiled.info["n_slots"], 8))
+    written = np.zeros(tiled.info["n_slots"], dtype=bool)
+    sub = np.zeros((T, 32))
+    for m in range(16):
+        for b in range(4):
+            if (m >> b) & 1:
+                sub[:, m] += 1.0 if unit else theta_T8[:, b]
+                sub[:, 16 + m] += 1.0 if unit else theta_T8[:, 4 + b]
+    for row in desc[: tiled.info["n_tiles"]]:
+        v = tile_views(blob, row)
+        nc = v["n_classes"]
+        tab = sub[v["loci"]]
+        s = np.zeros(nc)
+        off = 0
+        assert v["nplane"].sum() == v["n_pairs"] and (np.diff(v["nplane"].astype(int)) <= 0).all() and v["nplane"][0] == nc
+        for p in range(v["n_planes"]):
+            n_p = int(v["nplane"][p])
+            w = v["pairs"][off:off + n_p].astype(np.int64)
+            l, m = w >> 8, w & 255
+            assert (l < v["n_loci"]).all() and (m > 0).all()
+            s[:n_p] += tab[l, m & 15] + tab[l, 16 + (m >> 4)]
+            off += n_p
+        wts = v["count"] / s
+        acc = np.zeros(v["n_loci"] * 32)
+        prev_key = -1
+        for it in v["items"]:
+            start, ln, key = int(it) & 0xFFFF, ((int(it) >> 16) & 15) + 1, int(it) >> 20
+            assert key >= prev_key and start + ln <= v["n_entries"]
+            prev_key = key
+            idx = v["ents"][start:start + ln]
+            assert (idx < nc).all()
+            acc[key] += wts[idx].sum()
+        acc = acc.reshape(v["n_loci"], 32)
+        W = np.zeros((v["n_loci"], 8))
+        for h in range(8):
+            if (v["full"] >> h) & 1:
+                W[:, h] += acc[:, 0]
+            half, bit = h >> 2, h & 3
+            for val in range(1, 16):
+                if (val >> bit) & 1:
+                    W[:, h] += acc[:, 16 * half + val]
+        assert not written[v["slots"]].any()
+        written[v["slots"]] = True
+        partial[v["slots"]] = W
+    assert written.all()
+    out = np.zeros((T, 8))
+    ld = tiled.arrays["locus_desc"].reshape(-1, 4)
+    seen = np.zeros(T, dtype=bool)
+    for t, a, b, _ in ld:
+        assert not seen[t]
+        seen[t] = True
+        out[t] = partial[a:b].sum(axis=0)
+    assert seen.all()
+    return out
