@@ -952,8 +952,9 @@ __global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(
 //   phase 0 subset-sum table rows of the tile's loci -> shared (UNIT / prepare(): popcounts, so the normaliser is nnz)
 //   phase 1 one thread per class: s = sum over its pair words of tab[l][m & 15] + tab[l][16 + (m >> 4)];  w = count / s
 //   phase 2 one thread per work item (<= 16 local class ids of one (locus, nibble bucket)): isum = sum of w[id]
-//   phase 3 one thread per (local locus, haplotype): the bucket sums that contain the haplotype, items in order ->
-//           one 64-byte partial per (tile, locus) slot; k_locus_acc adds a locus' slots in slot order.
+//   phase 3 a: the item sums of a bucket, added in item order;  b: one thread per (local locus, haplotype) adds the bucket
+//           sums that contain the haplotype -> one 64-byte partial per (tile, locus) slot; k_locus_acc adds a locus'
+//           slots in slot order.
 // No atomics on the data path and a fixed summation order everywhere: bit-reproducible.  The per-haplotype masking of
 // the two-pass column pass (4 instructions per (entry, haplotype)) is replaced by bucket sums: a partial mask costs one
 // add per non-zero nibble, and the 15 + 15 + 1 bucket sums of a locus are expanded to haplotypes once per tile.
@@ -965,7 +966,7 @@ constexpr int kTileThreads = GBRS_TILE_THREADS;
 constexpr int kTabStride = 33;  // doubles per locus row of the shared subset table (odd: rows start on different banks)
 
 struct TileSmem {  // byte offsets into dynamic shared memory; identical on host and device
-  uint32_t buf_a, buf_b, w, tab, krange, slots, misc, total;
+  uint32_t buf_a, buf_b, w, tab, isum, slots, misc, total;
 };
 __host__ __device__ inline TileSmem tile_smem_layout(const gbrs_em_dev& d) {
   auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
@@ -973,10 +974,9 @@ __host__ __device__ inline TileSmem tile_smem_layout(const gbrs_em_dev& d) {
   uint32_t o = 0;
   L.buf_a = o; o = up(o + (uint32_t) d.tile_max_a_bytes);
   L.buf_b = o; o = up(o + (uint32_t) d.tile_max_b_bytes);
-  L.w = o; o = up(o + 8u * (uint32_t) (d.tile_max_classes + 1));
-  const uint32_t tab = 8u * (uint32_t) (kTabStride * d.tile_max_loci), isum = 8u * (uint32_t) d.tile_max_items;
-  L.tab = o; o = up(o + (tab > isum ? tab : isum));  // the table (phases 0-1) and the item sums (phases 2-3) share it
-  L.krange = o; o = up(o + 4u * 32u * (uint32_t) d.tile_max_loci);
+  L.w = o; o = up(o + 8u * (uint32_t) (d.tile_max_classes + 8));  // + the always-zero slot padding ids point at
+  L.tab = o; o = up(o + 8u * (uint32_t) (kTabStride * d.tile_max_loci));  // subset table (phases 0-1), then bucket sums
+  L.isum = o; o = up(o + 8u * (uint32_t) (d.tile_max_items + 1));
   L.slots = o; o = up(o + 4u * (uint32_t) d.tile_max_loci);
   L.misc = o; o += 64;  // two mbarriers, the next tile index
   L.total = o;
@@ -1014,6 +1014,24 @@ __device__ __forceinline__ void tile_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 #endif
 
+// sum of the weights of one work item: N index words are read (possibly past the item: the packer pads the entry array),
+// the ones beyond `len` are redirected to the always-zero weight slot, all N gathers are in flight before the adds
+template <int N>
+__device__ __forceinline__ double tile_item_sum(const uint16_t* __restrict__ e, uint32_t len, const double* __restrict__ w,
+                                                uint32_t zero_slot) {
+  uint32_t idx[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) idx[i] = (uint32_t) i < len ? (uint32_t) e[i] : zero_slot;
+  double v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = w[idx[i]];
+#pragma unroll
+  for (int st = 1; st < N; st <<= 1)  // fixed tree: (0+1)+(2+3) ...
+#pragma unroll
+    for (int i = 0; i + st < N; i += 2 * st) v[i] += v[i + st];
+  return v[0];
+}
+
 template <bool UNIT>
 __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant__ gbrs_em_dev d) {
 #ifdef GBRS_SIMT_EMULATION
@@ -1027,14 +1045,15 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
   unsigned char* const buf_b = smem + L.buf_b;
   double* const w = reinterpret_cast<double*>(smem + L.w);
   double* const tab = reinterpret_cast<double*>(smem + L.tab);
-  double* const isum = tab;
-  uint16_t* const krange = reinterpret_cast<uint16_t*>(smem + L.krange);  // [key][2]: first item, one past the last
+  double* const bsum = tab;  // [local locus][32] bucket sums: the table is dead by then
+  double* const isum = reinterpret_cast<double*>(smem + L.isum);
   uint32_t* const slot_of = reinterpret_cast<uint32_t*>(smem + L.slots);
   uint64_t* const bar_a = reinterpret_cast<uint64_t*>(smem + L.misc);
   uint64_t* const bar_b = bar_a + 1;
   int* const s_next = reinterpret_cast<int*>(bar_a + 2);
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n_tiles = (int) d.n_tiles;
+  const uint32_t zero_slot = (uint32_t) d.tile_max_classes;
   const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.tile_desc);
 
   if (tid == 0) {
@@ -1044,6 +1063,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
+    w[zero_slot] = 0.0;
   }
   __syncthreads();
   int cur = *s_next;
@@ -1060,50 +1080,42 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(buf_a);
     const int nc = (int) hdr[GBRS_TH_CLASSES], nl = (int) hdr[GBRS_TH_LOCI], n_planes = (int) hdr[GBRS_TH_PLANES];
     const int n_items = (int) hdr[GBRS_TH_ITEMS];
-    const uint32_t full = hdr[GBRS_TH_FLAGS], off_ents = hdr[GBRS_TH_OFF_ENTS];
+    const uint32_t full = hdr[GBRS_TH_FLAGS], off_ents = hdr[GBRS_TH_OFF_ENTS], off_order = hdr[GBRS_TH_OFF_ORDER];
     const uint32_t* loci = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_LOCI]);
     const uint32_t* slots = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_SLOTS]);
     const uint16_t* nplane = reinterpret_cast<const uint16_t*>(buf_a + hdr[GBRS_TH_OFF_NPLANE]);
     const double* cnt = reinterpret_cast<const double*>(buf_a + hdr[GBRS_TH_OFF_COUNT]);
     const uint16_t* pw = reinterpret_cast<const uint16_t*>(buf_a + hdr[GBRS_TH_OFF_PAIRS]);
 
-    // ---- phase 0: table rows, key ranges, slots; claim the next tile ---------------------------------------------
+    // ---- phase 0: table rows and slots of the tile's loci; claim the next tile -----------------------------------
     if (tid == 0) *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
     for (int i = tid; i < nl * 32; i += nthr) {
       const int l = i >> 5, sl = i & 31;
       tab[l * kTabStride + sl] = UNIT ? (double) __popc(sl & 15) : __ldg(d.subsets + (size_t) loci[l] * 32 + sl);
-      reinterpret_cast<uint32_t*>(krange)[i] = 0u;
     }
     for (int l = tid; l < nl; l += nthr) slot_of[l] = slots[l];
     __syncthreads();
     const int nxt = *s_next;
 
-    // ---- phase 1: class weights ----------------------------------------------------------------------------------------
-    constexpr int CPT = 4;  // classes per thread and round, interleaved for instruction-level parallelism
-    for (int base = 0; base < nc; base += CPT * nthr) {
-      double s[CPT];
-#pragma unroll
-      for (int u = 0; u < CPT; ++u) s[u] = 0.0;
+    // ---- phase 1: class weights, four neighbouring classes per thread (one 64-bit load per plane) -------------------
+    for (int q = tid; 4 * q < nc; q += nthr) {
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
       uint32_t off = 0;
       for (int p = 0; p < n_planes; ++p) {
         const int np = (int) nplane[p];
-        if (base + tid >= np) break;  // classes are sorted by width: none of this thread's classes has a pair p
-        uint32_t wd[CPT];
+        if (4 * q >= np) break;  // classes are sorted by width: none of these four has a pair p
+        const uint2 v = *reinterpret_cast<const uint2*>(pw + off + 4 * q);  // padding words add exactly 0.0
+        const uint32_t wd[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
 #pragma unroll
-        for (int u = 0; u < CPT; ++u) {
-          const int j = base + u * nthr + tid;
-          wd[u] = j < np ? (uint32_t) pw[off + j] : 0u;  // local locus 0 with an empty mask adds exactly 0.0
-        }
-#pragma unroll
-        for (int u = 0; u < CPT; ++u) {
+        for (int u = 0; u < 4; ++u) {
           const double* row = tab + (wd[u] >> 8) * kTabStride;
           s[u] += row[wd[u] & 15u] + row[16 + ((wd[u] >> 4) & 15u)];
         }
-        off += (uint32_t) np;
+        off += ((uint32_t) np + 3u) & ~3u;
       }
 #pragma unroll
-      for (int u = 0; u < CPT; ++u) {
-        const int j = base + u * nthr + tid;
+      for (int u = 0; u < 4; ++u) {
+        const int j = 4 * q + u;
         if (j < nc) w[j] = fast_div(cnt[j], s[u]);
       }
     }
@@ -1113,28 +1125,37 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
       tile_bulk_load(buf_a, d.tile_blob + (size_t) td.x * 16, td.y, bar_a);
     }
 
-    // ---- phase 2: item sums ----------------------------------------------------------------------------------------------
+    // ---- phase 2: item sums (items visited longest first: the lanes of a warp see equal lengths) ------------------------
+    for (int i = tid; i < nl * 32; i += nthr) bsum[i] = 0.0;
     tile_mbar_wait(bar_b, phase);
+    const uint32_t* items = reinterpret_cast<const uint32_t*>(buf_b);
     {
-      const uint32_t* items = reinterpret_cast<const uint32_t*>(buf_b);
+      const uint16_t* order = reinterpret_cast<const uint16_t*>(buf_b + off_order);
       const uint16_t* ents = reinterpret_cast<const uint16_t*>(buf_b + off_ents);
-      for (int it = tid; it < n_items; it += nthr) {
+      for (int base = 0; base < n_items; base += nthr) {
+        const int slot = base + tid;
+        const bool valid = slot < n_items;
+        const uint32_t it = valid ? (uint32_t) order[slot] : 0u;
         const uint32_t word = items[it];
-        const uint32_t start = word & 0xFFFFu, len = ((word >> 16) & 15u) + 1u, key = word >> 20;
-        const uint16_t* e = ents + start;
-        double a0 = 0.0, a1 = 0.0;
-        uint32_t i = 0;
-        for (; i + 1 < len; i += 2) {
-          a0 += w[e[i]];
-          a1 += w[e[i + 1]];
-        }
-        if (i < len) a0 += w[e[i]];
-        const uint32_t prev = it > 0 ? items[it - 1] >> 20 : 0xFFFFFFFFu;
-        const uint32_t next = it + 1 < n_items ? items[it + 1] >> 20 : 0xFFFFFFFFu;
-        if (prev != key) krange[2 * key] = (uint16_t) it;
-        if (next != key) krange[2 * key + 1] = (uint16_t) (it + 1);
-        isum[it] = a0 + a1;  // (the table is dead: every thread passed the barrier after phase 1)
+        const uint32_t len = valid ? ((word >> 16) & 15u) + 1u : 0u;
+        const uint16_t* e = ents + (word & 0xFFFFu);
+        const uint32_t longest = __reduce_max_sync(0xFFFFFFFFu, len);
+        double a;
+        if (longest <= 2u) a = tile_item_sum<2>(e, len, w, zero_slot);
+        else if (longest <= 4u) a = tile_item_sum<4>(e, len, w, zero_slot);
+        else if (longest <= 8u) a = tile_item_sum<8>(e, len, w, zero_slot);
+        else a = tile_item_sum<16>(e, len, w, zero_slot);
+        if (valid) isum[it] = a;
       }
+    }
+    __syncthreads();
+    // ---- phase 3a: bucket sums = the item sums of one key, added in item order by the thread of the key's first item --
+    for (int it = tid; it < n_items; it += nthr) {
+      const uint32_t key = items[it] >> 20;
+      if (it > 0 && (items[it - 1] >> 20) == key) continue;
+      double a = isum[it];
+      for (int j = it + 1; j < n_items && (items[j] >> 20) == key; ++j) a += isum[j];
+      bsum[key] = a;
     }
     __syncthreads();  // part B is no longer read
     if (tid == 0 && nxt < n_tiles) {
@@ -1142,24 +1163,21 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
       tile_bulk_load(buf_b, d.tile_blob + (size_t) td.x * 16 + td.y, td.z, bar_b);
     }
 
-    // ---- phase 3: bucket sums -> haplotypes -> the tile's slots -------------------------------------------------------
+    // ---- phase 3b: buckets -> haplotypes -> the tile's slots ---------------------------------------------------------------
     for (int q = tid; q < nl * 8; q += nthr) {
       const int l = q >> 3, h = q & 7;
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(krange) + l * 32;
-      auto seg = [&](int bucket) {
-        const uint32_t r = kr[bucket];
-        double a = 0.0;
-        for (uint32_t i = r & 0xFFFFu; i < (r >> 16); ++i) a += isum[i];
-        return a;
-      };
-      double W = ((full >> h) & 1u) ? seg(0) : 0.0;
-      const int half = (h >> 2) * 16, bit = 1 << (h & 3);
+      const double* b = bsum + l * 32 + (h >> 2) * 16;
+      const int bit = h & 3;
+      double W = ((full >> h) & 1u) ? bsum[l * 32] : 0.0;
+      // the eight nibble values that contain bit `bit`, ascending
 #pragma unroll
-      for (int v = 1; v < 16; ++v)
-        if (v & bit) W += seg(half + v);
+      for (int k = 0; k < 8; ++k) {
+        const int hi = k >> bit << (bit + 1), lo = k & ((1 << bit) - 1);
+        W += b[hi | (1 << bit) | lo];
+      }
       d.tile_partial[(size_t) slot_of[l] * GBRS_HPAD + h] = W;
     }
-    __syncthreads();  // item sums, key ranges and slots are free for the next tile
+    __syncthreads();  // bucket sums, item sums and slots are free for the next tile
     if (nxt >= n_tiles) break;
     cur = nxt;
     phase ^= 1u;

@@ -37,7 +37,7 @@ struct TileStat {
   int64_t first = 0;  // index into `order` of the tile's first class
   int32_t n_classes = 0, n_loci = 0, n_pairs = 0, n_entries = 0, n_items = 0, n_planes = 0;
   int64_t a_bytes = 0, b_bytes = 0, blob_off = 0;
-  uint32_t off_loci = 0, off_slots = 0, off_nplane = 0, off_count = 0, off_pairs = 0, off_ents = 0;
+  uint32_t off_loci = 0, off_slots = 0, off_nplane = 0, off_count = 0, off_pairs = 0, off_ents = 0, off_order = 0;
 };
 
 // entries a pair word contributes to the tile's locus-major copy
@@ -55,7 +55,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
   const int maxE = q.max_entries > 0 ? q.max_entries : 4608;
   const int maxI = q.max_items > 0 ? q.max_items : 1536;
   const int ilen = q.item_len > 0 ? q.item_len : 16;
-  if (maxC > 2048 || maxL > 128 || maxE > 65535 || ilen > 16 || maxP < maxL || maxE < 2 * maxL || maxI < 2 * maxL) {
+  if (maxC > 2048 || maxL > 128 || maxE > 65535 || maxI > 65535 || ilen > 16 || maxP < maxL || maxE < 2 * maxL || maxI < 2 * maxL) {
     gbrs_set_error("gbrs_tiles_create: tile caps out of range"); return GBRS_E_ARG;
   }
   const OmpThreadsGuard omp_guard(pack_threads());
@@ -168,11 +168,14 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
       t.off_slots = (uint32_t) o;  o = align_up(o + 4 * (int64_t) t.n_loci, 16);
       t.off_nplane = (uint32_t) o; o = align_up(o + 2 * (int64_t) t.n_planes, 16);
       t.off_count = (uint32_t) o;  o = align_up(o + 8 * (int64_t) t.n_classes, 16);
-      t.off_pairs = (uint32_t) o;  o = align_up(o + 2 * (int64_t) t.n_pairs, 16);
+      // every plane is padded to a multiple of 4 words (one thread reads the words of 4 neighbouring classes at once)
+      t.off_pairs = (uint32_t) o;  o = align_up(o + 2 * ((int64_t) t.n_pairs + 3 * (int64_t) t.n_planes), 16);
       t.a_bytes = o;
       int64_t ob = align_up(4 * (int64_t) t.n_items, 16);
+      t.off_order = (uint32_t) ob;
+      ob = align_up(ob + 2 * (int64_t) t.n_items, 16);
       t.off_ents = (uint32_t) ob;
-      ob = align_up(ob + 2 * (int64_t) t.n_entries, 16);
+      ob = align_up(ob + 2 * (int64_t) t.n_entries + 32, 16);  // + 32: the item loops may read up to 15 words past an item
       t.b_bytes = ob;
       t.blob_off = blob_bytes;
       blob_bytes = align_up(blob_bytes + t.a_bytes + t.b_bytes, 128);
@@ -220,6 +223,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
         hdr[GBRS_TH_B_BYTES] = (uint32_t) t.b_bytes;
         hdr[GBRS_TH_OFF_ENTS] = t.off_ents;
         hdr[GBRS_TH_FLAGS] = full;  // the mask value that means "all haplotypes"
+        hdr[GBRS_TH_OFF_ORDER] = t.off_order;
         // locus list
         loci.clear();
         for (int64_t i = t.first; i < t.first + t.n_classes; ++i) {
@@ -246,7 +250,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
         keyed.clear();
         {
           std::vector<uint32_t> plane_off((size_t) t.n_planes + 1, 0);
-          for (int p = 0; p < t.n_planes; ++p) plane_off[p + 1] = plane_off[p] + nplane[p];
+          for (int p = 0; p < t.n_planes; ++p) plane_off[p + 1] = plane_off[p] + ((uint32_t) nplane[p] + 3u) / 4u * 4u;
           for (int j = 0; j < t.n_classes; ++j) {
             const uint32_t b = rowptr[cls[j]], e = rowptr[cls[j] + 1];
             for (uint32_t p = b; p < e; ++p) {
@@ -279,6 +283,15 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
         }
         if (ni != t.n_items) { failed = 1; continue; }
         for (size_t i = 0; i < keyed.size(); ++i) ents[i] = (uint16_t) (keyed[i] & 0xFFFFu);
+        // visiting order of the items: longest first, so that the lanes of a warp walk items of (nearly) equal length
+        uint16_t* ord = reinterpret_cast<uint16_t*>(B + t.off_order);
+        {
+          uint32_t cnt_len[17] = {0}, pos[17] = {0};  // indexed by item length 1..16
+          for (int i = 0; i < ni; ++i) ++cnt_len[((items[i] >> 16) & 15u) + 1u];
+          uint32_t running = 0;
+          for (int len = 16; len >= 1; --len) { pos[len] = running; running += cnt_len[len]; }
+          for (int i = 0; i < ni; ++i) ord[pos[((items[i] >> 16) & 15u) + 1u]++] = (uint16_t) i;
+        }
       }
     }
     if (failed) { delete R; gbrs_set_error("gbrs_tiles_create: internal inconsistency while filling the tiles"); return GBRS_E_ARG; }

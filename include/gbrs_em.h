@@ -112,9 +112,12 @@ int gbrs_pack_free(gbrs_pack_t p);
  * locus, are cut into TILES (contiguous class ranges that touch at most `max_loci` distinct loci).  Everything a tile
  * needs is one contiguous blob, staged into shared memory with two bulk copies:
  *   part A  header, the tile's locus list + output slots, class counts, pair words as 16-bit (local locus | mask),
- *           laid out in "planes" (plane p = the p-th pair of every class that has one; classes sorted by width)
- *   part B  the tile's own locus-major copy for the M-step: 16-bit local class ids grouped by (local locus, nibble
- *           bucket) and cut into work items of at most `item_len` ids
+ *           laid out in "planes" (plane p = the p-th pair of every class that has one; classes sorted by descending
+ *           width, so plane p holds classes 0 .. nplane[p]-1; every plane is padded to a multiple of 4 words with
+ *           zero words = local locus 0 with an empty mask)
+ *   part B  the tile's own locus-major copy for the M-step: work item words (sorted by key), a visiting order of the
+ *           items (uint16, longest first), and 16-bit local class ids grouped by (local locus, nibble bucket) and cut
+ *           into items of at most `item_len` ids
  * The kernel computes the class weights (E-step) into shared memory and reduces them per (locus, haplotype) without
  * leaving the SM -- no weight vector, no second full-size copy and no atomics; every tile writes one 64-byte partial
  * per locus it touches into its own slot, and the locus kernel sums a locus' slots in a fixed order (bit-reproducible).
@@ -158,7 +161,8 @@ int gbrs_tiles_free(gbrs_tiles_t t);
 enum { GBRS_TH_CLASSES = 0, GBRS_TH_LOCI = 1, GBRS_TH_PLANES = 2, GBRS_TH_PAIRS = 3, GBRS_TH_ENTRIES = 4,
        GBRS_TH_ITEMS = 5, GBRS_TH_OFF_LOCI = 6, GBRS_TH_OFF_SLOTS = 7, GBRS_TH_OFF_NPLANE = 8, GBRS_TH_OFF_COUNT = 9,
        GBRS_TH_OFF_PAIRS = 10, GBRS_TH_A_BYTES = 11, GBRS_TH_B_BYTES = 12, GBRS_TH_OFF_ENTS = 13 /* in part B; items at 0 */,
-       GBRS_TH_FLAGS = 14, GBRS_TH_WORDS = 16 };
+       GBRS_TH_FLAGS = 14 /* the mask value meaning "all haplotypes" */, GBRS_TH_OFF_ORDER = 15 /* in part B */,
+       GBRS_TH_WORDS = 16 };
 /* M-step work item word: first entry (16 bits) | (entries - 1) << 16 (4 bits) | key << 20 (12 bits),
  * key = local locus * 32 + bucket; bucket 0 = the pair hits all H haplotypes, 1..15 = value of the low mask nibble,
  * 17..31 = 16 + value of the high mask nibble (a partial mask contributes one entry per non-zero nibble). */

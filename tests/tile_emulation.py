@@ -28,8 +28,10 @@ def tile_views(blob, desc_row):
     o = a0 + int(hdr[_lib.TH_OFF_COUNT])
     v["count"] = blob[o:o + 8 * nc].view(np.float64)
     o = a0 + int(hdr[_lib.TH_OFF_PAIRS])
-    v["pairs"] = blob[o:o + 2 * npairs].view(np.uint16)
+    v["pairs"] = blob[o:o + 2 * (npairs + 3 * npl)].view(np.uint16)
     v["items"] = _u32(blob, b0, ni)
+    o = b0 + int(hdr[_lib.TH_OFF_ORDER])
+    v["order"] = blob[o:o + 2 * ni].view(np.uint16)
     o = b0 + int(hdr[_lib.TH_OFF_ENTS])
     v["ents"] = blob[o:o + 2 * ne].view(np.uint16)
     return v
@@ -59,9 +61,13 @@ def numerator_W(tiled, theta_T8, T, unit=False):
             l, m = w >> 8, w & 255
             assert (l < v["n_loci"]).all() and (m > 0).all()
             s[:n_p] += tab[l, m & 15] + tab[l, 16 + (m >> 4)]
-            off += n_p
+            pad = (n_p + 3) // 4 * 4
+            assert (v["pairs"][off + n_p:off + pad] == 0).all()  # padding words add exactly nothing
+            off += pad
         wts = v["count"] / s
         acc = np.zeros(v["n_loci"] * 32)
+        lens = ((v["items"][v["order"]] >> 16) & 15).astype(int)
+        assert sorted(v["order"].tolist()) == list(range(v["n_items"])) and (np.diff(lens) <= 0).all()
         prev_key = -1
         for it in v["items"]:
             start, ln, key = int(it) & 0xFFFF, ((int(it) >> 16) & 15) + 1, int(it) >> 20
