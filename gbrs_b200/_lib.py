@@ -61,8 +61,9 @@ class TilesInfo(C.Structure):
 
 # blob header words (include/gbrs_em.h)
 (TH_CLASSES, TH_LOCI, TH_PLANES, TH_PAIRS, TH_ENTRIES, TH_ITEMS, TH_OFF_LOCI, TH_OFF_SLOTS, TH_OFF_NPLANE, TH_OFF_COUNT,
- TH_OFF_PAIRS, TH_A_BYTES, TH_B_BYTES, TH_OFF_ENTS, TH_FLAGS, TH_OFF_ORDER) = range(16)
-TH_WORDS = 16
+ TH_OFF_PAIRS, TH_A_BYTES, TH_B_BYTES, TH_OFF_ENTS, TH_FLAGS, TH_OFF_POS, TH_RUNS, TH_OFF_RUNKEY,
+ TH_OFF_RUNFIRST) = range(19)
+TH_WORDS = 20
 CTRL_TILE_NEXT = 13
 
 

@@ -1032,6 +1032,34 @@ __device__ __forceinline__ double tile_item_sum(const uint16_t* __restrict__ e, 
   return v[0];
 }
 
+// KC consecutive pair planes of four neighbouring classes (quad q): all plane words are loaded first, then all
+// 2 * 4 * KC table values, then the adds -- one shared-memory round trip per stage instead of one per plane.
+template <int KC>
+__device__ __forceinline__ void tile_quad_planes(const uint16_t* __restrict__ pw, const uint16_t* __restrict__ nplane, int p0,
+                                                 uint32_t& off, int q, const double* __restrict__ tab, double (&s)[4]) {
+  uint2 v[KC];
+#pragma unroll
+  for (int i = 0; i < KC; ++i) {
+    v[i] = *reinterpret_cast<const uint2*>(pw + off + 4 * q);  // padding words (local locus 0, empty mask) add 0.0
+    off += ((uint32_t) nplane[p0 + i] + 3u) & ~3u;
+  }
+  double x[KC][4][2];
+#pragma unroll
+  for (int i = 0; i < KC; ++i) {
+    const uint32_t wd[4] = {v[i].x & 0xFFFFu, v[i].x >> 16, v[i].y & 0xFFFFu, v[i].y >> 16};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double* row = tab + (wd[u] >> 8) * kTabStride;
+      x[i][u][0] = row[wd[u] & 15u];
+      x[i][u][1] = row[16 + ((wd[u] >> 4) & 15u)];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < KC; ++i)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] += x[i][u][0] + x[i][u][1];
+}
+
 template <bool UNIT>
 __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant__ gbrs_em_dev d) {
 #ifdef GBRS_SIMT_EMULATION
@@ -1080,7 +1108,9 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(buf_a);
     const int nc = (int) hdr[GBRS_TH_CLASSES], nl = (int) hdr[GBRS_TH_LOCI], n_planes = (int) hdr[GBRS_TH_PLANES];
     const int n_items = (int) hdr[GBRS_TH_ITEMS];
-    const uint32_t full = hdr[GBRS_TH_FLAGS], off_ents = hdr[GBRS_TH_OFF_ENTS], off_order = hdr[GBRS_TH_OFF_ORDER];
+    const int n_runs = (int) hdr[GBRS_TH_RUNS];
+    const uint32_t full = hdr[GBRS_TH_FLAGS], off_ents = hdr[GBRS_TH_OFF_ENTS], off_pos = hdr[GBRS_TH_OFF_POS];
+    const uint32_t off_runkey = hdr[GBRS_TH_OFF_RUNKEY], off_runfirst = hdr[GBRS_TH_OFF_RUNFIRST];
     const uint32_t* loci = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_LOCI]);
     const uint32_t* slots = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_SLOTS]);
     const uint16_t* nplane = reinterpret_cast<const uint16_t*>(buf_a + hdr[GBRS_TH_OFF_NPLANE]);
@@ -1100,18 +1130,16 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
     // ---- phase 1: class weights, four neighbouring classes per thread (one 64-bit load per plane) -------------------
     for (int q = tid; 4 * q < nc; q += nthr) {
       double s[4] = {0.0, 0.0, 0.0, 0.0};
+      int width = 0;  // planes the quad's widest class (its first: classes are sorted by width) has a word in
+      while (width < n_planes && (int) nplane[width] > 4 * q) ++width;
       uint32_t off = 0;
-      for (int p = 0; p < n_planes; ++p) {
-        const int np = (int) nplane[p];
-        if (4 * q >= np) break;  // classes are sorted by width: none of these four has a pair p
-        const uint2 v = *reinterpret_cast<const uint2*>(pw + off + 4 * q);  // padding words add exactly 0.0
-        const uint32_t wd[4] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const double* row = tab + (wd[u] >> 8) * kTabStride;
-          s[u] += row[wd[u] & 15u] + row[16 + ((wd[u] >> 4) & 15u)];
+      for (int p0 = 0; p0 < width; p0 += 4) {
+        switch (width - p0) {
+          case 1: tile_quad_planes<1>(pw, nplane, p0, off, q, tab, s); break;
+          case 2: tile_quad_planes<2>(pw, nplane, p0, off, q, tab, s); break;
+          case 3: tile_quad_planes<3>(pw, nplane, p0, off, q, tab, s); break;
+          default: tile_quad_planes<4>(pw, nplane, p0, off, q, tab, s); break;
         }
-        off += ((uint32_t) np + 3u) & ~3u;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -1128,15 +1156,15 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
     // ---- phase 2: item sums (items visited longest first: the lanes of a warp see equal lengths) ------------------------
     for (int i = tid; i < nl * 32; i += nthr) bsum[i] = 0.0;
     tile_mbar_wait(bar_b, phase);
-    const uint32_t* items = reinterpret_cast<const uint32_t*>(buf_b);
     {
-      const uint16_t* order = reinterpret_cast<const uint16_t*>(buf_b + off_order);
+      const uint32_t* items = reinterpret_cast<const uint32_t*>(buf_b);
+      const uint16_t* pos = reinterpret_cast<const uint16_t*>(buf_b + off_pos);
       const uint16_t* ents = reinterpret_cast<const uint16_t*>(buf_b + off_ents);
       for (int base = 0; base < n_items; base += nthr) {
         const int slot = base + tid;
         const bool valid = slot < n_items;
-        const uint32_t it = valid ? (uint32_t) order[slot] : 0u;
-        const uint32_t word = items[it];
+        const uint32_t word = valid ? items[slot] : 0u;
+        const uint32_t at = valid ? (uint32_t) pos[slot] : 0u;
         const uint32_t len = valid ? ((word >> 16) & 15u) + 1u : 0u;
         const uint16_t* e = ents + (word & 0xFFFFu);
         const uint32_t longest = __reduce_max_sync(0xFFFFFFFFu, len);
@@ -1145,17 +1173,27 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
         else if (longest <= 4u) a = tile_item_sum<4>(e, len, w, zero_slot);
         else if (longest <= 8u) a = tile_item_sum<8>(e, len, w, zero_slot);
         else a = tile_item_sum<16>(e, len, w, zero_slot);
-        if (valid) isum[it] = a;
+        if (valid) isum[at] = a;  // item sums are kept in key order
       }
     }
     __syncthreads();
-    // ---- phase 3a: bucket sums = the item sums of one key, added in item order by the thread of the key's first item --
-    for (int it = tid; it < n_items; it += nthr) {
-      const uint32_t key = items[it] >> 20;
-      if (it > 0 && (items[it - 1] >> 20) == key) continue;
-      double a = isum[it];
-      for (int j = it + 1; j < n_items && (items[j] >> 20) == key; ++j) a += isum[j];
-      bsum[key] = a;
+    // ---- phase 3a: bucket sums: the item sums of one key, in item order ------------------------------------------------
+    {
+      const uint16_t* run_key = reinterpret_cast<const uint16_t*>(buf_b + off_runkey);
+      const uint16_t* run_first = reinterpret_cast<const uint16_t*>(buf_b + off_runfirst);
+      for (int r = tid; r < n_runs; r += nthr) {
+        int i = (int) run_first[r];
+        const int last = (int) run_first[r + 1];
+        double a0 = isum[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (++i; i + 3 < last; i += 4) {
+          a0 += isum[i];
+          a1 += isum[i + 1];
+          a2 += isum[i + 2];
+          a3 += isum[i + 3];
+        }
+        for (; i < last; ++i) a0 += isum[i];
+        bsum[run_key[r]] = (a0 + a1) + (a2 + a3);
+      }
     }
     __syncthreads();  // part B is no longer read
     if (tid == 0 && nxt < n_tiles) {

@@ -35,9 +35,10 @@ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct TileStat {
   int64_t first = 0;  // index into `order` of the tile's first class
-  int32_t n_classes = 0, n_loci = 0, n_pairs = 0, n_entries = 0, n_items = 0, n_planes = 0;
+  int32_t n_classes = 0, n_loci = 0, n_pairs = 0, n_entries = 0, n_items = 0, n_planes = 0, n_runs = 0;
   int64_t a_bytes = 0, b_bytes = 0, blob_off = 0;
-  uint32_t off_loci = 0, off_slots = 0, off_nplane = 0, off_count = 0, off_pairs = 0, off_ents = 0, off_order = 0;
+  uint32_t off_loci = 0, off_slots = 0, off_nplane = 0, off_count = 0, off_pairs = 0, off_ents = 0, off_pos = 0, off_runkey = 0,
+           off_runfirst = 0;
 };
 
 // entries a pair word contributes to the tile's locus-major copy
@@ -50,7 +51,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
   gbrs_tiles_params q{};
   if (prm) q = *prm;
   const int maxC = q.max_classes > 0 ? q.max_classes : 1024;
-  const int maxL = q.max_loci > 0 ? q.max_loci : 64;
+  const int maxL = q.max_loci > 0 ? q.max_loci : 32;
   const int maxP = q.max_pairs > 0 ? q.max_pairs : 3072;
   const int maxE = q.max_entries > 0 ? q.max_entries : 4608;
   const int maxI = q.max_items > 0 ? q.max_items : 1536;
@@ -105,7 +106,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
         }
         for (int attempt = 0; attempt < 2; ++attempt) {
           // what adding the class would cost in the current tile
-          int new_loci = 0, ent = 0, items = 0;
+          int new_loci = 0, ent = 0, items = 0, runs = 0;
           for (uint32_t p = b; p < e; ++p) {
             const uint32_t w = pairs[p], t = w & 0xFFFFFFu, m = w >> 24;
             new_loci += locus_stamp[t] != id;
@@ -120,6 +121,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
             for (int j = 0; j < nk; ++j) {
               const int cnt = key_stamp[keys[j]] == id ? key_count[keys[j]] : 0;
               items += cnt % ilen == 0;  // (two keys of one class never coincide: different buckets or loci)
+              runs += cnt == 0;
             }
           }
           const bool fits = cur.n_classes + 1 <= maxC && cur.n_loci + new_loci <= maxL && cur.n_pairs + k <= maxP &&
@@ -150,6 +152,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
           cur.n_pairs += k;
           cur.n_entries += ent;
           cur.n_items += items;
+          cur.n_runs += runs;
           cur.n_planes = std::max(cur.n_planes, k);
           break;
         }
@@ -172,8 +175,9 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
       t.off_pairs = (uint32_t) o;  o = align_up(o + 2 * ((int64_t) t.n_pairs + 3 * (int64_t) t.n_planes), 16);
       t.a_bytes = o;
       int64_t ob = align_up(4 * (int64_t) t.n_items, 16);
-      t.off_order = (uint32_t) ob;
-      ob = align_up(ob + 2 * (int64_t) t.n_items, 16);
+      t.off_pos = (uint32_t) ob;      ob = align_up(ob + 2 * (int64_t) t.n_items, 16);
+      t.off_runkey = (uint32_t) ob;   ob = align_up(ob + 2 * (int64_t) t.n_runs, 16);
+      t.off_runfirst = (uint32_t) ob; ob = align_up(ob + 2 * ((int64_t) t.n_runs + 1), 16);
       t.off_ents = (uint32_t) ob;
       ob = align_up(ob + 2 * (int64_t) t.n_entries + 32, 16);  // + 32: the item loops may read up to 15 words past an item
       t.b_bytes = ob;
@@ -201,7 +205,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
     int failed = 0;
 #pragma omp parallel
     {
-      std::vector<uint32_t> loci, cls, keyed;
+      std::vector<uint32_t> loci, cls, keyed, kitems;
 #pragma omp for schedule(dynamic, 8)
       for (int64_t u = 0; u < n_tiles; ++u) {
         const TileStat& t = tiles[u];
@@ -223,7 +227,10 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
         hdr[GBRS_TH_B_BYTES] = (uint32_t) t.b_bytes;
         hdr[GBRS_TH_OFF_ENTS] = t.off_ents;
         hdr[GBRS_TH_FLAGS] = full;  // the mask value that means "all haplotypes"
-        hdr[GBRS_TH_OFF_ORDER] = t.off_order;
+        hdr[GBRS_TH_OFF_POS] = t.off_pos;
+        hdr[GBRS_TH_RUNS] = (uint32_t) t.n_runs;
+        hdr[GBRS_TH_OFF_RUNKEY] = t.off_runkey;
+        hdr[GBRS_TH_OFF_RUNFIRST] = t.off_runfirst;
         // locus list
         loci.clear();
         for (int64_t i = t.first; i < t.first + t.n_classes; ++i) {
@@ -267,30 +274,41 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
         }
         if ((int) keyed.size() != t.n_entries) { failed = 1; continue; }
         std::sort(keyed.begin(), keyed.end());
-        uint32_t* items = reinterpret_cast<uint32_t*>(B);
+        // items in key order (scratch), runs per key
         uint16_t* ents = reinterpret_cast<uint16_t*>(B + t.off_ents);
-        int ni = 0;
+        uint16_t* run_key = reinterpret_cast<uint16_t*>(B + t.off_runkey);
+        uint16_t* run_first = reinterpret_cast<uint16_t*>(B + t.off_runfirst);
+        kitems.clear();
+        int nr = 0;
         for (size_t i = 0; i < keyed.size();) {
           const uint32_t key = keyed[i] >> 16;
           size_t j = i;
           while (j < keyed.size() && (keyed[j] >> 16) == key) ++j;
-          for (size_t s = i; s < j; s += (size_t) ilen) {
-            const uint32_t len = (uint32_t) std::min<size_t>((size_t) ilen, j - s);
-            if (ni < t.n_items) items[ni] = (uint32_t) s | ((len - 1) << 16) | (key << 20);
-            ++ni;
+          if (nr < t.n_runs) { run_key[nr] = (uint16_t) key; run_first[nr] = (uint16_t) kitems.size(); }
+          ++nr;
+          for (size_t st = i; st < j; st += (size_t) ilen) {
+            const uint32_t len = (uint32_t) std::min<size_t>((size_t) ilen, j - st);
+            kitems.push_back((uint32_t) st | ((len - 1) << 16));
           }
           i = j;
         }
-        if (ni != t.n_items) { failed = 1; continue; }
+        const int ni = (int) kitems.size();
+        if (ni != t.n_items || nr != t.n_runs) { failed = 1; continue; }
+        run_first[nr] = (uint16_t) ni;
         for (size_t i = 0; i < keyed.size(); ++i) ents[i] = (uint16_t) (keyed[i] & 0xFFFFu);
         // visiting order of the items: longest first, so that the lanes of a warp walk items of (nearly) equal length
-        uint16_t* ord = reinterpret_cast<uint16_t*>(B + t.off_order);
+        uint32_t* items = reinterpret_cast<uint32_t*>(B);
+        uint16_t* pos = reinterpret_cast<uint16_t*>(B + t.off_pos);
         {
-          uint32_t cnt_len[17] = {0}, pos[17] = {0};  // indexed by item length 1..16
-          for (int i = 0; i < ni; ++i) ++cnt_len[((items[i] >> 16) & 15u) + 1u];
+          uint32_t cnt_len[17] = {0}, at[17] = {0};  // indexed by item length 1..16
+          for (int i = 0; i < ni; ++i) ++cnt_len[((kitems[i] >> 16) & 15u) + 1u];
           uint32_t running = 0;
-          for (int len = 16; len >= 1; --len) { pos[len] = running; running += cnt_len[len]; }
-          for (int i = 0; i < ni; ++i) ord[pos[((items[i] >> 16) & 15u) + 1u]++] = (uint16_t) i;
+          for (int len = 16; len >= 1; --len) { at[len] = running; running += cnt_len[len]; }
+          for (int i = 0; i < ni; ++i) {
+            const uint32_t v = at[((kitems[i] >> 16) & 15u) + 1u]++;
+            items[v] = kitems[i];
+            pos[v] = (uint16_t) i;
+          }
         }
       }
     }

@@ -127,7 +127,7 @@ typedef struct gbrs_tiles* gbrs_tiles_t;
 
 typedef struct {   /* 0 = default */
   int32_t max_classes;  /* classes per tile                  (default 1024, at most 2048)           */
-  int32_t max_loci;     /* distinct loci per tile            (default 64, at most 128)              */
+  int32_t max_loci;     /* distinct loci per tile            (default 32, at most 128)              */
   int32_t max_pairs;    /* pair words per tile               (default 3072)                         */
   int32_t max_entries;  /* M-step entries per tile           (default 4608, at most 65535)          */
   int32_t max_items;    /* M-step work items per tile        (default 1536)                         */
@@ -157,15 +157,24 @@ int gbrs_tiles_get_info(gbrs_tiles_t t, gbrs_tiles_info* info);
 int gbrs_tiles_get_array(gbrs_tiles_t t, const char* name, const void** ptr, int64_t* bytes);
 int gbrs_tiles_free(gbrs_tiles_t t);
 
-/* Blob header: 16 uint32 words at the start of part A (byte offsets are relative to the start of part A). */
+/* Blob header: GBRS_TH_WORDS uint32 words at the start of part A (GBRS_TH_OFF_* are byte offsets relative to the start
+ * of the part they name). */
 enum { GBRS_TH_CLASSES = 0, GBRS_TH_LOCI = 1, GBRS_TH_PLANES = 2, GBRS_TH_PAIRS = 3, GBRS_TH_ENTRIES = 4,
        GBRS_TH_ITEMS = 5, GBRS_TH_OFF_LOCI = 6, GBRS_TH_OFF_SLOTS = 7, GBRS_TH_OFF_NPLANE = 8, GBRS_TH_OFF_COUNT = 9,
-       GBRS_TH_OFF_PAIRS = 10, GBRS_TH_A_BYTES = 11, GBRS_TH_B_BYTES = 12, GBRS_TH_OFF_ENTS = 13 /* in part B; items at 0 */,
-       GBRS_TH_FLAGS = 14 /* the mask value meaning "all haplotypes" */, GBRS_TH_OFF_ORDER = 15 /* in part B */,
-       GBRS_TH_WORDS = 16 };
-/* M-step work item word: first entry (16 bits) | (entries - 1) << 16 (4 bits) | key << 20 (12 bits),
- * key = local locus * 32 + bucket; bucket 0 = the pair hits all H haplotypes, 1..15 = value of the low mask nibble,
- * 17..31 = 16 + value of the high mask nibble (a partial mask contributes one entry per non-zero nibble). */
+       GBRS_TH_OFF_PAIRS = 10, GBRS_TH_A_BYTES = 11, GBRS_TH_B_BYTES = 12,
+       GBRS_TH_OFF_ENTS = 13 /* part B; the item words start at offset 0 of part B */,
+       GBRS_TH_FLAGS = 14 /* the mask value meaning "all haplotypes" */, GBRS_TH_OFF_POS = 15 /* part B */,
+       GBRS_TH_RUNS = 16, GBRS_TH_OFF_RUNKEY = 17 /* part B */, GBRS_TH_OFF_RUNFIRST = 18 /* part B */,
+       GBRS_TH_WORDS = 20 };
+/* Part B.  M-step work items are runs of at most `item_len` entries of ONE key, key = local locus * 32 + bucket;
+ * bucket 0 = the pair hits all H haplotypes, 1..15 = value of the low mask nibble, 17..31 = 16 + value of the high mask
+ * nibble (a partial mask contributes one entry per non-zero nibble).  Items are numbered in key order.
+ *   item words  uint32 [items], in VISITING order (longest item first, so the lanes of a warp see equal lengths):
+ *               first entry (16 bits) | (entries - 1) << 16
+ *   pos         uint16 [items]: the number (key order) of the item visited at that position
+ *   run_key     uint16 [runs], run_first uint16 [runs + 1]: the items run_first[r] .. run_first[r+1]-1 (key order) make up
+ *               key run_key[r]; keys without entries have no run
+ *   entries     uint16 local class ids, grouped by key */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Device descriptor: every pointer is a device pointer into a caller-owned buffer.

@@ -30,8 +30,13 @@ def tile_views(blob, desc_row):
     o = a0 + int(hdr[_lib.TH_OFF_PAIRS])
     v["pairs"] = blob[o:o + 2 * (npairs + 3 * npl)].view(np.uint16)
     v["items"] = _u32(blob, b0, ni)
-    o = b0 + int(hdr[_lib.TH_OFF_ORDER])
-    v["order"] = blob[o:o + 2 * ni].view(np.uint16)
+    o = b0 + int(hdr[_lib.TH_OFF_POS])
+    v["pos"] = blob[o:o + 2 * ni].view(np.uint16)
+    nr = int(hdr[_lib.TH_RUNS])
+    o = b0 + int(hdr[_lib.TH_OFF_RUNKEY])
+    v["run_key"] = blob[o:o + 2 * nr].view(np.uint16)
+    o = b0 + int(hdr[_lib.TH_OFF_RUNFIRST])
+    v["run_first"] = blob[o:o + 2 * (nr + 1)].view(np.uint16)
     o = b0 + int(hdr[_lib.TH_OFF_ENTS])
     v["ents"] = blob[o:o + 2 * ne].view(np.uint16)
     return v
@@ -66,16 +71,24 @@ def numerator_W(tiled, theta_T8, T, unit=False):
             off += pad
         wts = v["count"] / s
         acc = np.zeros(v["n_loci"] * 32)
-        lens = ((v["items"][v["order"]] >> 16) & 15).astype(int)
-        assert sorted(v["order"].tolist()) == list(range(v["n_items"])) and (np.diff(lens) <= 0).all()
-        prev_key = -1
-        for it in v["items"]:
-            start, ln, key = int(it) & 0xFFFF, ((int(it) >> 16) & 15) + 1, int(it) >> 20
-            assert key >= prev_key and start + ln <= v["n_entries"]
-            prev_key = key
+        ni = v["n_items"]
+        lens = ((v["items"] >> 16) & 15).astype(int) + 1
+        assert sorted(v["pos"].tolist()) == list(range(ni)) and (np.diff(lens) <= 0).all()
+        isum = np.zeros(ni)
+        covered = np.zeros(v["n_entries"], dtype=int)
+        for word, ps, ln in zip(v["items"], v["pos"], lens):
+            start = int(word) & 0xFFFF
+            assert start + ln <= v["n_entries"]
+            covered[start:start + ln] += 1
             idx = v["ents"][start:start + ln]
             assert (idx < nc).all()
-            acc[key] += wts[idx].sum()
+            isum[ps] = wts[idx].sum()
+        assert (covered == 1).all()
+        rf = v["run_first"].astype(int)
+        assert rf[0] == 0 and rf[-1] == ni and (np.diff(rf) > 0).all() and (np.diff(v["run_key"].astype(int)) > 0).all()
+        for r, key in enumerate(v["run_key"]):
+            assert key < v["n_loci"] * 32
+            acc[key] = isum[rf[r]:rf[r + 1]].sum()
         acc = acc.reshape(v["n_loci"], 32)
         W = np.zeros((v["n_loci"], 8))
         for h in range(8):
