@@ -59,11 +59,11 @@ class TilesInfo(C.Structure):
                 ("max_slots_per_locus", C.c_int32), ("item_len", C.c_int32)]
 
 
-# blob header words (include/gbrs_em.h)
-(TH_CLASSES, TH_LOCI, TH_PLANES, TH_PAIRS, TH_ENTRIES, TH_ITEMS, TH_OFF_LOCI, TH_OFF_SLOTS, TH_OFF_NPLANE, TH_OFF_COUNT,
- TH_OFF_PAIRS, TH_A_BYTES, TH_B_BYTES, TH_OFF_ENTS, TH_FLAGS, TH_OFF_POS, TH_RUNS, TH_OFF_RUNKEY,
- TH_OFF_RUNFIRST) = range(19)
-TH_WORDS = 20
+# blob header words / tile descriptor words (include/gbrs_em.h)
+(TH_CLASSES, TH_LOCI, TH_PLANES, TH_RUNS, TH_ITEMS, TH_SLICES, TH_A_BYTES, TH_FULL, TH_PAIRS, TH_ENTRIES, TH_B_BYTES,
+ TH_SELL_WORDS) = range(12)
+TH_WORDS = 12
+TD_WORDS = 16
 CTRL_TILE_NEXT = 13
 
 

@@ -945,13 +945,16 @@ __global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(
 // reduce of a contiguous range of classes without leaving the SM.
 //   reference: normalize_reads(READ) AlignmentPropertyMatrix.py:335-342 + sum(READ) :288-298 (and the theta multiply of
 //   EMfactory.py:204-208), i.e. everything between two theta updates except the division by the effective length.
-// One thread block walks tiles handed out by a device-side work counter (costliest first).  Per tile:
-//   stage   part A (locus list, counts, pair planes) and part B (the tile's locus-major copy) arrive in shared memory by
-//           two bulk copies (cp.async.bulk + mbarrier complete_tx); the copy of the NEXT tile's part A is issued as soon
-//           as phase 1 is through with the buffer, part B after phase 2 -- loads run under the compute of the other phases
+// One thread block walks tiles handed out by a device-side work counter (costliest first).  The tile's inputs are
+// streamed straight from its blob (every section is read once, fully coalesced: planes and sliced-ELL entries are laid out
+// lane-major); what the passes share lives in shared memory (~25 KB per block, so eight blocks fit an SM): the subset-sum
+// rows of the tile's loci, the class weights, the item and bucket sums.  The blob of the block's NEXT tile is prefetched
+// into L2 while the current one is worked on.  Per tile:
 //   phase 0 subset-sum table rows of the tile's loci -> shared (UNIT / prepare(): popcounts, so the normaliser is nnz)
-//   phase 1 one thread per class: s = sum over its pair words of tab[l][m & 15] + tab[l][16 + (m >> 4)];  w = count / s
-//   phase 2 one thread per work item (<= 16 local class ids of one (locus, nibble bucket)): isum = sum of w[id]
+//   phase 1 four neighbouring classes per thread: s = sum over their pair words of tab[l][m & 15] + tab[l][16 + (m >> 4)];
+//           w = count / s -> shared
+//   phase 2 one lane per work item (<= 16 local class ids of one (locus, nibble bucket)), 32 items per slice: isum = sum
+//           of w[id], all gathers of a slice in flight before the adds
 //   phase 3 a: the item sums of a bucket, added in item order;  b: one thread per (local locus, haplotype) adds the bucket
 //           sums that contain the haplotype -> one 64-byte partial per (tile, locus) slot; k_locus_acc adds a locus'
 //           slots in slot order.
@@ -962,86 +965,61 @@ __global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(
 #ifndef GBRS_TILE_THREADS
 #define GBRS_TILE_THREADS 256
 #endif
+#ifndef GBRS_TILE_MINBLOCKS
+#define GBRS_TILE_MINBLOCKS 6  // resident blocks per SM the tile kernel is compiled for (register budget)
+#endif
 constexpr int kTileThreads = GBRS_TILE_THREADS;
 constexpr int kTabStride = 33;  // doubles per locus row of the shared subset table (odd: rows start on different banks)
 
 struct TileSmem {  // byte offsets into dynamic shared memory; identical on host and device
-  uint32_t buf_a, buf_b, w, tab, isum, slots, misc, total;
+  uint32_t w, tab, isum, slots, misc, total;
 };
 __host__ __device__ inline TileSmem tile_smem_layout(const gbrs_em_dev& d) {
   auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
   TileSmem L;
   uint32_t o = 0;
-  L.buf_a = o; o = up(o + (uint32_t) d.tile_max_a_bytes);
-  L.buf_b = o; o = up(o + (uint32_t) d.tile_max_b_bytes);
   L.w = o; o = up(o + 8u * (uint32_t) (d.tile_max_classes + 8));  // + the always-zero slot padding ids point at
   L.tab = o; o = up(o + 8u * (uint32_t) (kTabStride * d.tile_max_loci));  // subset table (phases 0-1), then bucket sums
   L.isum = o; o = up(o + 8u * (uint32_t) (d.tile_max_items + 1));
   L.slots = o; o = up(o + 4u * (uint32_t) d.tile_max_loci);
-  L.misc = o; o += 64;  // two mbarriers, the next tile index
+  L.misc = o; o += 32 + 2 * 4 * GBRS_TD_WORDS;  // next tile index, two tile descriptors
   L.total = o;
   return L;
 }
 
-#ifdef GBRS_SIMT_EMULATION
-// host SIMT shim (tests/simt): the barrier word counts completed phases; the bulk copy is a memcpy by the issuing thread
-__device__ __forceinline__ void tile_mbar_init(uint64_t* bar) { __atomic_store_n(bar, 0ull, __ATOMIC_RELEASE); }
-__device__ __forceinline__ void tile_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  std::memcpy(dst, src, bytes);
-  __atomic_fetch_add(bar, 1ull, __ATOMIC_RELEASE);
-}
-__device__ __forceinline__ void tile_mbar_wait(uint64_t* bar, uint32_t parity) {
-  while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull) == parity) sched_yield();
-}
-#else
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tile_mbar_init(uint64_t* bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
-}
-// arm the barrier with the byte count, then start the copy that completes it (global -> shared, bulk / TMA engine)
-__device__ __forceinline__ void tile_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tile_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tTILE_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra TILE_DONE;\n\t"
-      "bra TILE_WAIT;\n\tTILE_DONE:\n\t}" ::"r"(smem_addr(bar)),
-      "r"(parity)
-      : "memory");
-}
+__device__ __forceinline__ void tile_prefetch_l2(const void* p, uint32_t bytes) {
+#ifndef GBRS_SIMT_EMULATION
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 #endif
+}
 
-// sum of the weights of one work item: N index words are read (possibly past the item: the packer pads the entry array),
-// the ones beyond `len` are redirected to the always-zero weight slot, all N gathers are in flight before the adds
+// sum of the weights of the entries of one lane's work item in a slice of padded length N: the N index words of the lane
+// are N coalesced 64-byte rows of the slice; all gathers are in flight before the adds (fixed tree: (0+1)+(2+3) ...)
 template <int N>
-__device__ __forceinline__ double tile_item_sum(const uint16_t* __restrict__ e, uint32_t len, const double* __restrict__ w,
-                                                uint32_t zero_slot) {
+__device__ __forceinline__ double tile_slice_sum(const uint16_t* __restrict__ e, const double* __restrict__ w) {
   uint32_t idx[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) idx[i] = (uint32_t) i < len ? (uint32_t) e[i] : zero_slot;
+  for (int i = 0; i < N; ++i) idx[i] = (uint32_t) __ldcs(e + 32 * i);
   double v[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = w[idx[i]];
 #pragma unroll
-  for (int st = 1; st < N; st <<= 1)  // fixed tree: (0+1)+(2+3) ...
+  for (int st = 1; st < N; st <<= 1)
 #pragma unroll
     for (int i = 0; i + st < N; i += 2 * st) v[i] += v[i + st];
   return v[0];
 }
 
 // KC consecutive pair planes of four neighbouring classes (quad q): all plane words are loaded first, then all
-// 2 * 4 * KC table values, then the adds -- one shared-memory round trip per stage instead of one per plane.
+// 2 * 4 * KC table values, then the adds -- one memory round trip per stage instead of one per plane.
 template <int KC>
-__device__ __forceinline__ void tile_quad_planes(const uint16_t* __restrict__ pw, const uint16_t* __restrict__ nplane, int p0,
+__device__ __forceinline__ void tile_quad_planes(const uint16_t* __restrict__ pw, const uint32_t* plane_words, int p0,
                                                  uint32_t& off, int q, const double* __restrict__ tab, double (&s)[4]) {
   uint2 v[KC];
 #pragma unroll
   for (int i = 0; i < KC; ++i) {
-    v[i] = *reinterpret_cast<const uint2*>(pw + off + 4 * q);  // padding words (local locus 0, empty mask) add 0.0
-    off += ((uint32_t) nplane[p0 + i] + 3u) & ~3u;
+    v[i] = __ldcs(reinterpret_cast<const uint2*>(pw + off + 4 * q));  // padding words (locus 0, empty mask) add 0.0
+    off += plane_words[p0 + i];
   }
   double x[KC][4][2];
 #pragma unroll
@@ -1061,129 +1039,142 @@ __device__ __forceinline__ void tile_quad_planes(const uint16_t* __restrict__ pw
 }
 
 template <bool UNIT>
-__global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant__ gbrs_em_dev d) {
+__global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(const __grid_constant__ gbrs_em_dev d,
+                                                                                const __grid_constant__ TileSmem L) {
 #ifdef GBRS_SIMT_EMULATION
   static unsigned char smem[232448] __attribute__((aligned(128)));
 #else
   extern __shared__ __align__(128) unsigned char smem[];
 #endif
   if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
-  const TileSmem L = tile_smem_layout(d);
-  unsigned char* const buf_a = smem + L.buf_a;
-  unsigned char* const buf_b = smem + L.buf_b;
   double* const w = reinterpret_cast<double*>(smem + L.w);
   double* const tab = reinterpret_cast<double*>(smem + L.tab);
   double* const bsum = tab;  // [local locus][32] bucket sums: the table is dead by then
   double* const isum = reinterpret_cast<double*>(smem + L.isum);
   uint32_t* const slot_of = reinterpret_cast<uint32_t*>(smem + L.slots);
-  uint64_t* const bar_a = reinterpret_cast<uint64_t*>(smem + L.misc);
-  uint64_t* const bar_b = bar_a + 1;
-  int* const s_next = reinterpret_cast<int*>(bar_a + 2);
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  int* const s_next = reinterpret_cast<int*>(smem + L.misc);
+  uint32_t* const s_desc = reinterpret_cast<uint32_t*>(smem + L.misc) + 8;  // [2][GBRS_TD_WORDS]
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
   const int n_tiles = (int) d.n_tiles;
-  const uint32_t zero_slot = (uint32_t) d.tile_max_classes;
-  const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.tile_desc);
 
-  if (tid == 0) {
-    tile_mbar_init(bar_a);
-    tile_mbar_init(bar_b);
-#ifndef GBRS_SIMT_EMULATION
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#endif
-    *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
-    w[zero_slot] = 0.0;
-  }
+  if (tid == 0) *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
   __syncthreads();
   int cur = *s_next;
   if (cur >= n_tiles) return;
-  if (tid == 0) {
-    const uint4 td = __ldg(descs + cur);
-    const unsigned char* src = d.tile_blob + (size_t) td.x * 16;
-    tile_bulk_load(buf_a, src, td.y, bar_a);
-    tile_bulk_load(buf_b, src + td.y, td.z, bar_b);
-  }
-  uint32_t phase = 0;
+  if (tid < GBRS_TD_WORDS) s_desc[tid] = __ldg(d.tile_desc + (size_t) cur * GBRS_TD_WORDS + tid);
+  __syncthreads();
+  int par = 0;
   for (;;) {
-    tile_mbar_wait(bar_a, phase);
-    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(buf_a);
-    const int nc = (int) hdr[GBRS_TH_CLASSES], nl = (int) hdr[GBRS_TH_LOCI], n_planes = (int) hdr[GBRS_TH_PLANES];
-    const int n_items = (int) hdr[GBRS_TH_ITEMS];
-    const int n_runs = (int) hdr[GBRS_TH_RUNS];
-    const uint32_t full = hdr[GBRS_TH_FLAGS], off_ents = hdr[GBRS_TH_OFF_ENTS], off_pos = hdr[GBRS_TH_OFF_POS];
-    const uint32_t off_runkey = hdr[GBRS_TH_OFF_RUNKEY], off_runfirst = hdr[GBRS_TH_OFF_RUNFIRST];
-    const uint32_t* loci = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_LOCI]);
-    const uint32_t* slots = reinterpret_cast<const uint32_t*>(buf_a + hdr[GBRS_TH_OFF_SLOTS]);
-    const uint16_t* nplane = reinterpret_cast<const uint16_t*>(buf_a + hdr[GBRS_TH_OFF_NPLANE]);
-    const double* cnt = reinterpret_cast<const double*>(buf_a + hdr[GBRS_TH_OFF_COUNT]);
-    const uint16_t* pw = reinterpret_cast<const uint16_t*>(buf_a + hdr[GBRS_TH_OFF_PAIRS]);
+    const uint32_t* dsc = s_desc + par * GBRS_TD_WORDS;
+    const unsigned char* const blob = d.tile_blob + (size_t) dsc[0] * 16;
+    const int nc = (int) (dsc[1] & 0xFFFFu), nl = (int) (dsc[1] >> 16);
+    const int n_planes = (int) (dsc[2] & 0xFFFFu), n_runs = (int) (dsc[2] >> 16);
+    const int n_items = (int) (dsc[3] & 0xFFFFu), n_slices = (int) (dsc[3] >> 16);
+    const uint32_t full = dsc[5];
+    const uint32_t off_loci = GBRS_TH_WORDS * 4, off_slots = dsc[8], off_nplane = dsc[9], off_count = dsc[10];
+    const uint32_t off_pairs = dsc[11];
+    const uint32_t* loci = reinterpret_cast<const uint32_t*>(blob + off_loci);
+    const uint32_t* slots = reinterpret_cast<const uint32_t*>(blob + off_slots);
+    const uint16_t* nplane = reinterpret_cast<const uint16_t*>(blob + off_nplane);
+    const double* cnt = reinterpret_cast<const double*>(blob + off_count);
+    const uint16_t* pw = reinterpret_cast<const uint16_t*>(blob + off_pairs);
+    const unsigned char* const part_b = blob + dsc[4];
+    const uint32_t off_pos = dsc[12], off_runkey = dsc[13], off_runfirst = dsc[14], off_ents = dsc[15];
 
     // ---- phase 0: table rows and slots of the tile's loci; claim the next tile -----------------------------------
-    if (tid == 0) *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
-    for (int i = tid; i < nl * 32; i += nthr) {
-      const int l = i >> 5, sl = i & 31;
-      tab[l * kTabStride + sl] = UNIT ? (double) __popc(sl & 15) : __ldg(d.subsets + (size_t) loci[l] * 32 + sl);
+    if (tid == 0) {
+      *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
+      w[nc] = 0.0;  // the slot padding entries point at
     }
-    for (int l = tid; l < nl; l += nthr) slot_of[l] = slots[l];
+    for (int i = tid; i < nl * 16; i += nthr) {  // 16 bytes of a 256-byte row per thread
+      const int l = i >> 4, c = i & 15;
+      double2 v;
+      if (UNIT) v = make_double2((double) __popc((2 * c) & 15), (double) __popc((2 * c + 1) & 15));
+      else v = ldg2(d.subsets + (size_t) __ldg(loci + l) * 32 + 2 * c);
+      tab[l * kTabStride + 2 * c] = v.x;
+      tab[l * kTabStride + 2 * c + 1] = v.y;
+    }
+    for (int l = tid; l < nl; l += nthr) slot_of[l] = __ldg(slots + l);
     __syncthreads();
     const int nxt = *s_next;
+    uint32_t next_word = 0;  // descriptor of the next tile: requested now, parked in shared memory after phase 1
+    if (tid < GBRS_TD_WORDS && nxt < n_tiles) next_word = __ldg(d.tile_desc + (size_t) nxt * GBRS_TD_WORDS + tid);
 
     // ---- phase 1: class weights, four neighbouring classes per thread (one 64-bit load per plane) -------------------
     for (int q = tid; 4 * q < nc; q += nthr) {
       double s[4] = {0.0, 0.0, 0.0, 0.0};
-      int width = 0;  // planes the quad's widest class (its first: classes are sorted by width) has a word in
-      while (width < n_planes && (int) nplane[width] > 4 * q) ++width;
+      const double2 c01 = __ldcs(reinterpret_cast<const double2*>(cnt + 4 * q));  // (the count section is padded)
+      const double2 c23 = __ldcs(reinterpret_cast<const double2*>(cnt + 4 * q) + 1);
       uint32_t off = 0;
-      for (int p0 = 0; p0 < width; p0 += 4) {
-        switch (width - p0) {
-          case 1: tile_quad_planes<1>(pw, nplane, p0, off, q, tab, s); break;
-          case 2: tile_quad_planes<2>(pw, nplane, p0, off, q, tab, s); break;
-          case 3: tile_quad_planes<3>(pw, nplane, p0, off, q, tab, s); break;
-          default: tile_quad_planes<4>(pw, nplane, p0, off, q, tab, s); break;
+      int p0 = 0;
+      while (p0 < n_planes) {
+        // sizes of up to four planes at once; planes the quad's widest class (its first) has no word in end the walk
+        uint32_t words[4];
+        int kc = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t np = p0 + i < n_planes ? (uint32_t) __ldg(nplane + p0 + i) : 0u;
+          words[i] = (np + 3u) & ~3u;
+          kc += np > (uint32_t) (4 * q);
         }
+        switch (kc) {
+          case 0: break;
+          case 1: tile_quad_planes<1>(pw, words, 0, off, q, tab, s); break;
+          case 2: tile_quad_planes<2>(pw, words, 0, off, q, tab, s); break;
+          case 3: tile_quad_planes<3>(pw, words, 0, off, q, tab, s); break;
+          default: tile_quad_planes<4>(pw, words, 0, off, q, tab, s); break;
+        }
+        if (kc < 4) break;
+        p0 += 4;
       }
+      const double c[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = 4 * q + u;
-        if (j < nc) w[j] = fast_div(cnt[j], s[u]);
+        if (j < nc) w[j] = fast_div(c[u], s[u]);
       }
     }
-    __syncthreads();  // part A and the table are no longer read
+    if (tid < GBRS_TD_WORDS) s_desc[(par ^ 1) * GBRS_TD_WORDS + tid] = next_word;
+    __syncthreads();  // the weights are complete, the table is no longer read, the next descriptor is readable
     if (tid == 0 && nxt < n_tiles) {
-      const uint4 td = __ldg(descs + nxt);
-      tile_bulk_load(buf_a, d.tile_blob + (size_t) td.x * 16, td.y, bar_a);
+      const uint32_t* nd = s_desc + (par ^ 1) * GBRS_TD_WORDS;
+      tile_prefetch_l2(d.tile_blob + (size_t) nd[0] * 16, nd[7]);
     }
 
-    // ---- phase 2: item sums (items visited longest first: the lanes of a warp see equal lengths) ------------------------
+    // ---- phase 2: item sums, one slice (32 items, sliced-ELL entries) per warp and round -------------------------------
     for (int i = tid; i < nl * 32; i += nthr) bsum[i] = 0.0;
-    tile_mbar_wait(bar_b, phase);
     {
-      const uint32_t* items = reinterpret_cast<const uint32_t*>(buf_b);
-      const uint16_t* pos = reinterpret_cast<const uint16_t*>(buf_b + off_pos);
-      const uint16_t* ents = reinterpret_cast<const uint16_t*>(buf_b + off_ents);
-      for (int base = 0; base < n_items; base += nthr) {
-        const int slot = base + tid;
-        const bool valid = slot < n_items;
-        const uint32_t word = valid ? items[slot] : 0u;
-        const uint32_t at = valid ? (uint32_t) pos[slot] : 0u;
-        const uint32_t len = valid ? ((word >> 16) & 15u) + 1u : 0u;
-        const uint16_t* e = ents + (word & 0xFFFFu);
-        const uint32_t longest = __reduce_max_sync(0xFFFFFFFFu, len);
+      const uint32_t* slices = reinterpret_cast<const uint32_t*>(part_b);
+      const uint16_t* pos = reinterpret_cast<const uint16_t*>(part_b + off_pos);
+      const uint16_t* ents = reinterpret_cast<const uint16_t*>(part_b + off_ents);
+      for (int sidx = warp; sidx < n_slices; sidx += nwarps) {
+        const uint32_t sw = __ldg(slices + sidx);
+        const int vpos = sidx * 32 + lane;
+        const uint32_t at = vpos < n_items ? (uint32_t) __ldg(pos + vpos) : 0xFFFFFFFFu;
+        const uint16_t* e = ents + (sw >> 5) + lane;
         double a;
-        if (longest <= 2u) a = tile_item_sum<2>(e, len, w, zero_slot);
-        else if (longest <= 4u) a = tile_item_sum<4>(e, len, w, zero_slot);
-        else if (longest <= 8u) a = tile_item_sum<8>(e, len, w, zero_slot);
-        else a = tile_item_sum<16>(e, len, w, zero_slot);
-        if (valid) isum[at] = a;  // item sums are kept in key order
+        switch (sw & 31u) {
+          case 1: a = tile_slice_sum<1>(e, w); break;
+          case 2: a = tile_slice_sum<2>(e, w); break;
+          case 3: a = tile_slice_sum<3>(e, w); break;
+          case 4: a = tile_slice_sum<4>(e, w); break;
+          case 6: a = tile_slice_sum<6>(e, w); break;
+          case 8: a = tile_slice_sum<8>(e, w); break;
+          case 12: a = tile_slice_sum<12>(e, w); break;
+          default: a = tile_slice_sum<16>(e, w); break;
+        }
+        if (at != 0xFFFFFFFFu) isum[at] = a;  // item sums are kept in key order
       }
     }
     __syncthreads();
     // ---- phase 3a: bucket sums: the item sums of one key, in item order ------------------------------------------------
     {
-      const uint16_t* run_key = reinterpret_cast<const uint16_t*>(buf_b + off_runkey);
-      const uint16_t* run_first = reinterpret_cast<const uint16_t*>(buf_b + off_runfirst);
+      const uint16_t* run_key = reinterpret_cast<const uint16_t*>(part_b + off_runkey);
+      const uint16_t* run_first = reinterpret_cast<const uint16_t*>(part_b + off_runfirst);
       for (int r = tid; r < n_runs; r += nthr) {
-        int i = (int) run_first[r];
-        const int last = (int) run_first[r + 1];
+        int i = (int) __ldg(run_first + r);
+        const int last = (int) __ldg(run_first + r + 1);
+        const uint32_t key = (uint32_t) __ldg(run_key + r);
         double a0 = isum[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
         for (++i; i + 3 < last; i += 4) {
           a0 += isum[i];
@@ -1192,14 +1183,10 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
           a3 += isum[i + 3];
         }
         for (; i < last; ++i) a0 += isum[i];
-        bsum[run_key[r]] = (a0 + a1) + (a2 + a3);
+        bsum[key] = (a0 + a1) + (a2 + a3);
       }
     }
-    __syncthreads();  // part B is no longer read
-    if (tid == 0 && nxt < n_tiles) {
-      const uint4 td = __ldg(descs + nxt);
-      tile_bulk_load(buf_b, d.tile_blob + (size_t) td.x * 16 + td.y, td.z, bar_b);
-    }
+    __syncthreads();
 
     // ---- phase 3b: buckets -> haplotypes -> the tile's slots ---------------------------------------------------------------
     for (int q = tid; q < nl * 8; q += nthr) {
@@ -1215,10 +1202,10 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_em(const __grid_constant_
       }
       d.tile_partial[(size_t) slot_of[l] * GBRS_HPAD + h] = W;
     }
-    __syncthreads();  // bucket sums, item sums and slots are free for the next tile
+    __syncthreads();  // bucket sums, item sums, weights and slots are free for the next tile
     if (nxt >= n_tiles) break;
     cur = nxt;
-    phase ^= 1u;
+    par ^= 1;
   }
 }
 
@@ -1666,7 +1653,7 @@ int launch_tiles(const gbrs_em_dev* d, cudaStream_t s) {
   }
   int64_t grid = (int64_t) sm_count() * occ;
   if (grid > d->n_tiles) grid = d->n_tiles;
-  k_tile_em<UNIT><<<(int) grid, kTileThreads, L.total, s>>>(*d);
+  k_tile_em<UNIT><<<(int) grid, kTileThreads, L.total, s>>>(*d, L);
   GBRS_LAUNCH_CHECK("k_tile_em");
   return GBRS_OK;
 }

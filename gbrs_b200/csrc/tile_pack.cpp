@@ -35,10 +35,9 @@ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct TileStat {
   int64_t first = 0;  // index into `order` of the tile's first class
-  int32_t n_classes = 0, n_loci = 0, n_pairs = 0, n_entries = 0, n_items = 0, n_planes = 0, n_runs = 0;
+  int32_t n_classes = 0, n_loci = 0, n_pairs = 0, n_entries = 0, n_items = 0, n_planes = 0, n_runs = 0, n_slices = 0;
   int64_t a_bytes = 0, b_bytes = 0, blob_off = 0;
-  uint32_t off_loci = 0, off_slots = 0, off_nplane = 0, off_count = 0, off_pairs = 0, off_ents = 0, off_pos = 0, off_runkey = 0,
-           off_runfirst = 0;
+  uint32_t off_loci = 0, off_slots = 0, off_a[4] = {0, 0, 0, 0}, off_b[4] = {0, 0, 0, 0};
 };
 
 // entries a pair word contributes to the tile's locus-major copy
@@ -52,11 +51,11 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
   if (prm) q = *prm;
   const int maxC = q.max_classes > 0 ? q.max_classes : 1024;
   const int maxL = q.max_loci > 0 ? q.max_loci : 32;
-  const int maxP = q.max_pairs > 0 ? q.max_pairs : 3072;
-  const int maxE = q.max_entries > 0 ? q.max_entries : 4608;
-  const int maxI = q.max_items > 0 ? q.max_items : 1536;
+  const int maxP = q.max_pairs > 0 ? q.max_pairs : 65535;   // pair words and entries are streamed, not staged:
+  const int maxE = q.max_entries > 0 ? q.max_entries : 65535; // no cap is needed beyond the 16-bit fields
+  const int maxI = q.max_items > 0 ? q.max_items : 1024;
   const int ilen = q.item_len > 0 ? q.item_len : 16;
-  if (maxC > 2048 || maxL > 128 || maxE > 65535 || maxI > 65535 || ilen > 16 || maxP < maxL || maxE < 2 * maxL || maxI < 2 * maxL) {
+  if (maxC > 2047 || maxL > 128 || maxE > 65535 || maxP > 65535 || maxI > 65535 || ilen > 16 || maxP < maxL || maxE < 2 * maxL || maxI < 2 * maxL) {
     gbrs_set_error("gbrs_tiles_create: tile caps out of range"); return GBRS_E_ARG;
   }
   const OmpThreadsGuard omp_guard(pack_threads());
@@ -161,26 +160,159 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
     }
     const int64_t n_tiles = (int64_t) tiles.size();
 
-    // ---- 3. blob geometry ------------------------------------------------------------------------------------------
-    int64_t blob_bytes = 0;
+    // ---- 3. build every tile into its own byte vector (parallel) -----------------------------------------------------
     auto* R = new gbrs_tiles();
     gbrs_tiles_info& info = R->info;
+    std::vector<std::vector<uint8_t>> bytes((size_t) n_tiles);
+    static const int kSliceLen[17] = {0, 1, 2, 3, 4, 6, 6, 8, 8, 12, 12, 12, 12, 16, 16, 16, 16};  // padded slice lengths
+    int failed = 0;
+#pragma omp parallel
+    {
+      std::vector<uint32_t> loci, cls, keyed, kitems, vis;
+#pragma omp for schedule(dynamic, 8)
+      for (int64_t u = 0; u < n_tiles; ++u) {
+        TileStat& t = tiles[u];
+        // locus list
+        loci.clear();
+        for (int64_t i = t.first; i < t.first + t.n_classes; ++i) {
+          const uint32_t c = order[i];
+          for (uint32_t p = rowptr[c]; p < rowptr[c + 1]; ++p) loci.push_back(pairs[p] & 0xFFFFFFu);
+        }
+        std::sort(loci.begin(), loci.end());
+        loci.erase(std::unique(loci.begin(), loci.end()), loci.end());
+        if ((int) loci.size() != t.n_loci) { failed = 1; continue; }
+        // classes by descending width (stable: smallest-locus order is kept inside a width)
+        cls.assign(order.begin() + t.first, order.begin() + t.first + t.n_classes);
+        std::stable_sort(cls.begin(), cls.end(), [&](uint32_t x, uint32_t y) {
+          return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
+        });
+        std::vector<uint32_t> nplane((size_t) t.n_planes, 0), plane_off((size_t) t.n_planes + 1, 0);
+        for (int j = 0; j < t.n_classes; ++j) {
+          const int k = (int) (rowptr[cls[j] + 1] - rowptr[cls[j]]);
+          for (int p = 0; p < k; ++p) ++nplane[p];
+        }
+        for (int p = 0; p < t.n_planes; ++p) plane_off[p + 1] = plane_off[p] + (nplane[p] + 3u) / 4u * 4u;
+        // part A geometry
+        const int64_t off_loci = GBRS_TH_WORDS * 4;
+        const int64_t off_slots = align_up(off_loci + 4 * (int64_t) t.n_loci, 16);
+        const int64_t off_nplane = align_up(off_slots + 4 * (int64_t) t.n_loci, 16);
+        const int64_t off_count = align_up(off_nplane + 2 * (int64_t) t.n_planes, 16);
+        const int64_t off_pairs = align_up(off_count + 8 * (int64_t) t.n_classes, 16);
+        const int64_t a_bytes = align_up(off_pairs + 2 * (int64_t) plane_off[t.n_planes], 16);
+        // the tile's locus-major copy: (key, class) sorted, cut into items, items sorted by length
+        keyed.clear();
+        std::vector<uint16_t> pw((size_t) plane_off[t.n_planes], 0);
+        for (int j = 0; j < t.n_classes; ++j) {
+          const uint32_t b = rowptr[cls[j]], e = rowptr[cls[j] + 1];
+          for (uint32_t p = b; p < e; ++p) {
+            const uint32_t w = pairs[p], loc = w & 0xFFFFFFu, m = w >> 24;
+            const uint32_t l = (uint32_t) (std::lower_bound(loci.begin(), loci.end(), loc) - loci.begin());
+            pw[plane_off[p - b] + j] = (uint16_t) ((l << 8) | m);
+            if (m == full) keyed.push_back(((l * 32u) << 16) | (uint32_t) j);
+            else {
+              if (m & 15u) keyed.push_back(((l * 32u + (m & 15u)) << 16) | (uint32_t) j);
+              if (m >> 4) keyed.push_back(((l * 32u + 16u + (m >> 4)) << 16) | (uint32_t) j);
+            }
+          }
+        }
+        if ((int) keyed.size() != t.n_entries) { failed = 1; continue; }
+        std::sort(keyed.begin(), keyed.end());
+        kitems.clear();  // key order: first entry | (len - 1) << 16
+        std::vector<uint16_t> run_key, run_first;
+        for (size_t i = 0; i < keyed.size();) {
+          const uint32_t key = keyed[i] >> 16;
+          size_t j = i;
+          while (j < keyed.size() && (keyed[j] >> 16) == key) ++j;
+          run_key.push_back((uint16_t) key);
+          run_first.push_back((uint16_t) kitems.size());
+          for (size_t st = i; st < j; st += (size_t) ilen) {
+            const uint32_t len = (uint32_t) std::min<size_t>((size_t) ilen, j - st);
+            kitems.push_back((uint32_t) st | ((len - 1) << 16));
+          }
+          i = j;
+        }
+        const int ni = (int) kitems.size(), nr = (int) run_key.size();
+        if (ni != t.n_items || nr != t.n_runs) { failed = 1; continue; }
+        run_first.push_back((uint16_t) ni);
+        vis.assign((size_t) ni, 0);  // visiting order: longest item first (stable)
+        {
+          uint32_t cnt_len[17] = {0}, at[17] = {0};
+          for (int i = 0; i < ni; ++i) ++cnt_len[((kitems[i] >> 16) & 15u) + 1u];
+          uint32_t running = 0;
+          for (int len = 16; len >= 1; --len) { at[len] = running; running += cnt_len[len]; }
+          for (int i = 0; i < ni; ++i) vis[at[((kitems[i] >> 16) & 15u) + 1u]++] = (uint32_t) i;
+        }
+        // slices of 32 items, entries transposed (entry i of the slice's lane l at offset i * 32 + l), padded with the
+        // zero slot (= local class id n_classes) up to the slice's padded length
+        const int n_slices = (ni + 31) / 32;
+        std::vector<uint32_t> slice_word((size_t) n_slices);
+        int64_t n_words = 0;
+        for (int sidx = 0; sidx < n_slices; ++sidx) {
+          const int len0 = (int) ((kitems[vis[(size_t) sidx * 32]] >> 16) & 15u) + 1;
+          const int L = kSliceLen[len0];
+          slice_word[sidx] = (uint32_t) (n_words << 5) | (uint32_t) L;
+          n_words += 32 * (int64_t) L;
+        }
+        if (n_words >= (int64_t(1) << 27)) { failed = 1; continue; }
+        const int64_t off_pos = align_up(4 * (int64_t) n_slices, 16);
+        const int64_t off_runkey = align_up(off_pos + 2 * (int64_t) ni, 16);
+        const int64_t off_runfirst = align_up(off_runkey + 2 * (int64_t) nr, 16);
+        const int64_t off_ents = align_up(off_runfirst + 2 * ((int64_t) nr + 1), 16);
+        const int64_t b_bytes = align_up(off_ents + 2 * n_words, 16);
+        std::vector<uint8_t>& out_bytes = bytes[u];
+        out_bytes.assign((size_t) (a_bytes + b_bytes), 0);
+        uint8_t* A = out_bytes.data();
+        uint8_t* B = A + a_bytes;
+        uint32_t* hdr = reinterpret_cast<uint32_t*>(A);
+        hdr[GBRS_TH_CLASSES] = (uint32_t) t.n_classes;
+        hdr[GBRS_TH_LOCI] = (uint32_t) t.n_loci;
+        hdr[GBRS_TH_PLANES] = (uint32_t) t.n_planes;
+        hdr[GBRS_TH_RUNS] = (uint32_t) nr;
+        hdr[GBRS_TH_ITEMS] = (uint32_t) ni;
+        hdr[GBRS_TH_SLICES] = (uint32_t) n_slices;
+        hdr[GBRS_TH_A_BYTES] = (uint32_t) a_bytes;
+        hdr[GBRS_TH_FULL] = full;
+        hdr[GBRS_TH_PAIRS] = (uint32_t) t.n_pairs;
+        hdr[GBRS_TH_ENTRIES] = (uint32_t) t.n_entries;
+        hdr[GBRS_TH_B_BYTES] = (uint32_t) b_bytes;
+        hdr[GBRS_TH_SELL_WORDS] = (uint32_t) n_words;
+        std::memcpy(A + off_loci, loci.data(), 4 * loci.size());
+        uint16_t* np16 = reinterpret_cast<uint16_t*>(A + off_nplane);
+        for (int p = 0; p < t.n_planes; ++p) np16[p] = (uint16_t) nplane[p];
+        double* cnt = reinterpret_cast<double*>(A + off_count);
+        for (int j = 0; j < t.n_classes; ++j) cnt[j] = count[cls[j]];
+        std::memcpy(A + off_pairs, pw.data(), 2 * pw.size());
+        std::memcpy(B, slice_word.data(), 4 * slice_word.size());
+        uint16_t* pos = reinterpret_cast<uint16_t*>(B + off_pos);
+        for (int v = 0; v < ni; ++v) pos[v] = (uint16_t) vis[v];
+        std::memcpy(B + off_runkey, run_key.data(), 2 * run_key.size());
+        std::memcpy(B + off_runfirst, run_first.data(), 2 * run_first.size());
+        uint16_t* ents = reinterpret_cast<uint16_t*>(B + off_ents);
+        for (int sidx = 0; sidx < n_slices; ++sidx) {
+          const int L = (int) (slice_word[sidx] & 31u);
+          uint16_t* base = ents + (slice_word[sidx] >> 5);
+          for (int lane = 0; lane < 32; ++lane) {
+            const int v = sidx * 32 + lane;
+            uint32_t st = 0, len = 0;
+            if (v < ni) { st = kitems[vis[v]] & 0xFFFFu; len = ((kitems[vis[v]] >> 16) & 15u) + 1u; }
+            for (int i = 0; i < L; ++i)
+              base[i * 32 + lane] = (uint32_t) i < len ? (uint16_t) (keyed[st + i] & 0xFFFFu) : (uint16_t) t.n_classes;
+          }
+        }
+        t.a_bytes = a_bytes;
+        t.b_bytes = b_bytes;
+        t.n_slices = n_slices;
+        t.off_loci = (uint32_t) off_loci;
+        t.off_slots = (uint32_t) off_slots;
+        t.off_a[0] = (uint32_t) off_slots; t.off_a[1] = (uint32_t) off_nplane; t.off_a[2] = (uint32_t) off_count; t.off_a[3] = (uint32_t) off_pairs;
+        t.off_b[0] = (uint32_t) off_pos; t.off_b[1] = (uint32_t) off_runkey; t.off_b[2] = (uint32_t) off_runfirst; t.off_b[3] = (uint32_t) off_ents;
+      }
+    }
+    if (failed) { delete R; gbrs_set_error("gbrs_tiles_create: internal inconsistency while filling the tiles"); return GBRS_E_ARG; }
+
+    // ---- 4. concatenate ------------------------------------------------------------------------------------------------
+    int64_t blob_bytes = 0;
     for (TileStat& t : tiles) {
-      int64_t o = GBRS_TH_WORDS * 4;
-      t.off_loci = (uint32_t) o;   o = align_up(o + 4 * (int64_t) t.n_loci, 16);
-      t.off_slots = (uint32_t) o;  o = align_up(o + 4 * (int64_t) t.n_loci, 16);
-      t.off_nplane = (uint32_t) o; o = align_up(o + 2 * (int64_t) t.n_planes, 16);
-      t.off_count = (uint32_t) o;  o = align_up(o + 8 * (int64_t) t.n_classes, 16);
-      // every plane is padded to a multiple of 4 words (one thread reads the words of 4 neighbouring classes at once)
-      t.off_pairs = (uint32_t) o;  o = align_up(o + 2 * ((int64_t) t.n_pairs + 3 * (int64_t) t.n_planes), 16);
-      t.a_bytes = o;
-      int64_t ob = align_up(4 * (int64_t) t.n_items, 16);
-      t.off_pos = (uint32_t) ob;      ob = align_up(ob + 2 * (int64_t) t.n_items, 16);
-      t.off_runkey = (uint32_t) ob;   ob = align_up(ob + 2 * (int64_t) t.n_runs, 16);
-      t.off_runfirst = (uint32_t) ob; ob = align_up(ob + 2 * ((int64_t) t.n_runs + 1), 16);
-      t.off_ents = (uint32_t) ob;
-      ob = align_up(ob + 2 * (int64_t) t.n_entries + 32, 16);  // + 32: the item loops may read up to 15 words past an item
-      t.b_bytes = ob;
       t.blob_off = blob_bytes;
       blob_bytes = align_up(blob_bytes + t.a_bytes + t.b_bytes, 128);
       info.max_classes = std::max(info.max_classes, t.n_classes);
@@ -199,120 +331,15 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
     info.n_tiles = n_tiles;
     info.blob_bytes = blob_bytes;
     info.item_len = ilen;
-    par_fill(R->blob, (size_t) blob_bytes, (uint8_t) 0);
-
-    // ---- 4. fill every tile (parallel); slots are assigned afterwards ---------------------------------------------------
-    int failed = 0;
-#pragma omp parallel
-    {
-      std::vector<uint32_t> loci, cls, keyed, kitems;
-#pragma omp for schedule(dynamic, 8)
-      for (int64_t u = 0; u < n_tiles; ++u) {
-        const TileStat& t = tiles[u];
-        uint8_t* A = R->blob.data() + t.blob_off;
-        uint8_t* B = A + t.a_bytes;
-        uint32_t* hdr = reinterpret_cast<uint32_t*>(A);
-        hdr[GBRS_TH_CLASSES] = (uint32_t) t.n_classes;
-        hdr[GBRS_TH_LOCI] = (uint32_t) t.n_loci;
-        hdr[GBRS_TH_PLANES] = (uint32_t) t.n_planes;
-        hdr[GBRS_TH_PAIRS] = (uint32_t) t.n_pairs;
-        hdr[GBRS_TH_ENTRIES] = (uint32_t) t.n_entries;
-        hdr[GBRS_TH_ITEMS] = (uint32_t) t.n_items;
-        hdr[GBRS_TH_OFF_LOCI] = t.off_loci;
-        hdr[GBRS_TH_OFF_SLOTS] = t.off_slots;
-        hdr[GBRS_TH_OFF_NPLANE] = t.off_nplane;
-        hdr[GBRS_TH_OFF_COUNT] = t.off_count;
-        hdr[GBRS_TH_OFF_PAIRS] = t.off_pairs;
-        hdr[GBRS_TH_A_BYTES] = (uint32_t) t.a_bytes;
-        hdr[GBRS_TH_B_BYTES] = (uint32_t) t.b_bytes;
-        hdr[GBRS_TH_OFF_ENTS] = t.off_ents;
-        hdr[GBRS_TH_FLAGS] = full;  // the mask value that means "all haplotypes"
-        hdr[GBRS_TH_OFF_POS] = t.off_pos;
-        hdr[GBRS_TH_RUNS] = (uint32_t) t.n_runs;
-        hdr[GBRS_TH_OFF_RUNKEY] = t.off_runkey;
-        hdr[GBRS_TH_OFF_RUNFIRST] = t.off_runfirst;
-        // locus list
-        loci.clear();
-        for (int64_t i = t.first; i < t.first + t.n_classes; ++i) {
-          const uint32_t c = order[i];
-          for (uint32_t p = rowptr[c]; p < rowptr[c + 1]; ++p) loci.push_back(pairs[p] & 0xFFFFFFu);
-        }
-        std::sort(loci.begin(), loci.end());
-        loci.erase(std::unique(loci.begin(), loci.end()), loci.end());
-        if ((int) loci.size() != t.n_loci) { failed = 1; continue; }
-        std::memcpy(A + t.off_loci, loci.data(), 4 * loci.size());
-        // classes by descending width (stable: smallest-locus order is kept inside a width)
-        cls.assign(order.begin() + t.first, order.begin() + t.first + t.n_classes);
-        std::stable_sort(cls.begin(), cls.end(), [&](uint32_t x, uint32_t y) {
-          return rowptr[x + 1] - rowptr[x] > rowptr[y + 1] - rowptr[y];
-        });
-        uint16_t* nplane = reinterpret_cast<uint16_t*>(A + t.off_nplane);
-        double* cnt = reinterpret_cast<double*>(A + t.off_count);
-        uint16_t* pw = reinterpret_cast<uint16_t*>(A + t.off_pairs);
-        for (int j = 0; j < t.n_classes; ++j) {
-          const int k = (int) (rowptr[cls[j] + 1] - rowptr[cls[j]]);
-          for (int p = 0; p < k; ++p) ++nplane[p];
-          cnt[j] = count[cls[j]];
-        }
-        keyed.clear();
-        {
-          std::vector<uint32_t> plane_off((size_t) t.n_planes + 1, 0);
-          for (int p = 0; p < t.n_planes; ++p) plane_off[p + 1] = plane_off[p] + ((uint32_t) nplane[p] + 3u) / 4u * 4u;
-          for (int j = 0; j < t.n_classes; ++j) {
-            const uint32_t b = rowptr[cls[j]], e = rowptr[cls[j] + 1];
-            for (uint32_t p = b; p < e; ++p) {
-              const uint32_t w = pairs[p], loc = w & 0xFFFFFFu, m = w >> 24;
-              const uint32_t l = (uint32_t) (std::lower_bound(loci.begin(), loci.end(), loc) - loci.begin());
-              pw[plane_off[p - b] + j] = (uint16_t) ((l << 8) | m);
-              if (m == full) keyed.push_back(((l * 32u) << 16) | (uint32_t) j);
-              else {
-                if (m & 15u) keyed.push_back(((l * 32u + (m & 15u)) << 16) | (uint32_t) j);
-                if (m >> 4) keyed.push_back(((l * 32u + 16u + (m >> 4)) << 16) | (uint32_t) j);
-              }
-            }
-          }
-        }
-        if ((int) keyed.size() != t.n_entries) { failed = 1; continue; }
-        std::sort(keyed.begin(), keyed.end());
-        // items in key order (scratch), runs per key
-        uint16_t* ents = reinterpret_cast<uint16_t*>(B + t.off_ents);
-        uint16_t* run_key = reinterpret_cast<uint16_t*>(B + t.off_runkey);
-        uint16_t* run_first = reinterpret_cast<uint16_t*>(B + t.off_runfirst);
-        kitems.clear();
-        int nr = 0;
-        for (size_t i = 0; i < keyed.size();) {
-          const uint32_t key = keyed[i] >> 16;
-          size_t j = i;
-          while (j < keyed.size() && (keyed[j] >> 16) == key) ++j;
-          if (nr < t.n_runs) { run_key[nr] = (uint16_t) key; run_first[nr] = (uint16_t) kitems.size(); }
-          ++nr;
-          for (size_t st = i; st < j; st += (size_t) ilen) {
-            const uint32_t len = (uint32_t) std::min<size_t>((size_t) ilen, j - st);
-            kitems.push_back((uint32_t) st | ((len - 1) << 16));
-          }
-          i = j;
-        }
-        const int ni = (int) kitems.size();
-        if (ni != t.n_items || nr != t.n_runs) { failed = 1; continue; }
-        run_first[nr] = (uint16_t) ni;
-        for (size_t i = 0; i < keyed.size(); ++i) ents[i] = (uint16_t) (keyed[i] & 0xFFFFu);
-        // visiting order of the items: longest first, so that the lanes of a warp walk items of (nearly) equal length
-        uint32_t* items = reinterpret_cast<uint32_t*>(B);
-        uint16_t* pos = reinterpret_cast<uint16_t*>(B + t.off_pos);
-        {
-          uint32_t cnt_len[17] = {0}, at[17] = {0};  // indexed by item length 1..16
-          for (int i = 0; i < ni; ++i) ++cnt_len[((kitems[i] >> 16) & 15u) + 1u];
-          uint32_t running = 0;
-          for (int len = 16; len >= 1; --len) { at[len] = running; running += cnt_len[len]; }
-          for (int i = 0; i < ni; ++i) {
-            const uint32_t v = at[((kitems[i] >> 16) & 15u) + 1u]++;
-            items[v] = kitems[i];
-            pos[v] = (uint16_t) i;
-          }
-        }
-      }
+    R->blob.resize((size_t) blob_bytes);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t u = 0; u < n_tiles; ++u) {
+      uint8_t* dst = R->blob.data() + tiles[u].blob_off;
+      std::memcpy(dst, bytes[u].data(), bytes[u].size());
+      const int64_t end = u + 1 < n_tiles ? tiles[u + 1].blob_off : blob_bytes;
+      std::memset(dst + bytes[u].size(), 0, (size_t) (end - tiles[u].blob_off) - bytes[u].size());
+      std::vector<uint8_t>().swap(bytes[u]);
     }
-    if (failed) { delete R; gbrs_set_error("gbrs_tiles_create: internal inconsistency while filling the tiles"); return GBRS_E_ARG; }
 
     // ---- 5. output slots, locus-major; locus descriptors ---------------------------------------------------------------
     std::vector<uint32_t> slot_ptr((size_t) T + 1, 0);
@@ -351,13 +378,19 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
       std::iota(vo.begin(), vo.end(), 0u);
       auto cost = [&](uint32_t u) { return (int64_t) tiles[u].n_pairs * 2 + tiles[u].n_entries + 4 * tiles[u].n_items + 8 * tiles[u].n_loci; };
       std::stable_sort(vo.begin(), vo.end(), [&](uint32_t x, uint32_t y) { return cost(x) > cost(y); });
-      R->tile_desc.assign((size_t) std::max<int64_t>(n_tiles, 1) * 4, 0);
+      R->tile_desc.assign((size_t) std::max<int64_t>(n_tiles, 1) * GBRS_TD_WORDS, 0);
       for (int64_t i = 0; i < n_tiles; ++i) {
         const TileStat& t = tiles[vo[i]];
-        R->tile_desc[4 * (size_t) i + 0] = (uint32_t) (t.blob_off / 16);
-        R->tile_desc[4 * (size_t) i + 1] = (uint32_t) t.a_bytes;
-        R->tile_desc[4 * (size_t) i + 2] = (uint32_t) t.b_bytes;
-        R->tile_desc[4 * (size_t) i + 3] = vo[i];
+        uint32_t* dsc = R->tile_desc.data() + GBRS_TD_WORDS * (size_t) i;
+        dsc[0] = (uint32_t) (t.blob_off / 16);
+        dsc[1] = (uint32_t) t.n_classes | ((uint32_t) t.n_loci << 16);
+        dsc[2] = (uint32_t) t.n_planes | ((uint32_t) t.n_runs << 16);
+        dsc[3] = (uint32_t) t.n_items | ((uint32_t) t.n_slices << 16);
+        dsc[4] = (uint32_t) t.a_bytes;
+        dsc[5] = full;
+        dsc[6] = vo[i];
+        dsc[7] = (uint32_t) (t.a_bytes + t.b_bytes);
+        for (int k = 0; k < 4; ++k) { dsc[8 + k] = t.off_a[k]; dsc[12 + k] = t.off_b[k]; }
       }
     }
     *out = R;

@@ -126,11 +126,11 @@ int gbrs_pack_free(gbrs_pack_t p);
 typedef struct gbrs_tiles* gbrs_tiles_t;
 
 typedef struct {   /* 0 = default */
-  int32_t max_classes;  /* classes per tile                  (default 1024, at most 2048)           */
+  int32_t max_classes;  /* classes per tile                  (default 1024, at most 2047)           */
   int32_t max_loci;     /* distinct loci per tile            (default 32, at most 128)              */
-  int32_t max_pairs;    /* pair words per tile               (default 3072)                         */
-  int32_t max_entries;  /* M-step entries per tile           (default 4608, at most 65535)          */
-  int32_t max_items;    /* M-step work items per tile        (default 1536)                         */
+  int32_t max_pairs;    /* pair words per tile               (default and at most 65535)            */
+  int32_t max_entries;  /* M-step entries per tile           (default and at most 65535)            */
+  int32_t max_items;    /* M-step work items per tile        (default 1024)                         */
   int32_t item_len;     /* entries per work item             (default 16, at most 16)               */
 } gbrs_tiles_params;
 
@@ -151,30 +151,35 @@ int gbrs_tiles_create(gbrs_pack_t p, const gbrs_tiles_params* params, gbrs_tiles
 int gbrs_tiles_get_info(gbrs_tiles_t t, gbrs_tiles_info* info);
 /* Borrowed host pointers (valid until gbrs_tiles_free):
  *   "blob"        bytes  [blob_bytes]      the tile blobs, each starting at a multiple of 128 bytes
- *   "tile_desc"   uint32 [n_tiles][4]      per VISITING slot (costliest tile first): blob offset / 16, part A bytes,
- *                                          part B bytes, tile id
+ *   "tile_desc"   uint32 [n_tiles][16]     per VISITING slot (costliest tile first), see GBRS_TD_WORDS
  *   "locus_desc"  uint32 [T][4]            per visiting slot (most slots first): locus, first slot, one-past-last slot, 0 */
 int gbrs_tiles_get_array(gbrs_tiles_t t, const char* name, const void** ptr, int64_t* bytes);
 int gbrs_tiles_free(gbrs_tiles_t t);
 
-/* Blob header: GBRS_TH_WORDS uint32 words at the start of part A (GBRS_TH_OFF_* are byte offsets relative to the start
- * of the part they name). */
-enum { GBRS_TH_CLASSES = 0, GBRS_TH_LOCI = 1, GBRS_TH_PLANES = 2, GBRS_TH_PAIRS = 3, GBRS_TH_ENTRIES = 4,
-       GBRS_TH_ITEMS = 5, GBRS_TH_OFF_LOCI = 6, GBRS_TH_OFF_SLOTS = 7, GBRS_TH_OFF_NPLANE = 8, GBRS_TH_OFF_COUNT = 9,
-       GBRS_TH_OFF_PAIRS = 10, GBRS_TH_A_BYTES = 11, GBRS_TH_B_BYTES = 12,
-       GBRS_TH_OFF_ENTS = 13 /* part B; the item words start at offset 0 of part B */,
-       GBRS_TH_FLAGS = 14 /* the mask value meaning "all haplotypes" */, GBRS_TH_OFF_POS = 15 /* part B */,
-       GBRS_TH_RUNS = 16, GBRS_TH_OFF_RUNKEY = 17 /* part B */, GBRS_TH_OFF_RUNFIRST = 18 /* part B */,
-       GBRS_TH_WORDS = 20 };
-/* Part B.  M-step work items are runs of at most `item_len` entries of ONE key, key = local locus * 32 + bucket;
- * bucket 0 = the pair hits all H haplotypes, 1..15 = value of the low mask nibble, 17..31 = 16 + value of the high mask
- * nibble (a partial mask contributes one entry per non-zero nibble).  Items are numbered in key order.
- *   item words  uint32 [items], in VISITING order (longest item first, so the lanes of a warp see equal lengths):
- *               first entry (16 bits) | (entries - 1) << 16
- *   pos         uint16 [items]: the number (key order) of the item visited at that position
- *   run_key     uint16 [runs], run_first uint16 [runs + 1]: the items run_first[r] .. run_first[r+1]-1 (key order) make up
- *               key run_key[r]; keys without entries have no run
- *   entries     uint16 local class ids, grouped by key */
+/* A tile's blob = part A followed by part B (part B starts `a_bytes` after the tile's start); all sections start at
+ * multiples of 16 bytes in the order listed, so their offsets follow from the counts in the tile descriptor.
+ * Part A: header (GBRS_TH_WORDS uint32) | loci uint32 [n_loci] | slots uint32 [n_loci] | nplane uint16 [n_planes] |
+ *         count double [n_classes] | pair planes uint16 (plane p: nplane[p] words, padded to a multiple of 4)
+ * Part B: the tile's locus-major copy for the M-step.  A work item is a run of at most `item_len` entries (local class
+ *         ids) of ONE key, key = local locus * 32 + bucket; bucket 0 = the pair hits all H haplotypes, 1..15 = value of
+ *         the low mask nibble, 17..31 = 16 + value of the high mask nibble (a partial mask contributes one entry per
+ *         non-zero nibble).  Items are numbered in key order and VISITED longest first, 32 at a time: a SLICE is 32
+ *         consecutively visited items whose entries are stored transposed (sliced-ELL): entry i of the slice's lane l at
+ *         word i * 32 + l, padded with the local class id n_classes (whose weight slot is zero) up to the slice's
+ *         padded length (1, 2, 3, 4, 6, 8, 12 or 16).
+ *         slice words uint32 [n_slices]: first word of the slice << 5 | padded length
+ *         pos uint16 [n_items]: number (key order) of the item visited at that position
+ *         run_key uint16 [n_runs], run_first uint16 [n_runs + 1]: items run_first[r] .. run_first[r+1]-1 (key order) make
+ *         up key run_key[r]; keys without entries have no run
+ *         entries uint16 [sell_words] */
+enum { GBRS_TH_CLASSES = 0, GBRS_TH_LOCI = 1, GBRS_TH_PLANES = 2, GBRS_TH_RUNS = 3, GBRS_TH_ITEMS = 4, GBRS_TH_SLICES = 5,
+       GBRS_TH_A_BYTES = 6, GBRS_TH_FULL = 7 /* the mask value meaning "all haplotypes" */, GBRS_TH_PAIRS = 8,
+       GBRS_TH_ENTRIES = 9, GBRS_TH_B_BYTES = 10, GBRS_TH_SELL_WORDS = 11, GBRS_TH_WORDS = 12 };
+/* Tile descriptor, GBRS_TD_WORDS uint32 per visiting slot (costliest tile first; the kernel reads only this, never the
+ * header):  0 blob offset / 16 | 1 n_classes + (n_loci << 16) | 2 n_planes + (n_runs << 16) | 3 n_items + (n_slices << 16) |
+ *   4 a_bytes | 5 full mask | 6 tile id | 7 bytes of the tile's blob | 8-11 byte offsets of slots, nplane, count, pair
+ *   planes in part A | 12-15 byte offsets of pos, run_key, run_first, entries in part B */
+enum { GBRS_TD_WORDS = 16 };
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Device descriptor: every pointer is a device pointer into a caller-owned buffer.
@@ -218,7 +223,7 @@ typedef struct {
   const uint32_t* gene_loci;
   /* tile layout of the fused model-4 update (all NULL / 0: the two-pass kernels are used) */
   const uint8_t* tile_blob;
-  const uint32_t* tile_desc;       /* [n_tiles][4] */
+  const uint32_t* tile_desc;       /* [n_tiles][GBRS_TD_WORDS] */
   const uint32_t* tile_locus_desc; /* [T][4] */
   double* tile_partial;            /* [n_slots][8] per-(tile, locus) partial sums */
   int64_t n_tiles, n_tile_slots;
