@@ -963,27 +963,28 @@ __global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(
 // add per non-zero nibble, and the 15 + 15 + 1 bucket sums of a locus are expanded to haplotypes once per tile.
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef GBRS_TILE_THREADS
-#define GBRS_TILE_THREADS 256
+#define GBRS_TILE_THREADS 128
 #endif
 #ifndef GBRS_TILE_MINBLOCKS
-#define GBRS_TILE_MINBLOCKS 6  // resident blocks per SM the tile kernel is compiled for (register budget)
+#define GBRS_TILE_MINBLOCKS 8  // resident blocks per SM the tile kernel is compiled for (register budget)
 #endif
 constexpr int kTileThreads = GBRS_TILE_THREADS;
 constexpr int kTabStride = 33;  // doubles per locus row of the shared subset table (odd: rows start on different banks)
 
-struct TileSmem {  // byte offsets into dynamic shared memory; identical on host and device
-  uint32_t w, tab, isum, slots, misc, total;
+// Every WARP owns one tile at a time and a private slice of shared memory; nothing is shared between the warps of a block,
+// so there is no block barrier anywhere: a warp stalled on its loads never holds another one up.
+struct TileSmem {  // byte offsets inside a warp's slice of dynamic shared memory; identical on host and device
+  uint32_t w, tab, isum, slots, per_warp;
 };
 __host__ __device__ inline TileSmem tile_smem_layout(const gbrs_em_dev& d) {
-  auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
+  auto up = [](uint32_t x) { return (x + 15u) & ~15u; };
   TileSmem L;
   uint32_t o = 0;
-  L.w = o; o = up(o + 8u * (uint32_t) (d.tile_max_classes + 8));  // + the always-zero slot padding ids point at
+  L.w = o; o = up(o + 8u * (uint32_t) (d.tile_max_classes + 4));  // + the always-zero slot padding ids point at
   L.tab = o; o = up(o + 8u * (uint32_t) (kTabStride * d.tile_max_loci));  // subset table (phases 0-1), then bucket sums
   L.isum = o; o = up(o + 8u * (uint32_t) (d.tile_max_items + 1));
   L.slots = o; o = up(o + 4u * (uint32_t) d.tile_max_loci);
-  L.misc = o; o += 32 + 2 * 4 * GBRS_TD_WORDS;  // next tile index, two tile descriptors
-  L.total = o;
+  L.per_warp = (o + 127u) & ~127u;
   return L;
 }
 
@@ -1013,13 +1014,13 @@ __device__ __forceinline__ double tile_slice_sum(const uint16_t* __restrict__ e,
 // KC consecutive pair planes of four neighbouring classes (quad q): all plane words are loaded first, then all
 // 2 * 4 * KC table values, then the adds -- one memory round trip per stage instead of one per plane.
 template <int KC>
-__device__ __forceinline__ void tile_quad_planes(const uint16_t* __restrict__ pw, const uint32_t* plane_words, int p0,
+__device__ __forceinline__ void tile_quad_planes(const uint16_t* __restrict__ pw, const uint32_t* plane_words,
                                                  uint32_t& off, int q, const double* __restrict__ tab, double (&s)[4]) {
   uint2 v[KC];
 #pragma unroll
   for (int i = 0; i < KC; ++i) {
     v[i] = __ldcs(reinterpret_cast<const uint2*>(pw + off + 4 * q));  // padding words (locus 0, empty mask) add 0.0
-    off += plane_words[p0 + i];
+    off += plane_words[i];
   }
   double x[KC][4][2];
 #pragma unroll
@@ -1047,46 +1048,41 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
   extern __shared__ __align__(128) unsigned char smem[];
 #endif
   if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
-  double* const w = reinterpret_cast<double*>(smem + L.w);
-  double* const tab = reinterpret_cast<double*>(smem + L.tab);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* const mine = smem + (size_t) warp * L.per_warp;
+  double* const w = reinterpret_cast<double*>(mine + L.w);
+  double* const tab = reinterpret_cast<double*>(mine + L.tab);
   double* const bsum = tab;  // [local locus][32] bucket sums: the table is dead by then
-  double* const isum = reinterpret_cast<double*>(smem + L.isum);
-  uint32_t* const slot_of = reinterpret_cast<uint32_t*>(smem + L.slots);
-  int* const s_next = reinterpret_cast<int*>(smem + L.misc);
-  uint32_t* const s_desc = reinterpret_cast<uint32_t*>(smem + L.misc) + 8;  // [2][GBRS_TD_WORDS]
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  double* const isum = reinterpret_cast<double*>(mine + L.isum);
+  uint32_t* const slot_of = reinterpret_cast<uint32_t*>(mine + L.slots);
   const int n_tiles = (int) d.n_tiles;
-
-  if (tid == 0) *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
-  __syncthreads();
-  int cur = *s_next;
+  const int n_warps = (int) (gridDim.x * (blockDim.x >> 5));
+  // tiles are listed costliest first and dealt round-robin to the warps of the grid: every warp gets one tile of each
+  // cost tier (no work counter: the next tile is known at once, so its descriptor and blob can be requested early)
+  int cur = (int) (blockIdx.x + gridDim.x * warp);  // consecutive tiles go to different SMs
   if (cur >= n_tiles) return;
-  if (tid < GBRS_TD_WORDS) s_desc[tid] = __ldg(d.tile_desc + (size_t) cur * GBRS_TD_WORDS + tid);
-  __syncthreads();
-  int par = 0;
+  uint32_t dword = lane < GBRS_TD_WORDS ? __ldg(d.tile_desc + (size_t) cur * GBRS_TD_WORDS + lane) : 0u;
   for (;;) {
-    const uint32_t* dsc = s_desc + par * GBRS_TD_WORDS;
-    const unsigned char* const blob = d.tile_blob + (size_t) dsc[0] * 16;
-    const int nc = (int) (dsc[1] & 0xFFFFu), nl = (int) (dsc[1] >> 16);
-    const int n_planes = (int) (dsc[2] & 0xFFFFu), n_runs = (int) (dsc[2] >> 16);
-    const int n_items = (int) (dsc[3] & 0xFFFFu), n_slices = (int) (dsc[3] >> 16);
-    const uint32_t full = dsc[5];
-    const uint32_t off_loci = GBRS_TH_WORDS * 4, off_slots = dsc[8], off_nplane = dsc[9], off_count = dsc[10];
-    const uint32_t off_pairs = dsc[11];
-    const uint32_t* loci = reinterpret_cast<const uint32_t*>(blob + off_loci);
-    const uint32_t* slots = reinterpret_cast<const uint32_t*>(blob + off_slots);
-    const uint16_t* nplane = reinterpret_cast<const uint16_t*>(blob + off_nplane);
-    const double* cnt = reinterpret_cast<const double*>(blob + off_count);
-    const uint16_t* pw = reinterpret_cast<const uint16_t*>(blob + off_pairs);
-    const unsigned char* const part_b = blob + dsc[4];
-    const uint32_t off_pos = dsc[12], off_runkey = dsc[13], off_runfirst = dsc[14], off_ents = dsc[15];
+    const int nxt = cur + n_warps;
+    // the next tile: descriptor word into a register now, its blob towards L2 as soon as the descriptor is here
+    const uint32_t next_dword = (nxt < n_tiles && lane < GBRS_TD_WORDS) ? __ldg(d.tile_desc + (size_t) nxt * GBRS_TD_WORDS + lane) : 0u;
+    auto field = [&](int k) { return __shfl_sync(0xFFFFFFFFu, dword, k); };
+    const unsigned char* const blob = d.tile_blob + (size_t) field(0) * 16;
+    const uint32_t f1 = field(1), f2 = field(2), f3 = field(3);
+    const int nc = (int) (f1 & 0xFFFFu), nl = (int) (f1 >> 16);
+    const int n_planes = (int) (f2 & 0xFFFFu), n_runs = (int) (f2 >> 16);
+    const int n_items = (int) (f3 & 0xFFFFu), n_slices = (int) (f3 >> 16);
+    const unsigned char* const part_b = blob + field(4);
+    const uint32_t full = field(5);
+    const uint32_t* loci = reinterpret_cast<const uint32_t*>(blob + GBRS_TH_WORDS * 4);
+    const uint32_t* slots = reinterpret_cast<const uint32_t*>(blob + field(8));
+    const uint16_t* nplane = reinterpret_cast<const uint16_t*>(blob + field(9));
+    const double* cnt = reinterpret_cast<const double*>(blob + field(10));
+    const uint16_t* pw = reinterpret_cast<const uint16_t*>(blob + field(11));
 
-    // ---- phase 0: table rows and slots of the tile's loci; claim the next tile -----------------------------------
-    if (tid == 0) {
-      *s_next = atomicAdd(d.ctrl + GBRS_CTRL_TILE_NEXT, 1);
-      w[nc] = 0.0;  // the slot padding entries point at
-    }
-    for (int i = tid; i < nl * 16; i += nthr) {  // 16 bytes of a 256-byte row per thread
+    // ---- phase 0: table rows and slots of the tile's loci -----------------------------------------------------------
+    if (lane == 0) w[nc] = 0.0;  // the slot padding entries point at
+    for (int i = lane; i < nl * 16; i += 32) {  // 16 bytes of a 256-byte row per lane
       const int l = i >> 4, c = i & 15;
       double2 v;
       if (UNIT) v = make_double2((double) __popc((2 * c) & 15), (double) __popc((2 * c + 1) & 15));
@@ -1094,14 +1090,11 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
       tab[l * kTabStride + 2 * c] = v.x;
       tab[l * kTabStride + 2 * c + 1] = v.y;
     }
-    for (int l = tid; l < nl; l += nthr) slot_of[l] = __ldg(slots + l);
-    __syncthreads();
-    const int nxt = *s_next;
-    uint32_t next_word = 0;  // descriptor of the next tile: requested now, parked in shared memory after phase 1
-    if (tid < GBRS_TD_WORDS && nxt < n_tiles) next_word = __ldg(d.tile_desc + (size_t) nxt * GBRS_TD_WORDS + tid);
+    for (int l = lane; l < nl; l += 32) slot_of[l] = __ldg(slots + l);
+    __syncwarp();
 
-    // ---- phase 1: class weights, four neighbouring classes per thread (one 64-bit load per plane) -------------------
-    for (int q = tid; 4 * q < nc; q += nthr) {
+    // ---- phase 1: class weights, four neighbouring classes per lane (one 64-bit load per plane) ----------------------
+    for (int q = lane; 4 * q < nc; q += 32) {
       double s[4] = {0.0, 0.0, 0.0, 0.0};
       const double2 c01 = __ldcs(reinterpret_cast<const double2*>(cnt + 4 * q));  // (the count section is padded)
       const double2 c23 = __ldcs(reinterpret_cast<const double2*>(cnt + 4 * q) + 1);
@@ -1119,10 +1112,10 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
         }
         switch (kc) {
           case 0: break;
-          case 1: tile_quad_planes<1>(pw, words, 0, off, q, tab, s); break;
-          case 2: tile_quad_planes<2>(pw, words, 0, off, q, tab, s); break;
-          case 3: tile_quad_planes<3>(pw, words, 0, off, q, tab, s); break;
-          default: tile_quad_planes<4>(pw, words, 0, off, q, tab, s); break;
+          case 1: tile_quad_planes<1>(pw, words, off, q, tab, s); break;
+          case 2: tile_quad_planes<2>(pw, words, off, q, tab, s); break;
+          case 3: tile_quad_planes<3>(pw, words, off, q, tab, s); break;
+          default: tile_quad_planes<4>(pw, words, off, q, tab, s); break;
         }
         if (kc < 4) break;
         p0 += 4;
@@ -1134,20 +1127,19 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
         if (j < nc) w[j] = fast_div(c[u], s[u]);
       }
     }
-    if (tid < GBRS_TD_WORDS) s_desc[(par ^ 1) * GBRS_TD_WORDS + tid] = next_word;
-    __syncthreads();  // the weights are complete, the table is no longer read, the next descriptor is readable
-    if (tid == 0 && nxt < n_tiles) {
-      const uint32_t* nd = s_desc + (par ^ 1) * GBRS_TD_WORDS;
-      tile_prefetch_l2(d.tile_blob + (size_t) nd[0] * 16, nd[7]);
+    __syncwarp();  // the weights are complete, the table is no longer read
+    if (nxt < n_tiles) {
+      const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, next_dword, 0), b7 = __shfl_sync(0xFFFFFFFFu, next_dword, 7);
+      if (lane == 0) tile_prefetch_l2(d.tile_blob + (size_t) b0 * 16, b7);
     }
 
-    // ---- phase 2: item sums, one slice (32 items, sliced-ELL entries) per warp and round -------------------------------
-    for (int i = tid; i < nl * 32; i += nthr) bsum[i] = 0.0;
+    // ---- phase 2: item sums, one slice (32 items, sliced-ELL entries) at a time ----------------------------------------
+    for (int i = lane; i < nl * 32; i += 32) bsum[i] = 0.0;
     {
       const uint32_t* slices = reinterpret_cast<const uint32_t*>(part_b);
-      const uint16_t* pos = reinterpret_cast<const uint16_t*>(part_b + off_pos);
-      const uint16_t* ents = reinterpret_cast<const uint16_t*>(part_b + off_ents);
-      for (int sidx = warp; sidx < n_slices; sidx += nwarps) {
+      const uint16_t* pos = reinterpret_cast<const uint16_t*>(part_b + field(12));
+      const uint16_t* ents = reinterpret_cast<const uint16_t*>(part_b + field(15));
+      for (int sidx = 0; sidx < n_slices; ++sidx) {
         const uint32_t sw = __ldg(slices + sidx);
         const int vpos = sidx * 32 + lane;
         const uint32_t at = vpos < n_items ? (uint32_t) __ldg(pos + vpos) : 0xFFFFFFFFu;
@@ -1166,12 +1158,12 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
         if (at != 0xFFFFFFFFu) isum[at] = a;  // item sums are kept in key order
       }
     }
-    __syncthreads();
+    __syncwarp();
     // ---- phase 3a: bucket sums: the item sums of one key, in item order ------------------------------------------------
     {
-      const uint16_t* run_key = reinterpret_cast<const uint16_t*>(part_b + off_runkey);
-      const uint16_t* run_first = reinterpret_cast<const uint16_t*>(part_b + off_runfirst);
-      for (int r = tid; r < n_runs; r += nthr) {
+      const uint16_t* run_key = reinterpret_cast<const uint16_t*>(part_b + field(13));
+      const uint16_t* run_first = reinterpret_cast<const uint16_t*>(part_b + field(14));
+      for (int r = lane; r < n_runs; r += 32) {
         int i = (int) __ldg(run_first + r);
         const int last = (int) __ldg(run_first + r + 1);
         const uint32_t key = (uint32_t) __ldg(run_key + r);
@@ -1186,10 +1178,10 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
         bsum[key] = (a0 + a1) + (a2 + a3);
       }
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- phase 3b: buckets -> haplotypes -> the tile's slots ---------------------------------------------------------------
-    for (int q = tid; q < nl * 8; q += nthr) {
+    for (int q = lane; q < nl * 8; q += 32) {
       const int l = q >> 3, h = q & 7;
       const double* b = bsum + l * 32 + (h >> 2) * 16;
       const int bit = h & 3;
@@ -1202,10 +1194,10 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
       }
       d.tile_partial[(size_t) slot_of[l] * GBRS_HPAD + h] = W;
     }
-    __syncthreads();  // bucket sums, item sums, weights and slots are free for the next tile
+    __syncwarp();  // bucket sums, item sums, weights and slots are free for the next tile
     if (nxt >= n_tiles) break;
     cur = nxt;
-    par ^= 1;
+    dword = next_dword;
   }
 }
 
@@ -1635,25 +1627,27 @@ template <bool UNIT>
 int launch_tiles(const gbrs_em_dev* d, cudaStream_t s) {
   if (d->n_tiles <= 0) return GBRS_OK;
   const TileSmem L = tile_smem_layout(*d);
-  if (L.total > 227u * 1024u) { gbrs_set_error("tile kernel: tile caps exceed the shared memory of an SM"); return GBRS_E_LIMIT; }
+  const uint32_t smem_bytes = L.per_warp * (uint32_t) (kTileThreads / 32);
+  if (smem_bytes > 227u * 1024u) { gbrs_set_error("tile kernel: tile caps exceed the shared memory of an SM"); return GBRS_E_LIMIT; }
   static uint32_t attr_set = 0;  // per instantiation
   static std::unordered_map<uint32_t, int> occ_cache;
-  if (L.total > attr_set) {
-    GBRS_CUDA(cudaFuncSetAttribute(k_tile_em<UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) L.total));
-    attr_set = L.total;
+  if (smem_bytes > attr_set) {
+    GBRS_CUDA(cudaFuncSetAttribute(k_tile_em<UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes));
+    attr_set = smem_bytes;
   }
   int occ;
-  auto it = occ_cache.find(L.total);
+  auto it = occ_cache.find(smem_bytes);
   if (it == occ_cache.end()) {
     occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_em<UNIT>, kTileThreads, (size_t) L.total) != cudaSuccess || occ < 1) occ = 1;
-    occ_cache[L.total] = occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tile_em<UNIT>, kTileThreads, (size_t) smem_bytes) != cudaSuccess || occ < 1) occ = 1;
+    occ_cache[smem_bytes] = occ;
   } else {
     occ = it->second;
   }
+  const int64_t warps_per_block = kTileThreads / 32;
   int64_t grid = (int64_t) sm_count() * occ;
-  if (grid > d->n_tiles) grid = d->n_tiles;
-  k_tile_em<UNIT><<<(int) grid, kTileThreads, L.total, s>>>(*d, L);
+  if (grid * warps_per_block > d->n_tiles) grid = (d->n_tiles + warps_per_block - 1) / warps_per_block;
+  k_tile_em<UNIT><<<(int) grid, kTileThreads, smem_bytes, s>>>(*d, L);
   GBRS_LAUNCH_CHECK("k_tile_em");
   return GBRS_OK;
 }

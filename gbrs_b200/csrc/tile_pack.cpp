@@ -49,11 +49,11 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
   if (!P || !out) { gbrs_set_error("gbrs_tiles_create: null argument"); return GBRS_E_ARG; }
   gbrs_tiles_params q{};
   if (prm) q = *prm;
-  const int maxC = q.max_classes > 0 ? q.max_classes : 1024;
-  const int maxL = q.max_loci > 0 ? q.max_loci : 32;
+  const int maxC = q.max_classes > 0 ? q.max_classes : 128;
+  const int maxL = q.max_loci > 0 ? q.max_loci : 16;
   const int maxP = q.max_pairs > 0 ? q.max_pairs : 65535;   // pair words and entries are streamed, not staged:
   const int maxE = q.max_entries > 0 ? q.max_entries : 65535; // no cap is needed beyond the 16-bit fields
-  const int maxI = q.max_items > 0 ? q.max_items : 1024;
+  const int maxI = q.max_items > 0 ? q.max_items : 192;
   const int ilen = q.item_len > 0 ? q.item_len : 16;
   if (maxC > 2047 || maxL > 128 || maxE > 65535 || maxP > 65535 || maxI > 65535 || ilen > 16 || maxP < maxL || maxE < 2 * maxL || maxI < 2 * maxL) {
     gbrs_set_error("gbrs_tiles_create: tile caps out of range"); return GBRS_E_ARG;

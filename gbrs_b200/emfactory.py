@@ -209,8 +209,11 @@ class DevicePattern:
 
     def __init__(self, apm: APM = None, gene_of=None, hapmask=None, device=None, shard_rank=0, shard_count=1,
                  item_len=0, packed: PackedPattern = None, pin=False, tiles=None, tile_params=None):
-        """`tiles`: build the tile layout of the fused model-4 update (default: yes, unless GBRS_NO_TILES is set or a
-        class is too wide for a tile -- then the two-pass kernels serve model 4 as well)."""
+        """`tiles`: also build the tile layout and run model 4 / prepare through the fused single-pass tile kernel
+        (`k_tile_em`) instead of the two-pass kernels.  Opt-in (`tiles=True` or GBRS_TILES=1): parity-green and
+        bit-reproducible, but on B200 it is the slower of the two formulations at the benchmark shape (DESIGN.md
+        section 4: both are bound by instruction issue, and the tile kernel issues more).  A class touching more loci
+        than a tile may hold keeps the pattern on the two-pass kernels."""
         torch = _torch()
         self.device = _require_cuda(device)
         self.lib = _lib.load()
@@ -222,7 +225,7 @@ class DevicePattern:
         self.T, self.H = packed.T, packed.H
         self.n_ranks = shard_count
         if tiles is None:
-            tiles = os.environ.get("GBRS_NO_TILES") is None
+            tiles = os.environ.get("GBRS_TILES", "0") not in ("", "0")
         self.tiled = None
         if tiles:
             try:
@@ -437,7 +440,7 @@ class EMfactory:
     """A class that coordinates Expectation-Maximization (reference EMfactory.py:15-24)."""
 
     def __init__(self, alignments: APM, device=None, group=None, shard: bool | str | None = None, item_len: int = 0,
-                 poll_every: int = 4, locus_hapmask=None):
+                 poll_every: int = 4, locus_hapmask=None, tiles: bool | None = None, tile_params: dict | None = None):
         """`alignments`: the incidence matrix.  Additions to the reference signature (all optional):
         `device` CUDA device; `group` a torch.distributed process group (or `shard=True` for the default group) over
         which the alignment classes are row-sharded -- every rank passes the same full matrix and packs only its own
@@ -445,7 +448,8 @@ class EMfactory:
         different classes); `item_len` / `poll_every` are tuning knobs (column-pass work item size, iterations queued
         between reads of the device-side stop flag); `locus_hapmask` (uint8 [T], bit h = haplotype h of the locus is
         kept) applies the `-G` genotype restriction while packing, which is equivalent to -- and much cheaper than --
-        `alignments.multiply(gtmask, axis=2)` followed by `eliminate_zeros()` on the host matrices."""
+        `alignments.multiply(gtmask, axis=2)` followed by `eliminate_zeros()` on the host matrices; `tiles` /
+        `tile_params` select the fused single-pass tile kernel for model 4 (see DevicePattern)."""
         self.probability = alignments
         self._theta_host = None
         self._theta_dirty = False
@@ -459,6 +463,7 @@ class EMfactory:
         if self._hapmask is not None and self._hapmask.shape != (alignments.num_loci,):
             raise ValueError("locus_hapmask must hold one byte per locus")
         self._poll_every = poll_every
+        self._tiles, self._tile_params = tiles, tile_params
         self._pattern: DevicePattern | None = None
         self._gene_of = None
         self._counts_host = None
@@ -563,12 +568,13 @@ class EMfactory:
                     "eliminate_zeros() after masking; weighted (non-incidence) matrices are not supported")
             if self._presharded:
                 self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
-                                              item_len=self._item_len)
+                                              item_len=self._item_len, tiles=self._tiles, tile_params=self._tile_params)
                 self._pattern.n_ranks = self.world
                 self._pattern._build_descriptor()
             else:
                 self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
-                                              shard_rank=self.rank, shard_count=self.world, item_len=self._item_len)
+                                              shard_rank=self.rank, shard_count=self.world, item_len=self._item_len,
+                                              tiles=self._tiles, tile_params=self._tile_params)
             self._pattern.set_lengths(self.target_lengths)
             if self.world > 1:
                 self.fused_exchange = self._setup_fused_exchange(self._pattern)

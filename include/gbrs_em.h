@@ -126,11 +126,11 @@ int gbrs_pack_free(gbrs_pack_t p);
 typedef struct gbrs_tiles* gbrs_tiles_t;
 
 typedef struct {   /* 0 = default */
-  int32_t max_classes;  /* classes per tile                  (default 1024, at most 2047)           */
-  int32_t max_loci;     /* distinct loci per tile            (default 32, at most 128)              */
+  int32_t max_classes;  /* classes per tile                  (default 128, at most 2047)            */
+  int32_t max_loci;     /* distinct loci per tile            (default 16, at most 128)              */
   int32_t max_pairs;    /* pair words per tile               (default and at most 65535)            */
   int32_t max_entries;  /* M-step entries per tile           (default and at most 65535)            */
-  int32_t max_items;    /* M-step work items per tile        (default 1024)                         */
+  int32_t max_items;    /* M-step work items per tile        (default 192)                          */
   int32_t item_len;     /* entries per work item             (default 16, at most 16)               */
 } gbrs_tiles_params;
 
