@@ -159,20 +159,67 @@ def cpu_port_rate(T, n_classes, steps, warmup, model=4, diploid=False):
     return apm.nnz * steps / dt, dt / steps, apm.nnz
 
 
+def cpu_reference_rate(T, n_classes, steps, warmup, diploid=False):
+    """nnz/s of the UNMODIFIED reference (model 4): its own AlignmentPropertyMatrix + EMfactory, imported from the copy
+    oracle/make_ref.py staged into oracle/_ref/ (or from /root/reference where that is mounted), driven through its
+    public API: prepare(), then update_allelic_expression(model=4) per step -- the body of EMfactory.run's loop
+    (EMfactory.py:267-279).  Single host thread (scipy / numpy sparse loops).  None if the reference is not available."""
+    from oracle import ref_harness as rh
+
+    if not rh.reference_available():
+        return None
+    from gbrs_b200 import synth
+
+    d = synth.generate(T=T, N=n_classes, H=8, with_genotype=diploid)
+    rh.install_shim(False)
+    apm = rh.build_reference_apm(d, masked=diploid)
+    nnz = int(sum(m.nnz for m in apm.data))
+    with tempfile.TemporaryDirectory() as tmp:
+        lenfile = os.path.join(tmp, "len.tsv")
+        synth.write_length_file(d, lenfile)
+        em = rh.load_reference().EMfactory(apm)
+        t0 = time.perf_counter()
+        em.prepare(pseudocount=0.0, lenfile=lenfile)
+        t_prepare = time.perf_counter() - t0
+    for _ in range(warmup):
+        em.update_allelic_expression(model=4)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        em.update_allelic_expression(model=4)
+    dt = time.perf_counter() - t0
+    return nnz * steps / dt, dt / steps, nnz, t_prepare
+
+
+def cpu_baseline(T, n_classes, steps, warmup, model, diploid):
+    """(rate, s_per_step, nnz, kind, note): the reference itself for model 4, the oracle port otherwise."""
+    if model == 4:
+        try:
+            r = cpu_reference_rate(T, n_classes, steps, warmup, diploid)
+        except Exception as e:  # noqa: BLE001 - e.g. a missing dependency of the reference on this host
+            log(f"reference arm: the staged reference could not run ({type(e).__name__}: {e}); using the oracle port")
+            r = None
+        if r is not None:
+            return r[0], r[1], r[2], "reference", f"unmodified reference EMfactory.update_allelic_expression(model=4); prepare() took {r[3]:.1f} s"
+    rate, s_per, nnz = cpu_port_rate(T, n_classes, steps, warmup, model, diploid)
+    why = "models 1-3 of the reference crash on current scipy (SURVEY.md fact 3)" if model != 4 else "oracle/_ref not staged"
+    return rate, s_per, nnz, "port", f"oracle/em_oracle.py (numpy restatement of the reference; {why})"
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ncls = min(CPU_SAMPLE_CLASSES, wl["N"])
-    steps = max(1, min(args.steps, 10))
-    rate, s_per_step, nnz = cpu_port_rate(wl["T"], ncls, steps, min(args.warmup, 1), args.model, bool(wl.get("diploid")))
-    sample = f"{ncls} of {wl['N']} classes (nnz={nnz}), {steps} EM updates timed"
+    # the whole workload (same config as our arm), a handful of updates: ~3 s per update for the reference at C2
+    ncls = wl["N"] if args.model == 4 and wl["N"] <= 5_000_000 else min(CPU_SAMPLE_CLASSES, wl["N"])
+    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    rate, s_per_step, nnz, kind, note = cpu_baseline(wl["T"], ncls, steps, warm, args.model, bool(wl.get("diploid")))
+    sample = f"{ncls} of {wl['N']} classes (nnz={nnz}), {steps} EM updates timed after {warm} warm-up; {note}"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "warmup": warm, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+            "scaling": "strong" if wl.get("strong") else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "model": args.model, "sample": sample},
             "iterations_per_s_at_full_size": rate / (nnz * wl["N"] / ncls),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -180,6 +227,68 @@ def run_reference_arm(args, wl):
 # --------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------------
+def parity_checks(em, pat, d, world, rank, dev, diploid, model):
+    """Checks of the path that was just timed, at every world size (the JSON line carries the result):
+      conservation   sum of the expected counts == sum of the class counts over all ranks (every class' posterior sums to one)
+      theta          bit-identical on all ranks (element-wise MIN == MAX over ranks)
+      oracle         a small seeded problem, row-sharded over the same ranks through the same exchange, against the
+                     oracle on the union of the shards (6 fixed updates, model 4 and the timed model)"""
+    import torch
+    import torch.distributed as dist
+
+    from gbrs_b200 import synth
+    from gbrs_b200.emfactory import EMfactory
+    from oracle import em_oracle as eo
+
+    out = {}
+    counts = torch.from_numpy(np.ascontiguousarray(em.expected_read_counts())).to(dev)
+    tot = torch.tensor([float(counts.sum().item()), float(d.count.sum()) if not diploid else 0.0], dtype=torch.float64, device=dev)
+    theta = torch.from_numpy(np.ascontiguousarray(em.get_allelic_expression())).to(dev)
+    lo, hi = theta.clone(), theta.clone()
+    if world > 1:
+        # every rank holds the summed numerator already: the count total is per-rank data, the expected total is not
+        t2 = tot[1:].clone()
+        dist.all_reduce(t2)
+        tot[1] = t2[0]
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out["theta_identical_across_ranks"] = bool(torch.equal(lo, hi))
+    if not diploid:  # (with the -G restriction classes can lose all their alignments: the totals differ by design)
+        out["conservation_rel"] = abs(float(tot[0].item()) - float(tot[1].item())) / float(tot[1].item())
+    # small seeded problem through the same sharding
+    Ts, Ns = 2000, 40_000
+    ds = synth.generate(T=Ts, N=Ns, H=8, sample_index=100 + rank)
+    ems = EMfactory(synth.to_apm(ds), device=dev, shard="local" if world > 1 else None)
+    ems.target_lengths = synth.effective_lengths(ds)
+    ems.prepare()
+    rel = 0.0
+    if rank == 0:
+        parts = [synth.generate(T=Ts, N=Ns, H=8, sample_index=100 + r) for r in range(world)]
+        pc = np.concatenate([p.pair_class + r * Ns for r, p in enumerate(parts)])
+        oapm = eo.apm_from_pairs(Ts, 8, Ns * world, pc, np.concatenate([p.pair_locus for p in parts]),
+                                 np.concatenate([p.pair_mask for p in parts]), np.concatenate([p.count for p in parts]))
+        eff = eo.effective_length_table(parts[0].lengths)
+        gene_of = eo.gene_index(Ts, parts[0].groups())
+        want = eo.prepare(oapm, eff, 0.0)
+        rel = max(rel, float(np.abs(ems.get_allelic_expression() - want).max() / np.abs(want).max()))
+    for m in sorted({4, model}):
+        ems.run(model=m, tol=0.0, max_iters=6, verbose=False)
+        if rank == 0:
+            o = eo.run(oapm, want, m, eff, gene_of, tol=0.0, max_iters=6)
+            want = o["theta"]
+            rel = max(rel, float(np.abs(ems.get_allelic_expression() - want).max() / np.abs(want).max()))
+            rel = max(rel, float(np.abs(ems.expected_read_counts() - o["counts"]).max() / np.abs(o["counts"]).max()))
+    out["oracle_small_shard_relerr"] = rel
+    ok = out["theta_identical_across_ranks"] and out.get("conservation_rel", 0.0) < 1e-9 and rel < 1e-9
+    if world > 1:
+        flag = torch.tensor([1 if (ok or rank != 0) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    out["ok"] = bool(ok)
+    assert ok, f"parity check failed: {out}"
+    return out
+
+
 def run_gpu_arm(args, wl):
     import torch
     import torch.distributed as dist
@@ -351,12 +460,16 @@ def run_gpu_arm(args, wl):
                               "note": "SURVEY 8(d) pair+mask formula (each input once, theta in/out + lengths); the "
                                       "second (locus-major) copy and the weight vector are NOT counted"}}
 
-    # ---- e2e through the public API with host buffers ------------------------------------------------------------
+    # ---- e2e through the public API, from HOST buffers ----------------------------------------------------------------
+    # `e2e`: what a user's call sequence costs -- EMfactory(apm) on the host CSC matrices, prepare() (host packing of the
+    # incidence, H2D of the packed arrays, theta0), run(K updates), expected_read_counts() (D2H).  `e2e_resident`: the
+    # same without the host packer (the packed arrays are already in pinned host memory) -- what round 1 reported.
     for k in list(pat.host):
         pat.host[k] = pat.host[k].pin_memory()
     Ke = K
     sync_all()
-    def e2e_once():
+
+    def e2e_resident_once():
         t0 = time.perf_counter()
         pat.h2d_bytes = 0
         pat.upload()
@@ -371,30 +484,81 @@ def run_gpu_arm(args, wl):
         t4 = time.perf_counter()
         return t4 - t0, c, {"h2d_s": t1 - t0, "prepare_s": t2 - t1, "run_s": t3 - t2, "fetch_s": t4 - t3}
 
-    e2e_once()  # warm-up pass (first-use costs: pinned staging, graph instantiation paths), then the timed one
+    def e2e_full_once():
+        t0 = time.perf_counter()
+        em2 = EMfactory(apm, device=dev, shard="local" if world > 1 else None, locus_hapmask=hapmask)
+        em2.target_lengths = em.target_lengths
+        em2.prepare()  # pack on the host + H2D + theta0
+        t1 = time.perf_counter()
+        em2.run(model=model, tol=0.0, max_iters=Ke, verbose=False)
+        t2 = time.perf_counter()
+        c = em2.expected_read_counts()
+        torch.cuda.synchronize(dev)
+        t3 = time.perf_counter()
+        p2 = em2._pattern
+        parts = {"pack_s": p2.packed.pack_seconds, "tiles_s": p2.tiled.build_seconds if p2.tiled is not None else 0.0,
+                 "prepare_total_s": t1 - t0, "run_s": t2 - t1, "fetch_s": t3 - t2}
+        return t3 - t0, c, parts, p2.h2d_bytes, em2.num_iters
+
+    e2e_resident_once()  # warm-up pass (first-use costs: pinned staging, graph instantiation paths), then the timed one
     sync_all()
-    t_e2e, counts, e2e_parts = e2e_once()
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+    t_res, counts, res_parts = e2e_resident_once()
     assert em.num_iters == Ke
+    sync_all()
+    e2e_full_once()
+    sync_all()
+    t_e2e, counts2, e2e_parts, h2d_full, iters2 = e2e_full_once()
+    assert iters2 == Ke
+    if world > 1:
+        t = torch.tensor([t_e2e, t_res], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e, t_res = float(t[0].item()), float(t[1].item())
     if world == 1 and not diploid:
         assert abs(counts.sum() - d.count.sum()) < 1e-6 * counts.sum()
-    h2d = pat.h2d_bytes + 64 * T + 64 * T  # packed arrays + effective lengths (+ nothing else)
+        assert abs(counts2.sum() - d.count.sum()) < 1e-6 * counts2.sum()
+    h2d_res = pat.h2d_bytes + 64 * T + 64 * T  # packed arrays + effective lengths (+ nothing else)
     d2h = 2 * 64 * T + 2 * 8 * wl["T"] * 8 + 8 * Ke
-    e2e = {"value": nnz_total * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / Ke, "d2h_bytes_per_step": d2h / Ke,
-           "seconds": t_e2e, "parts": e2e_parts, "what": "H2D packed incidence (pinned) + prepare + run(%d updates) + D2H theta/counts/err "
-                                     "log through EMfactory" % Ke}
+    e2e = {"value": nnz_total * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": (h2d_full + 128 * T) / Ke,
+           "d2h_bytes_per_step": d2h / Ke, "seconds": t_e2e, "parts": e2e_parts,
+           "what": "EMfactory(apm).prepare() [host packing + H2D + theta0] + run(%d updates) + expected_read_counts() "
+                   "[D2H], from the host CSC matrices" % Ke}
+    e2e_resident = {"value": nnz_total * Ke / t_res, "unit": UNIT, "h2d_bytes_per_step": h2d_res / Ke,
+                    "d2h_bytes_per_step": d2h / Ke, "seconds": t_res, "parts": res_parts,
+                    "what": "H2D of the already packed incidence (pinned) + reset + run(%d updates) + D2H" % Ke}
 
-    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------------
+    # ---- the other three models on the same resident pattern (BASELINE config 3) ------------------------------------------
+    models_rec = None
+    if model == 4 and world == 1 and args.workload == "c2" and not args.no_models:
+        models_rec = {}
+        pat.ensure_full()
+        for m in (3, 2, 1):
+            for _ in range(2):
+                _lib.check(lib.gbrs_em_launch_local(C.byref(desc), m, stream))
+                _lib.check(lib.gbrs_em_launch_update(C.byref(desc), stream))
+            torch.cuda.synchronize(dev)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(torch.cuda.current_stream(dev))
+            for _ in range(5):
+                _lib.check(lib.gbrs_em_launch_local(C.byref(desc), m, stream))
+                _lib.check(lib.gbrs_em_launch_update(C.byref(desc), stream))
+            f1.record(torch.cuda.current_stream(dev))
+            torch.cuda.synchronize(dev)
+            mm = f0.elapsed_time(f1) / 5
+            models_rec[str(m)] = {"ms_per_step": mm, "value": nnz_total / (mm * 1e-3), "unit": UNIT, "steps": 5}
+        ctrl_m, _ = pat.read_ctrl()
+        assert ctrl_m[_lib.CTRL_ERROR] == 0
+
+    # ---- parity of the timed path (every run carries it; at N > 1 this is where the sharded result gets checked) ------
+    parity = parity_checks(em, pat, d, world, rank, dev, diploid, args.model)
+
+    # ---- CPU baseline (rank 0, N=1 only): a bounded sample of the same workload on the host cores ---------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu and not diploid:
+    if rank == 0 and world == 1 and not args.no_cpu:
         ncls = min(CPU_SAMPLE_CLASSES, wl["N"])
-        rate, s_per, nnz_s = cpu_port_rate(wl["T"], ncls, 5, 1, model)
-        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{ncls} of {wl['N']} classes (nnz={nnz_s}), 5 EM updates of oracle/em_oracle.py, "
-                         f"{s_per:.3f} s/update, host has {os.cpu_count()} logical cores (path is single-threaded)"}
+        rate, s_per, nnz_s, kind, note = cpu_baseline(wl["T"], ncls, 5, 1, model, diploid)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"{ncls} of {wl['N']} classes (nnz={nnz_s}), 5 EM updates, {s_per:.3f} s/update; {note}; host has "
+                         f"{os.cpu_count()} logical cores (the path is single-threaded)"}
 
     if rank == 0:
         launches_per_step = ((3 if tiled else 4) if world == 1 else (4 if tiled else 5)) + (1 if model != 4 else 0)
@@ -414,6 +578,7 @@ def run_gpu_arm(args, wl):
                                 "fused two-shot all-reduce of T x 8 fp64 over NVLink peer memory inside the locus kernels")
                                if em.fused_exchange else "NCCL all-reduce of T x 8 fp64 per step")},
                 "iterations_per_s": K / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "e2e_resident": e2e_resident, "parity": parity, "models": models_rec,
                 "gpu_launches": launches_per_step * K, "clocks": clocks,
                 "pack_seconds": pat.packed.pack_seconds}
         emit(line)
@@ -442,6 +607,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--model", type=int, default=4, choices=[1, 2, 3, 4])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-models", action="store_true", help="skip the models 1-3 sub-record of the default line")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

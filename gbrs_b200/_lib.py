@@ -42,7 +42,7 @@ class PackInfo(C.Structure):
     _fields_ = [("n_classes", C.c_int64), ("n_pairs", C.c_int64), ("n_runs", C.c_int64), ("n_items", C.c_int64),
                 ("n_entries", C.c_int64), ("n_long_items", C.c_int64), ("nnz", C.c_int64), ("nnz_total", C.c_int64), ("n_classes_total", C.c_int64),
                 ("entry_bytes", C.c_int32), ("n_gene_ids", C.c_int32), ("max_pairs_per_class", C.c_int32),
-                ("reserved", C.c_int32), ("bucket_class0", C.c_int64 * (GBRS_KMAX + 2)),
+                ("n_deep_loci", C.c_int32), ("bucket_class0", C.c_int64 * (GBRS_KMAX + 2)),
                 ("bucket_pair0", C.c_int64 * (GBRS_KMAX + 2))]
 
 
@@ -56,7 +56,8 @@ class TilesInfo(C.Structure):
                 ("n_items", C.c_int64), ("n_pairs", C.c_int64), ("n_classes", C.c_int64),
                 ("max_classes", C.c_int32), ("max_loci", C.c_int32), ("max_items", C.c_int32),
                 ("max_part_a_bytes", C.c_int32), ("max_part_b_bytes", C.c_int32), ("max_planes", C.c_int32),
-                ("max_slots_per_locus", C.c_int32), ("item_len", C.c_int32)]
+                ("max_slots_per_locus", C.c_int32), ("item_len", C.c_int32), ("n_deep_loci", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 # blob header words / tile descriptor words (include/gbrs_em.h)
@@ -80,8 +81,9 @@ class EmDev(C.Structure):
                 ("gene_of", C.c_void_p), ("gene_ptr", C.c_void_p), ("gene_loci", C.c_void_p),
                 ("tile_blob", C.c_void_p), ("tile_desc", C.c_void_p), ("tile_locus_desc", C.c_void_p),
                 ("tile_partial", C.c_void_p), ("n_tiles", C.c_int64), ("n_tile_slots", C.c_int64),
+                ("n_deep_loci", C.c_int32), ("dev_reserved", C.c_int32),
                 ("tile_max_classes", C.c_int32), ("tile_max_loci", C.c_int32), ("tile_max_items", C.c_int32),
-                ("tile_max_a_bytes", C.c_int32), ("tile_max_b_bytes", C.c_int32), ("tile_reserved", C.c_int32),
+                ("tile_max_a_bytes", C.c_int32), ("tile_max_b_bytes", C.c_int32), ("tile_n_deep_loci", C.c_int32),
                 ("theta", C.c_void_p), ("efflen", C.c_void_p), ("acc", C.c_void_p), ("iso", C.c_void_p),
                 ("weights", C.c_void_p), ("subsets", C.c_void_p), ("wit", C.c_void_p), ("part", C.c_void_p), ("gene_hap", C.c_void_p),
                 ("gamma", C.c_void_p), ("err_log", C.c_void_p), ("scal", C.c_void_p), ("ctrl", C.c_void_p)]

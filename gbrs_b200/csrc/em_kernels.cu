@@ -1217,7 +1217,11 @@ __device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t 
 }
 
 // acc[t][h] = theta[t][h] * sum_{items of t} wit[item][h]   ( = sum_n count[n] * P[n,t,h] ).  UNIT: theta == 1 (prepare).
-// One thread per (locus, haplotype slot); a locus has at most 128 items (packer), walked four loads at a time.
+// `wit` holds a locus' partial sums in consecutive 64-byte slots (column-pass items, or tile partials) and locus_desc lists
+// the loci deepest first.  A locus with more than GBRS_DEEP_LOCUS_ITEMS slots is summed by a whole warp (lane group g takes
+// slots g, g + 4, ... with four loads in flight, the groups are combined by two xor-shuffles: a fixed order); the others
+// take eight lanes, four loci per warp.  The serial eight-lane walk of a 128-slot locus used to cost 32 dependent L2 round
+// trips -- a 10 us floor under this kernel whatever the rest did.
 // FUSE (single rank only): also theta' = acc / efflen, iso' and the block partial of sum(iso'), i.e. k_locus_update.
 // Once the loop has stopped, k_converge has already flipped the ping-pong, so the theta that produced the weights in
 // `wit` is the *other* buffer: a single rank simply skips, a row-sharded rank recomputes the identical local numerator
@@ -1225,48 +1229,61 @@ __device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t 
 template <bool UNIT, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
   __shared__ double red[32];
-  if (blockIdx.x == 0 && threadIdx.x == 0) d.ctrl[GBRS_CTRL_TILE_NEXT] = 0;  // work counter of the next k_tile_em launch
+  if (blockIdx.x == 0 && threadIdx.x == 0) d.ctrl[GBRS_CTRL_TILE_NEXT] = 0;
   const bool done = !UNIT && d.ctrl[GBRS_CTRL_DONE];
   if (done && (honour_done || FUSE)) return;
   const int par = d.ctrl[GBRS_CTRL_PARITY];
   const double* __restrict__ th = d.theta + (size_t) (done ? (par ^ 1) : par) * d.T * GBRS_HPAD;
   double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
   double* __restrict__ iso = d.iso + (size_t) (par ^ 1) * d.T;
-  const int h = threadIdx.x & 7;
-  const int64_t total = (int64_t) d.T * GBRS_HPAD;
-  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  const int64_t rounds = (total + stride - 1) / stride;
-  double mine = 0.0;
-  // deepest loci first, and consecutive entries of locus_order go to different blocks (the deep loci are few: spread
-  // them over all SMs instead of piling them into the first blocks).  One 16-byte descriptor per locus (locus, first
-  // item, one-past-last item) instead of three dependent loads; the descriptor of the NEXT round is requested before
-  // this round's work, so that only one memory latency per round (item sums / theta / length) stays exposed.
-  const int64_t g_in_round = (int64_t) (threadIdx.x >> 3) * gridDim.x + blockIdx.x;
+  const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
+  const int64_t n_deep = d.n_deep_loci;
+  const int64_t total_slots = n_deep + ((d.T - n_deep + 3) >> 2);  // warp work slots: one deep locus, or four others
+  // consecutive slots go to different blocks (the deep loci are few: spread them over all SMs)
+  const int64_t warps_per_block = blockDim.x >> 5, nwarps = warps_per_block * gridDim.x;
+  const int64_t warp0 = (int64_t) (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  const int64_t rounds = (total_slots + nwarps - 1) / nwarps;
   const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.locus_desc);
-  uint4 nx = make_uint4(0u, 0u, 0u, 0u);
-  if (g_in_round < d.T) nx = __ldg(descs + g_in_round);
+  auto desc_index = [&](int64_t ws) { return ws < n_deep ? ws : n_deep + ((ws - n_deep) << 2) + grp; };
+  double mine = 0.0;
+  uint4 nx = make_uint4(0u, 0u, 0u, 0u);  // descriptor of the coming round, requested one round ahead
+  if (warp0 < total_slots && desc_index(warp0) < d.T) nx = __ldg(descs + desc_index(warp0));
   for (int64_t r = 0; r < rounds; ++r) {
-    const int64_t slot = r * (stride >> 3) + g_in_round;
-    const bool valid = slot < d.T;
+    const int64_t ws = warp0 + r * nwarps;
+    const bool deep = ws < n_deep;
+    const bool have = ws < total_slots && desc_index(ws) < d.T;  // this lane group has a locus
     const uint4 ld = nx;
     {
-      const int64_t next = slot + (stride >> 3);
+      const int64_t wn = ws + nwarps;
       nx = make_uint4(0u, 0u, 0u, 0u);
-      if (r + 1 < rounds && next < d.T) nx = __ldg(descs + next);
+      if (wn < total_slots && desc_index(wn) < d.T) nx = __ldg(descs + desc_index(wn));
     }
     const int64_t t = (int64_t) ld.x;
     const int64_t o = t * GBRS_HPAD + h;
-    uint32_t it = ld.y;
-    const uint32_t e = ld.z;
+    const uint32_t e = have ? ld.z : 0u;
+    const bool valid = have && (!deep || grp == 0);  // the lane group that finishes the locus
     const double th_o = (valid && !UNIT) ? th[o] : 1.0;
     const double len_o = (valid && FUSE) ? d.efflen[o] : 1.0;
     double W = 0.0;
-    for (; it + 3 < e; it += 4) {
-      const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 1) * GBRS_HPAD + h];
-      const double w2 = d.wit[(size_t) (it + 2) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 3) * GBRS_HPAD + h];
-      W += (w0 + w1) + (w2 + w3);
+    if (deep) {
+      uint32_t it = (have ? ld.y : 0u) + (uint32_t) grp;
+      for (; it + 12 < e; it += 16) {
+        const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 4) * GBRS_HPAD + h];
+        const double w2 = d.wit[(size_t) (it + 8) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 12) * GBRS_HPAD + h];
+        W += (w0 + w1) + (w2 + w3);
+      }
+      for (; it < e; it += 4) W += d.wit[(size_t) it * GBRS_HPAD + h];
+      W += __shfl_xor_sync(0xFFFFFFFFu, W, 8);
+      W += __shfl_xor_sync(0xFFFFFFFFu, W, 16);
+    } else {
+      uint32_t it = have ? ld.y : 0u;
+      for (; it + 3 < e; it += 4) {
+        const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 1) * GBRS_HPAD + h];
+        const double w2 = d.wit[(size_t) (it + 2) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 3) * GBRS_HPAD + h];
+        W += (w0 + w1) + (w2 + w3);
+      }
+      for (; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
     }
-    for (; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
     double a = 0.0;
     if (valid) {
       a = UNIT ? ((h < d.H) ? W : 0.0) : th_o * W;
@@ -1658,6 +1675,7 @@ inline gbrs_em_dev locus_view(const gbrs_em_dev* d, bool tiles) {
   if (tiles) {
     v.wit = d->tile_partial;
     v.locus_desc = d->tile_locus_desc;
+    v.n_deep_loci = d->tile_n_deep_loci;
   }
   return v;
 }

@@ -441,6 +441,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
         P->locus_desc[4 * (size_t) i + 0] = t;
         P->locus_desc[4 * (size_t) i + 1] = P->locus_item_ptr[t];
         P->locus_desc[4 * (size_t) i + 2] = P->locus_item_ptr[t + 1];
+        P->info.n_deep_loci += P->locus_item_ptr[t + 1] - P->locus_item_ptr[t] > GBRS_DEEP_LOCUS_ITEMS;
       }
     }
 

@@ -370,6 +370,7 @@ extern "C" int gbrs_tiles_create(gbrs_pack_t P, const gbrs_tiles_params* prm, gb
         R->locus_desc[4 * (size_t) i + 0] = lo[i];
         R->locus_desc[4 * (size_t) i + 1] = slot_ptr[lo[i]];
         R->locus_desc[4 * (size_t) i + 2] = slot_ptr[lo[i] + 1];
+        info.n_deep_loci += slot_ptr[lo[i] + 1] - slot_ptr[lo[i]] > GBRS_DEEP_LOCUS_ITEMS;
       }
     }
     // ---- 6. visiting order: costliest tile first (the work counter hands them out in this order) --------------------------

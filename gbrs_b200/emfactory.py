@@ -322,6 +322,7 @@ class DevicePattern:
         d.n_classes, d.n_pairs, d.n_runs, d.n_items = i["n_classes"], i["n_pairs"], i["n_runs"], i["n_items"]
         d.n_long_items, d.n_entries = i["n_long_items"], i["n_entries"]
         d.n_ranks, d.max_iters_cap = self.n_ranks, ERR_LOG_CAP
+        d.n_deep_loci = i["n_deep_loci"]
         for k in range(_lib.GBRS_KMAX + 2):
             d.bucket_class0[k] = i["bucket_class0"][k]
             d.bucket_pair0[k] = i["bucket_pair0"][k]
@@ -344,6 +345,7 @@ class DevicePattern:
             d.n_tiles, d.n_tile_slots = ti["n_tiles"], ti["n_slots"]
             d.tile_max_classes, d.tile_max_loci, d.tile_max_items = ti["max_classes"], ti["max_loci"], ti["max_items"]
             d.tile_max_a_bytes, d.tile_max_b_bytes = ti["max_part_a_bytes"], ti["max_part_b_bytes"]
+            d.tile_n_deep_loci = ti["n_deep_loci"]
         else:
             d.tile_blob = d.tile_desc = d.tile_locus_desc = d.tile_partial = None
             d.n_tiles = d.n_tile_slots = 0

@@ -31,6 +31,8 @@ extern "C" {
 #define GBRS_EM_ABI_VERSION 4
 #define GBRS_HPAD 8 /* haplotype slots per locus line */
 #define GBRS_KMAX 8 /* classes with up to this many (class, locus) pairs take the fixed-width row pass */
+#define GBRS_DEEP_LOCUS_ITEMS 8 /* a locus with more partial sums (column-pass items / tile slots) than this is summed by a
+                                  whole warp in the locus kernel instead of eight lanes */
 
 enum {
   GBRS_OK = 0,
@@ -84,7 +86,7 @@ typedef struct {
   int32_t entry_bytes; /* 4 or 8: width of the locus-major entry words */
   int32_t n_gene_ids;  /* 1 + max gene id */
   int32_t max_pairs_per_class;
-  int32_t reserved;
+  int32_t n_deep_loci;  /* loci with more than GBRS_DEEP_LOCUS_ITEMS work items (they come first in locus_desc) */
   /* Classes are ordered by (min(pairs, GBRS_KMAX + 1), smallest locus).  bucket_class0[k-1] / bucket_pair0[k-1] is the
    * first class / first pair word of the classes with exactly k pairs (k = 1..GBRS_KMAX); index GBRS_KMAX starts the
    * "long" classes (more than GBRS_KMAX pairs), index GBRS_KMAX+1 is the end (= n_classes / n_pairs). */
@@ -143,6 +145,8 @@ typedef struct {
   int32_t max_classes, max_loci, max_items, max_part_a_bytes, max_part_b_bytes, max_planes;
   int32_t max_slots_per_locus;
   int32_t item_len;
+  int32_t n_deep_loci;  /* loci with more than GBRS_DEEP_LOCUS_ITEMS slots (first in locus_desc) */
+  int32_t reserved;
 } gbrs_tiles_info;
 
 /* Builds the tile layout from a packed shard.  GBRS_E_LIMIT if a class touches more than `max_loci` loci (the caller
@@ -227,7 +231,8 @@ typedef struct {
   const uint32_t* tile_locus_desc; /* [T][4] */
   double* tile_partial;            /* [n_slots][8] per-(tile, locus) partial sums */
   int64_t n_tiles, n_tile_slots;
-  int32_t tile_max_classes, tile_max_loci, tile_max_items, tile_max_a_bytes, tile_max_b_bytes, tile_reserved;
+  int32_t n_deep_loci, dev_reserved; /* two-pass layout: loci with more than GBRS_DEEP_LOCUS_ITEMS items */
+  int32_t tile_max_classes, tile_max_loci, tile_max_items, tile_max_a_bytes, tile_max_b_bytes, tile_n_deep_loci;
   /* state */
   double* theta;    /* [2][T][8] ping-pong allelic expression */
   double* efflen;   /* [T][8] effective lengths (1.0 where unused / no length file) */

@@ -30,7 +30,11 @@ import types
 import numpy as np
 import scipy.sparse as sp
 
-REFERENCE_SRC = "/root/reference/src"
+# the mounted reference (build container), else the copy oracle/make_ref.py staged into the git-ignored oracle/_ref/
+# (that copy travels to the GPU box, where bench.py --impl reference times the unmodified reference)
+_CANDIDATES = tuple(c for c in (os.environ.get("GBRS_REFERENCE_SRC"), "/root/reference/src",
+                                os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")) if c)
+REFERENCE_SRC = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "gbrs", "emase"))), _CANDIDATES[0])
 
 
 def reference_available() -> bool:
@@ -164,7 +168,10 @@ def load_reference():
         sys.path.insert(0, REFERENCE_SRC)
     import gbrs.emase.AlignmentPropertyMatrix as apm_mod
     import gbrs.emase.EMfactory as em_mod
-    import gbrs.gbrs.emase_utils as gutils
+    try:  # the workflow functions are only needed for the end-to-end goldens (not staged into oracle/_ref)
+        import gbrs.gbrs.emase_utils as gutils
+    except ImportError:
+        gutils = None
 
     _mods = types.SimpleNamespace(apm_mod=apm_mod, em_mod=em_mod, gutils=gutils,
                                   APM=apm_mod.AlignmentPropertyMatrix, EMfactory=em_mod.EMfactory)

@@ -1,5 +1,11 @@
-"""Size-independent properties of the EM at BASELINE.json's full single-GPU size (configs[1]: 80k transcripts x 8
-haplotypes x 5M alignment classes, model 4), where the oracle is too slow to be the checker:
+"""BASELINE.json's configurations at (or near) full size.
+
+Oracle parity (the numpy restatement of the reference, oracle/em_oracle.py, on the host cores of the GPU box):
+  * config 2 -- 80k transcripts x 8 haplotypes x 5M classes, model 4 -- at FULL size, a fixed number of updates:
+    error trajectory to 1e-7 relative, theta / expected counts to 1e-9 (the north-star bar is 1e-6);
+  * config 3 -- the same locus shape under models 1, 2 and 3 -- on a 1M-class slice;
+  * config 4 -- diploid `-G` restriction -- on a 2M-class slice of the 20M-class shape.
+Size-independent properties at the full single-GPU size of config 2:
   * every class' responsibilities sum to one  ->  expected counts add up to the class counts, in prepare() and after
     every update;
   * expected counts are finite, non-negative, and zero wherever a (locus, haplotype) has no alignment;
@@ -80,6 +86,57 @@ def test_full_size_properties_model4():
     s = run_sharded(d, 4, 2, tol=0.0, max_iters=UPDATES)
     assert s["iters"] == UPDATES
     assert hp.relerr(s["counts"], counts) < 1e-10 and hp.relerr(s["theta"], theta) < 1e-10
+
+
+def gpu_fixed(d, model, updates, gtmask=None, **kw):
+    from gbrs_b200.emfactory import EMfactory
+    from gbrs_b200.quantify import hapmask_bytes
+
+    em = EMfactory(synth.to_apm(d), locus_hapmask=None if gtmask is None else hapmask_bytes(gtmask), **kw)
+    em.target_lengths = synth.effective_lengths(d)
+    em.prepare()
+    theta0 = em.get_allelic_expression()
+    em.run(model=model, tol=0.0, max_iters=updates, verbose=False)
+    return dict(theta0=theta0, theta=em.get_allelic_expression(), counts=em.expected_read_counts().copy(),
+                errs=em.err_history.copy(), iters=em.num_iters)
+
+
+def assert_parity(out, o, updates):
+    assert out["iters"] == o["iters"] == updates
+    assert hp.relerr(out["theta0"], o["theta0"]) < 1e-9
+    np.testing.assert_allclose(out["errs"], o["errs"], rtol=1e-7)
+    assert hp.relerr(out["theta"], o["theta"]) < 1e-9 and hp.relerr(out["counts"], o["counts"]) < 1e-9
+    floor = 1e-9 * o["counts"].sum()  # element-wise, the north-star bar
+    assert hp.elementwise_relerr(out["counts"], o["counts"], floor) < 1e-6
+
+
+@pytest.mark.gpu
+def test_config2_full_size_matches_oracle_model4():
+    """BASELINE config 2 at its full 5M classes: 12 fixed updates of the GPU path against the oracle."""
+    d = synth.generate(T=80_000, N=5_000_000, H=8)
+    o = hp.oracle_run(d, 4, tol=0.0, max_iters=UPDATES)
+    assert_parity(gpu_fixed(d, 4, UPDATES), o, UPDATES)
+    assert_parity(gpu_fixed(d, 4, UPDATES, tiles=True), o, UPDATES)  # the opt-in single-pass tile kernel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", [1, 2, 3])
+def test_config3_models_1_to_3_match_oracle_on_a_1m_class_slice(model):
+    """BASELINE config 3 (the C2 locus shape under models 1-3) on a 1M-class slice, 6 fixed updates."""
+    d = synth.generate(T=80_000, N=1_000_000, H=8)
+    o = hp.oracle_run(d, model, tol=0.0, max_iters=6)
+    assert_parity(gpu_fixed(d, model, 6), o, 6)
+
+
+@pytest.mark.gpu
+def test_config4_diploid_matches_oracle_on_a_2m_class_slice():
+    """BASELINE config 4 (diploid -G restriction, 80k loci) on a 2M-class slice, 8 fixed updates."""
+    d = synth.generate(T=80_000, N=2_000_000, H=8, with_genotype=True)
+    gm = synth.genotype_mask(d)
+    o = hp.oracle_run(d, 4, tol=0.0, max_iters=8, gtmask=gm)
+    out = gpu_fixed(d, 4, 8, gtmask=gm)
+    assert_parity(out, o, 8)
+    assert np.all(out["counts"][gm == 0] == 0.0)
 
 
 M1_FIXED_WORKER = r'''
