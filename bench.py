@@ -12,8 +12,10 @@ A *step* is one EM update (E-step + M-step + convergence test) over the resident
   cpu_baseline  the oracle port (numpy restatement of the reference's EM; the reference itself is pure Python and is not
             present on the GPU box) timed on a bounded sample of the same workload on the host cores
 
-N > 1 (torchrun): weak scaling -- every rank holds its own `workload`-sized row shard (different classes, same loci),
-one NCCL all-reduce of the T x 8 numerator per step; time = max over ranks.
+N > 1 (torchrun): weak scaling -- every rank holds its own `workload`-sized row shard (different classes, same loci); the
+T x 8 numerator is summed over the ranks once per step inside our own kernels over NVLink peer memory (GBRS_XCHG=nccl:
+a plain all-reduce); time = max over ranks.  Every line carries a `parity` record (conservation, theta identical on all
+ranks, a small problem sharded over the same ranks against the oracle).
 """
 from __future__ import annotations
 
@@ -531,6 +533,7 @@ def run_gpu_arm(args, wl):
     if model == 4 and world == 1 and args.workload == "c2" and not args.no_models:
         models_rec = {}
         pat.ensure_full()
+        _lib.check(lib.gbrs_em_run_begin(C.byref(desc), 0.0, 1000, stream))  # re-arm the loop (the e2e run has stopped it)
         for m in (3, 2, 1):
             for _ in range(2):
                 _lib.check(lib.gbrs_em_launch_local(C.byref(desc), m, stream))
@@ -546,7 +549,7 @@ def run_gpu_arm(args, wl):
             mm = f0.elapsed_time(f1) / 5
             models_rec[str(m)] = {"ms_per_step": mm, "value": nnz_total / (mm * 1e-3), "unit": UNIT, "steps": 5}
         ctrl_m, _ = pat.read_ctrl()
-        assert ctrl_m[_lib.CTRL_ERROR] == 0
+        assert ctrl_m[_lib.CTRL_ERROR] == 0 and ctrl_m[_lib.CTRL_ITERS] == 3 * 7, ctrl_m[:6]
 
     # ---- parity of the timed path (every run carries it; at N > 1 this is where the sharded result gets checked) ------
     parity = parity_checks(em, pat, d, world, rank, dev, diploid, args.model)
@@ -561,7 +564,8 @@ def run_gpu_arm(args, wl):
                          f"{os.cpu_count()} logical cores (the path is single-threaded)"}
 
     if rank == 0:
-        launches_per_step = ((3 if tiled else 4) if world == 1 else (4 if tiled else 5)) + (1 if model != 4 else 0)
+        pushed = world > 1 and em.fused_exchange and em.exchange_mode == "push"
+        launches_per_step = (3 if tiled else 4) + (1 if world > 1 and not pushed else 0) + (1 if model != 4 else 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -572,11 +576,13 @@ def run_gpu_arm(args, wl):
                            if tiled else "two-pass: class-major + locus-major copies",
                            "l2_policy": "inputs larger than L2 (packed incidence %.0f MB per GPU streams every step)"
                                         % ((pat.tiled.nbytes() if tiled else pat.packed.nbytes()) / 1e6),
-                           "exchange": "none" if world == 1 else (
-                               ("fused two-shot all-reduce of T x 8 fp64 inside the locus kernels: NVLS (multimem.ld_reduce / "
-                                "multimem.st on the NVSwitch multicast mapping)" if em.nvls_exchange else
-                                "fused two-shot all-reduce of T x 8 fp64 over NVLink peer memory inside the locus kernels")
-                               if em.fused_exchange else "NCCL all-reduce of T x 8 fp64 per step")},
+                           "exchange": "none" if world == 1 else {
+                               "push": "one launch per update: local numerator pushed into the owners' receive rows over NVLink "
+                                       "peer memory, slice sums broadcast by their owners, update (k_locus_xchg)",
+                               "pull": "fused two-shot all-reduce of T x 8 fp64 over NVLink peer memory inside the locus kernels",
+                               "nvls": "fused two-shot all-reduce of T x 8 fp64 inside the locus kernels: NVLS (multimem.ld_reduce / "
+                                       "multimem.st on the NVSwitch multicast mapping)",
+                               "nccl": "NCCL all-reduce of T x 8 fp64 per step"}[em.exchange_mode if em.fused_exchange else "nccl"]},
                 "iterations_per_s": K / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "e2e_resident": e2e_resident, "parity": parity, "models": models_rec,
                 "gpu_launches": launches_per_step * K, "clocks": clocks,

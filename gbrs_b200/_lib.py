@@ -81,7 +81,7 @@ class EmDev(C.Structure):
                 ("gene_of", C.c_void_p), ("gene_ptr", C.c_void_p), ("gene_loci", C.c_void_p),
                 ("tile_blob", C.c_void_p), ("tile_desc", C.c_void_p), ("tile_locus_desc", C.c_void_p),
                 ("tile_partial", C.c_void_p), ("n_tiles", C.c_int64), ("n_tile_slots", C.c_int64),
-                ("n_deep_loci", C.c_int32), ("dev_reserved", C.c_int32),
+                ("n_deep_loci", C.c_int32), ("xchg_timeout_ms", C.c_int32),
                 ("tile_max_classes", C.c_int32), ("tile_max_loci", C.c_int32), ("tile_max_items", C.c_int32),
                 ("tile_max_a_bytes", C.c_int32), ("tile_max_b_bytes", C.c_int32), ("tile_n_deep_loci", C.c_int32),
                 ("theta", C.c_void_p), ("efflen", C.c_void_p), ("acc", C.c_void_p), ("iso", C.c_void_p),

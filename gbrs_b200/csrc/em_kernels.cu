@@ -1369,6 +1369,206 @@ __global__ void __launch_bounds__(kThreads) k_locus_update(const __grid_constant
   if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Row-sharded update, push form (xchg_enabled == 2; the default between ranks): ONE launch does the local numerator, the
+// cross-rank sum and the update.  Every rank's symmetric buffer holds
+//     recv  [R][slice]  doubles: recv[s] = rank s' contribution to the loci THIS rank owns (slice = its share of T * 8)
+//     total [T * 8]     doubles: the summed numerator, written slice by slice by the owning ranks
+//     ready [8], done [8] u32 epoch flags
+//   A  numerator of the local shard; every value is stored straight into its OWNER's recv[me] with a peer store while
+//      the kernel is still computing (no publish + peer-load round trip); when the whole grid is through: ready[me] = e
+//      on every rank
+//   B  wait for all ready flags; the owner adds its slice over the ranks in rank order -- local loads -- and stores the
+//      totals into every rank's `total` (peer stores); when the grid is through: done[me] = e everywhere
+//   C  wait for all done flags; theta' = total / efflen, isoform totals, subset tables, block partials (as k_locus_update)
+// Each element is summed by exactly one rank in a fixed order: all ranks see the same bits and take the same stop
+// decision.  All blocks must be resident (they wait for each other through the tickets): the launcher sizes the grid by
+// the occupancy API.  Waits are bounded by a wall-clock limit (%globaltimer); on a timeout the error flag (3) and the stop
+// flag are raised and every block leaves -- nothing continues on partial sums.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__host__ __device__ inline int64_t push_slice_len(const gbrs_em_dev& d) {  // doubles per owner, even
+  return ((((int64_t) d.T * GBRS_HPAD + d.n_ranks - 1) / d.n_ranks) + 1) & ~(int64_t) 1;
+}
+__device__ __forceinline__ double* push_recv(const gbrs_em_dev& d, int owner, int src) {
+  return static_cast<double*>(d.xchg_peer[owner]) + (size_t) src * push_slice_len(d);
+}
+__device__ __forceinline__ double* push_total(const gbrs_em_dev& d, int r) {
+  return static_cast<double*>(d.xchg_peer[r]) + (size_t) d.n_ranks * push_slice_len(d);
+}
+__device__ __forceinline__ uint32_t* push_flags(const gbrs_em_dev& d, int r, int which /* 0 ready, 1 done */) {
+  return reinterpret_cast<uint32_t*>(push_total(d, r) + (size_t) d.T * GBRS_HPAD) + which * 8;
+}
+// thread 0 waits until every rank's flag has reached epoch e; false (for the whole block) on a timeout
+__device__ __forceinline__ bool push_wait(const gbrs_em_dev& d, int which, uint32_t e, int* s_fail) {
+  if (threadIdx.x == 0) {
+    const uint32_t* f = push_flags(d, d.xchg_rank, which);
+    const unsigned long long t0 = globaltimer_ns();
+    const unsigned long long limit = (unsigned long long) (d.xchg_timeout_ms > 0 ? d.xchg_timeout_ms : 20000) * 1000000ull;
+    int fail = 0;
+    for (int r = 0; r < d.n_ranks && !fail; ++r) {
+      unsigned spins = 0;
+      while ((int32_t) (ld_acquire_sys(f + r) - e) < 0) {
+        if ((++spins & 255u) == 0u &&
+            (globaltimer_ns() - t0 > limit || *reinterpret_cast<volatile int32_t*>(d.ctrl + GBRS_CTRL_ERROR) == 3)) {
+          fail = 1;
+          break;
+        }
+        __nanosleep(40);
+      }
+    }
+    if (fail) {
+      d.ctrl[GBRS_CTRL_ERROR] = 3;
+      d.ctrl[GBRS_CTRL_DONE] = 1;
+    }
+    *s_fail = fail;
+  }
+  __syncthreads();
+  return *s_fail == 0;
+}
+// every block calls it when it is through with a phase: the last one raises flag[me] = e on every rank
+__device__ __forceinline__ void push_signal(const gbrs_em_dev& d, int which, uint32_t e, int ticket_slot) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // this block's stores (also the peer stores) are ordered before its ticket
+    const int ticket = atomicAdd(d.ctrl + ticket_slot, 1);
+    if (ticket == (int) gridDim.x - 1) {
+      d.ctrl[ticket_slot] = 0;
+      if (which == 1) d.ctrl[GBRS_CTRL_XEPOCH] = (int32_t) e;
+      __threadfence_system();  // one system-scope fence for the whole grid, then the flags back to back
+      for (int r = 0; r < d.n_ranks; ++r) st_relaxed_sys_u32(push_flags(d, r, which) + d.xchg_rank, e);
+    }
+  }
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constant__ gbrs_em_dev d) {
+  __shared__ double red[32];
+  __shared__ int s_fail;
+  if (blockIdx.x == 0 && threadIdx.x == 0) d.ctrl[GBRS_CTRL_TILE_NEXT] = 0;
+  if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;  // every rank takes the same decision: the epochs stay in step
+  const uint32_t e = (uint32_t) d.ctrl[GBRS_CTRL_XEPOCH] + 1u;  // read by every block before the last one bumps it
+  const int par = d.ctrl[GBRS_CTRL_PARITY];
+  const int me = d.xchg_rank;
+  const int64_t slice = push_slice_len(d);
+  const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
+  // ---- A: local numerator, pushed to the owners ----------------------------------------------------------------------
+  {
+    const double* __restrict__ th = d.theta + (size_t) par * d.T * GBRS_HPAD;
+    const int64_t n_deep = d.n_deep_loci;
+    const int64_t total_slots = n_deep + ((d.T - n_deep + 3) >> 2);
+    const int64_t nwarps = (int64_t) (blockDim.x >> 5) * gridDim.x;
+    const int64_t warp0 = (int64_t) (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const int64_t rounds = (total_slots + nwarps - 1) / nwarps;
+    const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.locus_desc);
+    auto desc_index = [&](int64_t ws) { return ws < n_deep ? ws : n_deep + ((ws - n_deep) << 2) + grp; };
+    uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+    if (warp0 < total_slots && desc_index(warp0) < d.T) nx = __ldg(descs + desc_index(warp0));
+    for (int64_t r = 0; r < rounds; ++r) {
+      const int64_t ws = warp0 + r * nwarps;
+      const bool deep = ws < n_deep;
+      const bool have = ws < total_slots && desc_index(ws) < d.T;
+      const uint4 ld = nx;
+      {
+        const int64_t wn = ws + nwarps;
+        nx = make_uint4(0u, 0u, 0u, 0u);
+        if (wn < total_slots && desc_index(wn) < d.T) nx = __ldg(descs + desc_index(wn));
+      }
+      const int64_t o = (int64_t) ld.x * GBRS_HPAD + h;
+      const uint32_t end = have ? ld.z : 0u;
+      const bool valid = have && (!deep || grp == 0);
+      const double th_o = (valid && !UNIT) ? th[o] : 1.0;
+      double W = 0.0;
+      if (deep) {
+        uint32_t it = (have ? ld.y : 0u) + (uint32_t) grp;
+        for (; it + 12 < end; it += 16) {
+          const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 4) * GBRS_HPAD + h];
+          const double w2 = d.wit[(size_t) (it + 8) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 12) * GBRS_HPAD + h];
+          W += (w0 + w1) + (w2 + w3);
+        }
+        for (; it < end; it += 4) W += d.wit[(size_t) it * GBRS_HPAD + h];
+        W += __shfl_xor_sync(0xFFFFFFFFu, W, 8);
+        W += __shfl_xor_sync(0xFFFFFFFFu, W, 16);
+      } else {
+        uint32_t it = have ? ld.y : 0u;
+        for (; it + 3 < end; it += 4) {
+          const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 1) * GBRS_HPAD + h];
+          const double w2 = d.wit[(size_t) (it + 2) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 3) * GBRS_HPAD + h];
+          W += (w0 + w1) + (w2 + w3);
+        }
+        for (; it < end; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
+      }
+      if (valid) {
+        const double a = UNIT ? ((h < d.H) ? W : 0.0) : th_o * W;
+        const int owner = (int) (o / slice);
+        st_relaxed_sys_f64(push_recv(d, owner, me) + (o - (int64_t) owner * slice), a);
+      }
+    }
+  }
+  push_signal(d, 0, e, GBRS_CTRL_TICKET + 1);
+  // ---- B: sum my slice over the ranks, broadcast the totals ---------------------------------------------------------
+  if (!push_wait(d, 0, e, &s_fail)) return;
+  {
+    const int64_t total_n = (int64_t) d.T * GBRS_HPAD;
+    const int64_t lo = slice * me, hi = lo + slice < total_n ? lo + slice : total_n;  // (both even)
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = lo + 2 * ((int64_t) blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 2 * stride) {
+      double2 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) v[r] = ld_relaxed_sys_f64x2(push_recv(d, me, r) + (i - lo));
+      double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) {
+          sum.x += v[r].x;
+          sum.y += v[r].y;
+        }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) st_relaxed_sys_f64x2(push_total(d, r) + i, sum);
+    }
+  }
+  push_signal(d, 1, e, GBRS_CTRL_TICKET + 2);
+  // ---- C: the update, from the totals every owner has stored here -------------------------------------------------------
+  if (!push_wait(d, 1, e, &s_fail)) return;
+  {
+    const double* __restrict__ src = push_total(d, me);
+    double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
+    double* __restrict__ iso = d.iso + (size_t) (par ^ 1) * d.T;
+    const int64_t total = (int64_t) d.T * GBRS_HPAD;
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    const int64_t rounds = (total + stride - 1) / stride;
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    double mine = 0.0;
+    for (int64_t r = 0; r < rounds; ++r, i += stride) {
+      double v = 0.0;
+      const bool valid = i < total;
+      if (valid) {
+        const double a = __ldcg(src + i);  // written by peers: never through a stale L1 line
+        d.acc[i] = a;                      // the summed numerator, where the reports read it
+        v = fast_div(a, d.efflen[i]);
+        dst[i] = v;
+      }
+      const double sum8 = group8_sum(v);
+      if (valid && h == 0) {
+        iso[i >> 3] = sum8;
+        mine += sum8;
+      }
+      write_subset_rows(d, i >> 3, h, v, valid);
+    }
+    const double bs = block_sum(mine, red);
+    if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
+  }
+}
+
 // Stop test of EMfactory.run (EMfactory.py:267-279) on the device.
 //   INIT: record sum of the current isoform totals as "prev" (after prepare / set_theta).  Launched with one block.
 //   else: err = sum_t | iso'[t] * 1e6 / S' - iso[t] * 1e6 / S |, log it, flip the ping-pong, decide.  Many blocks:
@@ -1589,6 +1789,21 @@ int check_exchange(const gbrs_em_dev* d) {
   return GBRS_OK;
 }
 
+// grid of the push-form update kernel: all blocks resident, one (locus, haplotype) per thread at most
+template <bool UNIT>
+int push_grid(const gbrs_em_dev* d) {
+  int g = resident_grid(k_locus_xchg<UNIT>, (int64_t) d->T * GBRS_HPAD);
+  return g > kHalfSlots ? kHalfSlots : g;
+}
+
+template <bool UNIT>
+int launch_push(const gbrs_em_dev* d, cudaStream_t s) {
+  if (int rc = check_exchange(d)) return rc;
+  k_locus_xchg<UNIT><<<push_grid<UNIT>(d), kThreads, 0, s>>>(*d);
+  GBRS_LAUNCH_CHECK("k_locus_xchg");
+  return GBRS_OK;
+}
+
 // Fused NVLink exchange (descriptor flag); otherwise the caller all-reduces `acc` between the two halves of an update.
 int launch_exchange(const gbrs_em_dev* d, cudaStream_t s) {
   if (!d->xchg_enabled) return GBRS_OK;
@@ -1698,6 +1913,7 @@ extern "C" int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream) {
     if (int rc = launch_column<1>(d, d->ent_cls, false, s)) return rc;
   }
   const gbrs_em_dev lv = locus_view(d, tiles);
+  if (d->n_ranks > 1 && d->xchg_enabled == 2) return launch_push<true>(&lv, s);  // numerator + exchange + theta0 in one launch
   k_locus_acc<true, false><<<acc_grid(d), kThreads, 0, s>>>(lv, false);
   GBRS_LAUNCH_CHECK("k_locus_acc<unit>");
   return GBRS_OK;
@@ -1706,11 +1922,15 @@ extern "C" int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream) {
 extern "C" int gbrs_em_prepare_finish(const gbrs_em_dev* d, double pseudocount, void* stream) {
   if (int rc = check_dev(d, "gbrs_em_prepare_finish")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int lg = locus_grid(d);
-  if (int rc = launch_exchange(d, s)) return rc;
-  // theta[1] = acc / efflen ; then make it the current estimate
-  k_locus_update<true><<<lg, kThreads, 0, s>>>(*d);
-  GBRS_LAUNCH_CHECK("k_locus_update");
+  int lg = locus_grid(d);
+  if (d->n_ranks > 1 && d->xchg_enabled == 2) {
+    lg = push_grid<true>(d);  // gbrs_em_prepare_local has done exchange and update already; its blocks wrote the partials
+  } else {
+    if (int rc = launch_exchange(d, s)) return rc;
+    // theta[1] = acc / efflen ; then make it the current estimate
+    k_locus_update<true><<<lg, kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_locus_update");
+  }
   k_flip_parity<<<1, 32, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_flip_parity");
   k_converge<true><<<1, kThreads, 0, s>>>(*d, lg);
@@ -1848,7 +2068,7 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
     gbrs_set_error("The read normalization model should be 1, 2, 3, or 4."); return GBRS_E_ARG;  // EMfactory.py:209-212
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool honour_done = d->n_ranks <= 1 && !estep_only;
+  const bool honour_done = (d->n_ranks <= 1 || d->xchg_enabled == 2) && !estep_only;
   const bool tiles = model == 4 && d->tile_blob != nullptr;
   int rc = GBRS_OK;
   if (!tiles && d->tile_blob)
@@ -1917,9 +2137,13 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   if (rc) return rc;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[2], s));
   const gbrs_em_dev lv = locus_view(d, tiles);
-  if (d->n_ranks <= 1 && !estep_only) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(lv, true);
-  else k_locus_acc<false, false><<<acc_grid(d), kThreads, 0, s>>>(lv, false);
-  GBRS_LAUNCH_CHECK("k_locus_acc");
+  if (d->n_ranks > 1 && d->xchg_enabled == 2 && !estep_only) {
+    if (int rcp = launch_push<false>(&lv, s)) return rcp;
+  } else {
+    if (d->n_ranks <= 1 && !estep_only) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(lv, true);
+    else k_locus_acc<false, false><<<acc_grid(d), kThreads, 0, s>>>(lv, false);
+    GBRS_LAUNCH_CHECK("k_locus_acc");
+  }
   if (ev) {
     GBRS_CUDA(cudaEventRecord(ev[3], s));
     ++prof->used;
@@ -1931,7 +2155,9 @@ extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
   if (int rc = check_dev(d, "gbrs_em_launch_update")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int nparts = acc_grid(d);  // single rank: k_locus_acc already produced theta', iso' and the partial sums
-  if (d->n_ranks > 1) {
+  if (d->n_ranks > 1 && d->xchg_enabled == 2) {
+    nparts = push_grid<false>(d);  // k_locus_xchg (queued by gbrs_em_launch_local) has updated theta already
+  } else if (d->n_ranks > 1) {
     nparts = locus_grid(d);
     static const bool two_launches = std::getenv("GBRS_XCHG_SPLIT") != nullptr;  // A/B knob: reduce as its own kernel
     if (d->xchg_enabled && !two_launches) {

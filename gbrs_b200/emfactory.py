@@ -474,6 +474,7 @@ class EMfactory:
         self.rank, self.world = 0, 1
         self.fused_exchange = False
         self.nvls_exchange = False
+        self.exchange_mode = "nccl"
         if shard is None:
             shard = group is not None
         self._presharded = shard == "local"
@@ -597,19 +598,24 @@ class EMfactory:
         torch = _torch()
         import torch.distributed as dist
 
-        # fused / p2p: peer loads and stores | nvls: in-switch reduction where the box has a multicast mapping | nccl:
-        # plain all-reduce.  NVLS is opt-in: a multimem f64 access moves 8 bytes per request (no vector form for f64) and
-        # measured slower than peer loads both on 2 ranks (47.8 vs 20.9 us per exchange) and on 8 (44.1 vs 36.5 us),
-        # although it moves 2/R of the numerator per rank instead of 2(R-1)/R.
-        mode = os.environ.get("GBRS_XCHG", "fused")
-        if self.world < 2 or self.world > 8 or mode not in ("fused", "nvls", "p2p"):
+        # GBRS_XCHG: push (default; also "fused") the one-launch push form | pull (also "p2p") the round-1 pull form: the
+        # owner of a slice loads it from every peer | nvls: pull form with the in-switch reduction where the box has a
+        # multicast mapping (a multimem f64 access moves 8 bytes per request: measured slower than peer loads on 2 and on
+        # 8 ranks) | nccl: plain all-reduce between the two halves of an update.
+        mode = os.environ.get("GBRS_XCHG", "push")
+        mode = {"fused": "push", "p2p": "pull"}.get(mode, mode)
+        if self.world < 2 or self.world > 8 or mode not in ("push", "pull", "nvls"):
             return False
         use_mc = mode == "nvls"
         ok, buf, hdl, mc = 1, None, None, 0
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
-            n_doubles = 2 * 8 * pat.T + 16
+            if mode == "push":  # recv[R][slice] | total | flags (include/gbrs_em.h)
+                slice_len = ((8 * pat.T + self.world - 1) // self.world + 1) & ~1
+                n_doubles = self.world * slice_len + 8 * pat.T + 16
+            else:  # acc_local | acc_total | flags
+                n_doubles = 2 * 8 * pat.T + 16
             buf = symm_mem.empty(n_doubles, dtype=torch.float64, device=pat.device)
             buf.zero_()
             hdl = symm_mem.rendezvous(buf, group=self._group if self._group is not None else dist.group.WORLD)
@@ -628,7 +634,9 @@ class EMfactory:
             return False
         self.nvls_exchange = bool(int(flag[1].item()))
         pat._xchg = (buf, hdl)
-        pat.desc.xchg_enabled = 1
+        pat.desc.xchg_enabled = 2 if mode == "push" else 1
+        pat.desc.xchg_timeout_ms = int(os.environ.get("GBRS_XCHG_TIMEOUT_MS", "0"))
+        self.exchange_mode = mode
         pat.desc.xchg_mc = mc if self.nvls_exchange else None
         pat.desc.xchg_rank = self.rank
         for r in range(self.world):

@@ -200,8 +200,12 @@ typedef struct {
   int64_t bucket_class0[GBRS_KMAX + 2]; /* see gbrs_pack_info */
   int64_t bucket_pair0[GBRS_KMAX + 2];
   /* Fused cross-rank exchange over NVLink peer memory (optional, 2..8 ranks).  xchg_peer[r] is rank r's symmetric
-   * exchange buffer as mapped into THIS process ( (2 * 64 * T + 128) bytes, zeroed once before first use ); with
-   * xchg_enabled == 0 the caller sums `acc` over ranks between gbrs_em_launch_local and gbrs_em_launch_update. */
+   * exchange buffer as mapped into THIS process, zeroed once before first use.  xchg_enabled:
+   *   0  the caller sums `acc` over ranks between gbrs_em_launch_local and gbrs_em_launch_update (e.g. ncclAllReduce)
+   *   1  pull form: acc_local | acc_total | flags, (2 * 64 * T + 128) bytes; the owner of a slice loads it from every peer
+   *   2  push form (default): recv[R][slice] | total | flags, (8 * (R * slice + 8 * T) + 128) bytes with
+   *      slice = ((8 * T + R - 1) / R + 1) & ~1; every rank stores its values into the owners' recv rows while computing
+   *      them, and the whole update is one launch (gbrs_em_launch_update then only runs the stop test) */
   int32_t xchg_enabled;
   int32_t xchg_rank;
   void* xchg_peer[8];
@@ -231,7 +235,9 @@ typedef struct {
   const uint32_t* tile_locus_desc; /* [T][4] */
   double* tile_partial;            /* [n_slots][8] per-(tile, locus) partial sums */
   int64_t n_tiles, n_tile_slots;
-  int32_t n_deep_loci, dev_reserved; /* two-pass layout: loci with more than GBRS_DEEP_LOCUS_ITEMS items */
+  int32_t n_deep_loci;     /* two-pass layout: loci with more than GBRS_DEEP_LOCUS_ITEMS items */
+  int32_t xchg_timeout_ms; /* wall-clock limit of a wait for peer flags; 0 = 20 s.  On a timeout the error flag (3) and the
+                              stop flag are set and every block of the kernel leaves */
   int32_t tile_max_classes, tile_max_loci, tile_max_items, tile_max_a_bytes, tile_max_b_bytes, tile_n_deep_loci;
   /* state */
   double* theta;    /* [2][T][8] ping-pong allelic expression */

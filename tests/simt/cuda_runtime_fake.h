@@ -66,6 +66,10 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSucces
 // the NVSwitch multimem instructions have no host meaning and trap.
 #define SIMT_PTX_UNSUPPORTED() __builtin_trap()
 inline unsigned simt_ld_acquire_u32(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline unsigned long long simt_globaltimer_ns() {
+  return (unsigned long long) std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 inline void simt_st_release_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 // rcp.approx.ftz.f64: a reciprocal good to ~20 bits (the seed of fast_div's Newton steps) -- modelled as the exact
 // reciprocal with the low 32 mantissa bits cleared, so that the refinement steps have real work to do

@@ -196,7 +196,7 @@ def test_emulated_row_shards_equal_the_unsharded_run(model, R):
     assert o["iters"] == it and hp.relerr(ref["counts"], o["counts"]) < 1e-12
 
 
-def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1):
+def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1, mode=2, timeout_ms=0, absent=()):
     """R ranks = R private instances of the emulated library running at the same time in R host threads, their
     symmetric exchange buffers in shared host memory: the fused NVLink exchange (k_locus_acc publishes and raises
     `ready`, the reduce step sums a slice with peer loads and raises `done`, the update waits for it) runs for real.
@@ -214,10 +214,12 @@ def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1):
         apm = synth.to_apm(d)
         pats = [simt_em.HostPattern(apm, gene_of=gene_of, shard_rank=r, shard_count=R,
                                     lib=simt_em.load_instance(f"rank{r}", tsan)) for r in range(R)]
-        bufs = [np.zeros(2 * 8 * d.T + 16) for _ in range(R)]
+        slice_len = ((8 * d.T + R - 1) // R + 1) & ~1
+        n_doubles = R * slice_len + 8 * d.T + 16 if mode == 2 else 2 * 8 * d.T + 16  # push | pull layout
+        bufs = [np.zeros(n_doubles) for _ in range(R)]
         for r, p in enumerate(pats):
             p.efflen[:, : d.H] = eff.T
-            p.desc.xchg_enabled, p.desc.xchg_rank, p.desc.xchg_mc = 1, r, None
+            p.desc.xchg_enabled, p.desc.xchg_rank, p.desc.xchg_mc, p.desc.xchg_timeout_ms = mode, r, None, timeout_ms
             for q in range(R):
                 p.desc.xchg_peer[q] = bufs[q].ctypes.data
         errors, iters = [], [0] * R
@@ -237,7 +239,7 @@ def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1):
             except BaseException as e:  # noqa: BLE001 - reported by the main thread
                 errors.append((r, repr(e)))
 
-        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(R)]
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(R) if r not in absent]
         for t in threads:
             t.start()
         for t in threads:
@@ -249,10 +251,11 @@ def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1):
         os.environ.pop("GBRS_SIMT_SMS", None)
 
 
-@pytest.mark.parametrize("R,model", [(2, 4), (3, 2)])
-def test_emulated_fused_exchange_between_concurrent_ranks(R, model):
+@pytest.mark.parametrize("R,model,mode", [(2, 4, 2), (3, 2, 2), (3, 4, 1), (2, 1, 1)])
+def test_emulated_fused_exchange_between_concurrent_ranks(R, model, mode):
+    """mode 2: the one-launch push form (k_locus_xchg); mode 1: the pull form."""
     d = synth.generate(T=70, N=900, H=8, sample_index=12)
-    pats, iters = _run_fused_ranks(d, model, R, 1e-3, 60, poll=2)
+    pats, iters = _run_fused_ranks(d, model, R, 1e-3, 60, poll=2, mode=mode)
     o = hp.oracle_run(d, model, tol=1e-3, max_iters=60)
     assert iters == [o["iters"]] * R
     for p in pats:  # bit-identical on every rank: each element of the numerator is summed by exactly one rank
@@ -260,6 +263,35 @@ def test_emulated_fused_exchange_between_concurrent_ranks(R, model):
         assert np.array_equal(p.acc, pats[0].acc)
     assert hp.relerr(pats[0].current_theta(), o["theta"]) < 1e-12
     assert hp.relerr(pats[0].acc[:, : d.H].T, o["counts"]) < 1e-12
+
+
+def test_emulated_exchange_timeout_stops_every_block():
+    """A peer that never shows up: the wait is bounded by wall-clock time, the error flag (3) and the stop flag are
+    raised and the kernel returns -- no block continues on partial sums, nothing hangs."""
+    import ctypes as C
+    import time
+
+    from gbrs_b200 import _lib
+
+    d = synth.generate(T=40, N=300, H=8, sample_index=3)
+    os.environ["GBRS_SIMT_SMS"] = "1"
+    try:
+        R = 2
+        p = simt_em.HostPattern(synth.to_apm(d), shard_rank=0, shard_count=R, lib=simt_em.load_instance("rank0"))
+        slice_len = ((8 * d.T + R - 1) // R + 1) & ~1
+        bufs = [np.zeros(R * slice_len + 8 * d.T + 16) for _ in range(R)]
+        p.desc.xchg_enabled, p.desc.xchg_rank, p.desc.xchg_mc, p.desc.xchg_timeout_ms = 2, 0, None, 150
+        for q in range(R):
+            p.desc.xchg_peer[q] = bufs[q].ctypes.data
+        t0 = time.time()
+        p.check(p.lib.gbrs_em_prepare_local(C.byref(p.desc), None))  # rank 1 never raises its flag
+        assert time.time() - t0 < 30
+        assert int(p.ctrl[_lib.CTRL_ERROR]) == 3 and int(p.ctrl[_lib.CTRL_DONE]) == 1
+        theta_before = p.theta.copy()
+        p.check(p.lib.gbrs_em_launch_local(C.byref(p.desc), 4, None))  # stopped: queued work is a no-op
+        assert np.array_equal(p.theta, theta_before)
+    finally:
+        os.environ.pop("GBRS_SIMT_SMS", None)
 
 
 def test_fused_exchange_is_race_free_under_thread_sanitizer():

@@ -1,6 +1,7 @@
 """Two real GPUs (skipped on a single-GPU box): `EMfactory(shard=True)` under torchrun / NCCL.  Every rank packs its
-own contiguous slice of the alignment classes, the T x 8 numerator is all-reduced once per update (fused exchange with
-NVLS where the box offers a multicast mapping, fused exchange with peer loads only, NCCL), and all ranks must reach the
+own contiguous slice of the alignment classes, the T x 8 numerator is summed over the ranks once per update (push: the
+one-launch push form over NVLink peer memory, the default; pull: the owner loads its slice from every peer; nvls: pull with
+the in-switch reduction where the box offers a multicast mapping; nccl: plain all-reduce), and all ranks must reach the
 reference's iteration count and results."""
 import os
 import subprocess
@@ -30,16 +31,16 @@ for name in ("em_small_m4", "em_small_m2", "em_small_m1_biggenes", "em_small_m3_
     if g["masked"]:
         apm.multiply(g["gtmask"], axis=2); apm.eliminate_zeros()
     em = EMfactory(apm, shard=True, poll_every=3)
-    want_fused = os.environ.get("GBRS_XCHG", "fused") in ("fused", "nvls", "p2p")
+    want_fused = os.environ.get("GBRS_XCHG", "push") in ("push", "fused", "pull", "nvls", "p2p")
     em.target_lengths = synth.effective_lengths(d)
     em.prepare(pseudocount=g["pseudocount"])
     assert hp.relerr(em.get_allelic_expression(), g["theta0"]) < 1e-9
     em.run(model=g["model"], tol=g["tol"], max_iters=g["max_iters"], verbose=False)
     assert em.num_iters == g["iters"], (name, em.num_iters, g["iters"])
     if want_fused and rank == 0 and name == "em_small_m4":
-        print("fused exchange in use:", em.fused_exchange, "NVLS:", em.nvls_exchange)
-        assert em.fused_exchange and (em.nvls_exchange or os.environ.get("GBRS_XCHG") != "p2p" or True)
-        assert not (os.environ.get("GBRS_XCHG") == "p2p" and em.nvls_exchange)
+        print("fused exchange in use:", em.fused_exchange, "mode:", em.exchange_mode, "NVLS:", em.nvls_exchange)
+        assert em.fused_exchange and em.exchange_mode == {"fused": "push", "p2p": "pull"}.get(os.environ["GBRS_XCHG"], os.environ["GBRS_XCHG"])
+        assert not (os.environ.get("GBRS_XCHG") in ("pull", "push") and em.nvls_exchange)
     assert hp.relerr(em.allelic_expression, g["theta"]) < 1e-9
     assert hp.relerr(em.expected_read_counts(), g["counts"]) < 1e-9
     np.testing.assert_allclose(em.err_history, g["errs"], rtol=1e-7, atol=1e-7)
@@ -53,7 +54,7 @@ print("rank", rank, "ok")
 '''
 
 
-@pytest.mark.parametrize("xchg", ["nvls", "p2p", "nccl"])
+@pytest.mark.parametrize("xchg", ["push", "pull", "nvls", "nccl"])
 def test_two_gpu_sharded_run_matches_reference(tmp_path, xchg):
     import torch
 
