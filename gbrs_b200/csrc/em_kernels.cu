@@ -1226,6 +1226,57 @@ __device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t 
 // Once the loop has stopped, k_converge has already flipped the ping-pong, so the theta that produced the weights in
 // `wit` is the *other* buffer: a single rank simply skips, a row-sharded rank recomputes the identical local numerator
 // from it (the in-place cross-rank sum that follows must always start from the local values).
+// The walk both numerator kernels share: every warp takes work slots (one deep locus, or four others) round-robin,
+// consecutive slots going to different blocks, and calls f(t, h, W, valid) with W = the sum of the locus' slots for
+// haplotype lane h.  All 32 lanes call f in every round of their warp (f may use warp collectives); `valid` marks the
+// eight lanes that finish a locus.  32-bit index arithmetic throughout: T * 8 < 2^27.
+template <class F>
+__device__ __forceinline__ void locus_walk(const gbrs_em_dev& d, F&& f) {
+  const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
+  const int T = d.T, n_deep = d.n_deep_loci;
+  const int total_slots = n_deep + ((T - n_deep + 3) >> 2);
+  const int nwarps = (int) (blockDim.x >> 5) * (int) gridDim.x;
+  const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.locus_desc);
+  const double* __restrict__ wit = d.wit + h;
+  int ws = (int) (threadIdx.x >> 5) * (int) gridDim.x + (int) blockIdx.x;
+  auto fetch = [&](int w) {  // descriptor of this lane group's locus in slot w (.w != 0: none)
+    const int di = w < n_deep ? w : n_deep + ((w - n_deep) << 2) + grp;
+    return (w < total_slots && di < T) ? __ldg(descs + di) : make_uint4(0u, 0u, 0u, 0xFFFFFFFFu);
+  };
+  uint4 nx = fetch(ws);  // requested one round ahead
+  for (; ws < total_slots; ws += nwarps) {
+    const uint4 ld = nx;
+    nx = fetch(ws + nwarps);
+    const bool deep = ws < n_deep, have = ld.w == 0u;
+    const uint32_t e = ld.z;  // (0 without a locus: the loops below do nothing)
+    double W = 0.0;
+    if (deep) {
+      uint32_t it = ld.y + (uint32_t) grp;
+      for (; it + 12 < e; it += 16) {
+        const double w0 = wit[(size_t) it * GBRS_HPAD], w1 = wit[(size_t) (it + 4) * GBRS_HPAD];
+        const double w2 = wit[(size_t) (it + 8) * GBRS_HPAD], w3 = wit[(size_t) (it + 12) * GBRS_HPAD];
+        W += (w0 + w1) + (w2 + w3);
+      }
+      for (; it < e; it += 4) W += wit[(size_t) it * GBRS_HPAD];
+      W += __shfl_xor_sync(0xFFFFFFFFu, W, 8);
+      W += __shfl_xor_sync(0xFFFFFFFFu, W, 16);
+    } else {
+      uint32_t it = ld.y;
+      if (it + 1 == e) {  // the commonest case: one slot
+        W = wit[(size_t) it * GBRS_HPAD];
+      } else {
+        for (; it + 3 < e; it += 4) {
+          const double w0 = wit[(size_t) it * GBRS_HPAD], w1 = wit[(size_t) (it + 1) * GBRS_HPAD];
+          const double w2 = wit[(size_t) (it + 2) * GBRS_HPAD], w3 = wit[(size_t) (it + 3) * GBRS_HPAD];
+          W += (w0 + w1) + (w2 + w3);
+        }
+        for (; it < e; ++it) W += wit[(size_t) it * GBRS_HPAD];
+      }
+    }
+    f((int) ld.x, h, W, have && (!deep || grp == 0));
+  }
+}
+
 template <bool UNIT, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const gbrs_em_dev d, bool honour_done) {
   __shared__ double red[32];
@@ -1236,64 +1287,19 @@ __global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const g
   const double* __restrict__ th = d.theta + (size_t) (done ? (par ^ 1) : par) * d.T * GBRS_HPAD;
   double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
   double* __restrict__ iso = d.iso + (size_t) (par ^ 1) * d.T;
-  const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
-  const int64_t n_deep = d.n_deep_loci;
-  const int64_t total_slots = n_deep + ((d.T - n_deep + 3) >> 2);  // warp work slots: one deep locus, or four others
-  // consecutive slots go to different blocks (the deep loci are few: spread them over all SMs)
-  const int64_t warps_per_block = blockDim.x >> 5, nwarps = warps_per_block * gridDim.x;
-  const int64_t warp0 = (int64_t) (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-  const int64_t rounds = (total_slots + nwarps - 1) / nwarps;
-  const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.locus_desc);
-  auto desc_index = [&](int64_t ws) { return ws < n_deep ? ws : n_deep + ((ws - n_deep) << 2) + grp; };
+  double* __restrict__ out = (!FUSE && d.xchg_enabled) ? xchg_acc_local(d, d.xchg_rank) : d.acc;
   double mine = 0.0;
-  uint4 nx = make_uint4(0u, 0u, 0u, 0u);  // descriptor of the coming round, requested one round ahead
-  if (warp0 < total_slots && desc_index(warp0) < d.T) nx = __ldg(descs + desc_index(warp0));
-  for (int64_t r = 0; r < rounds; ++r) {
-    const int64_t ws = warp0 + r * nwarps;
-    const bool deep = ws < n_deep;
-    const bool have = ws < total_slots && desc_index(ws) < d.T;  // this lane group has a locus
-    const uint4 ld = nx;
-    {
-      const int64_t wn = ws + nwarps;
-      nx = make_uint4(0u, 0u, 0u, 0u);
-      if (wn < total_slots && desc_index(wn) < d.T) nx = __ldg(descs + desc_index(wn));
-    }
-    const int64_t t = (int64_t) ld.x;
-    const int64_t o = t * GBRS_HPAD + h;
-    const uint32_t e = have ? ld.z : 0u;
-    const bool valid = have && (!deep || grp == 0);  // the lane group that finishes the locus
-    const double th_o = (valid && !UNIT) ? th[o] : 1.0;
-    const double len_o = (valid && FUSE) ? d.efflen[o] : 1.0;
-    double W = 0.0;
-    if (deep) {
-      uint32_t it = (have ? ld.y : 0u) + (uint32_t) grp;
-      for (; it + 12 < e; it += 16) {
-        const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 4) * GBRS_HPAD + h];
-        const double w2 = d.wit[(size_t) (it + 8) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 12) * GBRS_HPAD + h];
-        W += (w0 + w1) + (w2 + w3);
-      }
-      for (; it < e; it += 4) W += d.wit[(size_t) it * GBRS_HPAD + h];
-      W += __shfl_xor_sync(0xFFFFFFFFu, W, 8);
-      W += __shfl_xor_sync(0xFFFFFFFFu, W, 16);
-    } else {
-      uint32_t it = have ? ld.y : 0u;
-      for (; it + 3 < e; it += 4) {
-        const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 1) * GBRS_HPAD + h];
-        const double w2 = d.wit[(size_t) (it + 2) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 3) * GBRS_HPAD + h];
-        W += (w0 + w1) + (w2 + w3);
-      }
-      for (; it < e; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
-    }
+  locus_walk(d, [&](int t, int h, double W, bool valid) {
+    const int o = t * GBRS_HPAD + h;
     double a = 0.0;
     if (valid) {
-      a = UNIT ? ((h < d.H) ? W : 0.0) : th_o * W;
-      if (!FUSE && d.xchg_enabled) xchg_acc_local(d, d.xchg_rank)[o] = a;
-      else d.acc[o] = a;
+      a = UNIT ? ((h < d.H) ? W : 0.0) : th[o] * W;
+      out[o] = a;
     }
     if (FUSE) {
       double v = 0.0;
       if (valid) {
-        v = fast_div(a, len_o);
+        v = fast_div(a, d.efflen[o]);
         dst[o] = v;
       }
       const double s = group8_sum(v);
@@ -1303,7 +1309,7 @@ __global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const g
       }
       write_subset_rows(d, t, h, v, valid);
     }
-  }
+  });
   if (FUSE) {
     const double bs = block_sum(mine, red);
     if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
@@ -1342,12 +1348,12 @@ __global__ void __launch_bounds__(kThreads) k_locus_update(const __grid_constant
   double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
   double* __restrict__ iso = d.iso + (size_t) (FROM_ACC ? (par ^ 1) : par) * d.T;
   const int lane8 = threadIdx.x & 7;
-  const int64_t total = (int64_t) d.T * GBRS_HPAD;
-  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  const int64_t rounds = (total + stride - 1) / stride;
-  int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = d.T * GBRS_HPAD;
+  const int stride = (int) (gridDim.x * blockDim.x);
+  const int rounds = (total + stride - 1) / stride;
+  int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
   double mine = 0.0;
-  for (int64_t r = 0; r < rounds; ++r, i += stride) {
+  for (int r = 0; r < rounds; ++r, i += stride) {
     double v = 0.0;
     const bool valid = i < total;
     if (valid) {
@@ -1458,68 +1464,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
   const int par = d.ctrl[GBRS_CTRL_PARITY];
   const int me = d.xchg_rank;
   const int64_t slice = push_slice_len(d);
-  const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
+  const int h = threadIdx.x & 7;
   // ---- A: local numerator, pushed to the owners ----------------------------------------------------------------------
   {
     const double* __restrict__ th = d.theta + (size_t) par * d.T * GBRS_HPAD;
-    const int64_t n_deep = d.n_deep_loci;
-    const int64_t total_slots = n_deep + ((d.T - n_deep + 3) >> 2);
-    const int64_t nwarps = (int64_t) (blockDim.x >> 5) * gridDim.x;
-    const int64_t warp0 = (int64_t) (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-    const int64_t rounds = (total_slots + nwarps - 1) / nwarps;
-    const uint4* __restrict__ descs = reinterpret_cast<const uint4*>(d.locus_desc);
-    auto desc_index = [&](int64_t ws) { return ws < n_deep ? ws : n_deep + ((ws - n_deep) << 2) + grp; };
-    uint4 nx = make_uint4(0u, 0u, 0u, 0u);
-    if (warp0 < total_slots && desc_index(warp0) < d.T) nx = __ldg(descs + desc_index(warp0));
-    for (int64_t r = 0; r < rounds; ++r) {
-      const int64_t ws = warp0 + r * nwarps;
-      const bool deep = ws < n_deep;
-      const bool have = ws < total_slots && desc_index(ws) < d.T;
-      const uint4 ld = nx;
-      {
-        const int64_t wn = ws + nwarps;
-        nx = make_uint4(0u, 0u, 0u, 0u);
-        if (wn < total_slots && desc_index(wn) < d.T) nx = __ldg(descs + desc_index(wn));
-      }
-      const int64_t o = (int64_t) ld.x * GBRS_HPAD + h;
-      const uint32_t end = have ? ld.z : 0u;
-      const bool valid = have && (!deep || grp == 0);
-      const double th_o = (valid && !UNIT) ? th[o] : 1.0;
-      double W = 0.0;
-      if (deep) {
-        uint32_t it = (have ? ld.y : 0u) + (uint32_t) grp;
-        for (; it + 12 < end; it += 16) {
-          const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 4) * GBRS_HPAD + h];
-          const double w2 = d.wit[(size_t) (it + 8) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 12) * GBRS_HPAD + h];
-          W += (w0 + w1) + (w2 + w3);
-        }
-        for (; it < end; it += 4) W += d.wit[(size_t) it * GBRS_HPAD + h];
-        W += __shfl_xor_sync(0xFFFFFFFFu, W, 8);
-        W += __shfl_xor_sync(0xFFFFFFFFu, W, 16);
-      } else {
-        uint32_t it = have ? ld.y : 0u;
-        for (; it + 3 < end; it += 4) {
-          const double w0 = d.wit[(size_t) it * GBRS_HPAD + h], w1 = d.wit[(size_t) (it + 1) * GBRS_HPAD + h];
-          const double w2 = d.wit[(size_t) (it + 2) * GBRS_HPAD + h], w3 = d.wit[(size_t) (it + 3) * GBRS_HPAD + h];
-          W += (w0 + w1) + (w2 + w3);
-        }
-        for (; it < end; ++it) W += d.wit[(size_t) it * GBRS_HPAD + h];
-      }
+    const int slice32 = (int) slice;
+    locus_walk(d, [&](int t, int hh, double W, bool valid) {
       if (valid) {
-        const double a = UNIT ? ((h < d.H) ? W : 0.0) : th_o * W;
-        const int owner = (int) (o / slice);
-        st_relaxed_sys_f64(push_recv(d, owner, me) + (o - (int64_t) owner * slice), a);
+        const int o = t * GBRS_HPAD + hh;
+        const double a = UNIT ? ((hh < d.H) ? W : 0.0) : th[o] * W;
+        const int owner = o / slice32;
+        st_relaxed_sys_f64(push_recv(d, owner, me) + (o - owner * slice32), a);
       }
-    }
+    });
   }
   push_signal(d, 0, e, GBRS_CTRL_TICKET + 1);
   // ---- B: sum my slice over the ranks, broadcast the totals ---------------------------------------------------------
   if (!push_wait(d, 0, e, &s_fail)) return;
   {
-    const int64_t total_n = (int64_t) d.T * GBRS_HPAD;
-    const int64_t lo = slice * me, hi = lo + slice < total_n ? lo + slice : total_n;  // (both even)
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t i = lo + 2 * ((int64_t) blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 2 * stride) {
+    const int total_n = d.T * GBRS_HPAD;
+    const int lo = (int) slice * me, hi = lo + (int) slice < total_n ? lo + (int) slice : total_n;  // (both even)
+    const int stride = (int) (gridDim.x * blockDim.x);
+    for (int i = lo + 2 * (int) (blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 2 * stride) {
       double2 v[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
@@ -1543,12 +1509,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     const double* __restrict__ src = push_total(d, me);
     double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
     double* __restrict__ iso = d.iso + (size_t) (par ^ 1) * d.T;
-    const int64_t total = (int64_t) d.T * GBRS_HPAD;
-    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    const int64_t rounds = (total + stride - 1) / stride;
-    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = d.T * GBRS_HPAD;
+    const int stride = (int) (gridDim.x * blockDim.x);
+    const int rounds = (total + stride - 1) / stride;
+    int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
     double mine = 0.0;
-    for (int64_t r = 0; r < rounds; ++r, i += stride) {
+    for (int r = 0; r < rounds; ++r, i += stride) {
       double v = 0.0;
       const bool valid = i < total;
       if (valid) {
