@@ -41,6 +41,11 @@ WORKLOADS = {
     "c4": dict(T=80000, N=20_000_000, diploid=True, strong=True,
                label="diploid quantify -G -M 4: 80k transcripts x 2 of 8 haplotypes per locus x 20M classes, row-sharded"),
     "c4small": dict(T=8000, N=2_000_000, diploid=True, strong=True, label="reduced diploid (debug only)"),
+    # BASELINE config 5: batched cohort, 96 independent samples' EMs dealt to the GPUs (no communication)
+    "c5": dict(T=80000, N=1_000_000, cohort=96, strong=True,
+               label="batched cohort: 96 independent DO samples (80k transcripts x 8 haplotypes x 1M classes each), multiway "
+                     "EM to convergence (tol 1e-4), samples dealt round-robin to the GPUs"),
+    "c5small": dict(T=4000, N=100_000, cohort=16, strong=True, label="reduced cohort (debug only)"),
 }
 CPU_SAMPLE_CLASSES = 1_000_000
 METRIC = "em_alignment_nnz_per_s"
@@ -229,6 +234,18 @@ def run_reference_arm(args, wl):
 # --------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------------------
+def pin_apm(apm):
+    """Move the index arrays and counts of the host CSC matrices into pinned memory (in place)."""
+    import torch
+
+    for m in apm.data:
+        for name in ("indices", "indptr"):
+            a = getattr(m, name)
+            setattr(m, name, torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy())
+    if apm.count is not None:
+        apm.count = torch.from_numpy(np.ascontiguousarray(apm.count, dtype=np.float64)).pin_memory().numpy()
+
+
 def parity_checks(em, pat, d, world, rank, dev, diploid, model):
     """Checks of the path that was just timed, at every world size (the JSON line carries the result):
       conservation   sum of the expected counts == sum of the class counts over all ranks (every class' posterior sums to one)
@@ -291,6 +308,112 @@ def parity_checks(em, pat, d, world, rank, dev, diploid, model):
     return out
 
 
+def run_cohort_arm(args, wl):
+    """BASELINE config 5.  A step = one whole sample: H2D of its CSC matrices (pinned host memory), packing on the device,
+    prepare, EM to convergence, D2H of theta and the expected counts -- through gbrs_b200.cohort.quantify_cohort.  The
+    samples are resident in host memory when the timed region starts (reading alignment files is not part of the metric);
+    each rank generates a few distinct samples and cycles through them."""
+    import torch
+    import torch.distributed as dist
+
+    from gbrs_b200 import cohort, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n_samples = wl["cohort"]
+    mine = cohort.my_share(n_samples, rank, world)
+    distinct = min(4, len(mine))
+    apms = []
+    base = synth.generate(T=wl["T"], N=1000, H=8)
+    eff = synth.effective_lengths(base)  # shared by the cohort (same transcriptome)
+    for j in range(distinct):
+        dj = synth.generate(T=wl["T"], N=wl["N"], H=8, sample_index=rank * distinct + j)
+        a = synth.to_apm(dj)
+        pin_apm(a)
+        apms.append(a)
+    slot = {i: k % distinct for k, i in enumerate(mine)}
+
+    def load(i):
+        return apms[slot[i]]
+
+    class _Shared:  # hands the effective lengths to quantify_cohort without a file
+        pass
+
+    def run_once(stats):
+        from gbrs_b200.emfactory import EMfactory
+
+        orig = EMfactory._read_lengths
+        EMfactory._read_lengths = lambda self, lenfile, read_length: eff  # the table a targets.info file would give
+        try:
+            return cohort.quantify_cohort(list(range(n_samples)), load, model=args.model, lenfile="<shared>", rank=rank,
+                                          world=world, device=dev, stats=stats)
+        finally:
+            EMfactory._read_lengths = orig
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    run_once({})  # warm-up pass over the whole share (graph instantiation, allocator pools, pinned staging)
+    sync_all()
+    stats = {}
+    t0 = time.perf_counter()
+    res = run_once(stats)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    tt = torch.tensor([wall, stats["device_s"], float(stats["nnz_iters"]), float(sum(r["iters"] for r in res.values()))],
+                      dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        wall = float(mx[0].item())
+    busy = float(tt[1].item()) / (world * wall)
+    clocks = sampler.stop() if sampler else None
+    # parity: the first sample of rank 0 against the oracle (same iteration count, counts to 1e-9)
+    parity = None
+    if rank == 0:
+        from oracle import em_oracle as eo
+
+        d0 = synth.generate(T=wl["T"], N=wl["N"], H=8, sample_index=0)
+        oapm = eo.apm_from_pairs(d0.T, d0.H, d0.N, d0.pair_class, d0.pair_locus, d0.pair_mask, d0.count)
+        o = eo.run(oapm, eo.prepare(oapm, eff, 0.0), args.model, eff,
+                   eo.gene_index(d0.T, d0.groups()) if args.model != 4 else None, tol=1e-4)
+        r0 = res[mine[0]]
+        rel = float(np.abs(r0["counts"] - o["counts"]).max() / np.abs(o["counts"]).max())
+        parity = {"iters": [int(r0["iters"]), int(o["iters"])], "counts_relerr": rel, "ok": r0["iters"] == o["iters"] and rel < 1e-9}
+        assert parity["ok"], parity
+        nnz_iters, iters = float(tt[2].item()), float(tt[3].item())
+        line = {"metric": METRIC, "value": nnz_iters / wall, "unit": UNIT, "n_gpus": world, "steps": n_samples, "warmup": n_samples,
+                "ms_per_step": wall / n_samples * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["label"], "model": args.model, "samples": n_samples, "classes_per_sample": wl["N"],
+                           "distinct_samples_per_rank": distinct, "l2_policy": "every sample's matrices stream from pinned host memory"},
+                "samples_per_s": n_samples / wall, "em_updates_total": iters, "gpu_busy_fraction": busy,
+                "e2e": {"value": nnz_iters / wall, "unit": UNIT, "h2d_bytes_per_step": float(sum(m.indices.nbytes + m.indptr.nbytes for m in apms[0].data) + apms[0].count.nbytes),
+                        "d2h_bytes_per_step": 2.0 * 8 * 8 * wl["T"], "seconds": wall,
+                        "what": "quantify_cohort over all samples: per sample H2D of the CSC matrices, device packing, prepare, "
+                                "EM to convergence, D2H of theta and counts"},
+                "parity": parity, "clocks": clocks, "gpu_launches": int(iters) * 4}
+        emit(line)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_gpu_arm(args, wl):
     import torch
     import torch.distributed as dist
@@ -326,7 +449,9 @@ def run_gpu_arm(args, wl):
 
         hapmask = importlib.import_module("gbrs_b200.quantify").hapmask_bytes(synth.genotype_mask(d))
     t_gen = time.perf_counter() - t0
-    em = EMfactory(apm, device=dev, shard="local" if world > 1 else None, locus_hapmask=hapmask)
+    # the resident pattern of the device-timed run comes from the host packer (its arrays also feed `e2e_resident` and the
+    # layout statistics); the `e2e` passes below build their own pattern the default way (device packer)
+    em = EMfactory(apm, device=dev, shard="local" if world > 1 else None, locus_hapmask=hapmask, pack="host")
     em.target_lengths = synth.effective_lengths(d)  # same table prepare() would parse from a targets.info file
     t0 = time.perf_counter()
     em.prepare()  # gene tables + pack + upload + theta0
@@ -468,6 +593,7 @@ def run_gpu_arm(args, wl):
     # same without the host packer (the packed arrays are already in pinned host memory) -- what round 1 reported.
     for k in list(pat.host):
         pat.host[k] = pat.host[k].pin_memory()
+    pin_apm(apm)  # the inputs of `e2e` are copied from pinned host memory
     Ke = K
     sync_all()
 
@@ -498,7 +624,8 @@ def run_gpu_arm(args, wl):
         torch.cuda.synchronize(dev)
         t3 = time.perf_counter()
         p2 = em2._pattern
-        parts = {"pack_s": p2.packed.pack_seconds, "tiles_s": p2.tiled.build_seconds if p2.tiled is not None else 0.0,
+        parts = {"pack_s": p2.packed.pack_seconds, "packer": "device (gbrs_pack_device)" if p2.on_device else "host (gbrs_pack_create)",
+                 "tiles_s": p2.tiled.build_seconds if p2.tiled is not None else 0.0,
                  "prepare_total_s": t1 - t0, "run_s": t2 - t1, "fetch_s": t3 - t2}
         return t3 - t0, c, parts, p2.h2d_bytes, em2.num_iters
 
@@ -522,8 +649,8 @@ def run_gpu_arm(args, wl):
     d2h = 2 * 64 * T + 2 * 8 * wl["T"] * 8 + 8 * Ke
     e2e = {"value": nnz_total * Ke / t_e2e, "unit": UNIT, "h2d_bytes_per_step": (h2d_full + 128 * T) / Ke,
            "d2h_bytes_per_step": d2h / Ke, "seconds": t_e2e, "parts": e2e_parts,
-           "what": "EMfactory(apm).prepare() [host packing + H2D + theta0] + run(%d updates) + expected_read_counts() "
-                   "[D2H], from the host CSC matrices" % Ke}
+           "what": "EMfactory(apm).prepare() [H2D of the CSC matrices from pinned memory, packing on the device, theta0] + "
+                   "run(%d updates) + expected_read_counts() [D2H]" % Ke}
     e2e_resident = {"value": nnz_total * Ke / t_res, "unit": UNIT, "h2d_bytes_per_step": h2d_res / Ke,
                     "d2h_bytes_per_step": d2h / Ke, "seconds": t_res, "parts": res_parts,
                     "what": "H2D of the already packed incidence (pinned) + reset + run(%d updates) + D2H" % Ke}
@@ -586,7 +713,7 @@ def run_gpu_arm(args, wl):
                 "iterations_per_s": K / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "e2e_resident": e2e_resident, "parity": parity, "models": models_rec,
                 "gpu_launches": launches_per_step * K, "clocks": clocks,
-                "pack_seconds": pat.packed.pack_seconds}
+                "pack_seconds": e2e_parts["pack_s"], "pack_seconds_host_packer": pat.packed.pack_seconds}
         emit(line)
     # teardown: drop the captured graph (it holds NCCL work) before the communicator, and never hang on exit
     graph = None
@@ -618,6 +745,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl)
+    elif wl.get("cohort"):
+        run_cohort_arm(args, wl)
     else:
         run_gpu_arm(args, wl)
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("GBRS_LIB_PATH") or os.path.join(HERE, "_C", "libgbrs_
 GBRS_HPAD = 8
 GBRS_KMAX = 8
 GBRS_PART_SLOTS = 4096
-ABI_VERSION = 4
+ABI_VERSION = 5
 CTRL_ITERS, CTRL_DONE, CTRL_ERROR, CTRL_PARITY, CTRL_MAX_ITERS, CTRL_PREPARED = range(6)
 SCAL_ERR, SCAL_SUM_PREV, SCAL_TARGET, SCAL_SUM_CUR = range(4)
 
@@ -44,6 +44,14 @@ class PackInfo(C.Structure):
                 ("entry_bytes", C.c_int32), ("n_gene_ids", C.c_int32), ("max_pairs_per_class", C.c_int32),
                 ("n_deep_loci", C.c_int32), ("bucket_class0", C.c_int64 * (GBRS_KMAX + 2)),
                 ("bucket_pair0", C.c_int64 * (GBRS_KMAX + 2))]
+
+
+class DevicePack(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rowptr", "pairs", "count", "runptr", "ent_cls", "ent_pair", "ent_run", "item_desc",
+                                          "locus_desc", "gene_of", "gene_ptr", "gene_loci")]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_int64, C.c_char_p, C.c_void_p)
 
 
 class TilesParams(C.Structure):
@@ -105,6 +113,8 @@ SYMBOLS = {
     "gbrs_pack_get_info": (C.c_int, [C.c_void_p, C.POINTER(PackInfo)]),
     "gbrs_pack_get_array": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "gbrs_pack_free": (C.c_int, [C.c_void_p]),
+    "gbrs_pack_device": (C.c_int, [C.POINTER(PackInput), ALLOC_FN, C.c_void_p, C.c_void_p, C.POINTER(PackInfo),
+                                   C.POINTER(DevicePack)]),
     "gbrs_tiles_create": (C.c_int, [C.c_void_p, C.POINTER(TilesParams), C.POINTER(C.c_void_p)]),
     "gbrs_tiles_get_info": (C.c_int, [C.c_void_p, C.POINTER(TilesInfo)]),
     "gbrs_tiles_get_array": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

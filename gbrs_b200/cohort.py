@@ -2,11 +2,18 @@
 
 Replicas only: samples do not interact, so they are dealt round-robin to the ranks of a
 torch.distributed job (or all run on the one local GPU) and each is quantified by its own `EMfactory`; there is no
-collective on the data path.  Device buffers of a finished sample are released before the next one is packed, so any
-number of samples fits.
+collective on the data path.  What a sample costs the GPU is milliseconds (packing on the device + a converged EM);
+what it costs the host -- reading and inflating the alignment file -- is far more, so the samples of a rank form a
+pipeline: a loader thread fetches sample i+1 (the user's `load` callback: file read / inflate / pinning release the
+GIL) while the device packs and runs sample i.  The effective-length table and the gene grouping are shared by the
+samples of a cohort (same transcriptome): they are parsed once.  Device buffers of a finished sample are released
+before the next one is packed, so any number of samples fits.
 """
 from __future__ import annotations
 
+import queue
+import threading
+import time
 from typing import Callable, Iterable, Sequence
 
 from . import utils
@@ -22,15 +29,49 @@ def my_share(n_samples: int, rank: int = 0, world: int = 1) -> list[int]:
     return list(range(rank, n_samples, world))
 
 
+def _prefetch(indices, samples, load, depth):
+    """Yield (index, apm, seconds spent loading) with up to `depth` samples loaded ahead by a background thread."""
+    if depth <= 0:
+        for i in indices:
+            t0 = time.perf_counter()
+            apm = load(samples[i])
+            yield i, apm, time.perf_counter() - t0
+        return
+    q: queue.Queue = queue.Queue(maxsize=depth)
+
+    def worker():
+        try:
+            for i in indices:
+                t0 = time.perf_counter()
+                apm = load(samples[i])
+                q.put((i, apm, time.perf_counter() - t0))
+        except BaseException as e:  # noqa: BLE001 - re-raised by the consumer
+            q.put(e)
+        q.put(None)
+
+    th = threading.Thread(target=worker, name="gbrs-cohort-loader", daemon=True)
+    th.start()
+    while True:
+        item = q.get()
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+    th.join()
+
+
 def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocount: float = 0.0,
                     lenfile: str | None = None, read_length: int = 100, tol: float = 0.0001, max_iters: int = 999,
                     device=None, rank: int | None = None, world: int | None = None,
-                    on_done: Callable | None = None) -> dict:
+                    on_done: Callable | None = None, prefetch: int = 2, stats: dict | None = None) -> dict:
     """Run the EM of every sample this rank owns.
 
     samples   any sequence of sample descriptors (file names, ids ...)
     load      callable(sample) -> AlignmentPropertyMatrix (groups attached if gene-level output is wanted)
     on_done   optional callable(sample, EMfactory) invoked after each sample (e.g. to write its report files)
+    prefetch  samples loaded ahead by the loader thread (0: load in line)
+    stats     optional dict, filled with the wall / device / loading seconds of this rank's share
     Returns {sample index: dict(theta=H x T depths, counts=H x T expected read counts, iters=int)}.
     """
     if rank is None or world is None:
@@ -42,17 +83,35 @@ def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocou
                 rank, world = dist.get_rank(), dist.get_world_size()
         except Exception:  # noqa: BLE001
             pass
+    import torch
+
     out = {}
-    for i in my_share(len(samples), rank, world):
-        apm = load(samples[i])
+    shared_lengths = None  # H x T effective lengths, parsed from `lenfile` by the first sample
+    t_wall = time.perf_counter()
+    t_load = t_dev = 0.0
+    nnz_iters = 0
+    for i, apm, dt_load in _prefetch(my_share(len(samples), rank, world), samples, load, prefetch):
+        t_load += dt_load
+        t0 = time.perf_counter()
         em = EMfactory(apm, device=device)  # no process group: the sample is not sharded
-        em.prepare(pseudocount=pseudocount, lenfile=lenfile, read_length=read_length)
+        if shared_lengths is not None:
+            em.target_lengths = shared_lengths
+            em.prepare(pseudocount=pseudocount)
+        else:
+            em.prepare(pseudocount=pseudocount, lenfile=lenfile, read_length=read_length)
+            shared_lengths = em.target_lengths
         em.run(model=model, tol=tol, max_iters=max_iters, verbose=False)
         out[i] = dict(theta=em.get_allelic_expression(), counts=em.expected_read_counts().copy(), iters=em.num_iters)
+        torch.cuda.synchronize(em._pattern.device)
+        t_dev += time.perf_counter() - t0
+        nnz_iters += em._pattern.info["nnz"] * em.num_iters
         if on_done is not None:
             on_done(samples[i], em)
         logger.info(f"sample {i}: {em.num_iters} EM updates")
         del em
+    if stats is not None:
+        stats.update(wall_s=time.perf_counter() - t_wall, device_s=t_dev, load_s=t_load, samples=len(out),
+                     nnz_iters=nnz_iters)
     return out
 
 

@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "_C")
 LIB = os.path.join(OUT_DIR, "libgbrs_em.so")
 SOURCES = [os.path.join(HERE, "em_kernels.cu"), os.path.join(HERE, "ec_kernels.cu"), os.path.join(HERE, "hmm_kernels.cu"),
+           os.path.join(HERE, "gpu_pack.cu"),
            os.path.join(HERE, "pack.cpp"), os.path.join(HERE, "tile_pack.cpp"),
            os.path.join(HERE, "report.cpp")]
 HEADERS = [os.path.join(ROOT, "include", "gbrs_em.h"), os.path.join(HERE, "pack_internal.h")]

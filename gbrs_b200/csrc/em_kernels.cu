@@ -1400,6 +1400,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// 16-byte multicast store (a store moves bits: the f32 vector form carries two doubles; multimem has no f64 vector form)
+__device__ __forceinline__ void multimem_st_f64x2(double* mc, double2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__int_as_float(__double2loint(v.x))),
+               "f"(__int_as_float(__double2hiint(v.x))), "f"(__int_as_float(__double2loint(v.y))),
+               "f"(__int_as_float(__double2hiint(v.y)))
+               : "memory");
+}
 __host__ __device__ inline int64_t push_slice_len(const gbrs_em_dev& d) {  // doubles per owner, even
   return ((((int64_t) d.T * GBRS_HPAD + d.n_ranks - 1) / d.n_ranks) + 1) & ~(int64_t) 1;
 }
@@ -1485,6 +1492,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     const int total_n = d.T * GBRS_HPAD;
     const int lo = (int) slice * me, hi = lo + (int) slice < total_n ? lo + (int) slice : total_n;  // (both even)
     const int stride = (int) (gridDim.x * blockDim.x);
+    // with an NVSwitch multicast mapping the totals leave this GPU once instead of once per peer
+    double* const mc_total = d.xchg_mc ? static_cast<double*>(d.xchg_mc) + (size_t) d.n_ranks * slice : nullptr;
     for (int i = lo + 2 * (int) (blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 2 * stride) {
       double2 v[8];
 #pragma unroll
@@ -1497,9 +1506,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
           sum.x += v[r].x;
           sum.y += v[r].y;
         }
+      if (mc_total) {
+        multimem_st_f64x2(mc_total + i, sum);  // one store, replicated to every rank by the switch
+      } else {
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r < d.n_ranks) st_relaxed_sys_f64x2(push_total(d, r) + i, sum);
+        for (int r = 0; r < 8; ++r)
+          if (r < d.n_ranks) st_relaxed_sys_f64x2(push_total(d, r) + i, sum);
+      }
     }
   }
   push_signal(d, 1, e, GBRS_CTRL_TICKET + 2);

@@ -75,6 +75,43 @@ def _require_cuda(device=None):
     return torch.device(device)
 
 
+def pack_input(apm: APM, gene_of=None, hapmask=None, shard_rank=0, shard_count=1, item_len=0):
+    """The `gbrs_pack_input` record for an incidence matrix (host packer and device packer take the same one) and the
+    list of arrays that must stay alive while it is in use."""
+    T, H, N = apm.shape
+    if not apm.finalized:
+        raise RuntimeError("The original matrix must be finalized.")
+    if H > _lib.GBRS_HPAD:
+        raise NotImplementedError("more than 8 haplotypes is not supported by the packed mask layout")
+    mats = [m if m.format == "csc" else m.tocsc() for m in apm.data]
+    indptr = [np.ascontiguousarray(m.indptr, dtype=np.int64) for m in mats]
+    wide = any(m.indices.dtype.itemsize == 8 for m in mats)
+    idx_t = np.int64 if wide else np.int32
+    indices = [np.ascontiguousarray(m.indices, dtype=idx_t) for m in mats]
+    keep = [indptr, indices]
+    inp = _lib.PackInput()
+    inp.T, inp.H, inp.N = T, H, N
+    inp.indptr = (C.c_void_p * H)(*[a.ctypes.data for a in indptr])
+    inp.indices = (C.c_void_p * H)(*[a.ctypes.data for a in indices])
+    inp.index_bytes = 8 if wide else 4
+    inp.values = None
+    count = None
+    if apm.count is not None:
+        count = np.ascontiguousarray(apm.count, dtype=np.float64)
+        if count.shape[0] != N:
+            raise RuntimeError("count vector length does not match the number of classes")
+        inp.count = count.ctypes.data
+    if hapmask is not None:
+        hapmask = np.ascontiguousarray(hapmask, dtype=np.uint8)
+        inp.locus_hapmask = hapmask.ctypes.data
+    if gene_of is not None:
+        gene_of = np.ascontiguousarray(gene_of, dtype=np.int32)
+        inp.gene_of = gene_of.ctypes.data
+    inp.shard_rank, inp.shard_count, inp.item_len = shard_rank, shard_count, item_len
+    keep += [count, hapmask, gene_of]
+    return inp, keep
+
+
 class _PackHandle:
     """Owns one gbrs_pack_t; the numpy views handed out by PackedPattern keep it alive through their ctypes buffers."""
 
@@ -97,36 +134,8 @@ class PackedPattern:
     def __init__(self, apm: APM, gene_of=None, hapmask=None, shard_rank=0, shard_count=1, item_len=0):
         lib = _lib.load()
         T, H, N = apm.shape
-        if not apm.finalized:
-            raise RuntimeError("The original matrix must be finalized.")
-        if H > _lib.GBRS_HPAD:
-            raise NotImplementedError("more than 8 haplotypes is not supported by the packed mask layout")
-        mats = [m if m.format == "csc" else m.tocsc() for m in apm.data]
-        indptr = [np.ascontiguousarray(m.indptr, dtype=np.int64) for m in mats]
-        wide = any(m.indices.dtype.itemsize == 8 for m in mats)
-        idx_t = np.int64 if wide else np.int32
-        indices = [np.ascontiguousarray(m.indices, dtype=idx_t) for m in mats]
-        keep = [indptr, indices]
-        inp = _lib.PackInput()
-        inp.T, inp.H, inp.N = T, H, N
-        inp.indptr = (C.c_void_p * H)(*[a.ctypes.data for a in indptr])
-        inp.indices = (C.c_void_p * H)(*[a.ctypes.data for a in indices])
-        inp.index_bytes = 8 if wide else 4
-        inp.values = None
-        count = None
-        if apm.count is not None:
-            count = np.ascontiguousarray(apm.count, dtype=np.float64)
-            if count.shape[0] != N:
-                raise RuntimeError("count vector length does not match the number of classes")
-            inp.count = count.ctypes.data
-        if hapmask is not None:
-            hapmask = np.ascontiguousarray(hapmask, dtype=np.uint8)
-            inp.locus_hapmask = hapmask.ctypes.data
-        if gene_of is not None:
-            gene_of = np.ascontiguousarray(gene_of, dtype=np.int32)
-            inp.gene_of = gene_of.ctypes.data
-        inp.shard_rank, inp.shard_count, inp.item_len = shard_rank, shard_count, item_len
-        keep += [count, hapmask, gene_of]
+        inp, keep = pack_input(apm, gene_of=gene_of, hapmask=hapmask, shard_rank=shard_rank, shard_count=shard_count,
+                               item_len=item_len)
         handle = C.c_void_p()
         t0 = time.perf_counter()
         _lib.check(lib.gbrs_pack_create(C.byref(inp), C.byref(handle)))
@@ -156,6 +165,61 @@ class PackedPattern:
 
     def nbytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays.values()))
+
+
+class DevicePacked:
+    """Result of gbrs_pack_device: the packed arrays live in device memory only (`tensors`: name -> uint8 torch tensor);
+    `info` / `T` / `H` / `has_genes` / `pack_seconds` as on PackedPattern.  There is no host copy (`arrays` is empty)."""
+
+    def __init__(self, apm: APM, device, gene_of=None, hapmask=None, shard_rank=0, shard_count=1, item_len=0):
+        torch = _torch()
+        lib = _lib.load()
+        T, H, N = apm.shape
+        inp, keep = pack_input(apm, gene_of=gene_of, hapmask=hapmask, shard_rank=shard_rank, shard_count=shard_count,
+                               item_len=item_len)
+        kept, temps = {}, []
+
+        def alloc(nbytes, tag, _user):
+            try:
+                t = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+            except Exception:  # noqa: BLE001 - out of device memory: the C side reports it
+                return None
+            tag = tag.decode()
+            if tag.startswith("tmp:"):
+                temps.append(t)
+            else:
+                kept[tag] = (t, int(nbytes))
+            return t.data_ptr()
+
+        cb = _lib.ALLOC_FN(alloc)
+        info, out = _lib.PackInfo(), _lib.DevicePack()
+        t0 = time.perf_counter()
+        with torch.cuda.device(device):
+            stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(lib.gbrs_pack_device(C.byref(inp), cb, None, stream, C.byref(info), C.byref(out)))
+        self.pack_seconds = time.perf_counter() - t0
+        del temps, keep
+        self.info = {f: getattr(info, f) for f, _ in _lib.PackInfo._fields_}
+        self.info["bucket_class0"] = list(info.bucket_class0)
+        self.info["bucket_pair0"] = list(info.bucket_pair0)
+        self.tensors = {k: t[:max(n, 1)] for k, (t, n) in kept.items()}
+        self.nbytes_exact = {k: n for k, (t, n) in kept.items()}
+        self.arrays = {}
+        self.T, self.H, self.N = T, H, N
+        self.has_genes = gene_of is not None
+
+    def nbytes(self) -> int:
+        return int(sum(self.nbytes_exact.values()))
+
+    def to_host(self) -> dict:
+        """The packed arrays as numpy arrays (tests: comparison with the host packer)."""
+        entry_t = np.uint32 if self.info["entry_bytes"] == 4 else np.uint64
+        out = {}
+        for k, t in self.tensors.items():
+            dt = _PACK_ARRAYS.get(k, np.uint8)
+            dt = entry_t if dt is None else dt
+            out[k] = t[: self.nbytes_exact[k]].cpu().numpy().view(dt).copy()
+        return out
 
 
 class _TilesHandle:
@@ -208,7 +272,7 @@ class DevicePattern:
     """Packed incidence + state vectors resident on one GPU, and the `gbrs_em_dev` descriptor pointing at them."""
 
     def __init__(self, apm: APM = None, gene_of=None, hapmask=None, device=None, shard_rank=0, shard_count=1,
-                 item_len=0, packed: PackedPattern = None, pin=False, tiles=None, tile_params=None):
+                 item_len=0, packed: PackedPattern = None, pin=False, tiles=None, tile_params=None, pack=None):
         """`tiles`: also build the tile layout and run model 4 / prepare through the fused single-pass tile kernel
         (`k_tile_em`) instead of the two-pass kernels.  Opt-in (`tiles=True` or GBRS_TILES=1): parity-green and
         bit-reproducible, but on B200 it is the slower of the two formulations at the benchmark shape (DESIGN.md
@@ -217,17 +281,29 @@ class DevicePattern:
         torch = _torch()
         self.device = _require_cuda(device)
         self.lib = _lib.load()
+        if tiles is None:
+            tiles = os.environ.get("GBRS_TILES", "0") not in ("", "0")
+        # `pack`: "gpu" (default) packs on the device (gbrs_pack_device: the CSC arrays go up as they are, the packed
+        # arrays never exist on the host); "host" uses the OpenMP packer (gbrs_pack_create) and uploads -- also taken when
+        # the device packer refuses the input or the tile layout (built from the host arrays) is wanted
+        if pack is None:
+            pack = os.environ.get("GBRS_PACK", "gpu")
+        if packed is None and pack == "gpu" and not tiles:
+            try:
+                packed = DevicePacked(apm, self.device, gene_of=gene_of, hapmask=hapmask, shard_rank=shard_rank,
+                                      shard_count=shard_count, item_len=item_len)
+            except NotImplementedError as e:  # GBRS_E_LIMIT
+                logger.info(f"device packer not used ({e}); packing on the host")
         if packed is None:
             packed = PackedPattern(apm, gene_of=gene_of, hapmask=hapmask, shard_rank=shard_rank,
                                    shard_count=shard_count, item_len=item_len)
         self.packed = packed
+        self.on_device = isinstance(packed, DevicePacked)
         self.info = packed.info
         self.T, self.H = packed.T, packed.H
         self.n_ranks = shard_count
-        if tiles is None:
-            tiles = os.environ.get("GBRS_TILES", "0") not in ("", "0")
         self.tiled = None
-        if tiles:
+        if tiles and not self.on_device:
             try:
                 self.tiled = TiledPattern(packed, **(tile_params or _tile_params_from_env()))
             except NotImplementedError as e:  # GBRS_E_LIMIT: a class wider than a tile
@@ -246,6 +322,11 @@ class DevicePattern:
         self.full = False
         i = self.info
         self._need_rowptr = i["bucket_class0"][_lib.GBRS_KMAX] < i["n_classes"]  # classes wider than GBRS_KMAX
+        if self.on_device:  # everything is resident already (the CSC arrays went up instead of the packed ones)
+            self.dev = dict(packed.tensors)
+            self.full = True
+            self.h2d_bytes = int(sum(m.indices.nbytes + m.indptr.nbytes for m in apm.data)) + (
+                apm.count.nbytes if apm.count is not None else 0)
         self.upload()
         self._alloc_state()
         self._build_descriptor()
@@ -442,7 +523,8 @@ class EMfactory:
     """A class that coordinates Expectation-Maximization (reference EMfactory.py:15-24)."""
 
     def __init__(self, alignments: APM, device=None, group=None, shard: bool | str | None = None, item_len: int = 0,
-                 poll_every: int = 4, locus_hapmask=None, tiles: bool | None = None, tile_params: dict | None = None):
+                 poll_every: int = 4, locus_hapmask=None, tiles: bool | None = None, tile_params: dict | None = None,
+                 pack: str | None = None):
         """`alignments`: the incidence matrix.  Additions to the reference signature (all optional):
         `device` CUDA device; `group` a torch.distributed process group (or `shard=True` for the default group) over
         which the alignment classes are row-sharded -- every rank passes the same full matrix and packs only its own
@@ -451,7 +533,8 @@ class EMfactory:
         between reads of the device-side stop flag); `locus_hapmask` (uint8 [T], bit h = haplotype h of the locus is
         kept) applies the `-G` genotype restriction while packing, which is equivalent to -- and much cheaper than --
         `alignments.multiply(gtmask, axis=2)` followed by `eliminate_zeros()` on the host matrices; `tiles` /
-        `tile_params` select the fused single-pass tile kernel for model 4 (see DevicePattern)."""
+        `tile_params` select the fused single-pass tile kernel for model 4, `pack` ("gpu" | "host") where the incidence is
+        packed (see DevicePattern)."""
         self.probability = alignments
         self._theta_host = None
         self._theta_dirty = False
@@ -465,7 +548,7 @@ class EMfactory:
         if self._hapmask is not None and self._hapmask.shape != (alignments.num_loci,):
             raise ValueError("locus_hapmask must hold one byte per locus")
         self._poll_every = poll_every
-        self._tiles, self._tile_params = tiles, tile_params
+        self._tiles, self._tile_params, self._pack = tiles, tile_params, pack
         self._pattern: DevicePattern | None = None
         self._gene_of = None
         self._counts_host = None
@@ -571,13 +654,14 @@ class EMfactory:
                     "eliminate_zeros() after masking; weighted (non-incidence) matrices are not supported")
             if self._presharded:
                 self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
-                                              item_len=self._item_len, tiles=self._tiles, tile_params=self._tile_params)
+                                              item_len=self._item_len, tiles=self._tiles, tile_params=self._tile_params,
+                                              pack=self._pack)
                 self._pattern.n_ranks = self.world
                 self._pattern._build_descriptor()
             else:
                 self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
                                               shard_rank=self.rank, shard_count=self.world, item_len=self._item_len,
-                                              tiles=self._tiles, tile_params=self._tile_params)
+                                              tiles=self._tiles, tile_params=self._tile_params, pack=self._pack)
             self._pattern.set_lengths(self.target_lengths)
             if self.world > 1:
                 self.fused_exchange = self._setup_fused_exchange(self._pattern)
@@ -606,7 +690,9 @@ class EMfactory:
         mode = {"fused": "push", "p2p": "pull"}.get(mode, mode)
         if self.world < 2 or self.world > 8 or mode not in ("push", "pull", "nvls"):
             return False
-        use_mc = mode == "nvls"
+        # the multicast mapping: the in-switch reduction of the nvls form; in the push form only the broadcast of the
+        # slice totals goes through it (one 16-byte store replicated by the switch instead of one per peer)
+        use_mc = mode == "nvls" or (mode == "push" and os.environ.get("GBRS_XCHG_MC", "1") != "0")
         ok, buf, hdl, mc = 1, None, None, 0
         try:
             import torch.distributed._symmetric_memory as symm_mem

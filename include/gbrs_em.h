@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GBRS_EM_ABI_VERSION 4
+#define GBRS_EM_ABI_VERSION 5
 #define GBRS_HPAD 8 /* haplotype slots per locus line */
 #define GBRS_KMAX 8 /* classes with up to this many (class, locus) pairs take the fixed-width row pass */
 #define GBRS_DEEP_LOCUS_ITEMS 8 /* a locus with more partial sums (column-pass items / tile slots) than this is summed by a
@@ -108,6 +108,31 @@ int gbrs_pack_get_info(gbrs_pack_t p, gbrs_pack_info* info);
  */
 int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64_t* bytes);
 int gbrs_pack_free(gbrs_pack_t p);
+
+/* Device-side packer: the same inputs (HOST arrays, pinned or not) and the same outputs as gbrs_pack_create -- array for
+ * array, bit for bit -- built on the GPU; the packed arrays stay in device memory (nothing returns to the host but the
+ * info record).  All device memory, results and temporaries alike, comes from the caller's allocator: `alloc(bytes, tag,
+ * user)` returns device memory (256-byte aligned) or NULL; tags starting with "tmp:" may be released as soon as the call
+ * returns, the others are the arrays named in gbrs_device_pack.  The call synchronises the stream.  GBRS_E_LIMIT for
+ * inputs it does not take (stored values, N >= 2^31, more than 2^32 stored entries): use gbrs_pack_create.
+ * No CPU fallback inside: without a CUDA device it fails with GBRS_E_CUDA. */
+typedef void* (*gbrs_alloc_fn)(int64_t bytes, const char* tag, void* user);
+typedef struct {
+  const uint32_t* rowptr;      /* [n_classes + 1] */
+  const uint32_t* pairs;       /* [n_pairs] */
+  const double* count;         /* [n_classes] */
+  const uint32_t* runptr;      /* [n_classes + 1] */
+  const void* ent_cls;         /* [n_entries] entry words (entry_bytes each) */
+  const void* ent_pair;
+  const void* ent_run;
+  const uint32_t* item_desc;   /* [n_items][4] */
+  const uint32_t* locus_desc;  /* [T][4] */
+  const int32_t* gene_of;      /* [T] */
+  const uint32_t* gene_ptr;    /* [n_gene_ids + 1] */
+  const uint32_t* gene_loci;   /* [T] */
+} gbrs_device_pack;
+int gbrs_pack_device(const gbrs_pack_input* in, gbrs_alloc_fn alloc, void* user, void* stream, gbrs_pack_info* info_out,
+                     gbrs_device_pack* out);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Tile layout of the fused model-4 update: the classes of a shard, ordered by their smallest

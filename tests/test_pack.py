@@ -273,3 +273,71 @@ def test_packer_and_row_builder_do_not_depend_on_the_thread_count(tmp_path):
         assert res.returncode == 0, res.stderr[-2000:]
         seen.add(res.stdout.strip())
     assert len(seen) == 1, seen
+
+
+# ---- the device-side packer (gpu_pack.cu) against the host packer: every array, bit for bit ---------------------------------
+def _device_pack_cases():
+    from gbrs_b200.quantify import hapmask_bytes
+
+    d = synth.generate(T=200, N=3000, H=8, sample_index=4, with_genotype=True)
+    return [
+        (synth.generate(T=60, N=900, H=8, sample_index=2), {}),
+        (synth.generate(T=120, N=1500, H=8, sample_index=9, wide_frac=0.08), dict(item_len=8)),
+        (synth.generate(T=40, N=300, H=3, sample_index=1), dict(no_genes=True)),
+        (d, dict(hapmask=hapmask_bytes(synth.genotype_mask(d)))),
+        (synth.generate(T=150, N=2500, H=8, sample_index=5), dict(shard_rank=1, shard_count=3, item_len=8)),
+        (synth.generate(T=30, N=200, H=1, sample_index=1), {}),
+    ]
+
+
+def _assert_same_pack(info, arrays, host):
+    bad = [k for k in info if info[k] != host.info[k]]
+    assert not bad, [(k, info[k], host.info[k]) for k in bad]
+    for k, a in arrays.items():
+        h = host.arrays[k]
+        assert a.shape == h.shape and np.array_equal(a, h), k
+
+
+@pytest.mark.skipif(__import__("shutil").which("g++") is None, reason="g++ is needed to build the SIMT emulation")
+@pytest.mark.parametrize("case", range(6))
+def test_emulated_device_packer_equals_host_packer(case):
+    """gpu_pack.cu executed on the CPU through the host SIMT shim (CUB served by a stable sort and a loop)."""
+    from gbrs_b200.emfactory import PackedPattern
+    from oracle import em_oracle as eo
+    from tests import simt_em
+
+    d, kw = _device_pack_cases()[case]
+    kw = dict(kw)
+    gene_of = None if kw.pop("no_genes", False) else eo.gene_index(d.T, d.groups())
+    apm = synth.to_apm(d)
+    info, arrays = simt_em.emulated_device_pack(apm, gene_of=gene_of, **kw)
+    _assert_same_pack(info, arrays, PackedPattern(apm, gene_of=gene_of, **kw))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", range(6))
+def test_device_packer_equals_host_packer(case):
+    from gbrs_b200.emfactory import DevicePacked, PackedPattern
+    from oracle import em_oracle as eo
+
+    d, kw = _device_pack_cases()[case]
+    kw = dict(kw)
+    gene_of = None if kw.pop("no_genes", False) else eo.gene_index(d.T, d.groups())
+    apm = synth.to_apm(d)
+    dp = DevicePacked(apm, "cuda:0", gene_of=gene_of, **kw)
+    _assert_same_pack(dp.info, dp.to_host(), PackedPattern(apm, gene_of=gene_of, **kw))
+
+
+@pytest.mark.gpu
+def test_device_packer_equals_host_packer_at_size():
+    """1M classes at the C2 locus shape, 64-bit class indices in the input."""
+    from gbrs_b200.emfactory import DevicePacked, PackedPattern
+    from oracle import em_oracle as eo
+
+    d = synth.generate(T=80_000, N=1_000_000, H=8)
+    apm = synth.to_apm(d)
+    for m in apm.data:
+        m.indices = m.indices.astype(np.int64)
+    gene_of = eo.gene_index(d.T, d.groups())
+    dp = DevicePacked(apm, "cuda:0", gene_of=gene_of)
+    _assert_same_pack(dp.info, dp.to_host(), PackedPattern(apm, gene_of=gene_of))
