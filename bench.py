@@ -344,19 +344,9 @@ def run_cohort_arm(args, wl):
     def load(i):
         return apms[slot[i]]
 
-    class _Shared:  # hands the effective lengths to quantify_cohort without a file
-        pass
-
     def run_once(stats):
-        from gbrs_b200.emfactory import EMfactory
-
-        orig = EMfactory._read_lengths
-        EMfactory._read_lengths = lambda self, lenfile, read_length: eff  # the table a targets.info file would give
-        try:
-            return cohort.quantify_cohort(list(range(n_samples)), load, model=args.model, lenfile="<shared>", rank=rank,
-                                          world=world, device=dev, stats=stats)
-        finally:
-            EMfactory._read_lengths = orig
+        return cohort.quantify_cohort(list(range(n_samples)), load, model=args.model, target_lengths=eff, rank=rank,
+                                      world=world, device=dev, stats=stats)
 
     def sync_all():
         torch.cuda.synchronize(dev)

@@ -64,7 +64,8 @@ def _prefetch(indices, samples, load, depth):
 def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocount: float = 0.0,
                     lenfile: str | None = None, read_length: int = 100, tol: float = 0.0001, max_iters: int = 999,
                     device=None, rank: int | None = None, world: int | None = None,
-                    on_done: Callable | None = None, prefetch: int = 2, stats: dict | None = None) -> dict:
+                    on_done: Callable | None = None, prefetch: int = 2, stats: dict | None = None,
+                    target_lengths=None) -> dict:
     """Run the EM of every sample this rank owns.
 
     samples   any sequence of sample descriptors (file names, ids ...)
@@ -72,6 +73,7 @@ def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocou
     on_done   optional callable(sample, EMfactory) invoked after each sample (e.g. to write its report files)
     prefetch  samples loaded ahead by the loader thread (0: load in line)
     stats     optional dict, filled with the wall / device / loading seconds of this rank's share
+    target_lengths  optional H x T effective-length table (instead of `lenfile`), shared by all samples
     Returns {sample index: dict(theta=H x T depths, counts=H x T expected read counts, iters=int)}.
     """
     if rank is None or world is None:
@@ -86,13 +88,20 @@ def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocou
     import torch
 
     out = {}
-    shared_lengths = None  # H x T effective lengths, parsed from `lenfile` by the first sample
+    shared_lengths = target_lengths  # H x T effective lengths; else parsed from `lenfile` by the first sample
     t_wall = time.perf_counter()
     t_load = t_dev = 0.0
     nnz_iters = 0
+    shared_groups = None
     for i, apm, dt_load in _prefetch(my_share(len(samples), rank, world), samples, load, prefetch):
         t_load += dt_load
         t0 = time.perf_counter()
+        # one grouping for the cohort: equal lists become ONE list object, so that the gene tables derived from it are
+        # built once (utils._cached)
+        if shared_groups is not None and apm.groups is not shared_groups and apm.groups == shared_groups:
+            apm.groups = shared_groups
+        elif shared_groups is None and getattr(apm, "groups", None):
+            shared_groups = apm.groups
         em = EMfactory(apm, device=device)  # no process group: the sample is not sharded
         if shared_lengths is not None:
             em.target_lengths = shared_lengths

@@ -550,6 +550,7 @@ class EMfactory:
         self._poll_every = poll_every
         self._tiles, self._tile_params, self._pack = tiles, tile_params, pack
         self._pattern: DevicePattern | None = None
+        self._weighted = False
         self._gene_of = None
         self._counts_host = None
         self.num_iters = 0
@@ -648,10 +649,11 @@ class EMfactory:
     def _ensure_pattern(self):
         if self._pattern is None:
             p = self.probability
-            if not p.is_pure_incidence():
-                raise NotImplementedError(
-                    "stored values other than 1.0 (or explicit zeros) in the alignment matrix: call "
-                    "eliminate_zeros() after masking; weighted (non-incidence) matrices are not supported")
+            # Stored values other than 1.0 (weighted or legacy files, explicit zeros): the reference's E-step starts with
+            # probability.reset(), which sets EVERY stored entry to 1 (Sparse3DMatrix.py:220-228) -- so the EM runs on the
+            # stored pattern, zeros included, and the values matter to prepare()'s initial normalisation only
+            # (EMfactory.py:95-104).  The pattern is packed as it is; reset() takes theta0 from the values on the host.
+            self._weighted = not p.is_pure_incidence()
             if self._presharded:
                 self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
                                               item_len=self._item_len, tiles=self._tiles, tile_params=self._tile_params,
@@ -798,14 +800,42 @@ class EMfactory:
         pat = self._ensure_pattern()
         if not fresh:  # a new pattern has just been given the lengths
             pat.set_lengths(self.target_lengths)
-        _lib.check(pat.lib.gbrs_em_prepare_local(C.byref(pat.desc), pat.stream()))
-        self._exchange(pat)
-        _lib.check(pat.lib.gbrs_em_prepare_finish(C.byref(pat.desc), float(pseudocount), pat.stream()))
+        if self._weighted:
+            if self.world > 1:
+                raise NotImplementedError("weighted alignment matrices are not supported in row-sharded runs")
+            pat.set_theta_HT(self._weighted_theta0(float(pseudocount)))
+        else:
+            _lib.check(pat.lib.gbrs_em_prepare_local(C.byref(pat.desc), pat.stream()))
+            self._exchange(pat)
+            _lib.check(pat.lib.gbrs_em_prepare_finish(C.byref(pat.desc), float(pseudocount), pat.stream()))
         ctrl, _ = pat.read_ctrl()
         self._raise_on_ctrl_error(ctrl, "the initial expression estimate")
         self._fetch_theta()
         self._counts_host = None
         self.num_iters = 0
+
+    def _weighted_theta0(self, pseudocount: float) -> np.ndarray:
+        """prepare()'s initial estimate for a matrix with stored values (EMfactory.py:95-111): normalize_reads(READ) on
+        the values, count-weighted column sums, division by the effective lengths, pseudocount rule.  Host, one pass --
+        initialisation only; the EM itself runs on the device on the stored pattern."""
+        p = self.probability
+        H, T = p.num_haplotypes, p.num_loci
+        rows = np.zeros(p.shape[2])
+        for m in p.data:
+            rows += np.asarray(m.sum(axis=1)).ravel()
+        cnt = np.ones(p.shape[2]) if p.count is None else np.asarray(p.count, dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            scale = np.where(rows != 0.0, cnt / rows, 0.0)
+        theta = np.vstack([np.asarray(m.T @ scale).ravel() for m in p.data])
+        if self.target_lengths is not None:
+            theta = theta / self.target_lengths
+        if pseudocount > 0.0:
+            total = theta.sum()
+            nz = np.nonzero(theta)[1]
+            theta[:, nz] += pseudocount
+            theta *= total / theta.sum()
+        assert theta.shape == (H, T)
+        return theta
 
     def get_allelic_expression(self, at_group_level: bool = False):
         if at_group_level:

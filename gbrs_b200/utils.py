@@ -46,9 +46,34 @@ def is_comment(s: str) -> bool:
     return s.startswith("#")
 
 
+_group_cache: dict = {}  # id(groups) -> (groups, num_loci, {"gene_index": ..., "grp_conv_mat": ...})
+
+
+def _cached(kind: str, num_loci: int, groups, build):
+    """Gene tables are derived from the `groups` list alone; the samples of a cohort share one list object, and walking
+    its ~10^5 python ints costs more than a whole EM.  One entry per live list object (the list is kept referenced, so its
+    id cannot be reused)."""
+    if groups is None:
+        return build()
+    key = id(groups)
+    ent = _group_cache.get(key)
+    if ent is None or ent[0] is not groups or ent[1] != num_loci or len(groups) != ent[2]:
+        if len(_group_cache) >= 8:
+            _group_cache.pop(next(iter(_group_cache)))
+        ent = (groups, num_loci, len(groups), {})
+        _group_cache[key] = ent
+    if kind not in ent[3]:
+        ent[3][kind] = build()
+    return ent[3][kind]
+
+
 def gene_index(num_loci: int, groups) -> np.ndarray:
     """int32 gene id per locus.  Loci listed in `groups[g]` get id g; loci in no group get unique ids
     >= len(groups) (they are their own singleton in the reference's `t2t_mat`, EMfactory.py:48-59)."""
+    return _cached("gene_index", num_loci, groups, lambda: _gene_index(num_loci, groups)).copy()
+
+
+def _gene_index(num_loci: int, groups) -> np.ndarray:
     g = np.full(num_loci, -1, dtype=np.int64)
     n_groups = len(groups) if groups is not None else 0
     if n_groups:
@@ -68,6 +93,10 @@ def gene_index(num_loci: int, groups) -> np.ndarray:
 
 def group_conversion_matrix(num_loci: int, groups):
     """T x G 0/1 CSC matrix (`grp_conv_mat`, EMfactory.py:42-47), built without the per-gene python loop."""
+    return _cached("grp_conv_mat", num_loci, groups, lambda: _group_conversion_matrix(num_loci, groups)).copy()
+
+
+def _group_conversion_matrix(num_loci: int, groups):
     from scipy.sparse import csc_matrix
 
     n_groups = len(groups)

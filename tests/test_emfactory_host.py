@@ -56,3 +56,24 @@ def test_packed_arrays_outlive_the_pattern_object():
     junk = [np.ones(1 << 16) for _ in range(8)]  # churn the allocator
     assert (int(pairs.astype(np.int64).sum()), float(count.sum())) == want and len(junk) == 8
     assert float(count.sum()) == float(d.count.sum())
+
+
+def test_weighted_matrix_initial_estimate_matches_reference_golden():
+    """Stored values other than 1 (and explicit zeros): prepare() takes theta0 from the values exactly like the reference
+    (golden written by the unmodified reference, oracle/make_golden_weighted.py).  Host arithmetic only."""
+    import os
+
+    from gbrs_b200.emfactory import EMfactory
+    from oracle.make_golden_weighted import weighted_values
+    from tests import helpers as hp
+
+    z = np.load(os.path.join(hp.GOLDEN, "em_weighted_m4.npz"))
+    d = synth.generate(T=int(z["T"]), N=int(z["N"]), H=int(z["H"]), sample_index=int(z["sample_index"]))
+    apm = synth.to_apm(d)
+    for h, v in enumerate(weighted_values(apm.data)):
+        apm.data[h].data = v
+    assert not apm.is_pure_incidence()
+    em = EMfactory.__new__(EMfactory)
+    em.probability, em.target_lengths = apm, synth.effective_lengths(d)
+    assert hp.relerr(em._weighted_theta0(0.0), z["theta0_nopc"]) < 1e-13
+    assert hp.relerr(em._weighted_theta0(float(z["pseudocount"])), z["theta0_pc"]) < 1e-13
