@@ -680,6 +680,11 @@ def run_gpu_arm(args, wl):
                "sample": f"{ncls} of {wl['N']} classes (nnz={nnz_s}), 5 EM updates, {s_per:.3f} s/update; {note}; host has "
                          f"{os.cpu_count()} logical cores (the path is single-threaded)"}
 
+    xphases = None
+    if world > 1 and em.fused_exchange and em.exchange_mode == "push":
+        st = pat.part[-8:-3].cpu().numpy() * 1e-3  # us since kernel start, block 0 of the last update
+        xphases = {"numerator_block0": float(st[0]), "all_ready": float(st[1]), "slice_reduced": float(st[2]),
+                   "all_done": float(st[3]), "update_done": float(st[4])}
     if rank == 0:
         pushed = world > 1 and em.fused_exchange and em.exchange_mode == "push"
         launches_per_step = (3 if tiled else 4) + (1 if world > 1 and not pushed else 0) + (1 if model != 4 else 0)
@@ -701,7 +706,7 @@ def run_gpu_arm(args, wl):
                                        "multimem.st on the NVSwitch multicast mapping)",
                                "nccl": "NCCL all-reduce of T x 8 fp64 per step"}[em.exchange_mode if em.fused_exchange else "nccl"]},
                 "iterations_per_s": K / (ms * 1e-3), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "e2e_resident": e2e_resident, "parity": parity, "models": models_rec,
+                "e2e_resident": e2e_resident, "parity": parity, "models": models_rec, "exchange_phases_us": xphases,
                 "gpu_launches": launches_per_step * K, "clocks": clocks,
                 "pack_seconds": e2e_parts["pack_s"], "pack_seconds_host_packer": pat.packed.pack_seconds}
         emit(line)

@@ -26,6 +26,20 @@
 
 #include "gbrs_em.h"
 
+// NVTX ranges around the phases of an update (row pass / column pass / locus kernel + exchange / stop test): visible in
+// Nsight Systems timelines; a no-op without an attached tool.  Header-only NVTX 3 (no link dependency).
+#ifndef GBRS_SIMT_EMULATION
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#else
+struct NvtxRange {
+  explicit NvtxRange(const char*) {}
+};
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------------------------------------------------
@@ -62,6 +76,7 @@ constexpr int kThreads = GBRS_THREADS;  // threads per block of every grid-strid
 #define GBRS_COL_MINBLOCKS 4  // resident blocks per SM the column pass is compiled for (64 registers at 256 threads)
 #endif
 constexpr uint32_t kLocusMask = 0xFFFFFFu;
+constexpr int kStampSlot = GBRS_PART_SLOTS - 8;  // k_locus_xchg: phase time stamps of block 0 (diagnostics, bench.py)
 
 int g_sm_count = 0;
 int sm_count() {
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m4_long(const gbrs_em_dev 
       if (UNIT) s += (double) __popc(w >> 24);
       else s += pair_sum(d.subsets, w);
     }
-    d.weights[n] = __ldg(d.count + n) / s;
+    d.weights[n] = fast_div(__ldg(d.count + n), s);
   }
 }
 
@@ -533,7 +548,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d, in
         D += pair_sum(d.subsets, w);
         gam = d.gamma[t];
       }
-      d.weights[run] = (D != 0.0) ? c * gam / total / D : 0.0;
+      d.weights[run] = (D != 0.0) ? fast_div(fast_div(c * gam, total), D) : 0.0;
     }
   }
 }
@@ -572,11 +587,11 @@ __global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d, in
         if (pair_sum(d.subsets, w) != 0.0) S += iso[t];
         gam = d.gamma[t];
       }
-      const double wg = (S != 0.0) ? c * gam / total / S : 0.0;
+      const double wg = (S != 0.0) ? fast_div(fast_div(c * gam, total), S) : 0.0;
       for (; p < q; ++p) {
         const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
         const double x = pair_sum(d.subsets, w);
-        d.weights[p] = (x != 0.0) ? wg * iso[t] / x : 0.0;
+        d.weights[p] = (x != 0.0) ? fast_div(wg * iso[t], x) : 0.0;
       }
     }
   }
@@ -631,14 +646,14 @@ __device__ __forceinline__ void row_class_m23(const gbrs_em_dev& d, const double
       const bool start = (p == 0) || (g[p] != g[p - 1]);
       if (start) {
         if (p > 0) ++run;
-        d.weights[run] = (grp[p] != 0.0) ? c * gam[p] / total / grp[p] : 0.0;
+        d.weights[run] = (grp[p] != 0.0) ? fast_div(fast_div(c * gam[p], total), grp[p]) : 0.0;
       }
     }
   } else {
 #pragma unroll
     for (int p = 0; p < K; ++p) {
-      const double wg = (grp[p] != 0.0) ? c * gam[p] / total / grp[p] : 0.0;
-      d.weights[pair0 + p] = (x[p] != 0.0) ? wg * it[p] / x[p] : 0.0;
+      const double wg = (grp[p] != 0.0) ? fast_div(fast_div(c * gam[p], total), grp[p]) : 0.0;
+      d.weights[pair0 + p] = (x[p] != 0.0) ? fast_div(wg * it[p], x[p]) : 0.0;
     }
   }
 }
@@ -712,10 +727,10 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d, in
       double Hs = 0.0;
 #pragma unroll
       for (int h = 0; h < 8; ++h) Hs += (Dh[h] != 0.0) ? hg[h] : 0.0;
-      const double wg = (Hs != 0.0) ? c * gam / total / Hs : 0.0;
+      const double wg = (Hs != 0.0) ? fast_div(fast_div(c * gam, total), Hs) : 0.0;
       double* out = d.weights + (size_t) run * GBRS_HPAD;
 #pragma unroll
-      for (int h = 0; h < 8; ++h) out[h] = (Dh[h] != 0.0) ? wg * hg[h] / Dh[h] : 0.0;
+      for (int h = 0; h < 8; ++h) out[h] = (Dh[h] != 0.0) ? fast_div(wg * hg[h], Dh[h]) : 0.0;
     }
   }
 }
@@ -771,8 +786,8 @@ __device__ __forceinline__ void row_class_m1(const gbrs_em_dev& d, const double*
     if (start) {
       if (p > 0) ++run;
       if (valid) {
-        const double wg = (Hs[p] != 0.0) ? c * gam[p] / total / Hs[p] : 0.0;
-        d.weights[(size_t) run * GBRS_HPAD + h] = (Dh[p] != 0.0) ? wg * hg[p] / Dh[p] : 0.0;
+        const double wg = (Hs[p] != 0.0) ? fast_div(fast_div(c * gam[p], total), Hs[p]) : 0.0;
+        d.weights[(size_t) run * GBRS_HPAD + h] = (Dh[p] != 0.0) ? fast_div(wg * hg[p], Dh[p]) : 0.0;
       }
     }
   }
@@ -1472,6 +1487,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
   const int me = d.xchg_rank;
   const int64_t slice = push_slice_len(d);
   const int h = threadIdx.x & 7;
+  // phase time stamps of block 0 (ns since the kernel started) for bench.py: part[kStampSlot + 0..5]
+  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t_start = stamp ? globaltimer_ns() : 0ull;
+  auto mark = [&](int i) { if (stamp) d.part[kStampSlot + i] = (double) (globaltimer_ns() - t_start); };
   // ---- A: local numerator, pushed to the owners ----------------------------------------------------------------------
   {
     const double* __restrict__ th = d.theta + (size_t) par * d.T * GBRS_HPAD;
@@ -1485,9 +1504,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
       }
     });
   }
+  mark(0);  // numerator of block 0 done
   push_signal(d, 0, e, GBRS_CTRL_TICKET + 1);
   // ---- B: sum my slice over the ranks, broadcast the totals ---------------------------------------------------------
   if (!push_wait(d, 0, e, &s_fail)) return;
+  mark(1);  // every rank's numerator has arrived
   {
     const int total_n = d.T * GBRS_HPAD;
     const int lo = (int) slice * me, hi = lo + (int) slice < total_n ? lo + (int) slice : total_n;  // (both even)
@@ -1515,9 +1536,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
       }
     }
   }
+  mark(2);  // slice of block 0 reduced and broadcast
   push_signal(d, 1, e, GBRS_CTRL_TICKET + 2);
   // ---- C: the update, from the totals every owner has stored here -------------------------------------------------------
   if (!push_wait(d, 1, e, &s_fail)) return;
+  mark(3);  // every owner's totals have arrived
   {
     const double* __restrict__ src = push_total(d, me);
     double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
@@ -1546,6 +1569,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     const double bs = block_sum(mine, red);
     if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
   }
+  mark(4);  // update of block 0 done
 }
 
 // Stop test of EMfactory.run (EMfactory.py:267-279) on the device.
@@ -1881,6 +1905,7 @@ inline gbrs_em_dev locus_view(const gbrs_em_dev* d, bool tiles) {
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream) {
   if (int rc = check_dev(d, "gbrs_em_prepare_local")) return rc;
+  NvtxRange nvtx_prep("gbrs:prepare");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   k_reset_ctrl<<<1, 32, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_reset_ctrl");
@@ -2067,6 +2092,8 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   const int cg = grid_for(d->n_classes);
   cudaEvent_t* ev = prof ? &prof->ev[(size_t) prof->used * 4] : nullptr;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[0], s));
+  {
+  NvtxRange nvtx_row(tiles ? "gbrs:tile_pass" : "gbrs:row_pass");
   if (tiles) {
     if (int rct = launch_tiles<false>(d, s)) return rct;
   } else if (d->n_classes > 0) {
@@ -2106,15 +2133,20 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
     }
     GBRS_LAUNCH_CHECK("k_weights");
   }
+  }
   if (ev) GBRS_CUDA(cudaEventRecord(ev[1], s));
+  {
+  NvtxRange nvtx_col("gbrs:column_pass");
   if (!tiles) switch (model) {
     case 4: rc = launch_column<1>(d, d->ent_cls, honour_done, s); break;
     case 3: rc = launch_column<1>(d, d->ent_run, honour_done, s); break;
     case 2: rc = launch_column<1>(d, d->ent_pair, honour_done, s); break;
     default: rc = launch_column<8>(d, d->ent_run, honour_done, s); break;
   }
+  }
   if (rc) return rc;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[2], s));
+  NvtxRange nvtx_locus(d->n_ranks > 1 && d->xchg_enabled == 2 ? "gbrs:locus_exchange_update" : "gbrs:locus_numerator");
   const gbrs_em_dev lv = locus_view(d, tiles);
   if (d->n_ranks > 1 && d->xchg_enabled == 2 && !estep_only) {
     if (int rcp = launch_push<false>(&lv, s)) return rcp;
@@ -2132,6 +2164,7 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
 
 extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
   if (int rc = check_dev(d, "gbrs_em_launch_update")) return rc;
+  NvtxRange nvtx_upd("gbrs:update_and_stop_test");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int nparts = acc_grid(d);  // single rank: k_locus_acc already produced theta', iso' and the partial sums
   if (d->n_ranks > 1 && d->xchg_enabled == 2) {
