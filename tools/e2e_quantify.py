@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--model", type=int, default=4)
     ap.add_argument("--diploid", action="store_true")
     ap.add_argument("--keep", default=None)
+    ap.add_argument("--profile", action="store_true", help="cProfile of the quantify() call on stderr")
     args = ap.parse_args()
 
     import numpy as np
@@ -64,10 +65,31 @@ def main():
     timed(emfactory.EMfactory, "run", "run_s")
     timed(emfactory.EMfactory, "report_depths", "reports_s")
     timed(emfactory.EMfactory, "report_read_counts", "reports_s")
-    timed(emfactory.PackedPattern, "__init__", "pack_s")
+    timed(emfactory.PackedPattern, "__init__", "pack_host_s")
+    timed(emfactory.DevicePacked, "__init__", "pack_device_s")
+    timed(emfactory.EMfactory, "_read_lengths", "read_lengths_s")
+    import torch
+
     t0 = time.perf_counter()
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    torch.cuda.synchronize()
+    times["cuda_context_s"] = time.perf_counter() - t0  # paid once per process, before quantify() is entered
+    import cProfile
+    import io
+    import pstats
+
+    pr = cProfile.Profile() if args.profile else None
+    t0 = time.perf_counter()
+    if pr:
+        pr.enable()
     qmod.quantify(alignment_file=aln, group_file=grp, length_file=ln, genotype_file=gt if args.diploid else None,
                   outbase=os.path.join(tmp, "out"), multiread_model=args.model, report_alignment_counts=True)
+    if pr:
+        pr.disable()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(35)
+        print(buf.getvalue()[:7000], file=sys.stderr)
     times["quantify_total_s"] = time.perf_counter() - t0
     times.update(marks)
     kind = "diploid" if args.diploid else "multiway"
