@@ -166,12 +166,12 @@ __device__ __forceinline__ double fast_div(double c, double s) {
   return fma(fma(-s, q, c), r, q);
 }
 
-// The same for divisors that may be denormal or huge (the partial normalisers of models 1-3: a gene run's share can
-// underflow towards zero while the class lives on its other runs).  rcp.approx flushes denormals, so outside the safe
-// range the IEEE division is taken.
-__device__ __forceinline__ double safe_div(double c, double s) {
+// The same for divisors that may be denormal or huge (an expression estimate handed in by the caller can make a class
+// normaliser underflow): rcp.approx flushes denormals, so outside the safe range the IEEE division is taken.
+__device__ __forceinline__ double guarded_div(double c, double s) {
   const double a = fabs(s);
-  return (a > 1e-290 && a < 1e290) ? fast_div(c, s) : c / s;
+  if (a > 1e-290 && a < 1e290) return fast_div(c, s);
+  return c / s;
 }
 
 // Sum over the 8 lanes of an aligned lane group; every lane gets the total.  Fixed order => deterministic.
@@ -447,7 +447,7 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
   }
 #pragma unroll
   for (int u = 0; u < UNR; ++u)
-    if (n[u] < class_end) d.weights[n[u]] = fast_div(cnt[u], s[u]);
+    if (n[u] < class_end) d.weights[n[u]] = guarded_div(cnt[u], s[u]);
 }
 
 template <bool UNIT>
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m4_long(const gbrs_em_dev 
       if (UNIT) s += (double) __popc(w >> 24);
       else s += pair_sum(d.subsets, w);
     }
-    d.weights[n] = fast_div(__ldg(d.count + n), s);
+    d.weights[n] = __ldg(d.count + n) / s;
   }
 }
 
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(kThreads) k_weights_m3(const gbrs_em_dev d, in
         D += pair_sum(d.subsets, w);
         gam = d.gamma[t];
       }
-      d.weights[run] = (D != 0.0) ? safe_div(safe_div(c * gam, total), D) : 0.0;
+      d.weights[run] = (D != 0.0) ? c * gam / total / D : 0.0;
     }
   }
 }
@@ -595,11 +595,11 @@ __global__ void __launch_bounds__(kThreads) k_weights_m2(const gbrs_em_dev d, in
         if (pair_sum(d.subsets, w) != 0.0) S += iso[t];
         gam = d.gamma[t];
       }
-      const double wg = (S != 0.0) ? safe_div(safe_div(c * gam, total), S) : 0.0;
+      const double wg = (S != 0.0) ? c * gam / total / S : 0.0;
       for (; p < q; ++p) {
         const uint32_t w = __ldg(d.pairs + p), t = w & kLocusMask;
         const double x = pair_sum(d.subsets, w);
-        d.weights[p] = (x != 0.0) ? safe_div(wg * iso[t], x) : 0.0;
+        d.weights[p] = (x != 0.0) ? wg * iso[t] / x : 0.0;
       }
     }
   }
@@ -654,14 +654,14 @@ __device__ __forceinline__ void row_class_m23(const gbrs_em_dev& d, const double
       const bool start = (p == 0) || (g[p] != g[p - 1]);
       if (start) {
         if (p > 0) ++run;
-        d.weights[run] = (grp[p] != 0.0) ? safe_div(safe_div(c * gam[p], total), grp[p]) : 0.0;
+        d.weights[run] = (grp[p] != 0.0) ? c * gam[p] / total / grp[p] : 0.0;
       }
     }
   } else {
 #pragma unroll
     for (int p = 0; p < K; ++p) {
-      const double wg = (grp[p] != 0.0) ? safe_div(safe_div(c * gam[p], total), grp[p]) : 0.0;
-      d.weights[pair0 + p] = (x[p] != 0.0) ? safe_div(wg * it[p], x[p]) : 0.0;
+      const double wg = (grp[p] != 0.0) ? c * gam[p] / total / grp[p] : 0.0;
+      d.weights[pair0 + p] = (x[p] != 0.0) ? wg * it[p] / x[p] : 0.0;
     }
   }
 }
@@ -735,10 +735,10 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d, in
       double Hs = 0.0;
 #pragma unroll
       for (int h = 0; h < 8; ++h) Hs += (Dh[h] != 0.0) ? hg[h] : 0.0;
-      const double wg = (Hs != 0.0) ? safe_div(safe_div(c * gam, total), Hs) : 0.0;
+      const double wg = (Hs != 0.0) ? c * gam / total / Hs : 0.0;
       double* out = d.weights + (size_t) run * GBRS_HPAD;
 #pragma unroll
-      for (int h = 0; h < 8; ++h) out[h] = (Dh[h] != 0.0) ? safe_div(wg * hg[h], Dh[h]) : 0.0;
+      for (int h = 0; h < 8; ++h) out[h] = (Dh[h] != 0.0) ? wg * hg[h] / Dh[h] : 0.0;
     }
   }
 }
@@ -794,8 +794,8 @@ __device__ __forceinline__ void row_class_m1(const gbrs_em_dev& d, const double*
     if (start) {
       if (p > 0) ++run;
       if (valid) {
-        const double wg = (Hs[p] != 0.0) ? safe_div(safe_div(c * gam[p], total), Hs[p]) : 0.0;
-        d.weights[(size_t) run * GBRS_HPAD + h] = (Dh[p] != 0.0) ? safe_div(wg * hg[p], Dh[p]) : 0.0;
+        const double wg = (Hs[p] != 0.0) ? c * gam[p] / total / Hs[p] : 0.0;
+        d.weights[(size_t) run * GBRS_HPAD + h] = (Dh[p] != 0.0) ? wg * hg[p] / Dh[p] : 0.0;
       }
     }
   }
@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = 4 * q + u;
-        if (j < nc) w[j] = fast_div(c[u], s[u]);
+        if (j < nc) w[j] = guarded_div(c[u], s[u]);
       }
     }
     __syncwarp();  // the weights are complete, the table is no longer read

@@ -3,7 +3,7 @@ zeros), produced by the unmodified reference in the build container:  python -m 
 
 What the reference does with such a file (and what gbrs_b200 must reproduce): prepare() normalises the stored values per
 class and takes theta0 from them (EMfactory.py:95-111); every E-step then starts with probability.reset(), which sets
-every stored entry -- explicit zeros included -- to 1 (Sparse3DMatrix.py:220-228).  Writes tests/golden/em_weighted_m4.npz."""
+every stored entry -- explicit zeros included -- to 1 (Sparse3DMatrix.py:220-228).  Writes tests/golden/weighted_m4.npz."""
 from __future__ import annotations
 
 import contextlib
@@ -66,7 +66,7 @@ def main():
         tag = "pc" if pc else "nopc"
         out[f"theta0_{tag}"], out[f"theta_{tag}"], out[f"iters_{tag}"] = theta0, np.asarray(em.allelic_expression).copy(), iters
         out[f"counts_{tag}"] = np.asarray(em.probability.sum(axis=ref.APM.Axis.READ)).copy()
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "em_weighted_m4.npz"), T=d.T, N=d.N, H=d.H, sample_index=21,
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "weighted_m4.npz"), T=d.T, N=d.N, H=d.H, sample_index=21,
                         pseudocount=0.7, **out)
     print({k: (v if np.isscalar(v) or getattr(v, "ndim", 1) == 0 else v.shape) for k, v in out.items()})
 

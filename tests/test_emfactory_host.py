@@ -67,7 +67,7 @@ def test_weighted_matrix_initial_estimate_matches_reference_golden():
     from oracle.make_golden_weighted import weighted_values
     from tests import helpers as hp
 
-    z = np.load(os.path.join(hp.GOLDEN, "em_weighted_m4.npz"))
+    z = np.load(os.path.join(hp.GOLDEN, "weighted_m4.npz"))
     d = synth.generate(T=int(z["T"]), N=int(z["N"]), H=int(z["H"]), sample_index=int(z["sample_index"]))
     apm = synth.to_apm(d)
     for h, v in enumerate(weighted_values(apm.data)):
