@@ -167,11 +167,12 @@ __device__ __forceinline__ double fast_div(double c, double s) {
 }
 
 // The same for divisors that may be denormal or huge (an expression estimate handed in by the caller can make a class
-// normaliser underflow): rcp.approx flushes denormals, so outside the safe range the IEEE division is taken.
+// normaliser underflow): rcp.approx flushes denormals and the Newton steps then produce NaN / inf; a non-finite quotient
+// is recomputed with the IEEE division (one compare on the common path).
 __device__ __forceinline__ double guarded_div(double c, double s) {
-  const double a = fabs(s);
-  if (a > 1e-290 && a < 1e290) return fast_div(c, s);
-  return c / s;
+  double q = fast_div(c, s);
+  if (!(fabs(q) <= 1.7976931348623157e308)) q = c / s;
+  return q;
 }
 
 // Sum over the 8 lanes of an aligned lane group; every lane gets the total.  Fixed order => deterministic.
