@@ -451,12 +451,14 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
     if (n[u] < class_end) d.weights[n[u]] = guarded_div(cnt[u], s[u]);
 }
 
-template <bool UNIT>
+// One launch per width range [KLO, KHI]: the narrow classes (four out of five have at most three pairs) are not compiled for
+// the register needs of the widest, so more of them are resident and more loads are in flight.
+template <bool UNIT, int KLO, int KHI>
 __global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__ gbrs_em_dev d,
                                                           const __grid_constant__ RowPlan plan) {
   if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
-  const int64_t total_units = plan.unit_end[GBRS_KMAX - 1];
+  const int64_t total_units = plan.unit_end[KHI - KLO];
   int i = 0;  // bucket index only ever advances along the warp's grid-stride walk
   int64_t unit0 = 0, unit1 = plan.unit_end[0];
   for (int64_t u = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < total_units; u += nwarps) {
@@ -464,20 +466,20 @@ __global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__
       unit0 = unit1;
       unit1 = plan.unit_end[++i];
     }
-    const int k = GBRS_KMAX - i;
+    const int k = KHI - i;
     const int64_t c0 = d.bucket_class0[k - 1], c1 = d.bucket_class0[k], p0 = d.bucket_pair0[k - 1];
     const int cpu = 32 * unr_of(k);
     const int64_t class0 = c0 + (u - unit0) * cpu;
+#define GBRS_ROW_CASE(K) \
+  case K:                \
+    if constexpr (K >= KLO && K <= KHI) row_classes_m4<K, UNIT>(d, class0, c1, c0, p0); \
+    break;
     switch (k) {
-      case 1: row_classes_m4<1, UNIT>(d, class0, c1, c0, p0); break;
-      case 2: row_classes_m4<2, UNIT>(d, class0, c1, c0, p0); break;
-      case 3: row_classes_m4<3, UNIT>(d, class0, c1, c0, p0); break;
-      case 4: row_classes_m4<4, UNIT>(d, class0, c1, c0, p0); break;
-      case 5: row_classes_m4<5, UNIT>(d, class0, c1, c0, p0); break;
-      case 6: row_classes_m4<6, UNIT>(d, class0, c1, c0, p0); break;
-      case 7: row_classes_m4<7, UNIT>(d, class0, c1, c0, p0); break;
-      default: row_classes_m4<8, UNIT>(d, class0, c1, c0, p0); break;
+      GBRS_ROW_CASE(1) GBRS_ROW_CASE(2) GBRS_ROW_CASE(3) GBRS_ROW_CASE(4)
+      GBRS_ROW_CASE(5) GBRS_ROW_CASE(6) GBRS_ROW_CASE(7) GBRS_ROW_CASE(8)
+      default: break;
     }
+#undef GBRS_ROW_CASE
   }
 }
 
@@ -667,30 +669,40 @@ __device__ __forceinline__ void row_class_m23(const gbrs_em_dev& d, const double
   }
 }
 
-template <int MODEL>
+template <int MODEL, int KLO, int KHI>
 __global__ void __launch_bounds__(kThreads) k_weights_m23_fixed(const __grid_constant__ gbrs_em_dev d) {
   if (d.ctrl[GBRS_CTRL_DONE]) return;
   const double* __restrict__ iso = d.iso + (size_t) d.ctrl[GBRS_CTRL_PARITY] * d.T;
-  const int64_t n_fixed = d.bucket_class0[GBRS_KMAX];
+  const int64_t first = d.bucket_class0[KLO - 1], end = d.bucket_class0[KHI];
   const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-  // classes are visited widest first (n_fixed - 1 down to 0): the expensive ones must not form the tail
-  for (int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; j < n_fixed; j += stride) {
-    const int64_t n = n_fixed - 1 - j;
-    int k = GBRS_KMAX;
+  // classes are visited widest first (end - 1 down to first): the expensive ones must not form the tail
+  for (int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; j < end - first; j += stride) {
+    const int64_t n = end - 1 - j;
+    int k = KHI;
     while (n < d.bucket_class0[k - 1]) --k;
     const uint32_t pair0 = (uint32_t) (d.bucket_pair0[k - 1] + (n - d.bucket_class0[k - 1]) * k);
     const uint32_t* __restrict__ pw = d.pairs + pair0;
+#define GBRS_M23_CASE(K) \
+  case K:                \
+    if constexpr (K >= KLO && K <= KHI) row_class_m23<K, MODEL>(d, iso, n, pw, pair0); \
+    break;
     switch (k) {
-      case 1: row_class_m23<1, MODEL>(d, iso, n, pw, pair0); break;
-      case 2: row_class_m23<2, MODEL>(d, iso, n, pw, pair0); break;
-      case 3: row_class_m23<3, MODEL>(d, iso, n, pw, pair0); break;
-      case 4: row_class_m23<4, MODEL>(d, iso, n, pw, pair0); break;
-      case 5: row_class_m23<5, MODEL>(d, iso, n, pw, pair0); break;
-      case 6: row_class_m23<6, MODEL>(d, iso, n, pw, pair0); break;
-      case 7: row_class_m23<7, MODEL>(d, iso, n, pw, pair0); break;
-      default: row_class_m23<8, MODEL>(d, iso, n, pw, pair0); break;
+      GBRS_M23_CASE(1) GBRS_M23_CASE(2) GBRS_M23_CASE(3) GBRS_M23_CASE(4)
+      GBRS_M23_CASE(5) GBRS_M23_CASE(6) GBRS_M23_CASE(7) GBRS_M23_CASE(8)
+      default: break;
     }
+#undef GBRS_M23_CASE
   }
+}
+
+template <int MODEL, int KLO, int KHI>
+int launch_m23_fixed(const gbrs_em_dev* d, cudaStream_t s) {
+  const int64_t n = d->bucket_class0[KHI] - d->bucket_class0[KLO - 1];
+  if (n > 0) {
+    k_weights_m23_fixed<MODEL, KLO, KHI><<<resident_grid(k_weights_m23_fixed<MODEL, KLO, KHI>, n), kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_weights_m23_fixed");
+  }
+  return GBRS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1826,21 +1838,29 @@ int launch_exchange(const gbrs_em_dev* d, cudaStream_t s) {
   return GBRS_OK;
 }
 
-template <bool UNIT>
-int launch_row_m4(const gbrs_em_dev* d, cudaStream_t s) {
+template <bool UNIT, int KLO, int KHI>
+int launch_row_m4_range(const gbrs_em_dev* d, cudaStream_t s) {
   RowPlan plan;
   int64_t units = 0;
   // the subset-sum tables of the current theta were written by the locus kernel of the previous update (or by
   // prepare / set_theta)
-  for (int i = 0; i < GBRS_KMAX; ++i) {
-    const int k = GBRS_KMAX - i, cpu = 32 * unr_of(k);
+  for (int i = 0; i <= KHI - KLO; ++i) {  // widest bucket of the range first
+    const int k = KHI - i, cpu = 32 * unr_of(k);
     units += (d->bucket_class0[k] - d->bucket_class0[k - 1] + cpu - 1) / cpu;
     plan.unit_end[i] = units;
   }
   if (units > 0) {
-    k_weights_m4<UNIT><<<resident_grid(k_weights_m4<UNIT>, units * 32), kThreads, 0, s>>>(*d, plan);
+    k_weights_m4<UNIT, KLO, KHI><<<resident_grid(k_weights_m4<UNIT, KLO, KHI>, units * 32), kThreads, 0, s>>>(*d, plan);
     GBRS_LAUNCH_CHECK("k_weights_m4");
   }
+  return GBRS_OK;
+}
+
+template <bool UNIT>
+int launch_row_m4(const gbrs_em_dev* d, cudaStream_t s) {
+  // one launch for all widths: here the narrow classes set the register budget (four classes per thread), so a split by
+  // width buys no occupancy and would cost a launch gap (models 2-3 do split: their wide classes need 64-98 registers)
+  if (int rc = launch_row_m4_range<UNIT, 1, GBRS_KMAX>(d, s)) return rc;
   const int64_t n_long = d->n_classes - d->bucket_class0[GBRS_KMAX];
   if (n_long > 0) {
     if (!d->rowptr) { gbrs_set_error("row pass: classes wider than GBRS_KMAX need rowptr"); return GBRS_E_ARG; }
@@ -2111,9 +2131,10 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
       case 3:
       case 2: {
         const int64_t n_fixed = d->bucket_class0[GBRS_KMAX], n_long = d->n_classes - n_fixed;
-        if (n_fixed > 0) {
-          if (model == 3) k_weights_m23_fixed<3><<<resident_grid(k_weights_m23_fixed<3>, n_fixed), kThreads, 0, s>>>(*d);
-          else k_weights_m23_fixed<2><<<resident_grid(k_weights_m23_fixed<2>, n_fixed), kThreads, 0, s>>>(*d);
+        if (n_fixed > 0) {  // wide classes first, then the narrow ones at their own (smaller) register budget
+          int rcf = model == 3 ? launch_m23_fixed<3, 4, GBRS_KMAX>(d, s) : launch_m23_fixed<2, 4, GBRS_KMAX>(d, s);
+          if (!rcf) rcf = model == 3 ? launch_m23_fixed<3, 1, 3>(d, s) : launch_m23_fixed<2, 1, 3>(d, s);
+          if (rcf) return rcf;
         }
         if (n_long > 0) {
           if (model == 3) k_weights_m3<<<grid_for(n_long), kThreads, 0, s>>>(*d, n_fixed);

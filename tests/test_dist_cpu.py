@@ -130,3 +130,92 @@ def test_two_rank_gloo_reconstruct_cohort(tmp_path):
         gp = np.load(base / f"out{i}.genoprobs.npz")
         for c in want["gamma"]:
             np.testing.assert_allclose(gp[c], want["gamma"][c], rtol=chk.RTOL, atol=1e-300)
+
+
+EM_COHORT_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["GBRS_ROOT"])
+import numpy as np, torch.distributed as dist
+from gbrs_b200 import cohort, synth
+from oracle import em_oracle as eo
+from tests import simt_em
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+
+class EmulatedEM:
+    """EMfactory's surface as far as quantify_cohort uses it, with the device replaced by the emulated library (the real
+    kernels and C ABI on the host SIMT shim): this box has no GPU, everything else is the product's cohort path."""
+    loaded = []
+
+    def __init__(self, apm, device=None):
+        self.apm, self.target_lengths = apm, None
+        EmulatedEM.loaded.append(apm.tag)
+
+    def prepare(self, pseudocount=0.0, lenfile=None, read_length=100):
+        if self.target_lengths is None:  # the first sample parses the table, the others get it handed over
+            assert lenfile == "shared.len"
+            self.target_lengths = SHARED_EFF
+        self.pat = simt_em.HostPattern(self.apm, gene_of=eo.gene_index(self.apm.num_loci, self.apm.groups))
+        self._pattern = self.pat
+        self.pat.device = None
+        self.pat.prepare(self.target_lengths, pseudocount)
+
+    def run(self, model, tol, max_iters, verbose=False):
+        self.out = self.pat.run(model, tol, max_iters)
+        self.num_iters = self.out["iters"]
+
+    def get_allelic_expression(self):
+        return self.out["theta"]
+
+    def expected_read_counts(self):
+        return self.out["counts"]
+
+import torch
+torch.cuda.synchronize = lambda *a, **k: None      # no device here
+cohort.EMfactory = EmulatedEM
+N_SAMPLES = 5
+datas = [synth.generate(T=40, N=300, H=4, sample_index=i) for i in range(N_SAMPLES)]
+SHARED_EFF = eo.effective_length_table(datas[0].lengths)
+
+def load(i):
+    apm = synth.to_apm(datas[i])
+    apm.tag = i
+    apm.groups = [list(g) for g in apm.groups]      # a fresh, equal list per sample: the cohort must share one
+    return apm
+
+stats = {}
+local = cohort.quantify_cohort(list(range(N_SAMPLES)), load, model=4, lenfile="shared.len", prefetch=2, stats=stats)
+assert sorted(local) == cohort.my_share(N_SAMPLES, rank, world) == EmulatedEM.loaded
+assert stats["samples"] == len(local) and stats["nnz_iters"] > 0
+merged = cohort.gather_results(local, N_SAMPLES)
+assert len(merged) == N_SAMPLES
+for i, r in enumerate(merged):                         # every rank holds every sample's result; each equals the oracle's
+    d = datas[i]
+    oapm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    o = eo.run(oapm, eo.prepare(oapm, SHARED_EFF, 0.0), 4, SHARED_EFF, None, tol=1e-4)
+    assert r["iters"] == o["iters"] and np.abs(r["counts"] - o["counts"]).max() < 1e-9 * np.abs(o["counts"]).max()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_em_cohort_split(tmp_path):
+    """Batched cohort mode (BASELINE config 5) under a 2-rank gloo job: round-robin split, loader thread, shared length
+    table and grouping, object all-gather of the per-sample results; the per-sample EM runs through the emulated library
+    and must equal the oracle's."""
+    import shutil
+
+    if shutil.which("g++") is None:
+        pytest.skip("g++ is needed to build the SIMT emulation")
+    from tests import simt_em
+
+    simt_em.build()  # once, before two ranks race to build it
+    script = tmp_path / "worker.py"
+    script.write_text(EM_COHORT_WORKER)
+    env = dict(os.environ, GBRS_ROOT=ROOT, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29519", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2

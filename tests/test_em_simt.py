@@ -251,7 +251,7 @@ def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1, mode=2, ti
         os.environ.pop("GBRS_SIMT_SMS", None)
 
 
-@pytest.mark.parametrize("R,model,mode", [(2, 4, 2), (3, 2, 2), (3, 4, 1), (2, 1, 1)])
+@pytest.mark.parametrize("R,model,mode", [(2, 4, 2), (3, 2, 2), (3, 4, 1)])
 def test_emulated_fused_exchange_between_concurrent_ranks(R, model, mode):
     """mode 2: the one-launch push form (k_locus_xchg); mode 1: the pull form."""
     d = synth.generate(T=70, N=900, H=8, sample_index=12)

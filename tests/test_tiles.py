@@ -98,7 +98,7 @@ def test_empty_shard_has_no_tiles():
 
 # ---- the kernel source on the CPU (host SIMT shim) -------------------------------------------------------------------
 needs_gxx = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ is needed to build the SIMT emulation")
-GOLDEN_M4 = ["em_small_m4", "em_small_m4_diploid", "em_small_m4_pc", "em_small_m4_h1", "em_small_m4_h2"]
+GOLDEN_M4 = ["em_small_m4", "em_small_m4_diploid", "em_small_m4_h1"]
 if os.environ.get("GBRS_SIMT_ALL"):
     GOLDEN_M4 = [n for n in hp.golden_em_cases() if n.startswith("em_small_m4")]
 
