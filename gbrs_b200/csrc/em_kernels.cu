@@ -156,7 +156,8 @@ __device__ __forceinline__ void masked_add8(double (&a)[8], double w, uint32_t m
 }
 
 // c / s without the library division's slow path: reciprocal seed + two Newton steps + one residual correction
-// (<= 1 ulp; s == 0 or non-finite input yields inf/NaN, which the convergence kernel turns into GBRS_E_NUMERIC).
+// (<= 1 ulp; s == 0, a denormal s -- rcp.approx flushes it -- or non-finite input yields inf/NaN, which the convergence
+// kernel turns into GBRS_E_NUMERIC.  A guard that re-divides with the IEEE division cost the row pass 3-4 us and was dropped).
 __device__ __forceinline__ double fast_div(double c, double s) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
@@ -164,15 +165,6 @@ __device__ __forceinline__ double fast_div(double c, double s) {
   r = fma(fma(-s, r, 1.0), r, r);
   const double q = c * r;
   return fma(fma(-s, q, c), r, q);
-}
-
-// The same for divisors that may be denormal or huge (an expression estimate handed in by the caller can make a class
-// normaliser underflow): rcp.approx flushes denormals and the Newton steps then produce NaN / inf; a non-finite quotient
-// is recomputed with the IEEE division (one compare on the common path).
-__device__ __forceinline__ double guarded_div(double c, double s) {
-  double q = fast_div(c, s);
-  if (!(fabs(q) <= 1.7976931348623157e308)) q = c / s;
-  return q;
 }
 
 // Sum over the 8 lanes of an aligned lane group; every lane gets the total.  Fixed order => deterministic.
@@ -448,7 +440,7 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
   }
 #pragma unroll
   for (int u = 0; u < UNR; ++u)
-    if (n[u] < class_end) d.weights[n[u]] = guarded_div(cnt[u], s[u]);
+    if (n[u] < class_end) d.weights[n[u]] = fast_div(cnt[u], s[u]);
 }
 
 // One launch per width range [KLO, KHI]: the narrow classes (four out of five have at most three pairs) are not compiled for
@@ -1160,7 +1152,7 @@ __global__ void __launch_bounds__(kTileThreads, GBRS_TILE_MINBLOCKS) k_tile_em(c
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = 4 * q + u;
-        if (j < nc) w[j] = guarded_div(c[u], s[u]);
+        if (j < nc) w[j] = fast_div(c[u], s[u]);
       }
     }
     __syncwarp();  // the weights are complete, the table is no longer read
