@@ -748,6 +748,92 @@ __global__ void __launch_bounds__(kThreads) k_weights_m1(const gbrs_em_dev d, in
   }
 }
 
+// Model 1, narrow classes (1..3 pairs: four classes out of five), one thread per class, no row pointers and no
+// data-dependent loops: the pair words, then the theta lines / gene ids / gene totals of all pairs, then the per-haplotype
+// gene totals of the runs are each one round of independent loads; the run structure (pairs of one gene are adjacent) is
+// resolved in registers.  Same sums in the same order as k_weights_m1, which keeps the wider classes.
+template <int K>
+__device__ __forceinline__ void row_class_m1_thread(const gbrs_em_dev& d, const double* __restrict__ th, int64_t n) {
+  const uint32_t pair0 = (uint32_t) (d.bucket_pair0[K - 1] + (n - d.bucket_class0[K - 1]) * K);
+  uint32_t w[K];
+#pragma unroll
+  for (int p = 0; p < K; ++p) w[p] = __ldg(d.pairs + pair0 + p);
+  const double c = __ldg(d.count + n);
+  uint32_t run = __ldg(d.runptr + n);
+  int32_t g[K];
+  double gam[K], x[K][8];
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    const uint32_t t = w[p] & kLocusMask, m = w[p] >> 24;
+    g[p] = __ldg(d.gene_of + t);
+    gam[p] = d.gamma[t];
+    double v[8];
+    load8(th + (size_t) t * GBRS_HPAD, v);
+#pragma unroll
+    for (int h = 0; h < 8; ++h) x[p][h] = ((m >> h) & 1u) ? v[h] : 0.0;
+  }
+  double hg[K][8];
+#pragma unroll
+  for (int p = 0; p < K; ++p) load8(d.gene_hap + (size_t) g[p] * GBRS_HPAD, hg[p]);
+  // per run start p: Dh[h] over the pairs of the run (in pair order), Hs over the haplotypes that are alive
+  double Dh[K][8], Hs[K];
+  bool start[K], alive[K];
+  double total = 0.0;
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    start[p] = (p == 0) || (g[p] != g[p - 1]);
+    double hs = 0.0;
+    bool any = false;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      double a = 0.0;
+#pragma unroll
+      for (int q = 0; q < K; ++q) a += (g[q] == g[p]) ? x[q][h] : 0.0;
+      Dh[p][h] = a;
+      hs += (a != 0.0) ? hg[p][h] : 0.0;
+      any = any || (a != 0.0);
+    }
+    Hs[p] = hs;
+    alive[p] = any;
+    total += (start[p] && any) ? gam[p] : 0.0;
+  }
+#pragma unroll
+  for (int p = 0; p < K; ++p) {
+    if (!start[p]) continue;
+    if (p > 0) ++run;
+    const double wg = (Hs[p] != 0.0) ? c * gam[p] / total / Hs[p] : 0.0;
+    double* out = d.weights + (size_t) run * GBRS_HPAD;
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {
+      const double o0 = (Dh[p][h] != 0.0) ? wg * hg[p][h] / Dh[p][h] : 0.0;
+      const double o1 = (Dh[p][h + 1] != 0.0) ? wg * hg[p][h + 1] / Dh[p][h + 1] : 0.0;
+      *reinterpret_cast<double2*>(out + h) = make_double2(o0, o1);
+    }
+  }
+  (void) alive;
+}
+
+constexpr int kM1Narrow = 3;
+template <int K>  // one launch per width: a class of one pair is not compiled for the registers three pairs need
+__global__ void __launch_bounds__(kThreads) k_weights_m1_narrow(const __grid_constant__ gbrs_em_dev d) {
+  if (d.ctrl[GBRS_CTRL_DONE]) return;
+  const double* __restrict__ th = theta_cur(d);
+  const int64_t first = d.bucket_class0[K - 1], end = d.bucket_class0[K];
+  const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+  for (int64_t n = first + (int64_t) blockIdx.x * blockDim.x + threadIdx.x; n < end; n += stride)
+    row_class_m1_thread<K>(d, th, n);
+}
+
+template <int K>
+int launch_m1_narrow(const gbrs_em_dev* d, cudaStream_t s) {
+  const int64_t n = d->bucket_class0[K] - d->bucket_class0[K - 1];
+  if (n > 0) {
+    k_weights_m1_narrow<K><<<resident_grid(k_weights_m1_narrow<K>, n), kThreads, 0, s>>>(*d);
+    GBRS_LAUNCH_CHECK("k_weights_m1_narrow");
+  }
+  return GBRS_OK;
+}
+
 // Model 1 for classes of 1..GBRS_KMAX pairs, eight lanes per class (opt-in: GBRS_M1_FIXED, not yet measured).  Lane h of a
 // group owns haplotype h: the theta line of a pair and the gene's per-haplotype totals are read as one 64-byte access
 // per group, the eight weights of a run are written as one 64-byte line, the class needs no row pointer (width bucket
@@ -908,17 +994,44 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
       for (uint32_t p0 = b + 4 * lanex; p0 < e; p0 += 4 * LANES * 2) column_steps<E, LANES, FULL, 2>(ents, wts, b, e, p0, a);
     }
   } else {
-    for (uint32_t p = b + lanex; p < e; p += LANES) {
-      const E ent = __ldg(ents + p);
-      const uint32_t m = (uint32_t) (ent >> SH);
-      double v[8];
-      load8(wts + (size_t) (ent & IDX) * GBRS_HPAD, v);
+    // Model 1: eight weights per index (one per haplotype).  Lane h of an 8-lane group owns haplotype h and the whole
+    // group walks the same entries: the entry words are one broadcast load, the eight weights of an entry one coalesced
+    // 64-byte access (a lane gathering the full 64-byte line by itself cost four 16-byte requests per entry, each a
+    // wavefront of its own: 223 us at C2), and no transposing reduction is needed at the end.
+    constexpr int G = LANES / 8;  // lane groups sharing the item: each takes every G-th quad of entries
+    const int grp = lanex >> 3;
+    double acc0 = 0.0, acc1 = 0.0;
+    auto quad = [&](uint32_t p, double& acc) {
+      E w4[4];
+      if (sizeof(E) == 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(ents + p));
+        w4[0] = (E) v.x; w4[1] = (E) v.y; w4[2] = (E) v.z; w4[3] = (E) v.w;
+      } else {
+        const ulonglong2 v0 = __ldg(reinterpret_cast<const ulonglong2*>(ents + p));
+        const ulonglong2 v1 = __ldg(reinterpret_cast<const ulonglong2*>(ents + p) + 1);
+        w4[0] = (E) v0.x; w4[1] = (E) v0.y; w4[2] = (E) v1.x; w4[3] = (E) v1.y;
+      }
+      double x[4];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) a[h] = fma(v[h], __hiloint2double(((m >> h) & 1u) ? 0x3FF00000 : 0, 0), a[h]);
+      for (int i = 0; i < 4; ++i) x[i] = __ldg(wts + (size_t) (w4[i] & IDX) * GBRS_HPAD + lane8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t bit = ((uint32_t) (w4[i] >> SH) >> lane8) & 1u;
+        acc = fma(x[i], __hiloint2double(bit ? 0x3FF00000 : 0, 0), acc);
+      }
+    };
+    uint32_t p = b + 4 * grp;
+    for (; p + 4 * G < e; p += 8 * G) {  // two quads (eight gathers) in flight
+      quad(p, acc0);
+      quad(p + 4 * G, acc1);
     }
+    if (p < e) quad(p, acc0);
+    a[0] = acc0 + acc1;
   }
   double tot;
-  if (FULL && VEC == 1) {
+  if (VEC == 8) {
+    tot = a[0];  // lane h already holds haplotype h of its group's share
+  } else if (FULL && VEC == 1) {
     tot = group8_sum(a[0]);
   } else {
     tot = group8_transpose_sum(a, lane8);
@@ -2137,6 +2250,17 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
       default: {
         // GBRS_M1_FIXED: eight lanes per class for the classes of up to GBRS_KMAX pairs (parity-tested, not yet timed)
         static const bool m1_fixed = std::getenv("GBRS_M1_FIXED") != nullptr;
+        static const bool m1_generic = std::getenv("GBRS_M1_GENERIC") != nullptr;  // A/B knob: the round-1 row pass for all
+        if (!m1_fixed && !m1_generic) {
+          // default: narrow classes thread-per-class without row pointers, the rest through the generic CSR walk
+          const int64_t n_narrow = d->bucket_class0[kM1Narrow], n_rest = d->n_classes - n_narrow;
+          if (n_rest > 0) k_weights_m1<<<grid_for(n_rest), kThreads, 0, s>>>(*d, n_narrow);
+          int rcn = launch_m1_narrow<3>(d, s);
+          if (!rcn) rcn = launch_m1_narrow<2>(d, s);
+          if (!rcn) rcn = launch_m1_narrow<1>(d, s);
+          if (rcn) return rcn;
+          break;
+        }
         const int64_t n_fixed = m1_fixed ? d->bucket_class0[GBRS_KMAX] : 0, n_long = d->n_classes - n_fixed;
         if (n_fixed > 0) {  // widest first
           int r8 = launch_m1_fixed<8>(d, s);
