@@ -318,6 +318,7 @@ class AlignmentPropertyMatrix:
         (Sparse3DMatrix.py:354-362): scale every column of every haplotype matrix."""
         if not self.finalized:
             raise RuntimeError("The original matrix must be finalized.")
+        self._pure_cache = None
         multiplier = np.asarray(multiplier)
         if multiplier.ndim == 2 and axis == 2:
             for h in range(self.shape[1]):
@@ -332,11 +333,20 @@ class AlignmentPropertyMatrix:
         for h in range(self.shape[1]):
             self.data[h].eliminate_zeros()
 
-    def is_pure_incidence(self) -> bool:
-        return all(bool(np.all(m.data == 1.0)) for m in self.data)
+    def is_pure_incidence(self, cache: bool = False) -> bool:
+        """True if every stored value is 1.0.  `cache=True` remembers the answer on the object (the cohort loader thread
+        asks ahead of time; a pass over the values of a million classes costs more than their EM) -- callers that change
+        the values afterwards must not rely on it (`multiply` and `reset` drop it)."""
+        if cache and getattr(self, "_pure_cache", None) is not None:
+            return self._pure_cache
+        pure = all(bool(np.all(m.data == 1.0)) for m in self.data)
+        if cache:
+            self._pure_cache = pure
+        return pure
 
     def reset(self):
         """Sparse3DMatrix.reset (Sparse3DMatrix.py:220-228): values := 1 on the current pattern."""
+        self._pure_cache = None
         if not self.finalized:
             raise RuntimeError("The original matrix must be finalized.")
         for h in range(self.shape[1]):

@@ -44,6 +44,7 @@ def _prefetch(indices, samples, load, depth):
             for i in indices:
                 t0 = time.perf_counter()
                 apm = load(samples[i])
+                apm.is_pure_incidence(cache=True)  # a pass over the stored values: done here, off the device's critical path
                 q.put((i, apm, time.perf_counter() - t0))
         except BaseException as e:  # noqa: BLE001 - re-raised by the consumer
             q.put(e)
@@ -72,7 +73,9 @@ def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocou
     load      callable(sample) -> AlignmentPropertyMatrix (groups attached if gene-level output is wanted)
     on_done   optional callable(sample, EMfactory) invoked after each sample (e.g. to write its report files)
     prefetch  samples loaded ahead by the loader thread (0: load in line)
-    stats     optional dict, filled with the wall / device / loading seconds of this rank's share
+    stats     optional dict, filled with the wall seconds of this rank's share, the seconds spent per sample in total
+              (`device_s`), in the phases where the host only waits for the GPU (`gpu_phase_s`: packing, run, fetch) and
+              in `load`
     target_lengths  optional H x T effective-length table (instead of `lenfile`), shared by all samples
     Returns {sample index: dict(theta=H x T depths, counts=H x T expected read counts, iters=int)}.
     """
@@ -90,7 +93,7 @@ def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocou
     out = {}
     shared_lengths = target_lengths  # H x T effective lengths; else parsed from `lenfile` by the first sample
     t_wall = time.perf_counter()
-    t_load = t_dev = 0.0
+    t_load = t_dev = t_gpu = 0.0
     nnz_iters = 0
     shared_groups = None
     for i, apm, dt_load in _prefetch(my_share(len(samples), rank, world), samples, load, prefetch):
@@ -109,17 +112,20 @@ def quantify_cohort(samples: Sequence, load: Callable, model: int = 4, pseudocou
         else:
             em.prepare(pseudocount=pseudocount, lenfile=lenfile, read_length=read_length)
             shared_lengths = em.target_lengths
+        t1 = time.perf_counter()
         em.run(model=model, tol=tol, max_iters=max_iters, verbose=False)
         out[i] = dict(theta=em.get_allelic_expression(), counts=em.expected_read_counts().copy(), iters=em.num_iters)
         torch.cuda.synchronize(em._pattern.device)
         t_dev += time.perf_counter() - t0
+        # phases in which the host only waits for the device: packing (H2D + kernels, ends with a sync) and run + fetch
+        t_gpu += getattr(getattr(em._pattern, "packed", None), "pack_seconds", 0.0) + (time.perf_counter() - t1)
         nnz_iters += em._pattern.info["nnz"] * em.num_iters
         if on_done is not None:
             on_done(samples[i], em)
         logger.info(f"sample {i}: {em.num_iters} EM updates")
         del em
     if stats is not None:
-        stats.update(wall_s=time.perf_counter() - t_wall, device_s=t_dev, load_s=t_load, samples=len(out),
+        stats.update(wall_s=time.perf_counter() - t_wall, device_s=t_dev, gpu_phase_s=t_gpu, load_s=t_load, samples=len(out),
                      nnz_iters=nnz_iters)
     return out
 

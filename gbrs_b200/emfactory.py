@@ -653,7 +653,7 @@ class EMfactory:
             # probability.reset(), which sets EVERY stored entry to 1 (Sparse3DMatrix.py:220-228) -- so the EM runs on the
             # stored pattern, zeros included, and the values matter to prepare()'s initial normalisation only
             # (EMfactory.py:95-104).  The pattern is packed as it is; reset() takes theta0 from the values on the host.
-            self._weighted = not p.is_pure_incidence()
+            self._weighted = not p.is_pure_incidence(cache=True)
             if self._presharded:
                 self._pattern = DevicePattern(p, gene_of=self._gene_of, hapmask=self._hapmask, device=self._device,
                                               item_len=self._item_len, tiles=self._tiles, tile_params=self._tile_params,
