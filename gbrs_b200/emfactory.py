@@ -46,6 +46,7 @@ _LAZY_ARRAYS = ("rowptr", "runptr", "ent_pair", "ent_run")
 _HOST_ONLY_ARRAYS = ("item_off", "item_order", "locus_order", "locus_item_ptr")
 
 
+_STAGING: dict = {}  # (device, T) -> pinned [T][8] staging buffer shared by the patterns of a process (used synchronously)
 _TILE_ARRAYS = ("tile_blob", "tile_desc", "tile_locus_desc")
 _GENE_ARRAYS = ("gene_ptr", "gene_loci", "gene_of")
 
@@ -441,7 +442,12 @@ class DevicePattern:
         """One pinned [T][8] host buffer for the small state transfers (theta, lengths, numerator): pageable copies of
         these 5 MB tables cost more than ten EM updates each."""
         if getattr(self, "_stage", None) is None:
-            self._stage = _torch().empty((self.T, 8), dtype=_torch().float64).pin_memory()
+            key = (str(self.device), self.T)
+            if key not in _STAGING:  # pinning 5 MB costs about a millisecond: one buffer per (device, T) and process
+                if len(_STAGING) >= 4:
+                    _STAGING.pop(next(iter(_STAGING)))
+                _STAGING[key] = _torch().empty((self.T, 8), dtype=_torch().float64).pin_memory()
+            self._stage = _STAGING[key]
         return self._stage
 
     def _fetch_T8(self, dev_tensor) -> np.ndarray:
@@ -536,8 +542,9 @@ class EMfactory:
         `tile_params` select the fused single-pass tile kernel for model 4, `pack` ("gpu" | "host") where the incidence is
         packed (see DevicePattern)."""
         self.probability = alignments
-        self._theta_host = None
-        self._theta_dirty = False
+        self._theta_host = None   # host copy of theta; fetched from the device on first use after it went stale
+        self._theta_stale = False  # the device holds a newer estimate than `_theta_host`
+        self._theta_dirty = False  # the host copy was assigned by the caller and not yet sent to the device
         self.grp_conv_mat = None
         self._t2t_mat = None
         self.target_lengths = None
@@ -573,12 +580,21 @@ class EMfactory:
     # ---------------------------------------------------------------------------------------------------------------
     @property
     def allelic_expression(self):
-        return self._theta_host
+        return self._theta()
 
     @allelic_expression.setter
     def allelic_expression(self, value):
         self._theta_host = None if value is None else np.array(value, dtype=np.float64, copy=True)
         self._theta_dirty = value is not None
+        self._theta_stale = False
+
+    def _theta(self):
+        """The host copy of theta, fetched lazily: prepare() / run() / an update only mark it stale, so a caller that never
+        looks (the cohort loop between prepare and run) pays no device-to-host copy."""
+        if self._theta_stale and self._pattern is not None:
+            self._theta_host = self._pattern.current_theta_HT()
+            self._theta_stale = False
+        return self._theta_host
 
     @property
     def t2t_mat(self):
@@ -779,7 +795,7 @@ class EMfactory:
             self._theta_dirty = False
 
     def _fetch_theta(self):
-        self._theta_host = self._pattern.current_theta_HT()
+        self._theta_stale = True
         self._theta_dirty = False
 
     # ---------------------------------------------------------------------------------------------------------------
@@ -839,8 +855,8 @@ class EMfactory:
 
     def get_allelic_expression(self, at_group_level: bool = False):
         if at_group_level:
-            return self._theta_host * self.grp_conv_mat
-        return self._theta_host.copy()
+            return self._theta() * self.grp_conv_mat
+        return self._theta().copy()
 
     def update_probability_at_read_level(self, model: int = 3) -> None:
         """E-step (EMfactory.py:146-212).  On the device the posterior is implicit: this queues the row pass and
@@ -972,10 +988,10 @@ class EMfactory:
         `allelic_expression` in place (:352-354)."""
         if grp_wise:
             lname = self.probability.gname
-            depths = np.asarray(self._theta_host * self.grp_conv_mat)
+            depths = np.asarray(self._theta() * self.grp_conv_mat)
         else:
             lname = self.probability.lname
-            depths = self._theta_host
+            depths = self._theta()
         if tpm:
             depths *= 1000000.0 / depths.sum()
             if not grp_wise:
