@@ -682,12 +682,16 @@ def run_gpu_arm(args, wl):
                          f"{os.cpu_count()} logical cores (the path is single-threaded)"}
 
     xphases = None
-    if world > 1 and em.fused_exchange and em.exchange_mode == "push":
+    if world > 1 and em.fused_exchange and em.exchange_mode in ("push", "tag"):
         st = pat.part[-8:-3].cpu().numpy() * 1e-3  # us since kernel start, block 0 of the last update
-        xphases = {"numerator_block0": float(st[0]), "all_ready": float(st[1]), "slice_reduced": float(st[2]),
-                   "all_done": float(st[3]), "update_done": float(st[4])}
+        if em.exchange_mode == "push":
+            xphases = {"numerator_block0": float(st[0]), "all_ready": float(st[1]), "slice_reduced": float(st[2]),
+                       "all_done": float(st[3]), "update_done": float(st[4])}
+        else:  # no flags to wait for: block 0's first complete pair of its slice, its slice done, its share of the update done
+            xphases = {"numerator_block0": float(st[0]), "first_pair_summed": float(st[1]), "slice_reduced": float(st[2]),
+                       "update_done": float(st[4])}
     if rank == 0:
-        pushed = world > 1 and em.fused_exchange and em.exchange_mode == "push"
+        pushed = world > 1 and em.fused_exchange and em.exchange_mode in ("push", "tag")
         launches_per_step = (3 if tiled else 4) + (1 if world > 1 and not pushed else 0) + (1 if model != 4 else 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if strong else "weak",
@@ -702,6 +706,9 @@ def run_gpu_arm(args, wl):
                            "exchange": "none" if world == 1 else {
                                "push": "one launch per update: local numerator pushed into the owners' receive rows over NVLink "
                                        "peer memory, slice sums broadcast by their owners, update (k_locus_xchg)",
+                               "tag": "one launch per update, no flags: every double of the numerator carries the parity of its "
+                                      "exchange in its sign bit and is polled by the thread that needs it (push to the owners' "
+                                      "receive rows, slice sums broadcast, update -- k_locus_xchg<.., TAG>)",
                                "pull": "fused two-shot all-reduce of T x 8 fp64 over NVLink peer memory inside the locus kernels",
                                "nvls": "fused two-shot all-reduce of T x 8 fp64 inside the locus kernels: NVLS (multimem.ld_reduce / "
                                        "multimem.st on the NVSwitch multicast mapping)",

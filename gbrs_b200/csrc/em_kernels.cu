@@ -1548,6 +1548,71 @@ __device__ __forceinline__ void multimem_st_f64x2(double* mc, double2 v) {
                "f"(__int_as_float(__double2hiint(v.y)))
                : "memory");
 }
+// ---- tag form (xchg_enabled == 3): every double carries its own "arrived" flag ---------------------------------------
+// The numerator is non-negative (counts >= 0, theta >= 0), so the sign bit of every transported double is free: exchange
+// number e writes it as e & 1 and a reader simply polls the ELEMENT until the bit has the value of its epoch.  An 8-byte
+// store is indivisible, so there is nothing to order: no ready / done flags, no grid-wide tickets, no system fences, no
+// extra bytes on the wire -- the owner starts adding a locus the moment its last contribution lands, and the update of
+// a locus starts the moment its total lands, while the rest of the grid is still computing.  Every element of recv and
+// total is rewritten in every exchange, so the previous exchange always leaves the opposite bit behind; the zero-filled
+// buffer (epoch 0) is "not arrived" for the first exchange (e = 1).
+constexpr unsigned long long kTagBit = 1ull << 63;
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_b64(const double* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_b64(double* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_relaxed_sys_b64x2(const double* p) {
+  ulonglong2 v;
+  asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_b64x2(double* p, ulonglong2 v) {
+  asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+__device__ __forceinline__ void multimem_st_b64x2(double* mc, ulonglong2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc),
+               "f"(__int_as_float((int) (uint32_t) v.x)), "f"(__int_as_float((int) (uint32_t) (v.x >> 32))),
+               "f"(__int_as_float((int) (uint32_t) v.y)), "f"(__int_as_float((int) (uint32_t) (v.y >> 32)))
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long tag_bits(double a, unsigned long long tag) {
+  return ((unsigned long long) __double_as_longlong(a) & ~kTagBit) | tag;
+}
+__device__ __forceinline__ double untag(unsigned long long v) { return __longlong_as_double((long long) (v & ~kTagBit)); }
+// Bounded wait of one thread: after 256 fruitless polls it looks at the clock and at the error flag; once failed (timeout
+// or another thread's failure) it never waits again, raises error 3 + the stop flag and lets the kernel run out on zeros.
+struct TagWait {
+  unsigned long long t0 = 0ull;
+  unsigned spins = 0u;
+  bool failed = false;
+  __device__ __forceinline__ bool give_up(const gbrs_em_dev& d) {
+    if (failed) return true;
+    if ((++spins & 255u) != 0u) return false;
+    const unsigned long long now = globaltimer_ns();
+    if (t0 == 0ull) t0 = now;
+    const unsigned long long limit = (unsigned long long) (d.xchg_timeout_ms > 0 ? d.xchg_timeout_ms : 20000) * 1000000ull;
+    if (now - t0 > limit || *reinterpret_cast<volatile int32_t*>(d.ctrl + GBRS_CTRL_ERROR) == 3) {
+      failed = true;
+      d.ctrl[GBRS_CTRL_ERROR] = 3;
+      d.ctrl[GBRS_CTRL_DONE] = 1;
+      return true;
+    }
+    __nanosleep(40);
+    return false;
+  }
+};
+__device__ __forceinline__ double tag_wait1(const gbrs_em_dev& d, const double* p, unsigned long long tag, TagWait& tw) {
+  unsigned long long v = ld_relaxed_sys_b64(p);
+  while ((v & kTagBit) != tag) {
+    if (tw.give_up(d)) return 0.0;
+    v = ld_relaxed_sys_b64(p);
+  }
+  return untag(v);
+}
 __host__ __device__ inline int64_t push_slice_len(const gbrs_em_dev& d) {  // doubles per owner, even
   return ((((int64_t) d.T * GBRS_HPAD + d.n_ranks - 1) / d.n_ranks) + 1) & ~(int64_t) 1;
 }
@@ -1602,7 +1667,7 @@ __device__ __forceinline__ void push_signal(const gbrs_em_dev& d, int which, uin
   }
 }
 
-template <bool UNIT>
+template <bool UNIT, bool TAG>
 __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constant__ gbrs_em_dev d) {
   __shared__ double red[32];
   __shared__ int s_fail;
@@ -1613,6 +1678,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
   const int me = d.xchg_rank;
   const int64_t slice = push_slice_len(d);
   const int h = threadIdx.x & 7;
+  const unsigned long long tag = (e & 1u) ? kTagBit : 0ull;  // tag form: the sign bit every double of this exchange carries
+  TagWait tw;
   // phase time stamps of block 0 (ns since the kernel started) for bench.py: part[kStampSlot + 0..5]
   const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
   const unsigned long long t_start = stamp ? globaltimer_ns() : 0ull;
@@ -1626,16 +1693,54 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
         const int o = t * GBRS_HPAD + hh;
         const double a = UNIT ? ((hh < d.H) ? W : 0.0) : th[o] * W;
         const int owner = o / slice32;
-        st_relaxed_sys_f64(push_recv(d, owner, me) + (o - owner * slice32), a);
+        double* const slot = push_recv(d, owner, me) + (o - owner * slice32);
+        if (TAG) {
+          if (a < 0.0) d.ctrl[GBRS_CTRL_ERROR] = 1;  // a negative theta: not an expression estimate (the sign bit is the tag)
+          st_relaxed_sys_b64(slot, tag_bits(a, tag));
+        } else {
+          st_relaxed_sys_f64(slot, a);
+        }
       }
     });
   }
   mark(0);  // numerator of block 0 done
-  push_signal(d, 0, e, GBRS_CTRL_TICKET + 1);
+  if (!TAG) push_signal(d, 0, e, GBRS_CTRL_TICKET + 1);
   // ---- B: sum my slice over the ranks, broadcast the totals ---------------------------------------------------------
-  if (!push_wait(d, 0, e, &s_fail)) return;
-  mark(1);  // every rank's numerator has arrived
-  {
+  if (!TAG && !push_wait(d, 0, e, &s_fail)) return;
+  if (!TAG) mark(1);  // every rank's numerator has arrived
+  if (TAG) {
+    const int total_n = d.T * GBRS_HPAD;
+    const int lo = (int) slice * me, hi = lo + (int) slice < total_n ? lo + (int) slice : total_n;  // (both even)
+    const int stride = (int) (gridDim.x * blockDim.x);
+    double* const mc_total = d.xchg_mc ? static_cast<double*>(d.xchg_mc) + (size_t) d.n_ranks * slice : nullptr;
+    bool first = true;
+    for (int i = lo + 2 * (int) (blockIdx.x * blockDim.x + threadIdx.x); i < hi; i += 2 * stride) {
+      ulonglong2 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) v[r] = ld_relaxed_sys_b64x2(push_recv(d, me, r) + (i - lo));
+      double2 sum = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < d.n_ranks) {
+          while ((v[r].x & kTagBit) != tag || (v[r].y & kTagBit) != tag) {  // not there yet: poll this pair
+            if (tw.give_up(d)) { v[r].x = v[r].y = tag; break; }
+            v[r] = ld_relaxed_sys_b64x2(push_recv(d, me, r) + (i - lo));
+          }
+          sum.x += untag(v[r].x);  // rank order: the same bits whichever rank owns the slice
+          sum.y += untag(v[r].y);
+        }
+      if (first) { mark(1); first = false; }  // first pair of block 0 complete
+      const ulonglong2 out = make_ulonglong2(tag_bits(sum.x, tag), tag_bits(sum.y, tag));
+      if (mc_total) {
+        multimem_st_b64x2(mc_total + i, out);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < d.n_ranks) st_relaxed_sys_b64x2(push_total(d, r) + i, out);
+      }
+    }
+  } else {
     const int total_n = d.T * GBRS_HPAD;
     const int lo = (int) slice * me, hi = lo + (int) slice < total_n ? lo + (int) slice : total_n;  // (both even)
     const int stride = (int) (gridDim.x * blockDim.x);
@@ -1663,10 +1768,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     }
   }
   mark(2);  // slice of block 0 reduced and broadcast
-  push_signal(d, 1, e, GBRS_CTRL_TICKET + 2);
+  if (!TAG) push_signal(d, 1, e, GBRS_CTRL_TICKET + 2);
   // ---- C: the update, from the totals every owner has stored here -------------------------------------------------------
-  if (!push_wait(d, 1, e, &s_fail)) return;
-  mark(3);  // every owner's totals have arrived
+  if (!TAG && !push_wait(d, 1, e, &s_fail)) return;
+  mark(3);  // every owner's totals have arrived (tag form: nothing to wait for here, the elements are polled below)
   {
     const double* __restrict__ src = push_total(d, me);
     double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
@@ -1680,7 +1785,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
       double v = 0.0;
       const bool valid = i < total;
       if (valid) {
-        const double a = __ldcg(src + i);  // written by peers: never through a stale L1 line
+        // written by peers: never through a stale L1 line (tag form: polled until this exchange's value is there)
+        const double a = TAG ? tag_wait1(d, src + i, tag, tw) : __ldcg(src + i);
         d.acc[i] = a;                      // the summed numerator, where the reports read it
         v = fast_div(a, d.efflen[i]);
         dst[i] = v;
@@ -1696,6 +1802,16 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
   }
   mark(4);  // update of block 0 done
+  if (TAG) {  // bookkeeping only, nobody waits for it: the last block to leave advances the epoch for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int ticket = atomicAdd(d.ctrl + GBRS_CTRL_TICKET + 1, 1);
+      if (ticket == (int) gridDim.x - 1) {
+        d.ctrl[GBRS_CTRL_TICKET + 1] = 0;
+        d.ctrl[GBRS_CTRL_XEPOCH] = (int32_t) e;
+      }
+    }
+  }
 }
 
 // Stop test of EMfactory.run (EMfactory.py:267-279) on the device.
@@ -1921,14 +2037,16 @@ int check_exchange(const gbrs_em_dev* d) {
 // grid of the push-form update kernel: all blocks resident, one (locus, haplotype) per thread at most
 template <bool UNIT>
 int push_grid(const gbrs_em_dev* d) {
-  int g = resident_grid(k_locus_xchg<UNIT>, (int64_t) d->T * GBRS_HPAD);
+  int g = d->xchg_enabled == 3 ? resident_grid(k_locus_xchg<UNIT, true>, (int64_t) d->T * GBRS_HPAD)
+                               : resident_grid(k_locus_xchg<UNIT, false>, (int64_t) d->T * GBRS_HPAD);
   return g > kHalfSlots ? kHalfSlots : g;
 }
 
 template <bool UNIT>
 int launch_push(const gbrs_em_dev* d, cudaStream_t s) {
   if (int rc = check_exchange(d)) return rc;
-  k_locus_xchg<UNIT><<<push_grid<UNIT>(d), kThreads, 0, s>>>(*d);
+  if (d->xchg_enabled == 3) k_locus_xchg<UNIT, true><<<push_grid<UNIT>(d), kThreads, 0, s>>>(*d);
+  else k_locus_xchg<UNIT, false><<<push_grid<UNIT>(d), kThreads, 0, s>>>(*d);
   GBRS_LAUNCH_CHECK("k_locus_xchg");
   return GBRS_OK;
 }
@@ -2051,7 +2169,7 @@ extern "C" int gbrs_em_prepare_local(const gbrs_em_dev* d, void* stream) {
     if (int rc = launch_column<1>(d, d->ent_cls, false, s)) return rc;
   }
   const gbrs_em_dev lv = locus_view(d, tiles);
-  if (d->n_ranks > 1 && d->xchg_enabled == 2) return launch_push<true>(&lv, s);  // numerator + exchange + theta0 in one launch
+  if (d->n_ranks > 1 && d->xchg_enabled >= 2) return launch_push<true>(&lv, s);  // numerator + exchange + theta0 in one launch
   k_locus_acc<true, false><<<acc_grid(d), kThreads, 0, s>>>(lv, false);
   GBRS_LAUNCH_CHECK("k_locus_acc<unit>");
   return GBRS_OK;
@@ -2061,7 +2179,7 @@ extern "C" int gbrs_em_prepare_finish(const gbrs_em_dev* d, double pseudocount, 
   if (int rc = check_dev(d, "gbrs_em_prepare_finish")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int lg = locus_grid(d);
-  if (d->n_ranks > 1 && d->xchg_enabled == 2) {
+  if (d->n_ranks > 1 && d->xchg_enabled >= 2) {
     lg = push_grid<true>(d);  // gbrs_em_prepare_local has done exchange and update already; its blocks wrote the partials
   } else {
     if (int rc = launch_exchange(d, s)) return rc;
@@ -2206,7 +2324,7 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
     gbrs_set_error("The read normalization model should be 1, 2, 3, or 4."); return GBRS_E_ARG;  // EMfactory.py:209-212
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool honour_done = (d->n_ranks <= 1 || d->xchg_enabled == 2) && !estep_only;
+  const bool honour_done = (d->n_ranks <= 1 || d->xchg_enabled >= 2) && !estep_only;
   const bool tiles = model == 4 && d->tile_blob != nullptr;
   int rc = GBRS_OK;
   if (!tiles && d->tile_blob)
@@ -2292,9 +2410,9 @@ static int launch_local_impl(const gbrs_em_dev* d, int model, void* stream, gbrs
   }
   if (rc) return rc;
   if (ev) GBRS_CUDA(cudaEventRecord(ev[2], s));
-  NvtxRange nvtx_locus(d->n_ranks > 1 && d->xchg_enabled == 2 ? "gbrs:locus_exchange_update" : "gbrs:locus_numerator");
+  NvtxRange nvtx_locus(d->n_ranks > 1 && d->xchg_enabled >= 2 ? "gbrs:locus_exchange_update" : "gbrs:locus_numerator");
   const gbrs_em_dev lv = locus_view(d, tiles);
-  if (d->n_ranks > 1 && d->xchg_enabled == 2 && !estep_only) {
+  if (d->n_ranks > 1 && d->xchg_enabled >= 2 && !estep_only) {
     if (int rcp = launch_push<false>(&lv, s)) return rcp;
   } else {
     if (d->n_ranks <= 1 && !estep_only) k_locus_acc<false, true><<<acc_grid(d), kThreads, 0, s>>>(lv, true);
@@ -2313,7 +2431,7 @@ extern "C" int gbrs_em_launch_update(const gbrs_em_dev* d, void* stream) {
   NvtxRange nvtx_upd("gbrs:update_and_stop_test");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int nparts = acc_grid(d);  // single rank: k_locus_acc already produced theta', iso' and the partial sums
-  if (d->n_ranks > 1 && d->xchg_enabled == 2) {
+  if (d->n_ranks > 1 && d->xchg_enabled >= 2) {
     nparts = push_grid<false>(d);  // k_locus_xchg (queued by gbrs_em_launch_local) has updated theta already
   } else if (d->n_ranks > 1) {
     nparts = locus_grid(d);

@@ -704,18 +704,20 @@ class EMfactory:
         # owner of a slice loads it from every peer | nvls: pull form with the in-switch reduction where the box has a
         # multicast mapping (a multimem f64 access moves 8 bytes per request: measured slower than peer loads on 2 and on
         # 8 ranks) | nccl: plain all-reduce between the two halves of an update.
+        # tag: the push form without any flag -- every double carries its own "arrived" bit (the sign bit, free because the
+        # numerator is non-negative) and is polled by the thread that needs it: no tickets, no fences, no handshakes.
         mode = os.environ.get("GBRS_XCHG", "push")
         mode = {"fused": "push", "p2p": "pull"}.get(mode, mode)
-        if self.world < 2 or self.world > 8 or mode not in ("push", "pull", "nvls"):
+        if self.world < 2 or self.world > 8 or mode not in ("push", "tag", "pull", "nvls"):
             return False
         # the multicast mapping: the in-switch reduction of the nvls form; in the push form only the broadcast of the
         # slice totals goes through it (one 16-byte store replicated by the switch instead of one per peer)
-        use_mc = mode == "nvls" or (mode == "push" and os.environ.get("GBRS_XCHG_MC", "1") != "0")
+        use_mc = mode == "nvls" or (mode in ("push", "tag") and os.environ.get("GBRS_XCHG_MC", "1") != "0")
         ok, buf, hdl, mc = 1, None, None, 0
         try:
             import torch.distributed._symmetric_memory as symm_mem
 
-            if mode == "push":  # recv[R][slice] | total | flags (include/gbrs_em.h)
+            if mode in ("push", "tag"):  # recv[R][slice] | total | flags (include/gbrs_em.h)
                 slice_len = ((8 * pat.T + self.world - 1) // self.world + 1) & ~1
                 n_doubles = self.world * slice_len + 8 * pat.T + 16
             else:  # acc_local | acc_total | flags
@@ -738,7 +740,7 @@ class EMfactory:
             return False
         self.nvls_exchange = bool(int(flag[1].item()))
         pat._xchg = (buf, hdl)
-        pat.desc.xchg_enabled = 2 if mode == "push" else 1
+        pat.desc.xchg_enabled = {"push": 2, "tag": 3}.get(mode, 1)
         pat.desc.xchg_timeout_ms = int(os.environ.get("GBRS_XCHG_TIMEOUT_MS", "0"))
         self.exchange_mode = mode
         pat.desc.xchg_mc = mc if self.nvls_exchange else None

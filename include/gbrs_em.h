@@ -230,7 +230,10 @@ typedef struct {
    *   1  pull form: acc_local | acc_total | flags, (2 * 64 * T + 128) bytes; the owner of a slice loads it from every peer
    *   2  push form (default): recv[R][slice] | total | flags, (8 * (R * slice + 8 * T) + 128) bytes with
    *      slice = ((8 * T + R - 1) / R + 1) & ~1; every rank stores its values into the owners' recv rows while computing
-   *      them, and the whole update is one launch (gbrs_em_launch_update then only runs the stop test) */
+   *      them, and the whole update is one launch (gbrs_em_launch_update then only runs the stop test)
+   *   3  tag form: the push form (same buffer, same single launch) without flags -- every transported double carries
+   *      the parity of its exchange number in its sign bit (the numerator is non-negative) and is polled by the thread
+   *      that needs it; no tickets, fences or handshakes.  Negative theta is reported as GBRS_E_NUMERIC */
   int32_t xchg_enabled;
   int32_t xchg_rank;
   void* xchg_peer[8];

@@ -71,6 +71,13 @@ inline unsigned long long simt_globaltimer_ns() {
              std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 inline void simt_st_release_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+// tag form of the exchange: a double and its "arrived" bit travel in one indivisible 8-byte access
+inline unsigned long long simt_ld_acquire_u64(const double* p) {
+  return __atomic_load_n(reinterpret_cast<const unsigned long long*>(p), __ATOMIC_ACQUIRE);
+}
+inline void simt_st_release_u64(double* p, unsigned long long v) {
+  __atomic_store_n(reinterpret_cast<unsigned long long*>(p), v, __ATOMIC_RELEASE);
+}
 // rcp.approx.ftz.f64: a reciprocal good to ~20 bits (the seed of fast_div's Newton steps) -- modelled as the exact
 // reciprocal with the low 32 mantissa bits cleared, so that the refinement steps have real work to do
 inline double simt_rcp_approx(double s) {

@@ -42,6 +42,15 @@ PTX = [  # the system-scope accesses of the multi-GPU exchange -> host equivalen
      r"\1.x = \2[0]; \1.y = \2[1];"),
     (r'asm volatile\("st\.relaxed\.sys\.global\.v2\.f64 \[%0\], \{%1, %2\};" ::"l"\((\w+)\), "d"\((\w+)\.x\), "d"\(\w+\.y\) : "memory"\);',
      r"\1[0] = \2.x; \1[1] = \2.y;"),
+    # tag form: self-validating doubles (the sign bit says which exchange wrote them) -> 8-byte atomics
+    (r'asm volatile\("ld\.relaxed\.sys\.global\.b64 %0, \[%1\];" : "=l"\((\w+)\) : "l"\((\w+)\) : "memory"\);',
+     r"\1 = simt_ld_acquire_u64(\2);"),
+    (r'asm volatile\("st\.relaxed\.sys\.global\.b64 \[%0\], %1;" ::"l"\((\w+)\), "l"\((\w+)\) : "memory"\);',
+     r"simt_st_release_u64(\1, \2);"),
+    (r'asm volatile\("ld\.relaxed\.sys\.global\.v2\.b64 \{%0, %1\}, \[%2\];" : "=l"\((\w+)\.x\), "=l"\(\w+\.y\) : "l"\((\w+)\) : "memory"\);',
+     r"\1.x = simt_ld_acquire_u64(\2); \1.y = simt_ld_acquire_u64(\2 + 1);"),
+    (r'asm volatile\("st\.relaxed\.sys\.global\.v2\.b64 \[%0\], \{%1, %2\};" ::"l"\((\w+)\), "l"\((\w+)\.x\), "l"\(\w+\.y\) : "memory"\);',
+     r"simt_st_release_u64(\1, \2.x); simt_st_release_u64(\1 + 1, \2.y);"),
 ]
 
 

@@ -215,7 +215,7 @@ def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1, mode=2, ti
         pats = [simt_em.HostPattern(apm, gene_of=gene_of, shard_rank=r, shard_count=R,
                                     lib=simt_em.load_instance(f"rank{r}", tsan)) for r in range(R)]
         slice_len = ((8 * d.T + R - 1) // R + 1) & ~1
-        n_doubles = R * slice_len + 8 * d.T + 16 if mode == 2 else 2 * 8 * d.T + 16  # push | pull layout
+        n_doubles = R * slice_len + 8 * d.T + 16 if mode >= 2 else 2 * 8 * d.T + 16  # push, tag | pull layout
         bufs = [np.zeros(n_doubles) for _ in range(R)]
         for r, p in enumerate(pats):
             p.efflen[:, : d.H] = eff.T
@@ -251,9 +251,10 @@ def _run_fused_ranks(d, model, R, tol, max_iters, tsan=False, poll=1, mode=2, ti
         os.environ.pop("GBRS_SIMT_SMS", None)
 
 
-@pytest.mark.parametrize("R,model,mode", [(2, 4, 2), (3, 2, 2), (3, 4, 1)])
+@pytest.mark.parametrize("R,model,mode", [(2, 4, 2), (3, 2, 2), (3, 4, 1), (2, 4, 3), (3, 3, 3)])
 def test_emulated_fused_exchange_between_concurrent_ranks(R, model, mode):
-    """mode 2: the one-launch push form (k_locus_xchg); mode 1: the pull form."""
+    """mode 2: the one-launch push form (k_locus_xchg); mode 1: the pull form; mode 3: the tag form (no flags: every
+    double carries the parity of its exchange in its sign bit and is polled by the thread that needs it)."""
     d = synth.generate(T=70, N=900, H=8, sample_index=12)
     pats, iters = _run_fused_ranks(d, model, R, 1e-3, 60, poll=2, mode=mode)
     o = hp.oracle_run(d, model, tol=1e-3, max_iters=60)
@@ -265,7 +266,8 @@ def test_emulated_fused_exchange_between_concurrent_ranks(R, model, mode):
     assert hp.relerr(pats[0].acc[:, : d.H].T, o["counts"]) < 1e-12
 
 
-def test_emulated_exchange_timeout_stops_every_block():
+@pytest.mark.parametrize("mode", [2, 3])
+def test_emulated_exchange_timeout_stops_every_block(mode):
     """A peer that never shows up: the wait is bounded by wall-clock time, the error flag (3) and the stop flag are
     raised and the kernel returns -- no block continues on partial sums, nothing hangs."""
     import ctypes as C
@@ -280,7 +282,7 @@ def test_emulated_exchange_timeout_stops_every_block():
         p = simt_em.HostPattern(synth.to_apm(d), shard_rank=0, shard_count=R, lib=simt_em.load_instance("rank0"))
         slice_len = ((8 * d.T + R - 1) // R + 1) & ~1
         bufs = [np.zeros(R * slice_len + 8 * d.T + 16) for _ in range(R)]
-        p.desc.xchg_enabled, p.desc.xchg_rank, p.desc.xchg_mc, p.desc.xchg_timeout_ms = 2, 0, None, 150
+        p.desc.xchg_enabled, p.desc.xchg_rank, p.desc.xchg_mc, p.desc.xchg_timeout_ms = mode, 0, None, 150
         for q in range(R):
             p.desc.xchg_peer[q] = bufs[q].ctypes.data
         t0 = time.time()
@@ -315,6 +317,8 @@ pats, iters = _run_fused_ranks(d, 4, 2, 0.0, 4, tsan=True)
 assert iters == [4, 4] and np.array_equal(pats[0].current_theta(), pats[1].current_theta())
 pats, iters = _run_fused_ranks(d, 1, 3, 0.0, 2, tsan=True)
 assert iters == [2, 2, 2]
+pats, iters = _run_fused_ranks(d, 4, 3, 0.0, 3, tsan=True, mode=3)  # tag form: nothing but the 8-byte accesses themselves
+assert iters == [3, 3, 3] and np.array_equal(pats[0].current_theta(), pats[2].current_theta())
 print("TSAN-RUN-OK")
 """
     env = dict(os.environ, LD_PRELOAD=rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0",

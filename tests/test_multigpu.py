@@ -31,7 +31,7 @@ for name in ("em_small_m4", "em_small_m2", "em_small_m1_biggenes", "em_small_m3_
     if g["masked"]:
         apm.multiply(g["gtmask"], axis=2); apm.eliminate_zeros()
     em = EMfactory(apm, shard=True, poll_every=3)
-    want_fused = os.environ.get("GBRS_XCHG", "push") in ("push", "fused", "pull", "nvls", "p2p")
+    want_fused = os.environ.get("GBRS_XCHG", "push") in ("push", "tag", "fused", "pull", "nvls", "p2p")
     em.target_lengths = synth.effective_lengths(d)
     em.prepare(pseudocount=g["pseudocount"])
     assert hp.relerr(em.get_allelic_expression(), g["theta0"]) < 1e-9
@@ -54,7 +54,7 @@ print("rank", rank, "ok")
 '''
 
 
-@pytest.mark.parametrize("xchg", ["push", "pull", "nvls", "nccl"])
+@pytest.mark.parametrize("xchg", ["push", "tag", "pull", "nvls", "nccl"])
 def test_two_gpu_sharded_run_matches_reference(tmp_path, xchg):
     import torch
 
