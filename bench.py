@@ -537,6 +537,12 @@ def run_gpu_arm(args, wl):
     _lib.check(lib.gbrs_prof_read(prof, C.byref(ms_row), C.byref(ms_col), C.byref(ms_acc), C.byref(nrec)))
     lib.gbrs_prof_free(prof)
     row_ms, col_ms, acc_ms = ms_row.value / K, ms_col.value / K, ms_acc.value / K
+    per_rank_ms = None
+    if world > 1:  # the step lasts as long as the slowest rank's passes plus the exchange: show every rank's kernel times
+        mine = torch.tensor([row_ms, col_ms, acc_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank_ms = [[round(float(x), 5) for x in t.tolist()] for t in allr]
     clocks = sampler.stop() if sampler else None
 
     # ---- algorithmic bytes -----------------------------------------------------------------
@@ -573,6 +579,7 @@ def run_gpu_arm(args, wl):
                 "share_of_step": dom_ms / (ms / K),
                 "per_kernel_ms": {("tile_pass" if tiled else "row_pass"): row_ms, "column_pass": col_ms, "locus_acc": acc_ms,
                                   "rest_of_step": max(ms / K - row_ms - col_ms - acc_ms, 0.0)},
+                "per_rank_row_column_locus_ms": per_rank_ms,
                 "iteration": {"algorithmic_bytes": bytes_iter, "achieved": bytes_iter / (ms / K * 1e-3) / 1e9,
                               "frac": bytes_iter / (ms / K * 1e-3) / 1e9 / peak,
                               "note": "SURVEY 8(d) pair+mask formula (each input once, theta in/out + lengths); the "
@@ -690,6 +697,13 @@ def run_gpu_arm(args, wl):
         else:  # no flags to wait for: block 0's first complete pair of its slice, its slice done, its share of the update done
             xphases = {"numerator_block0": float(st[0]), "first_pair_summed": float(st[1]), "slice_reduced": float(st[2]),
                        "update_done": float(st[4])}
+            raw = pat.part[-8:].cpu().numpy()
+            t0 = raw[3]
+            late = raw[5:8].copy().view(np.uint64).astype(np.float64)  # latest block's end of phases A / B / C (absolute)
+            mine = torch.tensor([(late[0] - t0) * 1e-3, (late[1] - t0) * 1e-3, (late[2] - t0) * 1e-3], dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            xphases["slowest_block_A_B_C_per_rank"] = [[round(float(x), 2) for x in t.tolist()] for t in allr]
     if rank == 0:
         pushed = world > 1 and em.fused_exchange and em.exchange_mode in ("push", "tag")
         launches_per_step = (3 if tiled else 4) + (1 if world > 1 and not pushed else 0) + (1 if model != 4 else 0)

@@ -1371,8 +1371,11 @@ __device__ __forceinline__ void write_subset_rows(const gbrs_em_dev& d, int64_t 
 // consecutive slots going to different blocks, and calls f(t, h, W, valid) with W = the sum of the locus' slots for
 // haplotype lane h.  All 32 lanes call f in every round of their warp (f may use warp collectives); `valid` marks the
 // eight lanes that finish a locus.  32-bit index arithmetic throughout: T * 8 < 2^27.
+// `pre0` / `pre1` (may be null): per-(locus, haplotype) tables (theta, effective lengths) whose value for the slot's locus is
+// requested together with the partial sums instead of after them -- one memory round trip less per round.
 template <class F>
-__device__ __forceinline__ void locus_walk(const gbrs_em_dev& d, F&& f) {
+__device__ __forceinline__ void locus_walk(const gbrs_em_dev& d, const double* __restrict__ pre0,
+                                           const double* __restrict__ pre1, F&& f) {
   const int lane = threadIdx.x & 31, h = lane & 7, grp = lane >> 3;
   const int T = d.T, n_deep = d.n_deep_loci;
   const int total_slots = n_deep + ((T - n_deep + 3) >> 2);
@@ -1390,6 +1393,9 @@ __device__ __forceinline__ void locus_walk(const gbrs_em_dev& d, F&& f) {
     nx = fetch(ws + nwarps);
     const bool deep = ws < n_deep, have = ld.w == 0u;
     const uint32_t e = ld.z;  // (0 without a locus: the loops below do nothing)
+    const bool fin = have && (!deep || grp == 0);  // the eight lanes that finish the locus
+    const int po = (int) ld.x * GBRS_HPAD + h;
+    const double p0 = (pre0 && fin) ? pre0[po] : 0.0, p1 = (pre1 && fin) ? pre1[po] : 0.0;
     double W = 0.0;
     if (deep) {
       uint32_t it = ld.y + (uint32_t) grp;
@@ -1414,7 +1420,7 @@ __device__ __forceinline__ void locus_walk(const gbrs_em_dev& d, F&& f) {
         for (; it < e; ++it) W += wit[(size_t) it * GBRS_HPAD];
       }
     }
-    f((int) ld.x, h, W, have && (!deep || grp == 0));
+    f((int) ld.x, h, W, fin, p0, p1);
   }
 }
 
@@ -1430,17 +1436,17 @@ __global__ void __launch_bounds__(kThreads, 1536 / kThreads) k_locus_acc(const g
   double* __restrict__ iso = d.iso + (size_t) (par ^ 1) * d.T;
   double* __restrict__ out = (!FUSE && d.xchg_enabled) ? xchg_acc_local(d, d.xchg_rank) : d.acc;
   double mine = 0.0;
-  locus_walk(d, [&](int t, int h, double W, bool valid) {
+  locus_walk(d, UNIT ? nullptr : th, FUSE ? d.efflen : nullptr, [&](int t, int h, double W, bool valid, double th_o, double len_o) {
     const int o = t * GBRS_HPAD + h;
     double a = 0.0;
     if (valid) {
-      a = UNIT ? ((h < d.H) ? W : 0.0) : th[o] * W;
+      a = UNIT ? ((h < d.H) ? W : 0.0) : th_o * W;
       out[o] = a;
     }
     if (FUSE) {
       double v = 0.0;
       if (valid) {
-        v = fast_div(a, d.efflen[o]);
+        v = fast_div(a, len_o);
         dst[o] = v;
       }
       const double s = group8_sum(v);
@@ -1591,6 +1597,9 @@ struct TagWait {
   bool failed = false;
   __device__ __forceinline__ bool give_up(const gbrs_em_dev& d) {
     if (failed) return true;
+    // back off between polls: a warp spinning flat out on system-scope loads takes issue slots and L2 request slots from
+    // the blocks of the same SM that are still computing, and from the peers' stores that are trying to land
+    __nanosleep(spins < 8u ? 32u : 128u);
     if ((++spins & 255u) != 0u) return false;
     const unsigned long long now = globaltimer_ns();
     if (t0 == 0ull) t0 = now;
@@ -1601,7 +1610,6 @@ struct TagWait {
       d.ctrl[GBRS_CTRL_DONE] = 1;
       return true;
     }
-    __nanosleep(40);
     return false;
   }
 };
@@ -1684,14 +1692,26 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
   const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
   const unsigned long long t_start = stamp ? globaltimer_ns() : 0ull;
   auto mark = [&](int i) { if (stamp) d.part[kStampSlot + i] = (double) (globaltimer_ns() - t_start); };
+  // tag form: slot 3 = block 0's absolute start (low 40 bits of the ns clock), slots 5..7 = the LATEST block's end of phase
+  // A / B / C on the same clock (the kernel lasts as long as its slowest block, not as long as block 0)
+  auto mark_max = [&](int i) {
+#ifndef GBRS_SIMT_EMULATION
+    if (TAG && threadIdx.x == 0)
+      atomicMax(reinterpret_cast<unsigned long long*>(d.part + kStampSlot + i), globaltimer_ns() & 0xFFFFFFFFFFull);
+#endif
+  };
+  if (TAG && stamp) {
+    d.part[kStampSlot + 3] = (double) (t_start & 0xFFFFFFFFFFull);
+    d.part[kStampSlot + 5] = d.part[kStampSlot + 6] = d.part[kStampSlot + 7] = 0.0;
+  }
   // ---- A: local numerator, pushed to the owners ----------------------------------------------------------------------
   {
     const double* __restrict__ th = d.theta + (size_t) par * d.T * GBRS_HPAD;
     const int slice32 = (int) slice;
-    locus_walk(d, [&](int t, int hh, double W, bool valid) {
+    locus_walk(d, UNIT ? nullptr : th, nullptr, [&](int t, int hh, double W, bool valid, double th_o, double) {
       if (valid) {
         const int o = t * GBRS_HPAD + hh;
-        const double a = UNIT ? ((hh < d.H) ? W : 0.0) : th[o] * W;
+        const double a = UNIT ? ((hh < d.H) ? W : 0.0) : th_o * W;
         const int owner = o / slice32;
         double* const slot = push_recv(d, owner, me) + (o - owner * slice32);
         if (TAG) {
@@ -1704,6 +1724,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     });
   }
   mark(0);  // numerator of block 0 done
+  mark_max(5);
   if (!TAG) push_signal(d, 0, e, GBRS_CTRL_TICKET + 1);
   // ---- B: sum my slice over the ranks, broadcast the totals ---------------------------------------------------------
   if (!TAG && !push_wait(d, 0, e, &s_fail)) return;
@@ -1768,10 +1789,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     }
   }
   mark(2);  // slice of block 0 reduced and broadcast
+  mark_max(6);
   if (!TAG) push_signal(d, 1, e, GBRS_CTRL_TICKET + 2);
   // ---- C: the update, from the totals every owner has stored here -------------------------------------------------------
   if (!TAG && !push_wait(d, 1, e, &s_fail)) return;
-  mark(3);  // every owner's totals have arrived (tag form: nothing to wait for here, the elements are polled below)
+  if (!TAG) mark(3);  // every owner's totals have arrived (tag form: nothing to wait for, the elements are polled below)
   {
     const double* __restrict__ src = push_total(d, me);
     double* __restrict__ dst = d.theta + (size_t) (par ^ 1) * d.T * GBRS_HPAD;
@@ -1779,29 +1801,62 @@ __global__ void __launch_bounds__(kThreads, 4) k_locus_xchg(const __grid_constan
     const int total = d.T * GBRS_HPAD;
     const int stride = (int) (gridDim.x * blockDim.x);
     const int rounds = (total + stride - 1) / stride;
-    int i = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    const int i0 = (int) (blockIdx.x * blockDim.x + threadIdx.x);
     double mine = 0.0;
-    for (int r = 0; r < rounds; ++r, i += stride) {
-      double v = 0.0;
-      const bool valid = i < total;
-      if (valid) {
-        // written by peers: never through a stale L1 line (tag form: polled until this exchange's value is there)
-        const double a = TAG ? tag_wait1(d, src + i, tag, tw) : __ldcg(src + i);
-        d.acc[i] = a;                      // the summed numerator, where the reports read it
-        v = fast_div(a, d.efflen[i]);
-        dst[i] = v;
+    // The rounds of a thread are independent: the totals (and lengths) of a whole batch of rounds are requested together and,
+    // in the tag form, polled together -- the thread waits once for the slowest of them instead of once per round, and the
+    // update of a batch costs one memory round trip instead of one per round.
+    constexpr int BATCH = 6;
+    for (int r0 = 0; r0 < rounds; r0 += BATCH) {
+      unsigned long long raw[BATCH];
+      double len[BATCH];
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {
+        const int i = i0 + (r0 + k) * stride;
+        const bool valid = r0 + k < rounds && i < total;
+        raw[k] = tag;
+        len[k] = 1.0;
+        if (valid) {  // written by peers: never through a stale L1 line
+          raw[k] = TAG ? ld_relaxed_sys_b64(src + i) : (unsigned long long) __double_as_longlong(__ldcg(src + i));
+          len[k] = d.efflen[i];
+        }
       }
-      const double sum8 = group8_sum(v);
-      if (valid && h == 0) {
-        iso[i >> 3] = sum8;
-        mine += sum8;
+      if (TAG) {
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+          const int i = i0 + (r0 + k) * stride;
+          while ((raw[k] & kTagBit) != tag) {  // not there yet (only ever true for a valid element)
+            if (tw.give_up(d)) { raw[k] = tag; break; }
+            raw[k] = ld_relaxed_sys_b64(src + i);
+          }
+        }
       }
-      write_subset_rows(d, i >> 3, h, v, valid);
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {
+        if (r0 + k < rounds) {  // (uniform over the grid: the warp collectives below are safe)
+          const int i = i0 + (r0 + k) * stride;
+          const bool valid = i < total;
+          double v = 0.0;
+          if (valid) {
+            const double a = TAG ? untag(raw[k]) : __longlong_as_double((long long) raw[k]);
+            d.acc[i] = a;  // the summed numerator, where the reports read it
+            v = fast_div(a, len[k]);
+            dst[i] = v;
+          }
+          const double sum8 = group8_sum(v);
+          if (valid && h == 0) {
+            iso[i >> 3] = sum8;
+            mine += sum8;
+          }
+          write_subset_rows(d, i >> 3, h, v, valid);
+        }
+      }
     }
     const double bs = block_sum(mine, red);
     if (threadIdx.x == 0) d.part[blockIdx.x] = bs;
   }
   mark(4);  // update of block 0 done
+  mark_max(7);
   if (TAG) {  // bookkeeping only, nobody waits for it: the last block to leave advances the epoch for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {

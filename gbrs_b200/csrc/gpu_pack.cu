@@ -12,7 +12,7 @@
 //   scan       rowstart = exclusive scan of nz                                               cub::DeviceScan (library)
 //   scatter    rec[rowstart[c] + k] = (locus << 3 | haplotype)                               k_gp_scatter
 //   merge      per class: sort its records, OR the haplotype bits of equal loci -> pair words, pair count, smallest locus
-//   order      classes of this shard by (min(pairs, 9) - 1, smallest locus), stable          cub::DeviceRadixSort (library)
+//   order      classes of this shard by (min(pairs, 9) - 1, smallest locus, second-smallest locus), stable   cub::DeviceRadixSort (library)
 //   fill       rowptr / count / pairs in the new order, pairs sorted by (gene, locus), (class, gene) runs
 //   loci       per-locus entry counts (partial / full masks), padded part sizes, item counts, their scans
 //   entries    pairs sorted by (locus, part, new class id) -> ent_cls / ent_pair / ent_run        cub::DeviceRadixSort
@@ -119,11 +119,12 @@ __device__ __forceinline__ void shell_sort(uint32_t* a, int n) {
 // per class: records (locus << 3 | hap) -> pair words (locus | mask << 24), compacted at the front of the class' segment
 __global__ void __launch_bounds__(kGpThreads) k_gp_merge(int64_t N, const uint32_t* __restrict__ rowstart,
                                                         const uint32_t* __restrict__ nz, uint32_t* __restrict__ rec,
-                                                        uint32_t* __restrict__ npair, uint32_t* __restrict__ minloc) {
+                                                        uint32_t* __restrict__ npair, uint32_t* __restrict__ minloc,
+                                                        uint32_t* __restrict__ secloc) {
   for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (int64_t) gridDim.x * blockDim.x) {
     const int n = (int) nz[c];
     uint32_t* a = rec + rowstart[c];
-    if (n == 0) { npair[c] = 0; minloc[c] = 0xFFFFFFFFu; continue; }
+    if (n == 0) { npair[c] = 0; minloc[c] = 0xFFFFFFFFu; secloc[c] = 0u; continue; }
     if (n <= 12) {  // insertion sort
       for (int i = 1; i < n; ++i) {
         const uint32_t v = a[i];
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_merge(int64_t N, const uint32
     }
     npair[c] = (uint32_t) k;
     minloc[c] = a[0] & kLoc;
+    secloc[c] = k > 1 ? (a[1] & kLoc) : 0u;  // second-smallest locus (> 0 when there is one): the minor key of the class order
   }
 }
 
@@ -579,6 +581,7 @@ extern "C" int gbrs_pack_device(const gbrs_pack_input* in, gbrs_alloc_fn alloc, 
   uint32_t* cursor = A.get<uint32_t>(N + 1, "tmp:cursor");
   uint32_t* npair = A.get<uint32_t>(N + 1, "tmp:npair");
   uint32_t* minloc = A.get<uint32_t>(N + 1, "tmp:minloc");
+  uint32_t* secloc = A.get<uint32_t>(N + 1, "tmp:secloc");
   uint32_t* rec = A.get<uint32_t>(nnz_in, "tmp:rec");
   int64_t* d_lohi = A.get<int64_t>(2, "tmp:lohi");
   unsigned long long* d_stats = A.get<unsigned long long>(8, "tmp:stats");
@@ -592,7 +595,7 @@ extern "C" int gbrs_pack_device(const gbrs_pack_input* in, gbrs_alloc_fn alloc, 
   if (N > 0)
     if (int rc = inclusive_scan_into(A, nz, rowstart + 1, N, s)) return rc;
   k_gp_scatter<<<col_grid, kGpThreads, 0, s>>>(col, rowstart, cursor, rec);
-  if (N > 0) k_gp_merge<<<gp_grid(N), kGpThreads, 0, s>>>(N, rowstart, nz, rec, npair, minloc);
+  if (N > 0) k_gp_merge<<<gp_grid(N), kGpThreads, 0, s>>>(N, rowstart, nz, rec, npair, minloc, secloc);
   k_gp_shard<<<1, 32, 0, s>>>(rowstart, N, in->shard_count, in->shard_rank, d_lohi);
 
   // ---- class order ---------------------------------------------------------------------------------------------------
@@ -604,7 +607,20 @@ extern "C" int gbrs_pack_device(const gbrs_pack_input* in, gbrs_alloc_fn alloc, 
   if (A.failed) { gbrs_set_error("gbrs_pack_device: allocation failed"); return GBRS_E_NOMEM; }
   if (N > 0) {
     k_gp_order_keys<<<gp_grid(N), kGpThreads, 0, s>>>(N, d_lohi, npair, minloc, okey, oval, d_stats);
-    if (int rc = sort_pairs(A, okey, okey2, oval, order, N, 32, s)) return rc;
+    // (width, smallest locus, second-smallest locus, class id): two stable sorts, minor key first.  Classes sharing their two
+    // smallest loci end up next to each other, so a warp of the row pass reads fewer distinct table rows and the entries of a
+    // locus gather runs of consecutive weights in the column pass.
+    uint32_t* sec_sorted = A.get<uint32_t>(N + 1, "tmp:sec_sorted");
+    uint32_t* val1 = A.get<uint32_t>(N + 1, "tmp:val1");
+    uint32_t* okey_g = A.get<uint32_t>(N + 1, "tmp:okey_g");
+    if (A.failed) { gbrs_set_error("gbrs_pack_device: allocation failed"); return GBRS_E_NOMEM; }
+    if (std::getenv("GBRS_NO_SECLOC") != nullptr) {  // A/B knob: the round-1 order (width, smallest locus, class id)
+      if (int rc = sort_pairs(A, okey, okey2, oval, order, N, 32, s)) return rc;
+    } else {
+      if (int rc = sort_pairs(A, secloc, sec_sorted, oval, val1, N, 24, s)) return rc;
+      k_gp_gather_u32<<<gp_grid(N), kGpThreads, 0, s>>>(N, val1, okey, okey_g);
+      if (int rc = sort_pairs(A, okey_g, okey2, val1, order, N, 32, s)) return rc;
+    }
   }
   k_gp_buckets<<<1, 32, 0, s>>>(okey2, N, d_buckets);
   GP_CUDA(cudaGetLastError());

@@ -151,9 +151,10 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     // Every thread owns a contiguous range of class ids and walks ALL merged entries (a sequential scan of the
     // locus-major list), keeping only the entries of its own classes: no atomics, and the loci come by in ascending
     // order, so the first locus seen for a class is its smallest one.
-    bigvec<uint32_t> npair, minloc, nz;
+    bigvec<uint32_t> npair, minloc, secloc, nz;
     par_fill(npair, (size_t) N, 0u);
     par_fill(minloc, (size_t) N, 0xFFFFFFFFu);
+    par_fill(secloc, (size_t) N, 0u);  // second-smallest locus (> 0 when there is one)
     par_fill(nz, (size_t) N, 0u);
     {
       int nt = 1;
@@ -173,6 +174,7 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
             ++npair[c];
             nz[c] += (uint32_t) __builtin_popcountll(src[i] & 0xFF);
             if (minloc[c] == 0xFFFFFFFFu) minloc[c] = (uint32_t) t;
+            else if (secloc[c] == 0u) secloc[c] = (uint32_t) t;
           }
         }
       }
@@ -198,7 +200,8 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     }
 
     lap("2 class counts + shard");
-    // ---- 3. order the shard's non-empty classes by (pairs capped at KMAX+1, smallest locus): stable counting sort ----
+    // ---- 3. order the shard's non-empty classes by (pairs capped at KMAX+1, smallest locus, second-smallest locus): stable
+    // counting sorts ----
     // Equal-width classes are contiguous so the row pass needs no row pointers for them; within a width the classes are
     // ordered by smallest locus so that neighbouring classes touch neighbouring theta lines.
     const int NB = GBRS_KMAX + 1;  // buckets: widths 1..KMAX, then "long"
@@ -219,8 +222,24 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
     for (int b = 0; b < NB; ++b) { bclass[b + 1] += bclass[b]; bpair[b + 1] += bpair[b]; }
     bigvec<uint32_t> new_id;
     par_fill(new_id, (size_t) N, 0xFFFFFFFFu);
-    for (int64_t c = lo; c < hi; ++c)
-      if (npair[c]) new_id[c] = (uint32_t) bucket[(size_t) bucket_of(npair[c]) * T + minloc[c]]++;
+    {
+      // minor key: the second-smallest locus (stable counting sort first, then the (width, smallest locus) one walks the
+      // classes in that order).  Classes sharing their two smallest loci end up next to each other: a warp of the row pass
+      // reads fewer distinct table rows, and the entries of a locus gather runs of consecutive weights in the column pass.
+      std::vector<int64_t> sec_start((size_t) T + 2, 0);
+      if (std::getenv("GBRS_NO_SECLOC") != nullptr)  // A/B knob: the round-1 order (width, smallest locus, class id)
+        for (int64_t c = lo; c < hi; ++c) secloc[c] = 0u;
+      for (int64_t c = lo; c < hi; ++c)
+        if (npair[c]) ++sec_start[(size_t) secloc[c] + 1];
+      for (int t = 0; t <= T; ++t) sec_start[(size_t) t + 1] += sec_start[(size_t) t];
+      bigvec<uint32_t> by_sec((size_t) n_classes);
+      for (int64_t c = lo; c < hi; ++c)
+        if (npair[c]) by_sec[(size_t) sec_start[secloc[c]]++] = (uint32_t) c;
+      for (int64_t i = 0; i < n_classes; ++i) {
+        const uint32_t c = by_sec[(size_t) i];
+        new_id[c] = (uint32_t) bucket[(size_t) bucket_of(npair[c]) * T + minloc[c]]++;
+      }
+    }
 
     lap("3 class order");
     auto* P = new gbrs_pack();

@@ -59,11 +59,14 @@ def test_pack_preserves_pattern(small):
     assert p.info["n_pairs"] == d.pairs and p.info["nnz"] == d.nnz == p.info["nnz_total"]
     assert packed_signatures(p) == class_signatures(d)
     a = p.arrays
-    # classes ordered by (number of pairs capped at KMAX+1, smallest locus); bucket tables consistent with rowptr
+    # classes ordered by (number of pairs capped at KMAX+1, smallest locus, second-smallest locus); bucket tables consistent
+    # with rowptr
     rp = a["rowptr"].astype(np.int64)
-    minloc = np.array([(a["pairs"][rp[n]:rp[n + 1]] & 0xFFFFFF).min() for n in range(p.info["n_classes"])])
+    loci = [np.sort(a["pairs"][rp[n]:rp[n + 1]] & 0xFFFFFF) for n in range(p.info["n_classes"])]
+    minloc = np.array([x[0] for x in loci], dtype=np.int64)
+    secloc = np.array([x[1] if len(x) > 1 else 0 for x in loci], dtype=np.int64)
     width = np.minimum(np.diff(rp), _lib.GBRS_KMAX + 1)
-    key = width * (1 << 24) + minloc
+    key = (width * (1 << 24) + minloc) * (1 << 24) + secloc
     assert np.all(np.diff(key) >= 0)
     bc, bp = p.info["bucket_class0"], p.info["bucket_pair0"]
     assert bc[0] == 0 and bc[-1] == p.info["n_classes"] and bp[-1] == p.info["n_pairs"]
