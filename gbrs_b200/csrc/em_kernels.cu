@@ -972,7 +972,9 @@ __device__ __forceinline__ void column_steps(const E* __restrict__ ents, const d
   }
 }
 
-// LANES = 8: four short items per warp (one per aligned 8-lane group); LANES = 32: one long item per warp.
+// LANES = 8: four short items per warp (one per aligned 8-lane group); LANES = 32: one long item per warp; LANES = 2 / 1
+// (VEC = 1 only): sixteen items of at most two quads / thirty-two items of one quad per warp -- a locus hit by a handful of
+// classes is one item of a few entries, and half of all items are that small: on eight lanes they left seven idle.
 // FULL: every entry of the item hits all H haplotypes -- a plain sum, broadcast to the H slots, no masking.
 template <typename E, int VEC, int LANES, bool FULL>
 __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __restrict__ ents, int64_t item, uint32_t b,
@@ -982,6 +984,30 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
   const double* __restrict__ wts = d.weights;
   const int lane = threadIdx.x & 31, lane8 = lane & 7, lanex = lane & (LANES - 1);
   double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (VEC == 1 && LANES <= 2) {
+    // one quad per lane, no loop; the lane (pair) keeps all eight haplotype sums and stores them itself
+    column_steps<E, LANES, FULL, 1>(ents, wts, b, e, b + 4 * lanex, a);
+    if (FULL) {
+      if (LANES == 2) a[0] += __shfl_xor_sync(0xFFFFFFFFu, a[0], 1);
+#pragma unroll
+      for (int h = 1; h < 8; ++h) a[h] = h < d.H ? a[0] : 0.0;
+    } else if (LANES == 2) {
+#pragma unroll
+      for (int h = 0; h < 8; ++h) a[h] += __shfl_xor_sync(0xFFFFFFFFu, a[h], 1);
+    }
+    if (item >= 0) {
+      double2* out = reinterpret_cast<double2*>(d.wit + item * GBRS_HPAD);
+      if (LANES == 1) {
+        out[0] = make_double2(a[0], a[1]); out[1] = make_double2(a[2], a[3]);
+        out[2] = make_double2(a[4], a[5]); out[3] = make_double2(a[6], a[7]);
+      } else if (lanex == 0) {
+        out[0] = make_double2(a[0], a[1]); out[1] = make_double2(a[2], a[3]);
+      } else {
+        out[2] = make_double2(a[4], a[5]); out[3] = make_double2(a[6], a[7]);
+      }
+    }
+    return;
+  }
   if (VEC == 1) {
     // Items start at a multiple of 4 entries and are padded with empty words, so every lane fetches four consecutive
     // entries per step (one 128-bit load for 32-bit words, two for 64-bit words); two steps and their eight weight
@@ -998,7 +1024,7 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
     // group walks the same entries: the entry words are one broadcast load, the eight weights of an entry one coalesced
     // 64-byte access (a lane gathering the full 64-byte line by itself cost four 16-byte requests per entry, each a
     // wavefront of its own: 223 us at C2), and no transposing reduction is needed at the end.
-    constexpr int G = LANES / 8;  // lane groups sharing the item: each takes every G-th quad of entries
+    constexpr int G = LANES >= 8 ? LANES / 8 : 1;  // lane groups sharing the item: each takes every G-th quad of entries
     const int grp = lanex >> 3;
     double acc0 = 0.0, acc1 = 0.0;
     auto quad = [&](uint32_t p, double& acc) {
@@ -1044,39 +1070,76 @@ __device__ __forceinline__ void column_item(const gbrs_em_dev& d, const E* __res
   if (item >= 0 && lanex < 8) d.wit[item * GBRS_HPAD + lane8] = tot;
 }
 
-// Warp work slots: slot < n_long_items -> the slot-th item of item_order (a long item, whole warp); otherwise four
-// short items.  item_order lists long items first, partial-mask items before full-mask ones, longest first.
+// Warp work slots over the visiting order of item_desc: [long partial | long full | short partial | short full], every part
+// longest first.  A long item takes a whole warp; short items of more than two quads take eight lanes (four per warp), of
+// two quads two lanes (sixteen per warp), of one quad one lane (thirty-two per warp).  The packers append the positions where
+// the short parts change kind / size class as a two-descriptor trailer behind the n_items descriptors:
+//   trailer[0] = {first short partial item of <= 8 words, of <= 4 words, first short full item, first short full of <= 8 words}
+//   trailer[1] = {first short full item of <= 4 words, 0, 0, 0}
+// Every slot holds items of one kind only, so a warp never mixes masked and plain sums.
 template <typename E, int VEC>
 __global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(const __grid_constant__ gbrs_em_dev d,
                                                              const E* __restrict__ ents, bool honour_done) {
   if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
-  const int64_t n_long = d.n_long_items;
-  const int64_t total_slots = n_long + ((d.n_items - n_long + 3) >> 2);
   const uint4* __restrict__ desc = reinterpret_cast<const uint4*>(d.item_desc);
-  auto slot_pos = [&](int64_t ws) { return ws < n_long ? ws : n_long + ((ws - n_long) << 2) + (lane >> 3); };
+  const uint4 tr0 = __ldg(desc + d.n_items), tr1 = __ldg(desc + d.n_items + 1);
+  constexpr int NSEG = 7;
+  // segment starts in items, items per warp slot (model 1 keeps eight lanes per short item: lane h owns haplotype h)
+  const int64_t seg_item[NSEG + 1] = {0, d.n_long_items, tr0.x, tr0.y, tr0.z, tr0.w, tr1.x, d.n_items};
+  constexpr int per[NSEG] = {1, 4, VEC == 1 ? 16 : 4, VEC == 1 ? 32 : 4, 4, VEC == 1 ? 16 : 4, VEC == 1 ? 32 : 4};
+  int64_t seg_slot[NSEG + 1];
+  seg_slot[0] = 0;
+#pragma unroll
+  for (int k = 0; k < NSEG; ++k) seg_slot[k + 1] = seg_slot[k] + (seg_item[k + 1] - seg_item[k] + per[k] - 1) / per[k];
+  const int64_t total_slots = seg_slot[NSEG];
+  // descriptor position of the item this lane works on in slot ws (-1: none) and the slot's segment
+  auto locate = [&](int64_t ws, int& seg) -> int64_t {
+    seg = 0;
+#pragma unroll
+    for (int k = 1; k < NSEG; ++k) seg += ws >= seg_slot[k];
+    int64_t pos = -1;
+#pragma unroll
+    for (int k = 0; k < NSEG; ++k)
+      if (seg == k) {
+        const int64_t i = seg_item[k] + (ws - seg_slot[k]) * per[k] + (lane / (32 / per[k]));
+        pos = i < seg_item[k + 1] ? i : -1;
+      }
+    return pos;
+  };
+  const uint4 none = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
   int64_t ws = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  uint4 nx = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);  // descriptor of the slot this lane handles in the coming iteration
-  if (ws < total_slots && slot_pos(ws) < d.n_items) nx = __ldg(desc + slot_pos(ws));
+  int seg = 0, seg_nx = 0;
+  uint4 nx = none;  // descriptor of the item this lane handles in the coming iteration
+  if (ws < total_slots) {
+    const int64_t pos = locate(ws, seg_nx);
+    if (pos >= 0) nx = __ldg(desc + pos);
+  }
   for (; ws < total_slots; ws += nwarps) {
     const uint4 cur = nx;
-    {  // fetch the descriptor of the following slot now and pull its entries towards L2
+    seg = seg_nx;
+    {  // fetch the descriptor of the following slot now
       const int64_t wn = ws + nwarps;
-      nx = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-      if (wn < total_slots && slot_pos(wn) < d.n_items) nx = __ldg(desc + slot_pos(wn));
+      nx = none;
+      if (wn < total_slots) {
+        const int64_t pos = locate(wn, seg_nx);
+        if (pos >= 0) nx = __ldg(desc + pos);
+      }
     }
     const int64_t item = cur.z == 0xFFFFFFFFu ? -1 : (int64_t) cur.z;
     const uint32_t b = cur.x, e = cur.y;
-    const bool full = cur.w & 1u;
-    // all 32 lanes must run both kinds when a warp straddles the partial/full boundary (shuffles are warp-wide)
-    const unsigned any_full = __ballot_sync(0xFFFFFFFFu, full), any_part = __ballot_sync(0xFFFFFFFFu, !full);
-    if (ws < n_long) {
-      if (full) column_item<E, VEC, 32, true>(d, ents, item, b, e);
-      else column_item<E, VEC, 32, false>(d, ents, item, b, e);
-    } else {
-      if (any_part) column_item<E, VEC, 8, false>(d, ents, full ? -1 : item, full ? 0u : b, full ? 0u : e);
-      if (any_full) column_item<E, VEC, 8, true>(d, ents, full ? item : -1, full ? b : 0u, full ? e : 0u);
+    switch (seg) {  // (uniform over the warp)
+      case 0:
+        if (cur.w & 1u) column_item<E, VEC, 32, true>(d, ents, item, b, e);
+        else column_item<E, VEC, 32, false>(d, ents, item, b, e);
+        break;
+      case 1: column_item<E, VEC, 8, false>(d, ents, item, b, e); break;
+      case 2: column_item<E, VEC, VEC == 1 ? 2 : 8, false>(d, ents, item, b, e); break;
+      case 3: column_item<E, VEC, VEC == 1 ? 1 : 8, false>(d, ents, item, b, e); break;
+      case 4: column_item<E, VEC, 8, true>(d, ents, item, b, e); break;
+      case 5: column_item<E, VEC, VEC == 1 ? 2 : 8, true>(d, ents, item, b, e); break;
+      default: column_item<E, VEC, VEC == 1 ? 1 : 8, true>(d, ents, item, b, e); break;
     }
   }
 }
@@ -2152,7 +2215,7 @@ template <int VEC>
 int launch_column(const gbrs_em_dev* d, const void* ents, bool honour_done, cudaStream_t s) {
   if (!ents) { gbrs_set_error("column pass: entry array missing from descriptor"); return GBRS_E_ARG; }
   if (d->n_items == 0) return GBRS_OK;
-  const int64_t threads = (d->n_long_items + ((d->n_items - d->n_long_items + 3) >> 2)) * 32;
+  const int64_t threads = (d->n_long_items + ((d->n_items - d->n_long_items + 3) >> 2)) * 32;  // (an upper bound: tiny items share warps)
   if (d->entry_bytes == 4)
     k_column_reduce<uint32_t, VEC><<<resident_grid(k_column_reduce<uint32_t, VEC>, threads), kThreads, 0, s>>>(
         *d, static_cast<const uint32_t*>(ents), honour_done);

@@ -357,17 +357,40 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_item_keys(int64_t n_items, in
 __global__ void __launch_bounds__(kGpThreads) k_gp_item_desc(int64_t n_items, const uint32_t* __restrict__ sorted_key,
                                                             const uint32_t* __restrict__ sorted_item,
                                                             const uint32_t* __restrict__ item_off, const uint8_t* __restrict__ item_full,
-                                                            uint32_t* __restrict__ item_desc, unsigned long long* n_long) {
-  unsigned long long mine = 0;
+                                                            uint32_t* __restrict__ item_desc, unsigned long long* n_long,
+                                                            unsigned long long* __restrict__ cls /* [5] size classes */) {
+  unsigned long long mine = 0, c[5] = {0, 0, 0, 0, 0};  // short partial: all, > 8 words, > 4 words; short full: > 8, > 4
   for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (int64_t) gridDim.x * blockDim.x) {
     const uint32_t it = sorted_item[i];
-    item_desc[4 * i + 0] = item_off[it];
-    item_desc[4 * i + 1] = item_off[it + 1];
+    const uint32_t b = item_off[it], e = item_off[it + 1], kind = sorted_key[i] >> 28, f = item_full[it];
+    item_desc[4 * i + 0] = b;
+    item_desc[4 * i + 1] = e;
     item_desc[4 * i + 2] = it;
-    item_desc[4 * i + 3] = item_full[it];
-    mine += (sorted_key[i] >> 28) < 2u;
+    item_desc[4 * i + 3] = f;
+    mine += kind < 2u;
+    if (kind >= 2u) {
+      c[0] += !f;
+      c[f ? 3 : 1] += e - b > 8u;
+      c[f ? 4 : 2] += e - b > 4u;
+    }
   }
   if (mine) atomicAdd(n_long, mine);
+  for (int k = 0; k < 5; ++k)
+    if (c[k]) atomicAdd(cls + k, c[k]);
+}
+
+// the trailer of item_desc (see k_column_reduce): positions where the short items change kind / size class
+__global__ void k_gp_item_trailer(int64_t n_items, const unsigned long long* __restrict__ n_long,
+                                  const unsigned long long* __restrict__ cls, uint32_t* __restrict__ item_desc) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long nl = *n_long, f0 = nl + cls[0];
+  uint32_t* tr = item_desc + 4 * n_items;
+  tr[0] = (uint32_t) (nl + cls[1]);
+  tr[1] = (uint32_t) (nl + cls[2]);
+  tr[2] = (uint32_t) f0;
+  tr[3] = (uint32_t) (f0 + cls[3]);
+  tr[4] = (uint32_t) (f0 + cls[4]);
+  tr[5] = tr[6] = tr[7] = 0u;
 }
 
 __global__ void __launch_bounds__(kGpThreads) k_gp_locus_keys(int T, const uint32_t* __restrict__ nitems, uint32_t* __restrict__ key,
@@ -720,18 +743,21 @@ extern "C" int gbrs_pack_device(const gbrs_pack_input* in, gbrs_alloc_fn alloc, 
   uint32_t* ikey2 = A.get<uint32_t>(n_items + 1, "tmp:ikey2");
   uint32_t* ival = A.get<uint32_t>(n_items + 1, "tmp:ival");
   uint32_t* ival2 = A.get<uint32_t>(n_items + 1, "tmp:ival2");
-  uint32_t* item_desc = A.get<uint32_t>(std::max<int64_t>(n_items, 1) * 4, "item_desc");
+  uint32_t* item_desc = A.get<uint32_t>((n_items + 2) * 4, "item_desc");  // + the two-descriptor trailer
+  unsigned long long* d_cls = A.get<unsigned long long>(8, "tmp:item_classes");
   uint32_t* tkey = A.get<uint32_t>(T, "tmp:tkey");
   uint32_t* tkey2 = A.get<uint32_t>(T, "tmp:tkey2");
   uint32_t* tval = A.get<uint32_t>(T, "tmp:tval");
   uint32_t* tval2 = A.get<uint32_t>(T, "tmp:tval2");
   uint32_t* locus_desc = A.get<uint32_t>((int64_t) T * 4, "locus_desc");
   if (A.failed) { gbrs_set_error("gbrs_pack_device: allocation failed"); return GBRS_E_NOMEM; }
+  GP_CUDA(cudaMemsetAsync(d_cls, 0, sizeof(unsigned long long) * 8, s));
   if (n_items > 0) {
     k_gp_item_keys<<<gp_grid(n_items), kGpThreads, 0, s>>>(n_items, item_len, item_off, item_full, ikey, ival);
     if (int rc = sort_pairs(A, ikey, ikey2, ival, ival2, n_items, 32, s)) return rc;
-    k_gp_item_desc<<<gp_grid(n_items), kGpThreads, 0, s>>>(n_items, ikey2, ival2, item_off, item_full, item_desc, d_stats + 2);
+    k_gp_item_desc<<<gp_grid(n_items), kGpThreads, 0, s>>>(n_items, ikey2, ival2, item_off, item_full, item_desc, d_stats + 2, d_cls);
   }
+  k_gp_item_trailer<<<1, 32, 0, s>>>(n_items, d_stats + 2, d_cls, item_desc);
   k_gp_locus_keys<<<gp_grid(T), kGpThreads, 0, s>>>(T, nitems, tkey, tval);
   if (int rc = sort_pairs(A, tkey, tkey2, tval, tval2, T, 32, s)) return rc;
   k_gp_locus_desc<<<gp_grid(T), kGpThreads, 0, s>>>(T, tval2, item_ptr, locus_desc, d_stats + 3);

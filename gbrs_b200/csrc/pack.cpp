@@ -435,7 +435,19 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
         return lx > ly;
       });
       P->item_order.assign((size_t) n_items, 0);
-      P->item_desc.assign((size_t) n_items * 4, 0);
+      // + a two-descriptor trailer: where the short items change kind / size class in the visiting order (the column pass
+      // gives an item of one quad one lane, of two quads two lanes, anything longer eight)
+      P->item_desc.assign((size_t) (n_items + 2) * 4, 0);
+      int64_t sp_all = 0, sp_gt8 = 0, sp_gt4 = 0, sf_gt8 = 0, sf_gt4 = 0;
+      for (int64_t i = 0; i < n_items; ++i) {
+        const int64_t len_i = len_of(idx[i]);
+        if (len_i <= item_len) {
+          const bool f = item_full[idx[i]];
+          sp_all += !f;
+          (f ? sf_gt8 : sp_gt8) += len_i > 8;
+          (f ? sf_gt4 : sp_gt4) += len_i > 4;
+        }
+      }
       for (int64_t i = 0; i < n_items; ++i) {
         P->item_order[i] = idx[i] | (item_full[idx[i]] ? 0x80000000u : 0u);
         P->info.n_long_items += len_of(idx[i]) > item_len;
@@ -445,6 +457,13 @@ extern "C" int gbrs_pack_create(const gbrs_pack_input* in, gbrs_pack_t* out) {
         P->item_desc[4 * i + 2] = idx[i];
         P->item_desc[4 * i + 3] = item_full[idx[i]];
       }
+      const int64_t nl = P->info.n_long_items, f0 = nl + sp_all;
+      uint32_t* tr = P->item_desc.data() + 4 * (size_t) n_items;
+      tr[0] = (uint32_t) (nl + sp_gt8);
+      tr[1] = (uint32_t) (nl + sp_gt4);
+      tr[2] = (uint32_t) f0;
+      tr[3] = (uint32_t) (f0 + sf_gt8);
+      tr[4] = (uint32_t) (f0 + sf_gt4);
     }
     // (3) loci in descending item count: the per-locus combine starts with the deepest loci.  locus_desc carries, per
     // visiting slot, everything the combine needs in one 16-byte load: locus, first item, one-past-last item.

@@ -114,6 +114,15 @@ def test_pack_preserves_pattern(small):
     for i, f in zip(order, isfull):  # full items hold only full-mask entries
         assert not f or np.all(np.isin(m_c[io[i]:io[i + 1]], (0, 0xFF)))
     desc = a["item_desc"].astype(np.int64).reshape(-1, 4)
+    # two-descriptor trailer: where the short items change kind / size class in the visiting order (k_column_reduce)
+    assert desc.shape[0] == p.info["n_items"] + 2
+    tr, desc = desc[p.info["n_items"]:].ravel(), desc[:p.info["n_items"]]
+    lens_d, nl = desc[:, 1] - desc[:, 0], p.info["n_long_items"]
+    short_p = (np.arange(len(desc)) >= nl) & (desc[:, 3] == 0)
+    short_f = (np.arange(len(desc)) >= nl) & (desc[:, 3] == 1)
+    f0 = nl + short_p.sum()
+    assert list(tr[:5]) == [nl + (short_p & (lens_d > 8)).sum(), nl + (short_p & (lens_d > 4)).sum(), f0,
+                            f0 + (short_f & (lens_d > 8)).sum(), f0 + (short_f & (lens_d > 4)).sum()] and not tr[5:].any()
     assert np.array_equal(desc[:, 2], order) and np.array_equal(desc[:, 3], isfull)
     assert np.array_equal(desc[:, 0], io[order]) and np.array_equal(desc[:, 1], io[order + 1])
     lo_ = a["locus_order"].astype(np.int64)
