@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None) ->
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC,-fopenmp,-O3", "-Xptxas", "-v" if verbose else "-O3",
            "-I", os.path.join(ROOT, "include"), "-cudart", "static", "-o", LIB + ".tmp"] + SOURCES + ["-lgomp", "-ldl"]
-    for knob in ("GBRS_THREADS", "GBRS_COL_MINBLOCKS", "GBRS_TILE_THREADS", "GBRS_TILE_MINBLOCKS"):  # tuning experiments only
+    for knob in ("GBRS_THREADS", "GBRS_COL_MINBLOCKS", "GBRS_ROW_MINBLOCKS", "GBRS_TILE_THREADS", "GBRS_TILE_MINBLOCKS"):  # tuning experiments only
         if os.environ.get(knob):
             cmd.insert(1, f"-D{knob}=" + os.environ[knob])
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -445,8 +445,11 @@ __device__ __forceinline__ void row_classes_m4(const gbrs_em_dev& d, int64_t cla
 
 // One launch per width range [KLO, KHI]: the narrow classes (four out of five have at most three pairs) are not compiled for
 // the register needs of the widest, so more of them are resident and more loads are in flight.
+#ifndef GBRS_ROW_MINBLOCKS
+#define GBRS_ROW_MINBLOCKS 1  // resident blocks per SM the model-4 row pass is compiled for (1: no register cap)
+#endif
 template <bool UNIT, int KLO, int KHI>
-__global__ void __launch_bounds__(kThreads) k_weights_m4(const __grid_constant__ gbrs_em_dev d,
+__global__ void __launch_bounds__(kThreads, GBRS_ROW_MINBLOCKS) k_weights_m4(const __grid_constant__ gbrs_em_dev d,
                                                           const __grid_constant__ RowPlan plan) {
   if (!UNIT && d.ctrl[GBRS_CTRL_DONE]) return;
   const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
