@@ -73,6 +73,35 @@ def test_emulated_wide_classes_short_items_and_alignment_counts():
     assert np.array_equal(aln, want["aln"]) and np.array_equal(uniq, want["uniq"]) and np.array_equal(lu, want["locus_uniq"])
 
 
+def test_emulated_column_pass_size_classes_and_dynamic_tickets():
+    """Every kind of column-pass work in one problem -- long items (a whole warp), short items of more than two quads
+    (eight lanes), of two quads (two lanes, sixteen per warp) and of one quad (one lane, thirty-two per warp), partial and
+    full -- at the default item length, with more tickets than warps so that the device work counter hands most of them
+    out; the trailer of item_desc agrees with the descriptors; two updates of models 4 and 3 against the oracle."""
+    d = synth.generate(T=60, N=5000, H=8, sample_index=21)
+    gene_of = eo.gene_index(d.T, d.groups())
+    pat = simt_em.HostPattern(synth.to_apm(d), gene_of=gene_of)
+    n_items, nl = pat.info["n_items"], pat.info["n_long_items"]
+    desc = pat.packed.arrays["item_desc"].reshape(-1, 4).astype(np.int64)
+    assert desc.shape[0] == n_items + 2
+    tr, desc = desc[n_items:].ravel(), desc[:n_items]
+    lens = desc[:, 1] - desc[:, 0]
+    p8, p4, f0, f8, f4 = (int(x) for x in tr[:5])
+    assert nl > 0 and nl < p8 < p4 < f0 <= f8 <= f4 <= n_items  # all partial size classes are present
+    assert np.all(lens[nl:p8] > 8) and np.all((lens[p8:p4] > 4) & (lens[p8:p4] <= 8)) and np.all(lens[p4:f0] <= 4)
+    assert not desc[nl:f0, 3].any() and desc[f0:, 3].all()
+    eff = eo.effective_length_table(d.lengths)
+    theta = pat.prepare(eff)
+    oapm = eo.apm_from_pairs(d.T, d.H, d.N, d.pair_class, d.pair_locus, d.pair_mask, d.count)
+    assert hp.relerr(theta, eo.prepare(oapm, eff, 0.0)) < 1e-12
+    for model in (4, 3, 4):
+        want = eo.sum_read(oapm, eo.e_step(oapm, theta, model, gene_of))
+        out = pat.run(model, tol=0.0, max_iters=1)
+        assert out["iters"] == 1 and hp.relerr(out["counts"], want) < 1e-12
+        theta = out["theta"]
+    assert int(pat.ctrl[13]) == 0  # the work counter is back at zero (the locus kernel resets it)
+
+
 def test_emulated_standalone_estep_does_not_move_the_state():
     """update_probability_at_read_level semantics (EMfactory.py:146-212): the E-step alone leaves only the numerator
     behind.  Two stand-alone E-steps followed by a full update must give exactly what one update gives."""
