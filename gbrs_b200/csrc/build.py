@@ -52,6 +52,8 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None) ->
     for knob in ("GBRS_THREADS", "GBRS_COL_MINBLOCKS", "GBRS_ROW_MINBLOCKS", "GBRS_TILE_THREADS", "GBRS_TILE_MINBLOCKS"):  # tuning experiments only
         if os.environ.get(knob):
             cmd.insert(1, f"-D{knob}=" + os.environ[knob])
+    for flag in os.environ.get("GBRS_DEFINES", "").split():  # tuning experiments only: bare -D flags
+        cmd.insert(1, "-D" + flag)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

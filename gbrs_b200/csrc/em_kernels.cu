@@ -1085,90 +1085,50 @@ __global__ void __launch_bounds__(kThreads, GBRS_COL_MINBLOCKS) k_column_reduce(
                                                              const E* __restrict__ ents, bool honour_done) {
   if (honour_done && d.ctrl[GBRS_CTRL_DONE]) return;
   const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t) gridDim.x * blockDim.x) >> 5;
   const uint4* __restrict__ desc = reinterpret_cast<const uint4*>(d.item_desc);
+  const uint4 tr0 = __ldg(desc + d.n_items), tr1 = __ldg(desc + d.n_items + 1);
   constexpr int NSEG = 7;
-  // log2 of the items per warp slot (model 1 keeps eight lanes per short item: lane h owns haplotype h)
-  constexpr int T2 = VEC == 1 ? 4 : 2, T1 = VEC == 1 ? 5 : 2;
-  // segment tables in shared memory: first item / first warp slot of every segment (32-bit: n_items < 2^31)
-  __shared__ int s_item[NSEG + 1], s_slot[NSEG + 1], s_lp[NSEG + 1];
-  if (threadIdx.x == 0) {
-    const uint4 tr0 = __ldg(desc + d.n_items), tr1 = __ldg(desc + d.n_items + 1);
-    const int it[NSEG + 1] = {0, (int) d.n_long_items, (int) tr0.x, (int) tr0.y, (int) tr0.z, (int) tr0.w, (int) tr1.x, (int) d.n_items};
-    const int lp[NSEG] = {0, 2, T2, T1, 2, T2, T1};
-    int slot = 0;
-    for (int k = 0; k < NSEG; ++k) {
-      s_item[k] = it[k];
-      s_slot[k] = slot;
-      s_lp[k] = lp[k];
-      slot += (it[k + 1] - it[k] + (1 << lp[k]) - 1) >> lp[k];
-    }
-    s_item[NSEG] = it[NSEG];
-    s_slot[NSEG] = slot;
-    s_lp[NSEG] = 0;
-  }
-  __syncthreads();
-  const int total_slots = s_slot[NSEG];
-  const int nwarps = (int) ((gridDim.x * blockDim.x) >> 5);
-  // The slot a warp looks at only ever moves forward, so the segment it lies in is tracked incrementally: one compare per
-  // slot, the tables are read again only when a boundary is crossed.
-  int seg_nx = 0, item0 = s_item[0], item1 = s_item[1], slot0 = 0, slot1 = s_slot[1], lp = s_lp[0];
-  auto locate = [&](int ws) -> int {  // descriptor position of the item this lane works on in slot ws (-1: none)
-    while (ws >= slot1) {
-      ++seg_nx;
-      item0 = item1; slot0 = slot1;
-      item1 = s_item[seg_nx + 1]; slot1 = s_slot[seg_nx + 1]; lp = s_lp[seg_nx];
-    }
-    const int i = item0 + ((ws - slot0) << lp) + (lane >> (5 - lp));
-    return i < item1 ? i : -1;
+  // segment starts in items, items per warp slot (model 1 keeps eight lanes per short item: lane h owns haplotype h)
+  const int64_t seg_item[NSEG + 1] = {0, d.n_long_items, tr0.x, tr0.y, tr0.z, tr0.w, tr1.x, d.n_items};
+  constexpr int per[NSEG] = {1, 4, VEC == 1 ? 16 : 4, VEC == 1 ? 32 : 4, 4, VEC == 1 ? 16 : 4, VEC == 1 ? 32 : 4};
+  int64_t seg_slot[NSEG + 1];
+  seg_slot[0] = 0;
+#pragma unroll
+  for (int k = 0; k < NSEG; ++k) seg_slot[k + 1] = seg_slot[k] + (seg_item[k + 1] - seg_item[k] + per[k] - 1) / per[k];
+  const int64_t total_slots = seg_slot[NSEG];
+  // descriptor position of the item this lane works on in slot ws (-1: none) and the slot's segment
+  auto locate = [&](int64_t ws, int& seg) -> int64_t {
+    seg = 0;
+#pragma unroll
+    for (int k = 1; k < NSEG; ++k) seg += ws >= seg_slot[k];
+    int64_t pos = -1;
+#pragma unroll
+    for (int k = 0; k < NSEG; ++k)
+      if (seg == k) {
+        const int64_t i = seg_item[k] + (ws - seg_slot[k]) * per[k] + (lane / (32 / per[k]));
+        pos = i < seg_item[k + 1] ? i : -1;
+      }
+    return pos;
   };
-  // Work is handed out dynamically, costliest first (the visiting order): a ticket is one long item or four consecutive
-  // short slots.  Every warp starts on the ticket of its own index and draws the following ones from a device counter
-  // (zeroed by the locus kernel that follows every column pass), so a warp that drew a 2048-entry item is not also owed a
-  // fixed share of everything else -- with the static round-robin the kernel lasted as long as its unluckiest warp (33 us
-  // against 22 us of mean busy time per warp).  Which warp sums an item does not change the item's sum.
-  const int n_long_slots = s_slot[1];
-  const int total_tickets = n_long_slots + ((total_slots - n_long_slots + 3) >> 2);
-  auto ticket_first = [&](int t) { return t < n_long_slots ? t : n_long_slots + ((t - n_long_slots) << 2); };
-  auto ticket_end = [&](int t) {
-    const int e = t < n_long_slots ? t + 1 : n_long_slots + ((t - n_long_slots + 1) << 2);
-    return e < total_slots ? e : total_slots;
-  };
-  int* const counter = d.ctrl + GBRS_CTRL_TILE_NEXT;
-  // the draw is issued when a ticket is started and looked at when it is finished: its latency is never waited for
-  auto draw = [&]() { return lane == 0 ? atomicAdd(counter, 1) : 0; };
   const uint4 none = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
-  int ticket = (int) (((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (ticket >= total_tickets) return;
-  int drawn = draw();
-  int ws = ticket_first(ticket), ws_end = ticket_end(ticket);
-  int seg = 0;
+  int64_t ws = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int seg = 0, seg_nx = 0;
   uint4 nx = none;  // descriptor of the item this lane handles in the coming iteration
-  {
-    const int pos = locate(ws);
+  if (ws < total_slots) {
+    const int64_t pos = locate(ws, seg_nx);
     if (pos >= 0) nx = __ldg(desc + pos);
   }
-  for (bool more = true; more;) {
+  for (; ws < total_slots; ws += nwarps) {
     const uint4 cur = nx;
     seg = seg_nx;
-    {  // the slot after this one (possibly the first of the next ticket): fetch its descriptor now
-      int wn = ws + 1;
-      if (wn >= ws_end) {
-        ticket = nwarps + __shfl_sync(0xFFFFFFFFu, drawn, 0);
-        if (ticket < total_tickets) {
-          drawn = draw();
-          wn = ticket_first(ticket);
-          ws_end = ticket_end(ticket);
-        } else {
-          wn = total_slots;
-        }
-      }
+    {  // fetch the descriptor of the following slot now
+      const int64_t wn = ws + nwarps;
       nx = none;
-      more = wn < total_slots;
-      if (more) {
-        const int pos = locate(wn);
+      if (wn < total_slots) {
+        const int64_t pos = locate(wn, seg_nx);
         if (pos >= 0) nx = __ldg(desc + pos);
       }
-      ws = wn;
     }
     const int64_t item = cur.z == 0xFFFFFFFFu ? -1 : (int64_t) cur.z;
     const uint32_t b = cur.x, e = cur.y;
