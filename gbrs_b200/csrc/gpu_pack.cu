@@ -8,9 +8,9 @@
 // threads) -- a hundred times the EM it feeds; here the same work is a transposition by counting (two passes of integer
 // atomics over the nnz), small per-class sorts, two radix sorts of ~10 M keys and a handful of scans:
 //
-//   count      nz[c] = alignments of class c that survive the haplotype mask                 k_gp_count (warp per column)
-//   scan       rowstart = exclusive scan of nz                                               cub::DeviceScan (library)
-//   scatter    rec[rowstart[c] + k] = (locus << 3 | haplotype)                               k_gp_scatter
+//   transpose  the stored entries that survive the haplotype mask, re-laid locus-major (k_gp_col_len, scan, k_gp_gen), are
+//              stable-sorted by class id (cub::DeviceRadixSort, library); rowstart from the sorted keys (k_gp_rowstart).
+//              (First form, GBRS_PACK_TRANSPOSE=count: k_gp_count, scan, k_gp_scatter through per-class cursors.)
 //   merge      per class: sort its records, OR the haplotype bits of equal loci -> pair words, pair count, smallest locus
 //   order      classes of this shard by (min(pairs, 9) - 1, smallest locus, second-smallest locus), stable   cub::DeviceRadixSort (library)
 //   fill       rowptr / count / pairs in the new order, pairs sorted by (gene, locus), (class, gene) runs
@@ -105,6 +105,46 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_scatter(const Columns c, cons
   });
 }
 
+// ---- transposition by sorting (default): the stored entries, re-laid locus-major, are stable-sorted by class id -------
+// column lengths in [locus][haplotype] order after the haplotype mask
+__global__ void __launch_bounds__(kGpThreads) k_gp_col_len(const Columns c, uint32_t* __restrict__ len) {
+  const int64_t n_cols = (int64_t) c.H * c.T;
+  for (int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; q < n_cols; q += (int64_t) gridDim.x * blockDim.x) {
+    const int t = (int) (q / c.H), h = (int) (q - (int64_t) t * c.H);
+    const int64_t* ip = c.indptr + (int64_t) h * (c.T + 1) + t;
+    const bool keep = !c.hapmask || ((c.hapmask[t] >> h) & 1);
+    len[q] = keep ? (uint32_t) (ip[1] - ip[0]) : 0u;
+  }
+}
+// one warp per (locus, haplotype) column: key = class id, value = (locus << 3 | haplotype), written at the column's place
+// in locus-major order -- a stable sort by class then leaves every class' records ordered by (locus, haplotype)
+__global__ void __launch_bounds__(kGpThreads) k_gp_gen(const Columns c, const uint32_t* __restrict__ colstart,
+                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int* bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t) gridDim.x * blockDim.x) >> 5, n_cols = (int64_t) c.H * c.T;
+  for (int64_t q = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_cols; q += n_warps) {
+    const uint32_t o = colstart[q], n = colstart[q + 1] - o;
+    if (n == 0) continue;
+    const int t = (int) (q / c.H), h = (int) (q - (int64_t) t * c.H);
+    const uint32_t* src = c.indices + c.hoff[h] + c.indptr[(int64_t) h * (c.T + 1) + t];
+    const uint32_t v = ((uint32_t) t << 3) | (uint32_t) h;
+    for (uint32_t i = lane; i < n; i += 32) {
+      uint32_t cls = src[i];
+      if ((int64_t) cls >= c.N) { *bad = 1; cls = 0u; }
+      keys[o + i] = cls;
+      vals[o + i] = v;
+    }
+  }
+}
+// rowstart[c] = first record of class c in the sorted list (n for the classes behind the last one; rowstart[N] = n)
+__global__ void __launch_bounds__(kGpThreads) k_gp_rowstart(const uint32_t* __restrict__ keys, int64_t n, int64_t N,
+                                                           uint32_t* __restrict__ rowstart) {
+  for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t prev = i > 0 ? (int64_t) keys[i - 1] : -1, cur = i < n ? (int64_t) keys[i] : N;
+    for (int64_t x = prev + 1; x <= cur; ++x) rowstart[x] = (uint32_t) i;
+  }
+}
+
 __device__ __forceinline__ void shell_sort(uint32_t* a, int n) {
   for (int gap = n >> 1; gap > 0; gap = gap == 2 ? 1 : (int) (gap / 2.2)) {
     for (int i = gap; i < n; ++i) {
@@ -117,15 +157,18 @@ __device__ __forceinline__ void shell_sort(uint32_t* a, int n) {
 }
 
 // per class: records (locus << 3 | hap) -> pair words (locus | mask << 24), compacted at the front of the class' segment
+// SORTED: the records of a class already come ordered by (locus, haplotype) (transposition by sorting)
+template <bool SORTED>
 __global__ void __launch_bounds__(kGpThreads) k_gp_merge(int64_t N, const uint32_t* __restrict__ rowstart,
-                                                        const uint32_t* __restrict__ nz, uint32_t* __restrict__ rec,
+                                                        uint32_t* __restrict__ rec,
                                                         uint32_t* __restrict__ npair, uint32_t* __restrict__ minloc,
                                                         uint32_t* __restrict__ secloc) {
   for (int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (int64_t) gridDim.x * blockDim.x) {
-    const int n = (int) nz[c];
+    const int n = (int) (rowstart[c + 1] - rowstart[c]);
     uint32_t* a = rec + rowstart[c];
     if (n == 0) { npair[c] = 0; minloc[c] = 0xFFFFFFFFu; secloc[c] = 0u; continue; }
-    if (n <= 12) {  // insertion sort
+    if (SORTED) {
+    } else if (n <= 12) {  // insertion sort
       for (int i = 1; i < n; ++i) {
         const uint32_t v = a[i];
         int j = i - 1;
@@ -614,11 +657,41 @@ extern "C" int gbrs_pack_device(const gbrs_pack_input* in, gbrs_alloc_fn alloc, 
   GP_CUDA(cudaMemsetAsync(rowstart, 0, sizeof(uint32_t), s));
   GP_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 8, s));
   const int col_grid = gp_grid((int64_t) H * T * 32);
-  k_gp_count<<<col_grid, kGpThreads, 0, s>>>(col, nz, d_bad);
-  if (N > 0)
-    if (int rc = inclusive_scan_into(A, nz, rowstart + 1, N, s)) return rc;
-  k_gp_scatter<<<col_grid, kGpThreads, 0, s>>>(col, rowstart, cursor, rec);
-  if (N > 0) k_gp_merge<<<gp_grid(N), kGpThreads, 0, s>>>(N, rowstart, nz, rec, npair, minloc, secloc);
+  const char* tr_env = std::getenv("GBRS_PACK_TRANSPOSE");
+  if (tr_env && std::string(tr_env) == "count") {
+    // A/B knob: the first form -- count per class, scan, scatter through per-class cursors (63 M atomics with a returned
+    // value: 3.0 ms at C2), then every class sorts its records (1.4 ms)
+    k_gp_count<<<col_grid, kGpThreads, 0, s>>>(col, nz, d_bad);
+    if (N > 0)
+      if (int rc = inclusive_scan_into(A, nz, rowstart + 1, N, s)) return rc;
+    k_gp_scatter<<<col_grid, kGpThreads, 0, s>>>(col, rowstart, cursor, rec);
+    if (N > 0) k_gp_merge<false><<<gp_grid(N), kGpThreads, 0, s>>>(N, rowstart, rec, npair, minloc, secloc);
+  } else {
+    // by sorting: the entries that survive the mask, re-laid locus-major (column starts by a scan over the T x H column
+    // lengths), are stable-sorted by class id (library radix sort over the bits of N); the records of a class then arrive
+    // ordered by (locus, haplotype) and merging them is one linear pass -- no atomics, no per-class sorts
+    const int64_t n_cols = (int64_t) H * T;
+    int64_t n_kept = 0;
+    for (int t = 0; t < T; ++t)
+      for (int h = 0; h < H; ++h)
+        if (!in->locus_hapmask || ((in->locus_hapmask[t] >> h) & 1)) n_kept += in->indptr[h][t + 1] - in->indptr[h][t];
+    uint32_t* collen = A.get<uint32_t>(n_cols + 1, "tmp:collen");
+    uint32_t* colstart = A.get<uint32_t>(n_cols + 1, "tmp:colstart");
+    uint32_t* keys = A.get<uint32_t>(n_kept, "tmp:keys");
+    uint32_t* keys2 = A.get<uint32_t>(n_kept, "tmp:keys2");
+    uint32_t* vals = A.get<uint32_t>(n_kept, "tmp:vals");
+    if (A.failed) { gbrs_set_error("gbrs_pack_device: allocation failed"); return GBRS_E_NOMEM; }
+    GP_CUDA(cudaMemsetAsync(colstart, 0, sizeof(uint32_t), s));
+    k_gp_col_len<<<gp_grid(n_cols), kGpThreads, 0, s>>>(col, collen);
+    if (int rc = inclusive_scan_into(A, collen, colstart + 1, n_cols, s)) return rc;
+    k_gp_gen<<<col_grid, kGpThreads, 0, s>>>(col, colstart, keys, vals, d_bad);
+    int bits = 1;
+    while ((int64_t(1) << bits) < N) ++bits;
+    if (n_kept > 0)
+      if (int rc = sort_pairs(A, keys, keys2, vals, rec, n_kept, bits, s)) return rc;
+    k_gp_rowstart<<<gp_grid(n_kept + 1), kGpThreads, 0, s>>>(keys2, n_kept, N, rowstart);
+    if (N > 0) k_gp_merge<true><<<gp_grid(N), kGpThreads, 0, s>>>(N, rowstart, rec, npair, minloc, secloc);
+  }
   k_gp_shard<<<1, 32, 0, s>>>(rowstart, N, in->shard_count, in->shard_rank, d_lohi);
 
   // ---- class order ---------------------------------------------------------------------------------------------------

@@ -361,24 +361,38 @@ class DevicePattern:
             return True
         return k in _LAZY_ARRAYS and not (k == "rowptr" and self._need_rowptr)
 
-    def ensure_full(self):
-        """Make the arrays of models 1-3 / the alignment counts resident too (no-op once done)."""
+    def _weights_len(self, model1: bool) -> int:
+        """Slots of the E-step weight vector: one per class (model 4), pair (2) or (class, gene) run (3); model 1 keeps
+        eight per run -- six times the others at the benchmark shape, so that size is only allocated when model 1 runs.
+        + 8 trailing slots that stay zero (padding entries point there)."""
+        i = self.info
+        runs = i["n_runs"] if self.packed.has_genes else 0
+        return max(i["n_classes"], i["n_pairs"], runs, 8 * runs if model1 else 0, 1) + 8
+
+    def ensure_full(self, model=None):
+        """Make the arrays of models 1-3 / the alignment counts resident too (no-op once done).  `model`: the model about to
+        run (None: any) -- model 1 needs the large weight vector."""
+        torch = _torch()
+        rebuilt = False
         if not self.full:
             self.upload(lazy=True)
             self.full = True
             if self.tiled is not None:  # work arrays of the two-pass kernels were placeholders
-                torch = _torch()
                 i = self.info
-                nw = max(i["n_classes"], i["n_pairs"], 8 * i["n_runs"] if self.packed.has_genes else 0, 1) + 8
-                self.weights = torch.zeros(nw, dtype=torch.float64, device=self.device)
+                self.weights = torch.zeros(self._weights_len(False), dtype=torch.float64, device=self.device)
                 self.wit = torch.zeros((max(i["n_items"], 1), 8), dtype=torch.float64, device=self.device)
+            rebuilt = True
+        if model in (None, 1) and self.weights.numel() < self._weights_len(True):
+            self.weights = torch.zeros(self._weights_len(True), dtype=torch.float64, device=self.device)
+            rebuilt = True
+        if rebuilt:
             self._build_descriptor()
 
     def _alloc_state(self):
         torch = _torch()
         T, dv, f64 = self.T, self.device, torch.float64
         i = self.info
-        nw = max(i["n_classes"], i["n_pairs"], 8 * i["n_runs"] if self.packed.has_genes else 0, 1) + 8
+        nw = self._weights_len(False)  # (model 1 grows it: ensure_full)
         n_wit = max(i["n_items"], 1)
         if self.tiled is not None:  # two-pass work arrays are allocated by ensure_full()
             nw, n_wit = 8, 1
@@ -512,7 +526,7 @@ class DevicePattern:
 
     def alignment_counts(self, gene_level=False, n_real_genes=0):
         torch = _torch()
-        self.ensure_full()
+        self.ensure_full(model=4)  # the run tables, not model 1's weight vector
         rows = n_real_genes if gene_level else self.T
         alloc = max(self.info["n_gene_ids"], rows) if gene_level else self.T
         aln = torch.zeros((alloc, 8), dtype=torch.float64, device=self.device)
@@ -868,7 +882,7 @@ class EMfactory:
             raise RuntimeError("The read normalization model should be 1, 2, 3, or 4.")
         pat = self._ensure_pattern()
         if model != 4:
-            pat.ensure_full()
+            pat.ensure_full(model)
         self._sync_theta_to_device()
         _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), 0.0, 1, pat.stream()))
         _lib.check(pat.lib.gbrs_em_launch_estep(C.byref(pat.desc), int(model), pat.stream()))
@@ -884,7 +898,7 @@ class EMfactory:
             raise RuntimeError("The read normalization model should be 1, 2, 3, or 4.")
         pat = self._ensure_pattern()
         if model != 4:
-            pat.ensure_full()
+            pat.ensure_full(model)
         self._sync_theta_to_device()
         _lib.check(pat.lib.gbrs_em_run_begin(C.byref(pat.desc), 0.0, 1, pat.stream()))
         _lib.check(pat.lib.gbrs_em_launch_local(C.byref(pat.desc), int(model), pat.stream()))
@@ -912,7 +926,7 @@ class EMfactory:
             raise ValueError(f"max_iters above {ERR_LOG_CAP} is not supported")
         pat = self._ensure_pattern()
         if model != 4:
-            pat.ensure_full()
+            pat.ensure_full(model)
         self._sync_theta_to_device()
         show = verbose and self.rank == 0  # one table, from rank 0 (a sharded run would print it world times)
         if show:
