@@ -326,6 +326,43 @@ def test_emulated_device_packer_equals_host_packer(case):
     _assert_same_pack(info, arrays, PackedPattern(apm, gene_of=gene_of, **kw))
 
 
+@pytest.mark.skipif(__import__("shutil").which("g++") is None, reason="g++ is needed to build the SIMT emulation")
+@pytest.mark.parametrize("transpose", ["sort", "count"])
+def test_emulated_device_packer_empty_classes_and_masked_loci(transpose, monkeypatch):
+    """Both forms of the device packer's transposition (stable sort of the locus-major entries / counting with per-class
+    cursors) on the corner cases of the class boundaries: classes without any alignment at the start, in the middle and at
+    the end of the id range, loci the genotype byte removes completely, and a matrix that is empty after masking."""
+    from scipy.sparse import csc_matrix
+
+    from gbrs_b200 import AlignmentPropertyMatrix as APM
+    from gbrs_b200.emfactory import PackedPattern
+    from tests import simt_em
+
+    monkeypatch.setenv("GBRS_PACK_TRANSPOSE", transpose)
+    rng = np.random.default_rng(5)
+    T, H, N = 23, 4, 400
+    dense = (rng.random((H, N, T)) < 0.04).astype(np.float64)
+    dense[:, :37, :] = 0       # no alignments for the first classes ...
+    dense[:, 150:171, :] = 0   # ... for a block in the middle ...
+    dense[:, N - 29:, :] = 0   # ... and for the last ones
+    apm = APM(shape=(T, H, N))
+    apm.data = [csc_matrix(dense[h]) for h in range(H)]
+    apm.count = rng.integers(1, 9, N).astype(np.float64)
+    apm.finalize()
+    mask = rng.integers(0, 1 << H, T).astype(np.uint8)
+    mask[[3, 11]] = 0  # loci dropped completely
+    for hapmask in (None, mask):
+        info, arrays = simt_em.emulated_device_pack(apm, hapmask=hapmask)
+        _assert_same_pack(info, arrays, PackedPattern(apm, hapmask=hapmask))
+        assert 0 < info["n_classes"] <= N - 37 - 21 - 29
+    # nothing survives the mask: an empty problem, the same numbers from both packers (zero-length arrays are not compared:
+    # the device packer never hands out a zero-byte allocation)
+    info, _ = simt_em.emulated_device_pack(apm, hapmask=np.zeros(T, dtype=np.uint8))
+    host = PackedPattern(apm, hapmask=np.zeros(T, dtype=np.uint8))
+    assert info["n_classes"] == 0 and info["n_pairs"] == 0 and info["nnz"] == 0
+    assert not [k for k in info if info[k] != host.info[k]]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", range(6))
 def test_device_packer_equals_host_packer(case):
