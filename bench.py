@@ -6,15 +6,20 @@ model 4, DO-mouse-scale shape, % of the HBM roofline).
 
 A *step* is one EM update (E-step + M-step + convergence test) over the resident packed incidence matrix.
   value     nnz * K / t          device-timed (CUDA events on the launch stream), inputs resident in HBM
-  e2e       same metric through the public `EMfactory` API from HOST buffers: H2D of the packed matrix (pinned) +
-            prepare + run(K iterations) + D2H of theta / counts / err log, all inside the timed region
-  roofline  dominant kernel: algorithmic bytes of that kernel / its mean device time, vs MEASURED_PEAKS.json
-  cpu_baseline  the oracle port (numpy restatement of the reference's EM; the reference itself is pure Python and is not
-            present on the GPU box) timed on a bounded sample of the same workload on the host cores
+  e2e       same metric through the public `EMfactory` API from HOST buffers: `EMfactory(apm).prepare()` [H2D of the H CSC
+            matrices from pinned memory, packing on the device, theta0] + run(K iterations) + D2H of the expected counts, all
+            inside the timed region; `e2e_resident` is the same with the already packed arrays (what round 1 called e2e)
+  roofline  dominant kernel (the longer of the row and the column pass): algorithmic bytes of that kernel / its mean device
+            time, vs MEASURED_PEAKS.json; `roofline.iteration`: the whole update by SURVEY 8(d)'s single-copy formula
+  cpu_baseline  the UNMODIFIED reference (its own AlignmentPropertyMatrix + EMfactory, staged byte for byte into the
+            git-ignored oracle/_ref/ by oracle/make_ref.py, `kind: "reference"`) timed on a bounded sample of the same
+            workload on one host core; the oracle port (`kind: "port"`) only where the reference cannot run (models 1-3 on
+            current scipy, or no staged copy)
+  models    (default line only) models 3, 2, 1 on the same resident pattern, 5 updates each (BASELINE config 3)
 
 N > 1 (torchrun): weak scaling -- every rank holds its own `workload`-sized row shard (different classes, same loci); the
-T x 8 numerator is summed over the ranks once per step inside our own kernels over NVLink peer memory (GBRS_XCHG=nccl:
-a plain all-reduce); time = max over ranks.  Every line carries a `parity` record (conservation, theta identical on all
+T x 8 numerator is summed over the ranks once per step inside our own kernels over NVLink peer memory (GBRS_XCHG=push, the
+default, | tag | pull | nvls; nccl: a plain all-reduce); time = max over ranks.  Every line carries a `parity` record (conservation, theta identical on all
 ranks, a small problem sharded over the same ranks against the oracle).
 """
 from __future__ import annotations
