@@ -5,13 +5,14 @@
 // What it replaces in the reference: the storage walk of Sparse3DMatrix (src/gbrs/emase/Sparse3DMatrix.py:26-66, the CSC
 // matrices are class-id lists per locus) re-laid for the two GPU passes; the `-G` restriction of quantify
 // (src/gbrs/gbrs/emase_utils.py:247-273) is applied while counting.  The host packer costs 0.2 s at 5 M classes (16
-// threads) -- a hundred times the EM it feeds; here the same work is a transposition by counting (two passes of integer
-// atomics over the nnz), small per-class sorts, two radix sorts of ~10 M keys and a handful of scans:
+// threads) -- a hundred times the EM it feeds; here the same work is a transposition by a stable radix sort of the stored
+// entries, one linear merge per class, three radix sorts of 5-10 M keys and a handful of scans (11 ms at 5 M classes incl.
+// the 293 MB over PCIe):
 //
 //   transpose  the stored entries that survive the haplotype mask, re-laid locus-major (k_gp_col_len, scan, k_gp_gen), are
 //              stable-sorted by class id (cub::DeviceRadixSort, library); rowstart from the sorted keys (k_gp_rowstart).
 //              (First form, GBRS_PACK_TRANSPOSE=count: k_gp_count, scan, k_gp_scatter through per-class cursors.)
-//   merge      per class: sort its records, OR the haplotype bits of equal loci -> pair words, pair count, smallest locus
+//   merge      per class: OR the haplotype bits of equal loci (records arrive ordered) -> pair words, pair count, smallest loci
 //   order      classes of this shard by (min(pairs, 9) - 1, smallest locus, second-smallest locus), stable   cub::DeviceRadixSort (library)
 //   fill       rowptr / count / pairs in the new order, pairs sorted by (gene, locus), (class, gene) runs
 //   loci       per-locus entry counts (partial / full masks), padded part sizes, item counts, their scans
@@ -641,7 +642,7 @@ extern "C" int gbrs_pack_device(const gbrs_pack_input* in, gbrs_alloc_fn alloc, 
   GP_CUDA(cudaMemcpyAsync(d_gene_loci, gene_loci.data(), sizeof(uint32_t) * (size_t) T, cudaMemcpyHostToDevice, s));
   if (d_count_in) GP_CUDA(cudaMemcpyAsync(d_count_in, in->count, sizeof(double) * (size_t) N, cudaMemcpyHostToDevice, s));
 
-  // ---- transposition by counting ---------------------------------------------------------------------------------------
+  // ---- transposition: CSC columns -> class rows --------------------------------------------------------------------------
   uint32_t* nz = A.get<uint32_t>(N + 1, "tmp:nz");
   uint32_t* rowstart = A.get<uint32_t>(N + 1, "tmp:rowstart");
   uint32_t* cursor = A.get<uint32_t>(N + 1, "tmp:cursor");
