@@ -324,6 +324,69 @@ def test_emulated_exchange_timeout_stops_every_block(mode):
         os.environ.pop("GBRS_SIMT_SMS", None)
 
 
+def test_emulated_tag_exchange_reports_a_negative_expression_value():
+    """The tag form carries its "arrived" bit in the sign of every transported double, so a negative numerator cannot be
+    transported: a theta with a negative value (not an expression estimate) raises the numeric error flag instead of being
+    summed silently as its absolute value."""
+    import ctypes as C
+    import threading
+
+    from gbrs_b200 import _lib
+
+    d = synth.generate(T=30, N=300, H=8, sample_index=6)
+    os.environ["GBRS_SIMT_SMS"] = "1"
+    try:
+        R = 2
+        apm = synth.to_apm(d)
+        pats = [simt_em.HostPattern(apm, shard_rank=r, shard_count=R, lib=simt_em.load_instance(f"rank{r}")) for r in range(R)]
+        slice_len = ((8 * d.T + R - 1) // R + 1) & ~1
+        bufs = [np.zeros(R * slice_len + 8 * d.T + 16) for _ in range(R)]
+        for r, p in enumerate(pats):
+            p.desc.xchg_enabled, p.desc.xchg_rank, p.desc.xchg_mc, p.desc.xchg_timeout_ms = 3, r, None, 0
+            for q in range(R):
+                p.desc.xchg_peer[q] = bufs[q].ctypes.data
+        errors = []
+        # a (locus, haplotype) slot none of whose classes has it as its only alignment: with a slightly negative theta there
+        # every class normaliser stays positive, so the slot's numerator theta * sum(w) is negative
+        nnz_of_class = np.bincount(d.pair_class, weights=synth._popcount8(d.pair_mask), minlength=d.N)
+        t_neg = h_neg = None
+        for t in np.argsort(-np.bincount(d.pair_locus, minlength=d.T)):
+            sel = d.pair_locus == t
+            for h in range(d.H):
+                hit = sel & (((d.pair_mask >> h) & 1) == 1)
+                if hit.any() and np.all(nnz_of_class[d.pair_class[hit]] >= 2):
+                    t_neg, h_neg = int(t), h
+                    break
+            if t_neg is not None:
+                break
+        assert t_neg is not None
+
+        def rank_main(r):
+            p = pats[r]
+            try:
+                p.check(p.lib.gbrs_em_prepare_local(C.byref(p.desc), None))
+                p.check(p.lib.gbrs_em_prepare_finish(C.byref(p.desc), 0.0, None))
+                assert p.ctrl[_lib.CTRL_ERROR] == 0
+                bad = np.zeros((d.T, 8))
+                bad[:, : d.H] = p.current_theta().T
+                bad[t_neg, h_neg] = -1e-9 * bad[:, : d.H].max()  # one slightly negative slot: its numerator is negative
+                p.check(p.lib.gbrs_em_set_theta(C.byref(p.desc), bad.ctypes.data, None))
+                p.check(p.lib.gbrs_em_run_begin(C.byref(p.desc), 0.0, 1, None))
+                p.check(p.lib.gbrs_em_launch_local(C.byref(p.desc), 4, None))
+            except BaseException as e:  # noqa: BLE001 - reported by the main thread
+                errors.append((r, repr(e)))
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(R)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=300)
+        assert not errors, errors
+        assert any(int(p.ctrl[_lib.CTRL_ERROR]) == 1 for p in pats)  # the rank(s) whose shard holds classes of that slot
+    finally:
+        os.environ.pop("GBRS_SIMT_SMS", None)
+
+
 def test_fused_exchange_is_race_free_under_thread_sanitizer():
     """Two and three concurrent ranks under ThreadSanitizer: every access to a peer's numerator must be ordered by the
     ready / done flags (with the flag store weakened to a relaxed store the sanitizer reports the peer loads)."""
