@@ -87,7 +87,7 @@ typedef struct {
   int32_t n_gene_ids;  /* 1 + max gene id */
   int32_t max_pairs_per_class;
   int32_t n_deep_loci;  /* loci with more than GBRS_DEEP_LOCUS_ITEMS work items (they come first in locus_desc) */
-  /* Classes are ordered by (min(pairs, GBRS_KMAX + 1), smallest locus).  bucket_class0[k-1] / bucket_pair0[k-1] is the
+  /* Classes are ordered by (min(pairs, GBRS_KMAX + 1), smallest locus, second-smallest locus, input class id).  bucket_class0[k-1] / bucket_pair0[k-1] is the
    * first class / first pair word of the classes with exactly k pairs (k = 1..GBRS_KMAX); index GBRS_KMAX starts the
    * "long" classes (more than GBRS_KMAX pairs), index GBRS_KMAX+1 is the end (= n_classes / n_pairs). */
   int64_t bucket_class0[GBRS_KMAX + 2];
@@ -103,7 +103,7 @@ int gbrs_pack_get_info(gbrs_pack_t p, gbrs_pack_info* info);
  *   "ent_cls" / "ent_pair" / "ent_run"  entry words [n_entries], locus-major (index | mask << (8*entry_bytes-8));
  *                                     padding words carry an empty mask and index n_classes / n_pairs / n_runs
  *   "item_off" uint32 [n_items+1]    "locus_item_ptr" uint32 [T+1]   "item_order" uint32 [n_items]
- *   "item_desc" uint32 [n_items][4]  "locus_order" uint32 [T]   "locus_desc" uint32 [T][4]
+ *   "item_desc" uint32 [n_items + 2][4] (two trailer descriptors, see gbrs_em_dev)  "locus_order" uint32 [T]   "locus_desc" uint32 [T][4]
  *   "gene_ptr" uint32 [n_gene_ids+1] "gene_loci" uint32 [T]     "gene_of" int32 [T]
  */
 int gbrs_pack_get_array(gbrs_pack_t p, const char* name, const void** ptr, int64_t* bytes);
@@ -125,7 +125,7 @@ typedef struct {
   const void* ent_cls;         /* [n_entries] entry words (entry_bytes each) */
   const void* ent_pair;
   const void* ent_run;
-  const uint32_t* item_desc;   /* [n_items][4] */
+  const uint32_t* item_desc;   /* [n_items + 2][4] */
   const uint32_t* locus_desc;  /* [T][4] */
   const int32_t* gene_of;      /* [T] */
   const uint32_t* gene_ptr;    /* [n_gene_ids + 1] */
@@ -250,7 +250,11 @@ typedef struct {
   const void* ent_run;
   const uint32_t* item_off;
   const uint32_t* item_order;   /* [n_items] item ids in visiting order, bit 31 = full-mask item */
-  const uint32_t* item_desc;    /* [n_items][4] per visiting slot: first entry, one-past-last entry, item id, flags */
+  const uint32_t* item_desc;    /* [n_items + 2][4] per visiting slot: first entry, one-past-last entry, item id, flags; then
+                                   a trailer of two descriptors with the visiting-order positions where the SHORT items change
+                                   kind / size class: {first short partial item of <= 8 words, of <= 4 words, first short full
+                                   item, first short full item of <= 8 words}, {first short full item of <= 4 words, 0, 0, 0}
+                                   (the column pass gives an item of one quad one lane, of two quads two, else eight) */
   const uint32_t* locus_order;  /* [T] loci in descending item count */
   const uint32_t* locus_desc;   /* [T][4] per visiting slot of locus_order: locus, first item, one-past-last item, 0 */
   const uint32_t* locus_item_ptr;
