@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GBRS_EM_ABI_VERSION 5
+#define GBRS_EM_ABI_VERSION 6
 #define GBRS_HPAD 8 /* haplotype slots per locus line */
 #define GBRS_KMAX 8 /* classes with up to this many (class, locus) pairs take the fixed-width row pass */
 #define GBRS_DEEP_LOCUS_ITEMS 8 /* a locus with more partial sums (column-pass items / tile slots) than this is summed by a
